@@ -1,0 +1,183 @@
+/* b2nerf.h -- C ABI of libb2nerf.so: the B200 (sm_100a) ray-marching hot path
+ * of Project-NeRF (encode -> MLP -> sample/mask/composite, forward + backward).
+ *
+ * The reference (CV-Project2025/Project-NeRF) is pure Python; its hot path is
+ * bound through torch ops and the external tiny-cuda-nn extension.  This header
+ * is what a maintainer binds instead (ctypes stub: INTEGRATION.md).  Each entry
+ * point cites the reference code it replaces (paths relative to the reference
+ * repository root).
+ *
+ * Conventions
+ *  - every function returns 0 on success or a negative B2N_E* code; it never
+ *    throws, never exits, never synchronises the stream, allocates nothing;
+ *  - all pointers are DEVICE pointers to contiguous row-major fp32 unless
+ *    stated; the caller owns every buffer; `stream` is a cudaStream_t;
+ *  - sizes are element counts; empty inputs (P == 0, B == 0) are a no-op;
+ *  - functions are stateless and re-entrant; device = current device.
+ */
+#ifndef B2NERF_H_
+#define B2NERF_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2N_ABI_VERSION 3
+
+#define B2N_OK 0
+#define B2N_EINVAL (-1)  /* bad argument (null pointer, size, unsupported shape) */
+#define B2N_ECUDA (-2)   /* CUDA launch/runtime error; see b2n_last_error()      */
+
+typedef void* b2n_stream_t; /* cudaStream_t */
+
+int b2n_abi_version(void);
+/* thread-local, valid until the next failing call on this thread */
+const char* b2n_last_error(void);
+
+/* activation codes shared by the linear / fused-MLP entry points */
+enum { B2N_ACT_NONE = 0, B2N_ACT_RELU = 1, B2N_ACT_SIGMOID = 2 };
+
+/* ------------------------------------------------------------------------
+ * Ray marching: stratified depths, occupancy test, compaction
+ * ---------------------------------------------------------------------- */
+
+/* Packs a bool occupancy grid (torch.bool [R,R,R], 1 byte/voxel, x slowest;
+ * src/renderer.py:29) into a bitfield of n_voxels/32 words (bit v%32 of word
+ * v/32).  n_voxels must be a multiple of 32. */
+int b2n_occ_pack_bits(const uint8_t* binary, int64_t n_voxels, uint32_t* bits, b2n_stream_t stream);
+
+/* DensityGrid.get_active_mask (src/renderer.py:134-166): voxel index =
+ * trunc((p + offset) * scale) per axis, valid iff 0 <= idx < R on all axes,
+ * mask = valid && grid bit.  pts [P,3] -> mask [P] (1 byte each, 0/1). */
+int b2n_occ_active_mask(const float* pts, int64_t P, const uint32_t* bits, int R, float offset, float scale,
+                        uint8_t* mask, b2n_stream_t stream);
+
+/* DensityGrid.update tail (src/renderer.py:119-131): grid = dynamic ?
+ * max(grid*decay, cur) : cur; binary = grid > threshold; also emits the packed
+ * bitfield and the number of active voxels (device int64 counter, zeroed by
+ * the call). */
+int b2n_occ_update(const float* cur_sigma, float* grid, int64_t n_voxels, int dynamic, float decay, float threshold,
+                   uint8_t* binary, uint32_t* bits, int64_t* n_active, b2n_stream_t stream);
+
+/* sample_stratified + point generation + occupancy test in one pass
+ * (src/renderer.py:186-201, :290-291, :305).
+ *   z_base/z_lo/z_hi [N]  unperturbed depths and the stratum bounds (host-built
+ *                         once with torch so they are bit-identical to the
+ *                         reference's linspace arithmetic);
+ *   u [B,N] or NULL       the U[0,1) jitter (torch.rand) -- NULL = no perturb;
+ *   bits or NULL          occupancy bitfield; NULL = every sample active;
+ * outputs
+ *   z [B,N]               z = lo + (hi - lo) * u   (or z_base)
+ *   mask_words [B,W]      W = (N+31)/32, bit s%32 of word s/32 = sample active
+ *   ray_count [B]         active samples of the ray (int32)                  */
+int b2n_march_mask(const float* rays_o, const float* rays_d, const float* z_base, const float* z_lo,
+                   const float* z_hi, const float* u, const uint32_t* bits, int R, float offset, float scale,
+                   int64_t B, int N, float* z, uint32_t* mask_words, int32_t* ray_count, b2n_stream_t stream);
+
+/* Exclusive scan of ray_count -> ray_offset [B+1] (int32; last = total).  If
+ * no sample is active the reference forces sample 0 of ray 0
+ * (src/renderer.py:309-311): the scan then sets bit 0 of mask_words[0],
+ * ray_count[0] = 1 and total = 1.  `total_out` is a device int32 (copy it to
+ * the host to size the compact buffers).  scratch: b2n_march_scan_scratch(B)
+ * bytes. */
+size_t b2n_march_scan_scratch(int64_t B);
+int b2n_march_scan(int32_t* ray_count, uint32_t* mask_words, int W, int64_t B, int32_t* ray_offset,
+                   int32_t* total_out, void* scratch, b2n_stream_t stream);
+
+/* Order-preserving compaction (the boolean-mask gathers of
+ * src/renderer.py:315-323): for every active sample, in (ray, sample) order,
+ * writes sample_idx (= ray*N + s), the point o + d*z, the normalised view
+ * direction d/|d| (src/renderer.py:294) and, if times != NULL, the ray's time.
+ * Any output pointer may be NULL.  mask_words == NULL means dense (all B*N). */
+int b2n_march_compact(const float* rays_o, const float* rays_d, const float* times, const float* z,
+                      const uint32_t* mask_words, const int32_t* ray_offset, int64_t B, int N,
+                      int32_t* sample_idx, float* pts, float* dirs, float* t_out, b2n_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Alpha compositing (volume_render, src/renderer.py:204-237; mean_delta_x,
+ * src/renderer.py:363-380)
+ *   rgb [P,3], sigma [P], dx [P,3] or NULL: per-sample fields, either dense
+ *   (P = B*N, mask_words == NULL) or compact (active samples only, in
+ *   (ray, sample) order; inactive samples count as rgb = sigma = dx = 0).
+ *   bg: [3] (bg_per_ray = 0) or [B,3] (bg_per_ray = 1) or NULL (no background).
+ * forward  -> color [B,3], depth [B], acc [B], mean_dx [B,3] (if dx)
+ * backward -> g_rgb [P,3], g_sigma [P], g_dx [P,3] (same layout as inputs)
+ * ---------------------------------------------------------------------- */
+int b2n_composite_fwd(const float* rgb, const float* sigma, const float* dx, const float* z, const float* rays_d,
+                      const float* bg, int bg_per_ray, const uint32_t* mask_words, const int32_t* ray_offset,
+                      int64_t B, int N, float* color, float* depth, float* acc, float* mean_dx,
+                      b2n_stream_t stream);
+int b2n_composite_bwd(const float* rgb, const float* sigma, const float* dx, const float* z, const float* rays_d,
+                      const float* bg, int bg_per_ray, const uint32_t* mask_words, const int32_t* ray_offset,
+                      int64_t B, int N, const float* g_color, const float* g_depth, const float* g_acc,
+                      const float* g_mean_dx, float* g_rgb, float* g_sigma, float* g_dx, b2n_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Fourier positional encoding (FourierRepresentation.forward,
+ * src/embeddings.py:22-32): out row = [x, sin((x*f0)*pi), cos(..), ...];
+ * written at column `col0` of a row-major buffer with leading dimension ld_out
+ * so that concatenations (src/core.py:276, src/decoders.py:83,159) need no
+ * extra pass.  bands: device [L].  D <= 4.
+ * backward accumulates (+=) into g_x [P,D] when accumulate != 0.
+ * ---------------------------------------------------------------------- */
+int b2n_pe_fwd(const float* x, int64_t P, int D, const float* bands, int L, float* out, int ld_out, int col0,
+               b2n_stream_t stream);
+int b2n_pe_bwd(const float* x, int64_t P, int D, const float* bands, int L, const float* g_out, int ld_g, int col0,
+               float* g_x, int accumulate, b2n_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Multiresolution hash grid (HashRepresentation.forward,
+ * src/embeddings.py:75-89 -> tinycudann HashGrid, 3-D, linear interpolation)
+ * ---------------------------------------------------------------------- */
+#define B2N_MAX_LEVELS 32
+typedef struct {
+  float scale;     /* exp2f(l*log2f(per_level_scale))*base - 1              */
+  uint32_t res;    /* ceil(scale) + 1                                        */
+  uint32_t size;   /* entries in this level                                  */
+  uint32_t offset; /* first entry of this level in the flat table            */
+  uint32_t hashed; /* 1: spatial hash, 0: dense x + y*res + z*res^2          */
+} b2n_hash_level;
+
+/* x [P,3] world coordinates; x01 = clamp((x + bound) / (2*bound), 0, 1);
+ * table: flat fp32 [n_entries * F] (F = 1, 2 or 4); out [P, L*F] written at col0 of ld_out. */
+int b2n_hash_fwd(const float* x, int64_t P, float bound, const float* table, const b2n_hash_level* levels_host,
+                 int L, int F, float* out, int ld_out, int col0, b2n_stream_t stream);
+/* g_table (fp32, same shape as table) is ACCUMULATED into (atomics); g_x [P,3]
+ * is overwritten (or accumulated when accumulate_x != 0); either may be NULL. */
+int b2n_hash_bwd(const float* x, int64_t P, float bound, const float* table, const b2n_hash_level* levels_host,
+                 int L, int F, const float* g_out, int ld_g, int col0, float* g_table, float* g_x, int accumulate_x,
+                 b2n_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * fp32 dense layers (torch.nn.Linear of NeRFDecoder / DeformationNetwork /
+ * TimeModulationNetwork, src/decoders.py:55-66,176-189,347, and the bias-free
+ * matrices of the tinycudann FullyFusedMLPs, src/decoders.py:111-134,285-295)
+ *   fwd   : Y[P,N]   = act(X[P,K] * W[N,K]^T + b)       b may be NULL
+ *   dgrad : dX[P,K]  = (dY[P,N] * W[N,K]) (.) act'(Xact)  Xact = the activation
+ *           output that produced X (NULL / B2N_ACT_NONE: no mask);
+ *           accumulate != 0: dX += ...
+ *   wgrad : dW[N,K] += dY^T X ; db[N] += colsum(dY)      (db may be NULL)
+ *   act_bwd: dZ = dY (.) act'(Y) in place on dY (Y = activation OUTPUT)
+ * ld* are leading dimensions (row strides, in elements).
+ * ---------------------------------------------------------------------- */
+int b2n_linear_fwd(const float* X, int ldx, const float* W, int ldw, const float* b, float* Y, int ldy, int64_t P,
+                   int K, int N, int act, b2n_stream_t stream);
+int b2n_linear_dgrad(const float* dY, int lddy, const float* W, int ldw, const float* Xact, int ldxa, int act,
+                     float* dX, int lddx, int64_t P, int K, int N, int accumulate, b2n_stream_t stream);
+int b2n_linear_wgrad(const float* dY, int lddy, const float* X, int ldx, float* dW, int lddw, float* db, int64_t P,
+                     int K, int N, b2n_stream_t stream);
+int b2n_act_bwd(float* dY, int lddy, const float* Y, int ldy, int64_t P, int N, int act, b2n_stream_t stream);
+
+/* sigma head of InstantNeRFDecoder (src/decoders.py:153):
+ * sigma[p] = softplus(h[p*ld + 0] - 5); backward: g_h0 += g_sigma * sigmoid(h0 - 5). */
+int b2n_sigma_head_fwd(const float* h, int ldh, int64_t P, float* sigma, b2n_stream_t stream);
+int b2n_sigma_head_bwd(const float* h, int ldh, int64_t P, const float* g_sigma, float* g_h, int ldg,
+                       b2n_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2NERF_H_ */

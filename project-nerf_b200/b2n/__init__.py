@@ -1,0 +1,8 @@
+"""b2n -- host binding of the B200 ray-marching kernels (libb2nerf.so).
+
+Importing this package loads the CUDA extension and raises ImportError if it
+has not been built: there is deliberately no CPU fallback.
+"""
+from . import _lib  # noqa: F401  (fails loudly when the .so is missing)
+from .ops import (HashGeometry, composite, fourier_encode, hash_encode, linear, sigma_head)  # noqa: F401
+from . import march  # noqa: F401

@@ -1,0 +1,131 @@
+"""ctypes binding of libb2nerf.so (C ABI declared in include/b2nerf.h).
+
+The library is built in-tree by ``project-nerf_b200/build.py`` and is the only
+compute path of this package: if it is missing the import FAILS -- there is no
+CPU or eager-PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb2nerf.so")
+
+ABI_VERSION = 3
+
+P, L, I, F = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
+
+# name -> argtypes (all functions return int unless listed in _RESTYPES)
+SIGNATURES = {
+    "b2n_abi_version": [],
+    "b2n_last_error": [],
+    "b2n_occ_pack_bits": [P, L, P, P],
+    "b2n_occ_active_mask": [P, L, P, I, F, F, P, P],
+    "b2n_occ_update": [P, P, L, I, F, F, P, P, P, P],
+    "b2n_march_mask": [P, P, P, P, P, P, P, I, F, F, L, I, P, P, P, P],
+    "b2n_march_scan_scratch": [L],
+    "b2n_march_scan": [P, P, I, L, P, P, P, P],
+    "b2n_march_compact": [P, P, P, P, P, P, L, I, P, P, P, P, P],
+    "b2n_composite_fwd": [P, P, P, P, P, P, I, P, P, L, I, P, P, P, P, P],
+    "b2n_composite_bwd": [P, P, P, P, P, P, I, P, P, L, I, P, P, P, P, P, P, P, P],
+    "b2n_pe_fwd": [P, L, I, P, I, P, I, I, P],
+    "b2n_pe_bwd": [P, L, I, P, I, P, I, I, P, I, P],
+    "b2n_hash_fwd": [P, L, F, P, P, I, I, P, I, I, P],
+    "b2n_hash_bwd": [P, L, F, P, P, I, I, P, I, I, P, P, I, P],
+    "b2n_linear_fwd": [P, I, P, I, P, P, I, L, I, I, I, P],
+    "b2n_linear_dgrad": [P, I, P, I, P, I, I, P, I, L, I, I, I, P],
+    "b2n_linear_wgrad": [P, I, P, I, P, I, P, L, I, I, P],
+    "b2n_act_bwd": [P, I, P, I, L, I, I, P],
+    "b2n_sigma_head_fwd": [P, I, L, P, P],
+    "b2n_sigma_head_bwd": [P, I, L, P, P, I, P],
+}
+_RESTYPES = {"b2n_last_error": ctypes.c_char_p, "b2n_march_scan_scratch": ctypes.c_size_t}
+
+
+class HashLevelC(ctypes.Structure):
+    """mirror of b2n_hash_level"""
+    _fields_ = [("scale", ctypes.c_float), ("res", ctypes.c_uint32), ("size", ctypes.c_uint32),
+                ("offset", ctypes.c_uint32), ("hashed", ctypes.c_uint32)]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: build the CUDA extension first (python project-nerf_b200/build.py). "
+            "This package has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the .so does not export it
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, ctypes.c_int)
+    v = lib.b2n_abi_version()
+    if v != ABI_VERSION:
+        raise ImportError(f"libb2nerf.so ABI {v} != binding ABI {ABI_VERSION}: rebuild")
+    return lib
+
+
+lib = _load()
+
+# launch accounting for bench.py ("gpu_launches"): every successful C-ABI call adds the
+# number of kernels that entry point launches.
+LAUNCHES = {"count": 0}
+_KERNELS_PER_CALL = {"b2n_march_scan": 3, "b2n_linear_wgrad": 2, "b2n_hash_bwd": 2}
+
+
+def ptr(t):
+    """device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class Profiler:
+    """Per-entry-point device timing with CUDA events on the launching stream (bench.py uses it
+    inside the timed region to get the dominant kernel's average duration for the roofline).
+    ``work`` is (algorithmic_bytes, flops) of the call as computed by the op wrapper."""
+
+    def __init__(self):
+        self.records = []        # (name, bytes, flops, start_event, end_event)
+
+    def summary(self):
+        """name -> dict(calls, ms, bytes, flops); call after torch.cuda.synchronize()."""
+        out = {}
+        for name, nbytes, flops, e0, e1 in self.records:
+            d = out.setdefault(name, dict(calls=0, ms=0.0, bytes=0.0, flops=0.0))
+            d["calls"] += 1
+            d["ms"] += e0.elapsed_time(e1)
+            d["bytes"] += nbytes
+            d["flops"] += flops
+        return out
+
+
+PROFILER = None      # set to a Profiler() to time every C-ABI call
+
+
+def call(name: str, *args, work=(0.0, 0.0)):
+    prof = PROFILER
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+    rc = getattr(lib, name)(*args)
+    if prof is not None:
+        e1.record()
+        prof.records.append((name, float(work[0]), float(work[1]), e0, e1))
+    if rc != 0:
+        msg = lib.b2n_last_error().decode(errors="replace")
+        if rc == -1:
+            raise ValueError(f"{name}: {msg}")
+        raise RuntimeError(f"{name} failed ({rc}): {msg}")
+    LAUNCHES["count"] += _KERNELS_PER_CALL.get(name, 1)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise ValueError("b2n ops need CUDA tensors: there is no CPU path in this package")

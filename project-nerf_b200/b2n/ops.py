@@ -1,0 +1,290 @@
+"""torch.autograd wrappers around the libb2nerf.so kernels.
+
+Every op takes/returns contiguous fp32 CUDA tensors on the current stream;
+``custom_fwd(cast_inputs=float32)`` makes them safe under the
+``torch.amp.autocast('cuda')`` regions of run.py:1092,1818.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import List, Optional, Sequence
+
+import numpy as np
+import torch
+from torch.amp import custom_bwd, custom_fwd
+
+from . import _lib
+from ._lib import HashLevelC, ptr, require_cuda, stream
+
+
+def call(name, *args, work=(0.0, 0.0)):
+    _lib.call(name, *args, work=work)        # late-bound so that _lib.PROFILER can be swapped at run time
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
+_ACT = {"none": ACT_NONE, "relu": ACT_RELU, "sigmoid": ACT_SIGMOID}
+
+
+def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+# ----------------------------------------------------------------------------
+# hash-grid geometry (host side; passed by value to the kernels)
+# ----------------------------------------------------------------------------
+
+_libm = ctypes.CDLL("libm.so.6")
+for _fn in ("exp2f", "log2f", "ceilf"):
+    getattr(_libm, _fn).restype = ctypes.c_float
+    getattr(_libm, _fn).argtypes = [ctypes.c_float]
+
+
+class HashGeometry:
+    """Per-level scale / resolution / size / offset of a tinycudann-style HashGrid
+    (semantics: SURVEY.md 8a/A2).  Computed once on the host in fp32 with libm,
+    like upstream does, and handed to every kernel call so that host and device
+    can never disagree on a resolution."""
+
+    def __init__(self, n_levels: int, base_resolution: int, per_level_scale: float, log2_hashmap_size: int,
+                 n_features: int = 2):
+        if not (1 <= n_levels <= 32):
+            raise ValueError("n_levels must be in [1, 32]")
+        if n_features not in (1, 2, 4):
+            raise ValueError("n_features_per_level must be 1, 2 or 4")
+        self.n_levels, self.n_features = n_levels, n_features
+        log2s = _libm.log2f(ctypes.c_float(per_level_scale))
+        arr = (HashLevelC * n_levels)()
+        offset = 0
+        self.levels = []
+        for l in range(n_levels):
+            e = float(np.float32(np.float32(l) * np.float32(log2s)))
+            scale = np.float32(np.float32(_libm.exp2f(ctypes.c_float(e))) * np.float32(base_resolution)) - np.float32(1.0)
+            res = int(_libm.ceilf(ctypes.c_float(float(scale)))) + 1
+            dense = res ** 3
+            size = min((min(dense, (1 << 31) - 1) + 7) // 8 * 8, 1 << log2_hashmap_size)
+            hashed = size < dense
+            arr[l] = HashLevelC(float(scale), res, size, offset, int(hashed))
+            self.levels.append((float(scale), res, size, offset, hashed))
+            offset += size
+        self.c_levels = arr
+        self.n_entries = offset
+        self.n_params = offset * n_features
+        self.out_dim = n_levels * n_features
+
+
+class _HashEncode(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, table, geom: HashGeometry, bound: float):
+        require_cuda(x, table)
+        x, table = _c(x), _c(table)
+        if x.dim() != 2 or x.shape[1] != 3:
+            raise ValueError("hash_encode expects x of shape [P, 3]")
+        if table.numel() != geom.n_params:
+            raise ValueError(f"hash table has {table.numel()} params, geometry needs {geom.n_params}")
+        Pn = x.shape[0]
+        out = torch.empty(Pn, geom.out_dim, device=x.device, dtype=torch.float32)
+        call("b2n_hash_fwd", ptr(x), Pn, float(bound), ptr(table), geom.c_levels, geom.n_levels, geom.n_features,
+             ptr(out), geom.out_dim, 0, stream(),
+             work=(Pn * (12 + geom.n_levels * geom.n_features * 4 * 9), 0.0))
+        ctx.save_for_backward(x, table)
+        ctx.geom, ctx.bound = geom, bound
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        x, table = ctx.saved_tensors
+        geom = ctx.geom
+        g = _c(g)
+        need_x, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        g_table = torch.zeros_like(table) if need_t else None
+        g_x = torch.empty_like(x) if need_x else None
+        if need_x or need_t:
+            call("b2n_hash_bwd", ptr(x), x.shape[0], float(ctx.bound), ptr(table), geom.c_levels, geom.n_levels,
+                 geom.n_features, ptr(g), geom.out_dim, 0, ptr(g_table), ptr(g_x), 0, stream(),
+                 work=(x.shape[0] * ((12 + geom.n_levels * geom.n_features * 4 * 17) * int(need_t)
+                                     + (24 + geom.n_levels * geom.n_features * 4 * 9) * int(need_x)), 0.0))
+        return g_x, g_table, None, None
+
+
+def hash_encode(x, table, geom: HashGeometry, bound: float):
+    """x [P,3] world coords (bound > 0) or unit-cube coords (bound == 0) -> [P, L*F]."""
+    return _HashEncode.apply(x, table, geom, bound)
+
+
+# ----------------------------------------------------------------------------
+# Fourier features
+# ----------------------------------------------------------------------------
+
+class _Fourier(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, bands):
+        require_cuda(x, bands)
+        x, bands = _c(x), _c(bands)
+        Pn, D = x.shape
+        L = bands.numel()
+        if D > 4:
+            raise ValueError("fourier_encode supports input_dim <= 4")
+        W = D + 2 * D * L
+        out = torch.empty(Pn, W, device=x.device, dtype=torch.float32)
+        call("b2n_pe_fwd", ptr(x), Pn, D, ptr(bands), L, ptr(out), W, 0, stream())
+        ctx.save_for_backward(x, bands)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        if not ctx.needs_input_grad[0]:
+            return None, None
+        x, bands = ctx.saved_tensors
+        g = _c(g)
+        gx = torch.empty_like(x)
+        call("b2n_pe_bwd", ptr(x), x.shape[0], x.shape[1], ptr(bands), bands.numel(), ptr(g), g.shape[1], 0,
+             ptr(gx), 0, stream())
+        return gx, None
+
+
+def fourier_encode(x, bands):
+    if bands.numel() == 0:
+        return x
+    return _Fourier.apply(x, bands)
+
+
+# ----------------------------------------------------------------------------
+# dense layers (fp32 exact path)
+# ----------------------------------------------------------------------------
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, W, b, act: int):
+        require_cuda(x, W, b)
+        x, W, b = _c(x), _c(W), _c(b)
+        Pn, K = x.shape
+        N = W.shape[0]
+        if W.shape[1] < K:
+            raise ValueError(f"linear: weight has {W.shape[1]} input columns, activations have {K}")
+        y = torch.empty(Pn, N, device=x.device, dtype=torch.float32)
+        # W may be wider than x (zero-padded FullyFusedMLP input columns): ldw = W.shape[1], K = x width
+        call("b2n_linear_fwd", ptr(x), K, ptr(W), W.shape[1], ptr(b), ptr(y), N, Pn, K, N, act, stream(),
+             work=(4.0 * Pn * (K + N), 2.0 * Pn * K * N))
+        ctx.save_for_backward(x, W, y if act != ACT_NONE else None)
+        ctx.act, ctx.has_b = act, b is not None
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, gy):
+        x, W, y = ctx.saved_tensors
+        Pn, K = x.shape
+        N = W.shape[0]
+        gy = _c(gy)
+        if ctx.act != ACT_NONE:
+            gy = gy.clone()
+            call("b2n_act_bwd", ptr(gy), N, ptr(y), N, Pn, N, ctx.act, stream())
+        gx = gW = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x)
+            call("b2n_linear_dgrad", ptr(gy), N, ptr(W), W.shape[1], None, 0, ACT_NONE, ptr(gx), K, Pn, K, N, 0,
+                 stream(), work=(4.0 * Pn * (K + N), 2.0 * Pn * K * N))
+        if ctx.needs_input_grad[1]:
+            gW = torch.zeros_like(W)
+            gb = torch.zeros(N, device=x.device, dtype=torch.float32) if ctx.has_b and ctx.needs_input_grad[2] else None
+            call("b2n_linear_wgrad", ptr(gy), N, ptr(x), K, ptr(gW), W.shape[1], ptr(gb), Pn, K, N, stream(),
+                 work=(4.0 * Pn * (K + N), 2.0 * Pn * K * N))
+        return gx, gW, gb, None
+
+
+def linear(x, W, b=None, act: str = "none"):
+    """act(x @ W[:, :x.shape[1]].T + b)"""
+    return _Linear.apply(x, W, b, _ACT[act])
+
+
+class _SigmaHead(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, h):
+        require_cuda(h)
+        h = _c(h)
+        Pn = h.shape[0]
+        sigma = torch.empty(Pn, 1, device=h.device, dtype=torch.float32)
+        call("b2n_sigma_head_fwd", ptr(h), h.shape[1], Pn, ptr(sigma), stream())
+        ctx.save_for_backward(h)
+        return sigma
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, gs):
+        h, = ctx.saved_tensors
+        gh = torch.zeros_like(h)
+        call("b2n_sigma_head_bwd", ptr(h), h.shape[1], h.shape[0], ptr(_c(gs)), ptr(gh), h.shape[1], stream())
+        return gh
+
+
+def sigma_head(h):
+    """softplus(h[:, 0:1] - 5)   (src/decoders.py:153)"""
+    return _SigmaHead.apply(h)
+
+
+# ----------------------------------------------------------------------------
+# compositing
+# ----------------------------------------------------------------------------
+
+class _Composite(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, rgb, sigma, dx, z, rays_d, bg, mask_words, ray_offset):
+        require_cuda(rgb, sigma, z, rays_d)
+        rgb, sigma, dx, z, rays_d, bg = _c(rgb), _c(sigma), _c(dx), _c(z), _c(rays_d), _c(bg)
+        B, N = z.shape
+        dev = z.device
+        color = torch.empty(B, 3, device=dev)
+        depth = torch.empty(B, device=dev)
+        acc = torch.empty(B, device=dev)
+        mdx = torch.empty(B, 3, device=dev) if dx is not None else None
+        per_ray = int(bg is not None and bg.dim() == 2)
+        if per_ray and bg.shape[0] != B:
+            raise ValueError("bg_color must be [3] or [n_rays, 3]")
+        call("b2n_composite_fwd", ptr(rgb), ptr(sigma), ptr(dx), ptr(z), ptr(rays_d), ptr(bg), per_ray,
+             ptr(mask_words), ptr(ray_offset), B, N, ptr(color), ptr(depth), ptr(acc), ptr(mdx), stream(),
+             work=(sigma.numel() * (16 + (12 if dx is not None else 0)) + 4.0 * B * N + 44.0 * B, 0.0))
+        ctx.save_for_backward(rgb, sigma, dx, z, rays_d, bg, mask_words, ray_offset)
+        ctx.per_ray = per_ray
+        if mdx is None:
+            mdx = torch.zeros(0, device=dev)
+            ctx.mark_non_differentiable(mdx)
+        return color, depth, acc, mdx
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, g_color, g_depth, g_acc, g_mdx):
+        rgb, sigma, dx, z, rays_d, bg, mask_words, ray_offset = ctx.saved_tensors
+        B, N = z.shape
+        g_rgb = torch.empty_like(rgb)
+        g_sigma = torch.empty_like(sigma)
+        g_dx = torch.empty_like(dx) if dx is not None else None
+        if dx is None:
+            g_mdx = None
+        call("b2n_composite_bwd", ptr(rgb), ptr(sigma), ptr(dx), ptr(z), ptr(rays_d), ptr(bg), ctx.per_ray,
+             ptr(mask_words), ptr(ray_offset), B, N, ptr(_c(g_color)), ptr(_c(g_depth)), ptr(_c(g_acc)),
+             ptr(_c(g_mdx)), ptr(g_rgb), ptr(g_sigma), ptr(g_dx), stream(),
+             work=(sigma.numel() * (32 + (24 if dx is not None else 0)) + 4.0 * B * N + 32.0 * B, 0.0))
+        return g_rgb, g_sigma, g_dx, None, None, None, None, None
+
+
+def composite(rgb, sigma, z, rays_d, bg=None, dx=None, mask_words=None, ray_offset=None):
+    """Alpha compositing of per-sample fields.  rgb [P,3], sigma [P] (or [P,1]),
+    dx [P,3]|None in dense (P = B*N) or compact layout (mask_words/ray_offset given).
+    Returns color [B,3], depth [B], acc [B], mean_dx [B,3] | None."""
+    sigma = sigma.reshape(-1)
+    rgb = rgb.reshape(-1, 3)
+    if dx is not None:
+        dx = dx.reshape(-1, 3)
+    color, depth, acc, mdx = _Composite.apply(rgb, sigma, dx, z, rays_d, bg, mask_words, ray_offset)
+    return color, depth, acc, (mdx if dx is not None else None)

@@ -1,0 +1,305 @@
+// Input encodings: Fourier features (FourierRepresentation, src/embeddings.py:13-32) and the
+// multiresolution hash grid that the reference obtains from tinycudann
+// (HashRepresentation, src/embeddings.py:46-89).  Outputs are written at a column offset of a
+// wider row-major buffer so the concatenations of src/core.py:276,348 and
+// src/decoders.py:83,159 cost no extra pass.
+#include "b2n_common.cuh"
+
+namespace b2n {
+
+// ----------------------------------------------------------------------------- Fourier
+// arg = (x * f) * pi in fp32, the reference's evaluation order; pi rounded to fp32 like the
+// np.pi python scalar is by torch.  The argument reaches ~1e4 rad, so the accurate
+// (range-reduced) sincosf is required, never __sinf.
+#define B2N_PI_F 3.14159274101257324f
+
+__global__ void k_pe_fwd(const float* __restrict__ x, int64_t P, int D, const float* __restrict__ bands, int L,
+                         float* __restrict__ out, int ld, int col0) {
+  // one thread per (point, input dim, band); band index L means the identity column
+  const int per_pt = D * (L + 1);
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * per_pt) return;
+  const int64_t p = i / per_pt;
+  const int rem = (int)(i - p * per_pt);
+  const int k = rem / D, d = rem - k * D;
+  const float xv = x[p * D + d];
+  float* row = out + p * ld + col0;
+  if (k == 0) {
+    row[d] = xv;
+  } else {
+    const float arg = __fmul_rn(__fmul_rn(xv, __ldg(bands + k - 1)), B2N_PI_F);
+    float s, c;
+    sincosf(arg, &s, &c);
+    row[D + 2 * (k - 1) * D + d] = s;
+    row[D + (2 * (k - 1) + 1) * D + d] = c;
+  }
+}
+
+__global__ void k_pe_bwd(const float* __restrict__ x, int64_t P, int D, const float* __restrict__ bands, int L,
+                         const float* __restrict__ g, int ld, int col0, float* __restrict__ gx, int accumulate) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P * D) return;
+  const int64_t p = i / D;
+  const int d = (int)(i - p * D);
+  const float xv = x[i];
+  const float* row = g + p * ld + col0;
+  float acc = row[d];
+  for (int k = 0; k < L; ++k) {
+    const float f = __ldg(bands + k);
+    const float arg = __fmul_rn(__fmul_rn(xv, f), B2N_PI_F);
+    float s, c;
+    sincosf(arg, &s, &c);
+    acc += (row[D + 2 * k * D + d] * c - row[D + (2 * k + 1) * D + d] * s) * (B2N_PI_F * f);
+  }
+  gx[i] = accumulate ? gx[i] + acc : acc;
+}
+
+// ----------------------------------------------------------------------------- hash grid
+struct Levels {
+  b2n_hash_level l[B2N_MAX_LEVELS];
+};
+
+__device__ __forceinline__ uint32_t corner_entry(const b2n_hash_level& lv, uint32_t cx, uint32_t cy, uint32_t cz) {
+  uint32_t idx;
+  if (lv.hashed) {
+    idx = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
+    idx &= lv.size - 1u;  // a hashed level always has size == 2^log2_hashmap_size
+  } else {
+    idx = cx + cy * lv.res + cz * lv.res * lv.res;
+    if (idx >= lv.size) idx %= lv.size;  // only the +1 corners at x01 == 1 wrap
+  }
+  return lv.offset + idx;
+}
+
+// world coordinate -> unit cube: clamp((x + bound) / (2 bound), 0, 1)   (embeddings.py:86-87)
+__device__ __forceinline__ float to_unit(float x, float bound, float two_bound, bool* inside) {
+  // bound == 0: the input already lives in the unit cube (tcnn-style ``encoding(x01)`` call)
+  const float xn = bound > 0.f ? __fdiv_rn(__fadd_rn(x, bound), two_bound) : x;
+  *inside = (xn >= 0.f) && (xn <= 1.f);  // clamp passes gradient on the closed interval
+  return fminf(fmaxf(xn, 0.f), 1.f);
+}
+
+struct Cell {
+  uint32_t g[3];
+  float w[3];
+};
+
+__device__ __forceinline__ Cell locate(const float x01[3], float scale) {
+  Cell c;
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float pos = __fadd_rn(__fmul_rn(x01[d], scale), 0.5f);
+    const float fl = floorf(pos);
+    c.g[d] = (uint32_t)(int)fl;
+    c.w[d] = pos - fl;
+  }
+  return c;
+}
+
+template <int F>
+__device__ __forceinline__ void load_feat(const float* __restrict__ table, uint32_t e, float v[F]) {
+  if (F == 2) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(table) + e);
+    v[0] = t.x, v[1] = t.y;
+  } else if (F == 4) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(table) + e);
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+  } else {
+#pragma unroll
+    for (int f = 0; f < F; ++f) v[f] = __ldg(table + (size_t)e * F + f);
+  }
+}
+
+// grid = (ceil(P/256), L): consecutive threads = consecutive points of ONE level, so a block's
+// gathers stay inside that level's slice of the table (L1/L2 locality), 8 independent gathers
+// in flight per thread.
+template <int F>
+__global__ void __launch_bounds__(256)
+k_hash_fwd(const float* __restrict__ x, int64_t P, float bound, float two_bound, const float* __restrict__ table,
+           const Levels lv, float* __restrict__ out, int ld, int col0) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const b2n_hash_level L = lv.l[blockIdx.y];
+  bool in;
+  float x01[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) x01[d] = to_unit(__ldg(x + 3 * p + d), bound, two_bound, &in);
+  const Cell c = locate(x01, L.scale);
+  float vals[8][F];
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    load_feat<F>(table, corner_entry(L, c.g[0] + (k & 1), c.g[1] + ((k >> 1) & 1), c.g[2] + ((k >> 2) & 1)), vals[k]);
+  float acc[F];
+#pragma unroll
+  for (int f = 0; f < F; ++f) acc[f] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float wt = ((k & 1) ? c.w[0] : 1.f - c.w[0]) * ((k & 2) ? c.w[1] : 1.f - c.w[1]) *
+                     ((k & 4) ? c.w[2] : 1.f - c.w[2]);
+#pragma unroll
+    for (int f = 0; f < F; ++f) acc[f] += wt * vals[k][f];
+  }
+  float* o = out + p * ld + col0 + blockIdx.y * F;
+#pragma unroll
+  for (int f = 0; f < F; ++f) o[f] = acc[f];
+}
+
+template <int F>
+__global__ void __launch_bounds__(256)
+k_hash_bwd_table(const float* __restrict__ x, int64_t P, float bound, float two_bound, const Levels lv,
+                 const float* __restrict__ g, int ld, int col0, float* __restrict__ g_table) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  const b2n_hash_level L = lv.l[blockIdx.y];
+  bool in;
+  float x01[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) x01[d] = to_unit(__ldg(x + 3 * p + d), bound, two_bound, &in);
+  const Cell c = locate(x01, L.scale);
+  float gv[F];
+  const float* gi = g + p * ld + col0 + blockIdx.y * F;
+#pragma unroll
+  for (int f = 0; f < F; ++f) gv[f] = gi[f];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float wt = ((k & 1) ? c.w[0] : 1.f - c.w[0]) * ((k & 2) ? c.w[1] : 1.f - c.w[1]) *
+                     ((k & 4) ? c.w[2] : 1.f - c.w[2]);
+    const uint32_t e = corner_entry(L, c.g[0] + (k & 1), c.g[1] + ((k >> 1) & 1), c.g[2] + ((k >> 2) & 1));
+    if (F == 2) {
+      atomicAdd(reinterpret_cast<float2*>(g_table) + e, make_float2(wt * gv[0], wt * gv[1]));
+    } else if (F == 4) {
+      atomicAdd(reinterpret_cast<float4*>(g_table) + e, make_float4(wt * gv[0], wt * gv[1], wt * gv[2], wt * gv[3]));
+    } else {
+#pragma unroll
+      for (int f = 0; f < F; ++f) atomicAdd(g_table + (size_t)e * F + f, wt * gv[f]);
+    }
+  }
+}
+
+// dL/dx = sum_levels scale_l * sum_f g_f * d(trilinear)/dw, chained through clamp and the
+// division by 2*bound.  One thread per point (the sum over levels stays in registers).
+template <int F>
+__global__ void __launch_bounds__(256)
+k_hash_bwd_input(const float* __restrict__ x, int64_t P, float bound, float two_bound,
+                 const float* __restrict__ table, const Levels lv, int nl, const float* __restrict__ g, int ld,
+                 int col0, float* __restrict__ gx, int accumulate) {
+  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  bool in[3];
+  float x01[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) x01[d] = to_unit(__ldg(x + 3 * p + d), bound, two_bound, &in[d]);
+  float gsum[3] = {0.f, 0.f, 0.f};
+  const float* gi = g + p * ld + col0;
+  for (int l = 0; l < nl; ++l) {
+    const b2n_hash_level L = lv.l[l];
+    const Cell c = locate(x01, L.scale);
+    float gv[F];
+#pragma unroll
+    for (int f = 0; f < F; ++f) gv[f] = gi[l * F + f];
+    float dot[8];  // <g, table[corner]>
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float v[F];
+      load_feat<F>(table, corner_entry(L, c.g[0] + (k & 1), c.g[1] + ((k >> 1) & 1), c.g[2] + ((k >> 2) & 1)), v);
+      float s = 0.f;
+#pragma unroll
+      for (int f = 0; f < F; ++f) s += gv[f] * v[f];
+      dot[k] = s;
+    }
+    const float wx = c.w[0], wy = c.w[1], wz = c.w[2];
+    // d/dwx: sum over (y,z) corners of weight_yz * (dot[x=1] - dot[x=0])
+    const float ddx = (1.f - wy) * (1.f - wz) * (dot[1] - dot[0]) + wy * (1.f - wz) * (dot[3] - dot[2]) +
+                      (1.f - wy) * wz * (dot[5] - dot[4]) + wy * wz * (dot[7] - dot[6]);
+    const float ddy = (1.f - wx) * (1.f - wz) * (dot[2] - dot[0]) + wx * (1.f - wz) * (dot[3] - dot[1]) +
+                      (1.f - wx) * wz * (dot[6] - dot[4]) + wx * wz * (dot[7] - dot[5]);
+    const float ddz = (1.f - wx) * (1.f - wy) * (dot[4] - dot[0]) + wx * (1.f - wy) * (dot[5] - dot[1]) +
+                      (1.f - wx) * wy * (dot[6] - dot[2]) + wx * wy * (dot[7] - dot[3]);
+    gsum[0] += L.scale * ddx, gsum[1] += L.scale * ddy, gsum[2] += L.scale * ddz;
+  }
+#pragma unroll
+  for (int d = 0; d < 3; ++d) {
+    const float v = in[d] ? (bound > 0.f ? gsum[d] / two_bound : gsum[d]) : 0.f;
+    gx[3 * p + d] = accumulate ? gx[3 * p + d] + v : v;
+  }
+}
+
+static int fill_levels(const b2n_hash_level* h, int L, Levels* out) {
+  if (!h || L <= 0 || L > B2N_MAX_LEVELS) return -1;
+  for (int i = 0; i < L; ++i) {
+    out->l[i] = h[i];
+    if (h[i].size == 0) return -1;
+    if (h[i].hashed && (h[i].size & (h[i].size - 1))) return -1;
+  }
+  return 0;
+}
+
+}  // namespace b2n
+
+using namespace b2n;
+
+extern "C" int b2n_pe_fwd(const float* x, int64_t P, int D, const float* bands, int L, float* out, int ld_out,
+                          int col0, b2n_stream_t stream) {
+  B2N_REQUIRE(P >= 0 && D > 0 && D <= 4 && L >= 0 && L <= 32, "bad shape");
+  if (P == 0) return B2N_OK;
+  B2N_REQUIRE(x && out && (L == 0 || bands), "null pointer");
+  B2N_REQUIRE(ld_out >= col0 + D + 2 * D * L && col0 >= 0, "output row too narrow");
+  k_pe_fwd<<<grid_for(P * D * (L + 1), 256), 256, 0, (cudaStream_t)stream>>>(x, P, D, bands, L, out, ld_out, col0);
+  return check_launch("b2n_pe_fwd");
+}
+
+extern "C" int b2n_pe_bwd(const float* x, int64_t P, int D, const float* bands, int L, const float* g_out, int ld_g,
+                          int col0, float* g_x, int accumulate, b2n_stream_t stream) {
+  B2N_REQUIRE(P >= 0 && D > 0 && D <= 4 && L >= 0 && L <= 32, "bad shape");
+  if (P == 0) return B2N_OK;
+  B2N_REQUIRE(x && g_out && g_x && (L == 0 || bands), "null pointer");
+  B2N_REQUIRE(ld_g >= col0 + D + 2 * D * L && col0 >= 0, "gradient row too narrow");
+  k_pe_bwd<<<grid_for(P * D, 256), 256, 0, (cudaStream_t)stream>>>(x, P, D, bands, L, g_out, ld_g, col0, g_x,
+                                                                  accumulate);
+  return check_launch("b2n_pe_bwd");
+}
+
+extern "C" int b2n_hash_fwd(const float* x, int64_t P, float bound, const float* table,
+                            const b2n_hash_level* levels_host, int L, int F, float* out, int ld_out, int col0,
+                            b2n_stream_t stream) {
+  B2N_REQUIRE(P >= 0 && (F == 1 || F == 2 || F == 4) && bound >= 0.f, "bad shape (F in {1,2,4})");
+  Levels lv;
+  B2N_REQUIRE(fill_levels(levels_host, L, &lv) == 0, "bad level table");
+  if (P == 0) return B2N_OK;
+  B2N_REQUIRE(x && table && out, "null pointer");
+  B2N_REQUIRE(ld_out >= col0 + L * F && col0 >= 0, "output row too narrow");
+  const dim3 grid(grid_for(P, 256), L);
+  const float tb = 2.0f * bound;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (F == 2) k_hash_fwd<2><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, out, ld_out, col0);
+  else if (F == 4) k_hash_fwd<4><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, out, ld_out, col0);
+  else k_hash_fwd<1><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, out, ld_out, col0);
+  return check_launch("b2n_hash_fwd");
+}
+
+extern "C" int b2n_hash_bwd(const float* x, int64_t P, float bound, const float* table,
+                            const b2n_hash_level* levels_host, int L, int F, const float* g_out, int ld_g, int col0,
+                            float* g_table, float* g_x, int accumulate_x, b2n_stream_t stream) {
+  B2N_REQUIRE(P >= 0 && (F == 1 || F == 2 || F == 4) && bound >= 0.f, "bad shape (F in {1,2,4})");
+  Levels lv;
+  B2N_REQUIRE(fill_levels(levels_host, L, &lv) == 0, "bad level table");
+  if (P == 0) return B2N_OK;
+  B2N_REQUIRE(x && g_out, "null pointer");
+  B2N_REQUIRE(ld_g >= col0 + L * F && col0 >= 0, "gradient row too narrow");
+  B2N_REQUIRE(!g_x || table, "input gradient needs the table");
+  const float tb = 2.0f * bound;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_table) {
+    const dim3 grid(grid_for(P, 256), L);
+    if (F == 2) k_hash_bwd_table<2><<<grid, 256, 0, st>>>(x, P, bound, tb, lv, g_out, ld_g, col0, g_table);
+    else if (F == 4) k_hash_bwd_table<4><<<grid, 256, 0, st>>>(x, P, bound, tb, lv, g_out, ld_g, col0, g_table);
+    else k_hash_bwd_table<1><<<grid, 256, 0, st>>>(x, P, bound, tb, lv, g_out, ld_g, col0, g_table);
+  }
+  if (g_x) {
+    const unsigned grid = grid_for(P, 256);
+    if (F == 2) k_hash_bwd_input<2><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, g_out, ld_g, col0, g_x, accumulate_x);
+    else if (F == 4) k_hash_bwd_input<4><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, g_out, ld_g, col0, g_x, accumulate_x);
+    else k_hash_bwd_input<1><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, g_out, ld_g, col0, g_x, accumulate_x);
+  }
+  return check_launch("b2n_hash_bwd");
+}

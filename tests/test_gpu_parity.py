@@ -1,0 +1,366 @@
+"""GPU parity suite (-m gpu): the CUDA path, called through the C ABI (b2n -> libb2nerf.so),
+against (a) the golden vectors generated from the reference and (b) the CPU oracle on seeded
+inputs.  Bars (north star): sample depths, occupancy decisions and hash indices BIT-EXACT;
+RGB / depth / acc / gradients within 1e-4 relative (max|a-b| / max|b|) in fp32."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from _util import GOLDEN, full_nerf_state_dict, load, rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import b2n
+    from b2n import march
+    from src import renderer
+    from src.core import NeuralField
+    return dict(b2n=b2n, march=march, renderer=renderer, NeuralField=NeuralField)
+
+
+def cu(t):
+    return t.to(DEV) if isinstance(t, torch.Tensor) else t
+
+
+# ------------------------------------------------------------------ sampling / occupancy (bit exact)
+@pytest.mark.parametrize("N", [64, 128, 2, 1])
+def test_sampling_bit_exact(mods, N):
+    g = load(f"sampling_N{N}")
+    B = g["u"].shape[0]
+    dummy = torch.zeros(B, 3, device=DEV)
+    m = mods["march"].march(dummy, dummy, g["near"], g["far"], N, cu(g["u"]))
+    assert torch.equal(m.z.cpu(), g["z_pert"])
+    m = mods["march"].march(dummy, dummy, g["near"], g["far"], N, None)
+    assert torch.equal(m.z.cpu(), g["z_flat"])
+
+
+@pytest.mark.parametrize("R", [4, 16, 128])
+def test_active_mask_bit_exact(mods, R):
+    g = load(f"mask_R{R}")
+    grid = mods["renderer"].DensityGrid(resolution=R, bound=g["bound"], threshold=0.01).to(DEV)
+    grid.binary_grid = cu(g["binary_grid"])
+    assert torch.equal(grid.get_active_mask(cu(g["pts"])).cpu(), g["mask"])
+    # in-place edits of the bool buffer must be picked up (bitfield cache keyed on _version)
+    grid.binary_grid.fill_(False)
+    assert not grid.get_active_mask(cu(g["pts"])).any()
+
+
+def test_march_mask_and_compaction_vs_oracle(mods):
+    from oracle import nerf_oracle as O
+    torch.manual_seed(0)
+    B, N, R, bound = 777, 128, 128, 1.5
+    ro, rd, _ = O.synthetic_rays(B, seed=3)
+    u = torch.rand(B, N)
+    occ = O.ball_occupancy(R, bound, 0.75)
+    z = O.sample_stratified(2.0, 6.0, N, B, u)
+    pts = (ro[:, None] + rd[:, None] * z[..., None]).reshape(-1, 3)
+    mask = O.active_mask(pts, occ, bound)
+    bits = mods["march"].pack_occupancy(cu(occ))
+    m = mods["march"].march(cu(ro), cu(rd), 2.0, 6.0, N, cu(u), bits=bits, R=R, bound=bound, want_idx=True)
+    assert torch.equal(m.z.cpu(), z)
+    assert m.n_active == int(mask.sum())
+    assert torch.equal(m.sample_idx.cpu().long(), mask.nonzero().squeeze(-1))          # order preserving
+    assert torch.equal(m.pts.cpu(), pts[mask])                                           # bit-exact points
+    vd = (rd / rd.norm(dim=-1, keepdim=True))[:, None].expand(-1, N, -1).reshape(-1, 3)[mask]
+    assert rel_err(m.dirs.cpu(), vd) < 1e-6
+    offs = torch.cat([torch.zeros(1, dtype=torch.long), mask.view(B, N).sum(1).cumsum(0)])
+    assert torch.equal(m.ray_offset.cpu().long(), offs)
+
+
+def test_march_empty_grid_forces_first_sample(mods):
+    """reference renderer.py:309-311: an all-empty mask still queries sample 0 of ray 0."""
+    B, N, R = 50, 64, 16
+    occ = torch.zeros(R, R, R, dtype=torch.bool, device=DEV)
+    bits = mods["march"].pack_occupancy(occ)
+    ro = torch.tensor([[0.0, 0.0, 4.0]], device=DEV).repeat(B, 1)
+    rd = torch.tensor([[0.0, 0.0, -1.0]], device=DEV).repeat(B, 1)
+    m = mods["march"].march(ro, rd, 2.0, 6.0, N, None, bits=bits, R=R, bound=1.5, want_idx=True)
+    assert m.n_active == 1 and m.sample_idx.tolist() == [0]
+    assert m.ray_offset.tolist() == [0] + [1] * B
+    assert torch.equal(m.pts.cpu(), torch.tensor([[0.0, 0.0, 2.0]]))
+
+
+def test_march_ragged_sizes(mods):
+    for B, N in ((0, 64), (1, 1), (3, 33), (2049, 31), (5000, 64)):
+        dummy = torch.zeros(B, 3, device=DEV)
+        m = mods["march"].march(dummy, dummy + 1, 2.0, 6.0, N, None)
+        assert m.z.shape == (B, N) and m.pts.shape == (B * N, 3)
+
+
+# ------------------------------------------------------------------ compositing
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "composite_*.npz"))))
+def test_composite_golden(mods, path):
+    g = load(os.path.basename(path)[:-4])
+    rgb, sigma = cu(g["rgb"]).requires_grad_(True), cu(g["sigma"]).requires_grad_(True)
+    bg = cu(g["bg"]) if g["bg"].numel() else None
+    c, d, a = mods["renderer"].volume_render(rgb, sigma, cu(g["z"]), cu(g["rays_d"]), bg_color=bg)
+    assert rel_err(c.cpu(), g["color"]) < TOL and rel_err(d.cpu(), g["depth"]) < TOL and rel_err(a.cpu(), g["acc"]) < TOL
+    loss = (c * cu(g["g_color"])).sum() + (d * cu(g["g_depth"])).sum() + (a * cu(g["g_acc"])).sum()
+    gr, gs = torch.autograd.grad(loss, [rgb, sigma])
+    assert rel_err(gr.cpu(), g["g_rgb"]) < TOL
+    assert rel_err(gs.cpu(), g["g_sigma"]) < TOL
+
+
+def test_composite_compact_with_dx_vs_oracle(mods):
+    from oracle import nerf_oracle as O
+    torch.manual_seed(1)
+    B, N = 300, 96
+    mask = torch.rand(B, N) < 0.3
+    mask[5] = False
+    mask[6] = True
+    z = torch.sort(torch.rand(B, N) * 4 + 2, dim=-1)[0]
+    rd = torch.randn(B, 3)
+    bg = torch.rand(B, 3)
+    Pn = int(mask.sum())
+    rgb_c = torch.rand(Pn, 3, dtype=torch.float64, requires_grad=True)
+    sig_c = (torch.rand(Pn, dtype=torch.float64) * 30).requires_grad_(True)
+    dx_c = torch.randn(Pn, 3, dtype=torch.float64, requires_grad=True)
+    flat = mask.reshape(-1)
+    rgb = torch.zeros(B * N, 3, dtype=torch.float64).index_put((flat,), rgb_c).view(B, N, 3)
+    sig = torch.zeros(B * N, dtype=torch.float64).index_put((flat,), sig_c).view(B, N)
+    dxd = torch.zeros(B * N, 3, dtype=torch.float64).index_put((flat,), dx_c).view(B, N, 3)
+    c, d, a = O.volume_render(rgb, sig, z.double(), rd.double(), bg.double())
+    w = O.composite_weights(sig, z.double(), rd.double())
+    mdx = (w[..., None] * dxd).sum(1)
+    gc, gd, ga, gm = torch.randn(B, 3), torch.randn(B), torch.randn(B), torch.randn(B, 3)
+    loss = (c * gc).sum() + (d * gd).sum() + (a * ga).sum() + (mdx * gm).sum()
+    ref = torch.autograd.grad(loss, [rgb_c, sig_c, dx_c])
+    # CUDA: compact layout through mask words / offsets
+    W = (N + 31) // 32
+    bitsarr = np.zeros((B, W * 32), dtype=bool)
+    bitsarr[:, :N] = mask.numpy()
+    words = np.packbits(bitsarr.reshape(B, W, 32), axis=-1, bitorder="little").view(np.uint32).reshape(B, W)
+    words = torch.from_numpy(words.view(np.int32).copy()).to(DEV)
+    offs = torch.cat([torch.zeros(1, dtype=torch.long), mask.sum(1).cumsum(0)]).int().to(DEV)
+    r2, s2, x2 = (t.detach().float().to(DEV).requires_grad_(True) for t in (rgb_c, sig_c, dx_c))
+    c2, d2, a2, m2 = mods["b2n"].composite(r2, s2, cu(z), cu(rd), bg=cu(bg), dx=x2, mask_words=words, ray_offset=offs)
+    for got, want in ((c2, c), (d2, d), (a2, a), (m2, mdx)):
+        assert rel_err(got.cpu(), want) < TOL
+    loss2 = (c2 * cu(gc)).sum() + (d2 * cu(gd)).sum() + (a2 * cu(ga)).sum() + (m2 * cu(gm)).sum()
+    got = torch.autograd.grad(loss2, [r2, s2, x2])
+    for gg, rr in zip(got, ref):
+        assert rel_err(gg.cpu(), rr) < TOL
+
+
+def test_composite_properties_full_size(mods):
+    """C2-sized batch (2^18 rays x 128 samples): weights sum to <= 1, linear in rgb, and the
+    dense and compact layouts agree when every sample is active."""
+    torch.manual_seed(2)
+    B, N = 2 ** 18, 128
+    sigma = torch.rand(B, N, device=DEV) * 2
+    rgb = torch.rand(B, N, 3, device=DEV)
+    z = torch.linspace(2, 6, N, device=DEV).expand(B, N).contiguous()
+    rd = torch.randn(B, 3, device=DEV)
+    c1, d1, a1, _ = mods["b2n"].composite(rgb, sigma, z, rd)
+    assert float(a1.max()) <= 1.0 + 1e-5 and float(a1.min()) >= 0.0
+    assert float(d1.min()) >= 0.0 and float(d1.max()) <= 6.0 + 1e-4
+    c2, _, _, _ = mods["b2n"].composite(rgb * 0.5, sigma, z, rd)
+    assert rel_err(c2, c1 * 0.5) < 1e-6
+    words = torch.full((B, 4), -1, dtype=torch.int32, device=DEV)
+    offs = (torch.arange(B + 1, device=DEV) * N).int()
+    c3, d3, a3, _ = mods["b2n"].composite(rgb, sigma, z, rd, mask_words=words, ray_offset=offs)
+    assert torch.equal(c3, c1) and torch.equal(d3, d1) and torch.equal(a3, a1)
+
+
+# ------------------------------------------------------------------ encoders
+@pytest.mark.parametrize("D,L", [(3, 10), (3, 4), (1, 10), (1, 6), (3, 0)])
+def test_fourier_golden(mods, D, L):
+    g = load(f"pe_D{D}_L{L}")
+    x = cu(g["x"]).requires_grad_(True)
+    y = mods["b2n"].fourier_encode(x, cu(g["bands"]))
+    # arguments are bit-identical to the reference's; sincosf vs the host libm differ by <= 2 ulp
+    assert (y.cpu() - g["y"]).abs().max() < 1e-6
+    if L:
+        gx, = torch.autograd.grad((y * cu(g["g_y"])).sum(), x)
+        assert rel_err(gx.cpu(), g["g_x"]) < TOL
+
+
+@pytest.mark.parametrize("tag", ["c2", "c5deform", "small"])
+def test_hash_encode_vs_oracle(mods, tag):
+    from oracle import nerf_oracle as O
+    g = load(f"hash_kat_{tag}")
+    c = g["cfg"]
+    geom = mods["b2n"].HashGeometry(c["n_levels"], c["base_resolution"], c["per_level_scale"],
+                                    c["log2_hashmap_size"], c["n_features_per_level"])
+    lv = O.hash_level_table(c["n_levels"], c["base_resolution"], c["per_level_scale"], c["log2_hashmap_size"])
+    assert [(l.scale, l.res, l.size, l.offset, l.hashed) for l in lv] == geom.levels      # host tables identical
+    torch.manual_seed(4)
+    table = torch.randn(geom.n_params) * 0.5
+    bound = 1.5
+    xw = torch.cat([(g["x"] * 2 - 1) * bound, (torch.rand(3000, 3) * 2 - 1) * bound * 1.1])   # some points outside
+    # integer KAT: a one-hot table per corner is overkill; instead compare features + both gradients
+    t_ref, x_ref = table.clone().requires_grad_(True), xw.clone().requires_grad_(True)
+    y_ref = O.hash_representation(x_ref, t_ref, lv, c["n_features_per_level"], bound)
+    gy = torch.randn_like(y_ref)
+    gt_ref, gx_ref = torch.autograd.grad((y_ref * gy).sum(), [t_ref, x_ref])
+    t_cu, x_cu = cu(table).requires_grad_(True), cu(xw).requires_grad_(True)
+    y = mods["b2n"].hash_encode(x_cu, t_cu, geom, bound)
+    assert rel_err(y.cpu(), y_ref) < 1e-5
+    gt, gx = torch.autograd.grad((y * cu(gy)).sum(), [t_cu, x_cu])
+    assert rel_err(gt.cpu(), gt_ref) < TOL
+    assert rel_err(gx.cpu(), gx_ref) < TOL
+    # which table entries receive gradient is an INDEX decision: must match exactly
+    assert torch.equal(gt.cpu() != 0, gt_ref != 0)
+
+
+def test_hash_index_kat_exact(mods):
+    """Integer KAT: with table[e] = e (entry id, exactly representable < 2^24) and a point sitting
+    on a lattice node, the feature equals the entry index of that node."""
+    g = load("hash_kat_c2")
+    c = g["cfg"]
+    geom = mods["b2n"].HashGeometry(c["n_levels"], c["base_resolution"], c["per_level_scale"],
+                                    c["log2_hashmap_size"], 1)
+    table = torch.arange(geom.n_entries, dtype=torch.float32, device=DEV)
+    ent = g["corner_entries"]                               # [L, 64, 8] (F-independent entry ids)
+    x = cu(g["x"])
+    y = mods["b2n"].hash_encode(x, table, geom, 0.0).cpu()   # unit-cube input
+    # trilinear blend of the 8 corner ids with the oracle's weights must reproduce y
+    for li, (scale, res, size, offset, hashed) in enumerate(geom.levels):
+        pos = g["x"] * torch.tensor(scale) + 0.5
+        w = pos - torch.floor(pos)
+        acc = torch.zeros(64, dtype=torch.float64)
+        for k in range(8):
+            wt = torch.ones(64, dtype=torch.float64)
+            for d in range(3):
+                wd = w[:, d].double()
+                wt = wt * (wd if (k >> d) & 1 else 1 - wd)
+            acc += wt * ent[li, :, k].double()
+        assert ((y[:, li].double() - acc).abs() / (acc.abs() + 1)).max() < 1e-5, li
+
+
+def test_linear_vs_torch(mods):
+    torch.manual_seed(5)
+    for (Pn, K, N, act) in ((1000, 63, 256, "relu"), (517, 319, 256, "relu"), (300, 256, 1, "relu"),
+                            (129, 283, 128, "none"), (64, 128, 3, "sigmoid"), (5, 21, 64, "relu"), (0, 8, 8, "none")):
+        x = torch.randn(Pn, K, requires_grad=True)
+        W = (torch.randn(N, K) / K ** 0.5).requires_grad_(True)
+        b = torch.randn(N, requires_grad=True)
+        y = torch.nn.functional.linear(x, W, b)
+        y = {"relu": torch.relu, "sigmoid": torch.sigmoid, "none": lambda v: v}[act](y)
+        gy = torch.randn_like(y)
+        x2, W2, b2 = (cu(t.detach()).requires_grad_(True) for t in (x, W, b))
+        y2 = mods["b2n"].linear(x2, W2, b2, act)
+        assert rel_err(y2.cpu(), y) < 1e-5
+        if Pn:
+            ref = torch.autograd.grad((y * gy).sum(), [x, W, b])
+            got = torch.autograd.grad((y2 * cu(gy)).sum(), [x2, W2, b2])
+            for a_, b_ in zip(got, ref):
+                assert rel_err(a_.cpu(), b_) < 2e-5
+
+
+# ------------------------------------------------------------------ fields and render_rays vs golden
+FIELDS = ["part2_nerf", "part2_instant", "part3_nerf", "part3_dtc", "part3_instant", "part4"]
+
+
+def _model_from(mods, cfg, sd):
+    model = mods["NeuralField"](cfg)
+    model.load_state_dict(sd)
+    return model.to(DEV)
+
+
+def _check_grads(model, loss, g, tol):
+    names = list(g["grads"]) + list(g["gradsum"])
+    params = dict(model.named_parameters())
+    grads = torch.autograd.grad(loss, [params[n] for n in names], allow_unused=True)
+    for n, gr in zip(names, grads):
+        gr = torch.zeros_like(params[n]) if gr is None else gr
+        gr = gr.cpu()
+        if n in g["grads"]:
+            assert rel_err(gr, g["grads"][n]) < tol, n
+        else:
+            s = torch.stack([gr.double().sum(), gr.double().abs().sum(), (gr.double() ** 2).sum()])
+            assert torch.allclose(s, g["gradsum"][n], rtol=5e-4, atol=1e-8), n
+            if n in g["gradhead"]:
+                assert rel_err(gr.reshape(-1)[:4096], g["gradhead"][n]) < tol, n
+
+
+@pytest.mark.parametrize("tag", FIELDS)
+def test_field_golden(mods, tag):
+    g = load(f"field_{tag}")
+    model = _model_from(mods, g["cfg"], g["sd"]).eval()
+    dyn = g["cfg"]["mode"] in ("part3", "part4")
+    out = model(cu(g["x"]), cu(g["d"]), t=cu(g["t"])) if dyn else model(cu(g["x"]), cu(g["d"]))
+    assert rel_err(out[0].cpu(), g["rgb"]) < TOL and rel_err(out[1].cpu(), g["sigma"]) < TOL
+    loss = (out[0] * cu(g["g_rgb"])).sum() + (out[1] * cu(g["g_sigma"])).sum()
+    if dyn:
+        assert rel_err(out[2].cpu(), g["dx"]) < TOL
+        loss = loss + (out[2] * cu(g["g_dx"])).sum()
+    _check_grads(model, loss, g, 2e-4)
+
+
+@pytest.mark.parametrize("tag", FIELDS + ["part2_nerf_full"])
+@pytest.mark.parametrize("pert", ["flat", "pert"])
+def test_render_rays_golden(mods, tag, pert):
+    g = load(f"render_{tag}_{pert}")
+    sd = g["sd"] if g["sd"] else full_nerf_state_dict(int(g["seed"]))
+    model = _model_from(mods, g["cfg"], sd).train(pert == "pert")
+    grid = None
+    if "binary_grid" in g:
+        grid = mods["renderer"].DensityGrid(resolution=g["binary_grid"].shape[0], bound=g["grid_bound"]).to(DEV)
+        grid.binary_grid = cu(g["binary_grid"])
+    times = cu(g["times"]) if "times" in g else None
+    out = mods["renderer"].render_rays(model, cu(g["rays_o"]), cu(g["rays_d"]), g["near"], g["far"],
+                                       int(g["n_samples"]), pert == "pert", density_grid=grid, times=times,
+                                       bg_color=cu(g["bg"]), _jitter=cu(g["u"]) if pert == "pert" else None)
+    assert len(out) == (4 if times is not None else 3)
+    assert rel_err(out[0].cpu(), g["color"]) < TOL
+    assert rel_err(out[1].cpu(), g["depth"]) < TOL
+    assert rel_err(out[2].cpu(), g["acc"]) < TOL
+    loss = (out[0] * cu(g["g_color"])).sum()
+    if "mean_delta_x" in g:
+        assert rel_err(out[3]["mean_delta_x"].cpu(), g["mean_delta_x"]) < TOL
+        loss = loss + (out[3]["mean_delta_x"] * cu(g["g_mdx"])).sum()
+    _check_grads(model, loss, g, 3e-4)
+
+
+@pytest.mark.parametrize("tag", ["part2_instant", "part3_instant", "part4"])
+def test_density_grid_update_golden(mods, tag):
+    g = load(f"gridupdate_{tag}")
+    model = _model_from(mods, g["cfg"], g["sd"]).eval()
+    R = g["grid1"].shape[0]
+    grid = mods["renderer"].DensityGrid(resolution=R, bound=g["cfg"]["scene_bound"], threshold=g["threshold"]).to(DEV)
+    part3 = g["cfg"]["mode"] == "part3"
+    r1 = grid.update(model, device=DEV, time=torch.tensor([[0.3]], device=DEV) if part3 else None)
+    assert rel_err(grid.grid.cpu(), g["grid1"]) < TOL
+    stable = (g["grid1"] - g["threshold"]).abs() > 1e-5 * max(1.0, g["threshold"])
+    assert torch.equal(grid.binary_grid.cpu()[stable], g["binary1"][stable])
+    assert abs(r1 - g["ratio1"]) < 3e-3
+    # run.py:1982-1985 passes extra keywords the reference signature lacks: must be accepted
+    r2 = grid.update(model, device=DEV, time=torch.tensor([[0.8]], device=DEV) if part3 else None, decay=0.95,
+                     auto_prune=True, threshold_multiplier=1.0)
+    assert rel_err(grid.grid.cpu(), g["grid2"]) < TOL
+    stable = (g["grid2"] - g["threshold"]).abs() > 1e-5 * max(1.0, g["threshold"])
+    assert torch.equal(grid.binary_grid.cpu()[stable], g["binary2"][stable])
+    assert abs(r2 - g["ratio2"]) < 3e-3
+    # the refreshed bitfield is what get_active_mask reads
+    pts = (torch.rand(5000, 3, device=DEV) * 2 - 1) * g["cfg"]["scene_bound"]
+    from oracle import nerf_oracle as O
+    assert torch.equal(grid.get_active_mask(pts).cpu(), O.active_mask(pts.cpu(), grid.binary_grid.cpu(), grid.bound))
+
+
+def test_state_dict_keys_match_reference(mods):
+    for tag in FIELDS:
+        g = load(f"field_{tag}")
+        model = mods["NeuralField"](g["cfg"])
+        assert set(model.state_dict()) == set(g["sd"])
+
+
+def test_amp_autocast_compatible(mods):
+    """run.py:1092 wraps render_rays in torch.amp.autocast('cuda'): ops must keep fp32 semantics."""
+    g = load("render_part4_flat")
+    model = _model_from(mods, g["cfg"], g["sd"]).eval()
+    grid = mods["renderer"].DensityGrid(resolution=g["binary_grid"].shape[0], bound=g["grid_bound"]).to(DEV)
+    grid.binary_grid = cu(g["binary_grid"])
+    with torch.amp.autocast("cuda"):
+        out = mods["renderer"].render_rays(model, cu(g["rays_o"]), cu(g["rays_d"]), g["near"], g["far"],
+                                           int(g["n_samples"]), False, density_grid=grid, times=cu(g["times"]),
+                                           bg_color=cu(g["bg"]))
+    assert out[0].dtype == torch.float32
+    assert rel_err(out[0].cpu(), g["color"]) < 2e-3      # autocast runs the torch glue (cat, blend) in fp16

@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""Throughput benchmark of the ray-marching hot path (contract: see the task brief / DESIGN.md).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], "C2"): Part 2 Instant-NeRF -- 16-level hash grid (T = 2^19,
+F = 2), 64-wide sigma/color MLPs, 128^3 occupancy grid, 2^18 rays per GPU x 128 samples per ray.
+A "step" is one full training iteration of run.py:579-630: target compositing, render_rays
+(jittered sampling, occupancy test, compaction, hash encode, MLPs, alpha compositing), MSE + TV
+loss, backward, gradient all-reduce (N > 1), per-group gradient clipping, AdamW, LR schedule.
+
+Prints ONE JSON line (rank 0).  ``value`` = train rays/s over all GPUs with the ray batches already
+resident in HBM; ``e2e`` = the same step fed from pinned HOST buffers (H2D of the batch and D2H of
+the loss inside the timed region).  ``--impl reference`` times the reference's CPU implementation
+of the same step (the oracle port; the real reference + tcnn shim if /root/reference is present)
+on a bounded ray sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "project-nerf_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+C2 = dict(mode="part2_instant", n_levels=16, n_features_per_level=2, log2_hashmap_size=19, base_resolution=16,
+          per_level_scale=1.5, scene_bound=1.5, L_embed_dir=4, hidden_dim=64)
+NEAR, FAR, N_SAMPLES, GRID_R, GRID_THR = 2.0, 6.0, 128, 128, 0.12
+RAYS_PER_GPU = 2 ** 18
+LR, WEIGHT_DECAY, ETA_MIN, TV_WEIGHT, TRAIN_ITERS = 0.01, 1e-5, 1e-4, 1e-6, 2000
+CPU_SAMPLE_RAYS = 1024
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b2n", choices=["b2n", "reference"])
+    ap.add_argument("--occupancy", default="dense", choices=["dense", "sparse"])
+    ap.add_argument("--rays", type=int, default=RAYS_PER_GPU, help="rays per GPU per step")
+    ap.add_argument("--cpu-rays", type=int, default=CPU_SAMPLE_RAYS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the sparse-occupancy and render legs")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------- CPU arm
+def cpu_train_rays_per_s(n_rays, steps, warmup, occupancy):
+    """The reference's CPU implementation of the same training step on a bounded ray sample."""
+    from oracle import nerf_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    ref_dir = os.environ.get("B2N_REFERENCE", "/root/reference")
+    occ = torch.ones(GRID_R, GRID_R, GRID_R, dtype=torch.bool) if occupancy == "dense" else O.ball_occupancy(GRID_R, 1.5)
+    bg = torch.ones(3)
+    kind = "port"
+    if os.path.isdir(os.path.join(ref_dir, "src")):
+        try:
+            from oracle import tcnn_shim
+            tcnn_shim.install()
+            sys.path.insert(0, ref_dir)
+            for m in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+                del sys.modules[m]
+            sys.path.remove(PKG)
+            from src.core import NeuralField as RefField
+            from src import renderer as RefR
+            kind = "reference"
+        except Exception:
+            kind = "port"
+    torch.manual_seed(0)
+    if kind == "reference":
+        model = RefField(C2).train()
+        params = list(model.parameters())
+        grid = RefR.DensityGrid(resolution=GRID_R, bound=1.5, threshold=GRID_THR)
+        grid.binary_grid = occ
+        table = model.representation.encoding.params
+
+        def render(ro, rd):
+            return RefR.render_rays(model, ro, rd, NEAR, FAR, N_SAMPLES, True, density_grid=grid, bg_color=bg)[0]
+    else:
+        sd = O.make_state_dict(C2, seed=0)
+        sd = {k: (v.requires_grad_(True) if "freq_bands" not in k else v) for k, v in sd.items()}
+        params = [v for k, v in sd.items() if v.requires_grad]
+        field = O.OracleField(C2, sd)
+        table = sd["representation.encoding.params"]
+
+        def render(ro, rd):
+            u = torch.rand(ro.shape[0], N_SAMPLES)
+            return O.render_rays(field, ro, rd, NEAR, FAR, N_SAMPLES, u, binary_grid=occ, grid_bound=1.5, bg_color=bg)[0]
+    opt = torch.optim.AdamW(params, lr=LR, weight_decay=WEIGHT_DECAY)
+    batches = [O.synthetic_rays(n_rays, seed=100 + i) for i in range(2)]
+
+    def step(i):
+        ro, rd, tgt = batches[i % len(batches)]
+        target = tgt[:, :3] * tgt[:, 3:4] + bg * (1.0 - tgt[:, 3:4])
+        loss = torch.nn.functional.mse_loss(render(ro, rd), target)
+        loss = loss + torch.mean(torch.abs(table[1:] - table[:-1])) * TV_WEIGHT
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_([table], 1.0)
+        torch.nn.utils.clip_grad_norm_([p for p in params if p is not table], 1.0)
+        opt.step()
+        return float(loss)
+
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    return dict(value=n_rays * steps / dt, unit="rays/s", cores=torch.get_num_threads(), kind=kind,
+                sample=f"{steps} training steps of {n_rays} rays x {N_SAMPLES} samples ({occupancy} occupancy), "
+                       f"torch CPU fp32, after {warmup} warm-up", ms_per_step=1e3 * dt / steps)
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    steps, warm = max(1, min(args.steps, 20)), max(0, min(args.warmup, 2))
+    r = cpu_train_rays_per_s(args.cpu_rays, steps, warm, args.occupancy)
+    line = {
+        "impl": "reference", "metric": "train_rays_per_s", "value": r["value"], "unit": "rays/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, args.cpu_rays),
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------- helpers
+def workload_config(args, rays):
+    return {
+        "workload": "C2 Part-2 Instant-NeRF training step: hash grid L=16 F=2 T=2^19 + 64-wide sigma/color MLPs "
+                    "+ 128^3 occupancy grid, synthetic 800x800 NeRF-Synthetic-shaped rays, AdamW + TV loss",
+        "rays_per_gpu": rays, "n_samples": N_SAMPLES, "occupancy": args.occupancy,
+        "occupancy_note": "dense = all voxels active (the reference's warm-up state, 100 % of samples evaluated); "
+                          "sparse = ball r=0.75 (~6.5 % of voxels)",
+        "l2": "per-step working set (activations, GBs) far exceeds the 126 MB L2; no explicit flush; "
+              "a fresh jitter draw and a rotating ray batch every step",
+        "parallelism": f"dp{args.gpus} (rays sharded, weights+tables replicated, one gradient all-reduce per step)",
+    }
+
+
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.03 <= t <= t1 + 0.03] or [r for t, r in self.rows if t >= t0 - 1.0]
+        sm = sorted(float(r[0]) for r in rows if r[0].replace(".", "").isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i] == "Active" for r in rows)]
+        pw = [float(r[2]) for r in rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": float(rows[0][1]) if rows and rows[0][1].replace(".", "").isdigit() else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(rows), "reasons": reasons}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel_name):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel_name)
+    return None
+
+
+# --------------------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference_arm(args, rank, world)
+
+    import torch.distributed as dist
+    import b2n
+    from b2n import _lib, synthetic
+    from b2n.dp import GradAllReducer
+    from src.core import NeuralField
+    from src.renderer import DensityGrid, render_rays
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl b2n) needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.rays
+
+    torch.manual_seed(0)                                   # replicated init on every rank
+    model = NeuralField(C2).to(dev).train()
+    table = model.representation.encoding.params
+
+    def make_grid(kind):
+        g = DensityGrid(resolution=GRID_R, bound=1.5, threshold=GRID_THR).to(dev)
+        if kind == "sparse":
+            g.binary_grid = synthetic.ball_occupancy(GRID_R, 1.5).to(dev)
+        return g
+
+    opt = torch.optim.AdamW(model.parameters(), lr=LR, weight_decay=WEIGHT_DECAY)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=TRAIN_ITERS, eta_min=ETA_MIN)
+    reducer = GradAllReducer(model, world)      # flat gradient buffer: one memset, one all-reduce
+    bg = torch.ones(3, device=dev)
+
+    n_pool = 3
+    host_pool = [tuple(t.pin_memory() for t in synthetic.random_rays(B, seed=1000 * rank + i)) for i in range(n_pool)]
+    dev_pool = [tuple(t.to(dev) for t in b) for b in host_pool]
+    h2d_bytes = sum(t.numel() * t.element_size() for t in host_pool[0])
+
+    def train_step(batch, grid):
+        rays_o, rays_d, rgba = batch
+        target = rgba[:, :3] * rgba[:, 3:4] + bg * (1.0 - rgba[:, 3:4])
+        pred, _, _ = render_rays(model=model, rays_o=rays_o, rays_d=rays_d, near=NEAR, far=FAR, n_samples=N_SAMPLES,
+                                 perturb=True, white_bkgd=True, density_grid=grid, bg_color=bg)
+        loss_rgb = torch.nn.functional.mse_loss(pred, target)
+        loss = loss_rgb + torch.mean(torch.abs(table[1:] - table[:-1])) * TV_WEIGHT
+        reducer.zero_grad()
+        loss.backward()
+        reducer.allreduce()
+        torch.nn.utils.clip_grad_norm_(model.representation.parameters(), max_norm=1.0)
+        torch.nn.utils.clip_grad_norm_(model.decoder.parameters(), max_norm=1.0)
+        opt.step()
+        sched.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- headline: device-resident batches, profiler + clock sampler on
+    grid = make_grid(args.occupancy)
+    sampler = ClockSampler(local) if rank == 0 else None      # started early: nvidia-smi needs ~1 s to start
+    for i in range(args.warmup):
+        train_step(dev_pool[i % n_pool], grid)
+    barrier()
+    prof = _lib.Profiler()
+    _lib.PROFILER = prof
+    launches0 = _lib.LAUNCHES["count"]
+    t_wall0 = time.time()
+    ms = timed(lambda i: train_step(dev_pool[i % n_pool], grid), args.steps, 0)
+    t_wall1 = time.time()
+    _lib.PROFILER = None
+    launches = _lib.LAUNCHES["count"] - launches0
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    value = world * B * args.steps / (ms * 1e-3)
+    summary = prof.summary()
+
+    # ---- e2e: pinned host batch -> H2D -> step -> D2H loss, every step
+    def e2e_step(i):
+        hb = host_pool[i % n_pool]
+        batch = tuple(t.to(dev, non_blocking=True) for t in hb)
+        return float(train_step(batch, grid).item())
+
+    ms_e2e = timed(e2e_step, args.steps, 1)
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+
+    extras = {}
+    if not args.no_extras:
+        # ---- the other occupancy case
+        other = "sparse" if args.occupancy == "dense" else "dense"
+        g2 = make_grid(other)
+        ms2 = timed(lambda i: train_step(dev_pool[i % n_pool], g2), args.steps, 2)
+        extras[f"train_rays_per_s_{other}"] = world * B * args.steps / (ms2 * 1e-3)
+        # ---- render Msamples/s (forward only, no jitter, no_grad)
+        model.eval()
+        with torch.no_grad():
+            def render(i):
+                ro, rd, _ = dev_pool[i % n_pool]
+                render_rays(model, ro, rd, NEAR, FAR, N_SAMPLES, False, density_grid=grid, bg_color=bg)
+            ms3 = timed(render, args.steps, 2)
+        model.train()
+        extras["render_msamples_per_s"] = world * B * N_SAMPLES * args.steps / (ms3 * 1e-3) / 1e6
+        extras["render_occupancy"] = args.occupancy
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, tensor_peak, peak_src = measured_peaks()
+    kernels = sorted(({"entry": k, "calls_per_step": v["calls"] / args.steps, "ms_per_step": v["ms"] / args.steps,
+                       "alg_gb_per_step": v["bytes"] / args.steps / 1e9,
+                       "gbs": (v["bytes"] / 1e9) / (v["ms"] * 1e-3) if v["ms"] > 0 else None,
+                       "tflops": (v["flops"] / 1e12) / (v["ms"] * 1e-3) if v["ms"] > 0 else None}
+                      for k, v in summary.items()), key=lambda d: -d["ms_per_step"])
+    top = kernels[0]
+    roofline = {"kernel": top["entry"], "bound": "hbm", "achieved": top["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": (top["gbs"] / hbm_peak) if top["gbs"] else None, "peak_source": peak_src,
+                "avg_launch_ms": top["ms_per_step"] / max(top["calls_per_step"], 1e-9),
+                "share_of_step": top["ms_per_step"] / (ms / args.steps),
+                "traffic": ncu_traffic(top["entry"])}
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_train_rays_per_s(args.cpu_rays, 3, 1, args.occupancy)
+        cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+
+    line = {
+        "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, B),
+        "clocks": clocks, "gpu_launches": launches,
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels[:12],
+    }
+    line.update(extras)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2N_ABI_VERSION 3
+#define B2N_ABI_VERSION 4
 
 #define B2N_OK 0
 #define B2N_EINVAL (-1)  /* bad argument (null pointer, size, unsupported shape) */
@@ -176,6 +176,28 @@ int b2n_act_bwd(float* dY, int lddy, const float* Y, int ldy, int64_t P, int N, 
 int b2n_sigma_head_fwd(const float* h, int ldh, int64_t P, float* sigma, b2n_stream_t stream);
 int b2n_sigma_head_bwd(const float* h, int ldh, int64_t P, const float* g_sigma, float* g_h, int ldg,
                        b2n_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Fused InstantNeRFDecoder (src/decoders.py:136-162: two tinycudann
+ * FullyFusedMLPs + softplus density head + concat + sigmoid) including the
+ * view-direction Fourier features (src/embeddings.py:22-32 applied to d,
+ * src/core.py:358).  bf16 tensor-core operands, fp32 accumulation; hidden
+ * width 64; pos_dim <= 64 (padded with zeros); L_dir <= 4 bands.
+ *   x_enc [P, pos_dim] (row stride ldx), dirs [P,3] unit view directions,
+ *   sigma_params flat [64*pad16(pos_dim) + 16*64], color_params flat
+ *   [64*48 + 64*64 + 16*64] (row-major [out,in] matrices, reference layout).
+ * forward  -> rgb [P,3], sigma [P]
+ * backward -> g_x_enc [P,pos_dim] (row stride ldg; may be NULL), and
+ *             ACCUMULATES into g_sigma_params / g_color_params (fp32).
+ * The backward recomputes the forward; nothing but the inputs is saved.
+ * ---------------------------------------------------------------------- */
+int b2n_instant_mlp_fwd(const float* x_enc, int ldx, int pos_dim, const float* dirs, const float* dir_bands,
+                        int L_dir, const float* sigma_params, const float* color_params, int64_t P, float* rgb,
+                        float* sigma, b2n_stream_t stream);
+int b2n_instant_mlp_bwd(const float* x_enc, int ldx, int pos_dim, const float* dirs, const float* dir_bands,
+                        int L_dir, const float* sigma_params, const float* color_params, int64_t P,
+                        const float* g_rgb, const float* g_sigma, float* g_x_enc, int ldg, float* g_sigma_params,
+                        float* g_color_params, b2n_stream_t stream);
 
 #ifdef __cplusplus
 }

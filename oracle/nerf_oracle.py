@@ -183,8 +183,14 @@ def fused_mlp_n_params(n_in, n_out, n_neurons, n_hidden) -> int:
     return sum(r * c for r, c in fused_mlp_shapes(n_in, n_out, n_neurons, n_hidden))
 
 
+def bf16_round(x: Tensor) -> Tensor:
+    """round-to-nearest-even to bfloat16 with a straight-through gradient (emulates the operand
+    rounding of the tensor-core kernels; accumulation stays in the working dtype)."""
+    return x + (x.to(torch.bfloat16).to(x.dtype) - x).detach()
+
+
 def fused_mlp(x: Tensor, params: Tensor, n_in: int, n_out: int, n_neurons: int,
-              n_hidden: int, out_act: str = "None") -> Tensor:
+              n_hidden: int, out_act: str = "None", emulate_bf16: bool = False) -> Tensor:
     """ReLU MLP without bias terms.  Input columns beyond ``n_in`` are padded
     with ZEROS (SURVEY.md A4 fixes this choice), so the padded weight columns
     never contribute; the padded output rows are computed and sliced away."""
@@ -193,10 +199,11 @@ def fused_mlp(x: Tensor, params: Tensor, n_in: int, n_out: int, n_neurons: int,
     if shapes[0][1] != n_in:
         h = F.pad(h, (0, shapes[0][1] - n_in))
     off = 0
+    q = bf16_round if emulate_bf16 else (lambda v: v)
     for li, (r, c) in enumerate(shapes):
         W = params[off:off + r * c].view(r, c).to(h.dtype)
         off += r * c
-        h = h @ W.t()
+        h = q(h) @ q(W).t()
         if li < len(shapes) - 1:
             h = torch.relu(h)
     h = h[:, :n_out]
@@ -230,14 +237,14 @@ def nerf_decoder(sd, prefix: str, x: Tensor, d: Tensor, num_layers=8, skip_layer
     return rgb, sigma
 
 
-def instant_decoder(sd, prefix: str, x_enc: Tensor, d_enc: Tensor, hidden=64):
+def instant_decoder(sd, prefix: str, x_enc: Tensor, d_enc: Tensor, hidden=64, emulate_bf16: bool = False):
     """sigma_net (in->64->16), sigma = softplus(h0-5), color_net on
     cat[h(16), d_enc] (->64->64->3, sigmoid)   (src/decoders.py:136-162)."""
     pos_dim, dir_dim = x_enc.shape[-1], d_enc.shape[-1]
-    h = fused_mlp(x_enc, sd[f"{prefix}.sigma_net.params"], pos_dim, 16, hidden, 1)
+    h = fused_mlp(x_enc, sd[f"{prefix}.sigma_net.params"], pos_dim, 16, hidden, 1, emulate_bf16=emulate_bf16)
     sigma = F.softplus(h[..., 0:1] - 5.0)
     rgb = fused_mlp(torch.cat([h, d_enc], dim=-1), sd[f"{prefix}.color_net.params"],
-                    16 + dir_dim, 3, hidden, 2, out_act="Sigmoid")
+                    16 + dir_dim, 3, hidden, 2, out_act="Sigmoid", emulate_bf16=emulate_bf16)
     return rgb, sigma
 
 

@@ -288,3 +288,56 @@ def composite(rgb, sigma, z, rays_d, bg=None, dx=None, mask_words=None, ray_offs
         dx = dx.reshape(-1, 3)
     color, depth, acc, mdx = _Composite.apply(rgb, sigma, dx, z, rays_d, bg, mask_words, ray_offset)
     return color, depth, acc, (mdx if dx is not None else None)
+
+
+# ----------------------------------------------------------------------------
+# fused 64-wide Instant decoder (bf16 tensor cores)
+# ----------------------------------------------------------------------------
+
+_MLP_PRECISION = {"mode": "bf16"}
+
+
+def set_mlp_precision(mode: str):
+    """'bf16' (default): fused tensor-core decoder, 1e-2 parity class, like the reference's fp16 tinycudann nets.
+    'fp32': layer-by-layer fp32 kernels, 1e-4 parity class."""
+    if mode not in ("bf16", "fp32"):
+        raise ValueError(mode)
+    _MLP_PRECISION["mode"] = mode
+
+
+def mlp_precision() -> str:
+    return _MLP_PRECISION["mode"]
+
+
+class _InstantMLP(torch.autograd.Function):
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x_enc, dirs, bands, sigma_params, color_params):
+        require_cuda(x_enc, dirs, bands, sigma_params, color_params)
+        x_enc, dirs, bands, sp, cp = _c(x_enc), _c(dirs), _c(bands), _c(sigma_params), _c(color_params)
+        Pn, pos_dim = x_enc.shape
+        rgb = torch.empty(Pn, 3, device=x_enc.device)
+        sigma = torch.empty(Pn, 1, device=x_enc.device)
+        flops = 2.0 * Pn * (64 * pos_dim + 16 * 64 + 64 * 43 + 64 * 64 + 3 * 64)
+        call("b2n_instant_mlp_fwd", ptr(x_enc), pos_dim, pos_dim, ptr(dirs), ptr(bands), bands.numel(), ptr(sp),
+             ptr(cp), Pn, ptr(rgb), ptr(sigma), stream(), work=(Pn * (4.0 * pos_dim + 12 + 16), flops))
+        ctx.save_for_backward(x_enc, dirs, bands, sp, cp)
+        return rgb, sigma
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, g_rgb, g_sigma):
+        x_enc, dirs, bands, sp, cp = ctx.saved_tensors
+        Pn, pos_dim = x_enc.shape
+        g_x = torch.empty_like(x_enc) if ctx.needs_input_grad[0] else None
+        g_sp, g_cp = torch.zeros_like(sp), torch.zeros_like(cp)
+        flops = 6.0 * Pn * (64 * pos_dim + 16 * 64 + 64 * 43 + 64 * 64 + 3 * 64)
+        call("b2n_instant_mlp_bwd", ptr(x_enc), pos_dim, pos_dim, ptr(dirs), ptr(bands), bands.numel(), ptr(sp),
+             ptr(cp), Pn, ptr(_c(g_rgb)), ptr(_c(g_sigma)), ptr(g_x), pos_dim, ptr(g_sp), ptr(g_cp), stream(),
+             work=(Pn * (8.0 * pos_dim + 12 + 16), flops))
+        return g_x, None, None, g_sp, g_cp
+
+
+def instant_mlp(x_enc, dirs, bands, sigma_params, color_params):
+    """Fused InstantNeRFDecoder on raw unit view directions: (rgb [P,3], sigma [P,1])."""
+    return _InstantMLP.apply(x_enc, dirs, bands, sigma_params, color_params)

@@ -110,16 +110,33 @@ __device__ __forceinline__ void load_feat(const float* __restrict__ table, uint3
   }
 }
 
-// grid = (ceil(P/256), L): consecutive threads = consecutive points of ONE level, so a block's
-// gathers stay inside that level's slice of the table (L1/L2 locality), 8 independent gathers
-// in flight per thread.
+// One thread per (point, level) ITEM, item = p * L + level: consecutive lanes hold consecutive
+// levels of the same point, so the feature row of a point (L*F floats) is written / read by
+// adjacent lanes as one contiguous segment (full 32 B sectors, streaming cache hints) while the
+// 8 gathers (or 8 reductions) of an item stay independent and in flight together.  The level
+// table sits in shared memory because lanes index it divergently.  Streaming (.cs) hints on the
+// per-point traffic keep the L2 for what is re-used: the table (forward) and its gradient
+// (backward, where every red.global that misses L2 costs a 32 B DRAM fill).
+struct SmemLevels {
+  b2n_hash_level l[B2N_MAX_LEVELS];
+};
+
+__device__ __forceinline__ void stage_levels(const Levels& lv, int nl, SmemLevels* s) {
+  if (threadIdx.x < nl) s->l[threadIdx.x] = lv.l[threadIdx.x];
+  __syncthreads();
+}
+
 template <int F>
 __global__ void __launch_bounds__(256)
 k_hash_fwd(const float* __restrict__ x, int64_t P, float bound, float two_bound, const float* __restrict__ table,
-           const Levels lv, float* __restrict__ out, int ld, int col0) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const b2n_hash_level L = lv.l[blockIdx.y];
+           const Levels lv, int nl, float* __restrict__ out, int ld, int col0) {
+  __shared__ SmemLevels sl;
+  stage_levels(lv, nl, &sl);
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= P * nl) return;
+  const int64_t p = item / nl;
+  const int level = (int)(item - p * nl);
+  const b2n_hash_level L = sl.l[level];
   bool in;
   float x01[3];
 #pragma unroll
@@ -139,27 +156,44 @@ k_hash_fwd(const float* __restrict__ x, int64_t P, float bound, float two_bound,
 #pragma unroll
     for (int f = 0; f < F; ++f) acc[f] += wt * vals[k][f];
   }
-  float* o = out + p * ld + col0 + blockIdx.y * F;
+  float* o = out + p * ld + col0 + level * F;
+  if (F == 2 && ((reinterpret_cast<uintptr_t>(o) & 7) == 0)) {
+    __stcs(reinterpret_cast<float2*>(o), make_float2(acc[0], acc[1]));
+  } else {
 #pragma unroll
-  for (int f = 0; f < F; ++f) o[f] = acc[f];
+    for (int f = 0; f < F; ++f) __stcs(o + f, acc[f]);
+  }
 }
 
 template <int F>
 __global__ void __launch_bounds__(256)
-k_hash_bwd_table(const float* __restrict__ x, int64_t P, float bound, float two_bound, const Levels lv,
+k_hash_bwd_table(const float* __restrict__ x, int64_t P, float bound, float two_bound, const Levels lv, int nl,
                  const float* __restrict__ g, int ld, int col0, float* __restrict__ g_table) {
-  const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= P) return;
-  const b2n_hash_level L = lv.l[blockIdx.y];
+  __shared__ SmemLevels sl;
+  stage_levels(lv, nl, &sl);
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= P * nl) return;
+  const int64_t p = item / nl;
+  const int level = (int)(item - p * nl);
+  const b2n_hash_level L = sl.l[level];
   bool in;
   float x01[3];
 #pragma unroll
   for (int d = 0; d < 3; ++d) x01[d] = to_unit(__ldg(x + 3 * p + d), bound, two_bound, &in);
   const Cell c = locate(x01, L.scale);
   float gv[F];
-  const float* gi = g + p * ld + col0 + blockIdx.y * F;
+  const float* gi = g + p * ld + col0 + level * F;
+  if (F == 2 && ((reinterpret_cast<uintptr_t>(gi) & 7) == 0)) {
+    const float2 t = __ldcs(reinterpret_cast<const float2*>(gi));
+    gv[0] = t.x, gv[1] = t.y;
+  } else {
 #pragma unroll
-  for (int f = 0; f < F; ++f) gv[f] = gi[f];
+    for (int f = 0; f < F; ++f) gv[f] = __ldcs(gi + f);
+  }
+  bool any = false;
+#pragma unroll
+  for (int f = 0; f < F; ++f) any |= (gv[f] != 0.f);
+  if (!any) return;  // nothing to scatter (e.g. samples that received no gradient)
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const float wt = ((k & 1) ? c.w[0] : 1.f - c.w[0]) * ((k & 2) ? c.w[1] : 1.f - c.w[1]) *
@@ -268,12 +302,12 @@ extern "C" int b2n_hash_fwd(const float* x, int64_t P, float bound, const float*
   if (P == 0) return B2N_OK;
   B2N_REQUIRE(x && table && out, "null pointer");
   B2N_REQUIRE(ld_out >= col0 + L * F && col0 >= 0, "output row too narrow");
-  const dim3 grid(grid_for(P, 256), L);
+  const unsigned grid = grid_for(P * L, 256);
   const float tb = 2.0f * bound;
   cudaStream_t st = (cudaStream_t)stream;
-  if (F == 2) k_hash_fwd<2><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, out, ld_out, col0);
-  else if (F == 4) k_hash_fwd<4><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, out, ld_out, col0);
-  else k_hash_fwd<1><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, out, ld_out, col0);
+  if (F == 2) k_hash_fwd<2><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, out, ld_out, col0);
+  else if (F == 4) k_hash_fwd<4><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, out, ld_out, col0);
+  else k_hash_fwd<1><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, out, ld_out, col0);
   return check_launch("b2n_hash_fwd");
 }
 
@@ -290,10 +324,10 @@ extern "C" int b2n_hash_bwd(const float* x, int64_t P, float bound, const float*
   const float tb = 2.0f * bound;
   cudaStream_t st = (cudaStream_t)stream;
   if (g_table) {
-    const dim3 grid(grid_for(P, 256), L);
-    if (F == 2) k_hash_bwd_table<2><<<grid, 256, 0, st>>>(x, P, bound, tb, lv, g_out, ld_g, col0, g_table);
-    else if (F == 4) k_hash_bwd_table<4><<<grid, 256, 0, st>>>(x, P, bound, tb, lv, g_out, ld_g, col0, g_table);
-    else k_hash_bwd_table<1><<<grid, 256, 0, st>>>(x, P, bound, tb, lv, g_out, ld_g, col0, g_table);
+    const unsigned grid = grid_for(P * L, 256);
+    if (F == 2) k_hash_bwd_table<2><<<grid, 256, 0, st>>>(x, P, bound, tb, lv, L, g_out, ld_g, col0, g_table);
+    else if (F == 4) k_hash_bwd_table<4><<<grid, 256, 0, st>>>(x, P, bound, tb, lv, L, g_out, ld_g, col0, g_table);
+    else k_hash_bwd_table<1><<<grid, 256, 0, st>>>(x, P, bound, tb, lv, L, g_out, ld_g, col0, g_table);
   }
   if (g_x) {
     const unsigned grid = grid_for(P, 256);

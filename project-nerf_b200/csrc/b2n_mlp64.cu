@@ -1,0 +1,656 @@
+// Fused 64-wide decoder of the hash-grid configs: InstantNeRFDecoder.forward
+// (src/decoders.py:136-162), i.e. the two tinycudann FullyFusedMLPs of the reference plus the
+// direction Fourier features (src/embeddings.py:22-32 on view dirs), the softplus(h0-5) density
+// head, the concat and the sigmoid -- one kernel forward, one kernel backward.
+//
+//   sigma_net : x[pos] -> 64 (ReLU) -> 16            (no biases, widths padded to 16)
+//   sigma     = softplus(h[0] - 5)
+//   color_net : cat[h(16), gamma(d)(27 -> 32)] -> 64 (ReLU) -> 64 (ReLU) -> 3 (sigmoid)
+//
+// Arithmetic: bf16 operands, fp32 accumulation on the tensor cores (mma.sync m16n8k16); the
+// reference runs these nets in fp16 inside tinycudann.  Activations never leave the SM:
+//   forward : each warp owns 32 points; layer outputs (C fragments) are re-packed in registers
+//             as the next layer's A fragments; weights are bf16 in shared memory (ldmatrix).
+//   backward: each warp owns 16 points of a 64-point block tile; the forward is recomputed, the
+//             data-gradient chain runs in registers (ldmatrix.trans on the same weights), every
+//             layer input / pre-activation gradient is staged once in shared memory as bf16 and
+//             the weight gradients dW = dZ^T * In are accumulated by tensor cores in registers
+//             over the whole persistent loop, then flushed with one atomicAdd per weight per CTA.
+#include <cuda_bf16.h>
+#include "b2n_common.cuh"
+
+namespace b2n {
+
+typedef __nv_bfloat16 bf16;
+
+constexpr int HID = 64;      // hidden width
+constexpr int GEO = 16;      // sigma_net output width
+constexpr int CIN = 48;      // color_net padded input width (16 + 27 -> 48)
+constexpr int PAD = 8;       // bf16 row padding: row stride = width + 8 keeps ldmatrix conflict-free
+constexpr int MLP_THREADS = 128;
+
+// ------------------------------------------------------------------------------ primitives
+__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack2(uint32_t v) {
+  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&v);
+  return __bfloat1622float2(b);
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+
+// C[mt][j] (16 x 8 tiles) += A[mt][kt] * W^T ; W in smem as [n][k] bf16, row stride S.
+template <int MT, int NT, int KT>
+__device__ __forceinline__ void gemm_fwd(float (&c)[MT][NT][4], const uint32_t (&a)[MT][KT][4], const bf16* W, int S,
+                                         int lane) {
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const bf16* row = W + (8 * j + (lane & 7)) * S;
+#pragma unroll
+    for (int q = 0; q < KT / 2; ++q) {
+      uint32_t b[4];
+      ldsm_x4(b, row + 32 * q + 8 * (lane >> 3));
+#pragma unroll
+      for (int m = 0; m < MT; ++m) {
+        mma16816(c[m][j], a[m][2 * q], b[0], b[1]);
+        mma16816(c[m][j], a[m][2 * q + 1], b[2], b[3]);
+      }
+    }
+    if (KT & 1) {
+      uint32_t b[2];
+      ldsm_x2(b, row + 16 * (KT - 1) + 8 * ((lane >> 3) & 1));
+#pragma unroll
+      for (int m = 0; m < MT; ++m) mma16816(c[m][j], a[m][KT - 1], b[0], b[1]);
+    }
+  }
+}
+
+// dIn[16 x 8*NTo] += dZ[16 x 16*KTz] * W ; W in smem as [n][k] (n is the reduction index).
+template <int NTo, int KTz>
+__device__ __forceinline__ void gemm_dgrad(float (&c)[NTo][4], const uint32_t (&a)[KTz][4], const bf16* W, int S,
+                                           int lane) {
+  static_assert(NTo % 2 == 0, "pairs of output tiles");
+#pragma unroll
+  for (int jp = 0; jp < NTo / 2; ++jp) {
+#pragma unroll
+    for (int kt = 0; kt < KTz; ++kt) {
+      uint32_t b[4];
+      ldsm_x4_t(b, W + (16 * kt + 8 * ((lane >> 3) & 1) + (lane & 7)) * S + 8 * (2 * jp + (lane >> 4)));
+      mma16816(c[2 * jp], a[kt], b[0], b[1]);
+      mma16816(c[2 * jp + 1], a[kt], b[2], b[3]);
+    }
+  }
+}
+
+// acc (16 rows of dW starting at n0, NTk*8 columns starting at k0) += dZ^T In over the 64 staged points.
+template <int NTk>
+__device__ __forceinline__ void wgrad_tile(float (&acc)[NTk][4], const bf16* dZ, int Sz, int n0, const bf16* In,
+                                           int Si, int k0, int lane) {
+  static_assert(NTk % 2 == 0, "pairs of tiles");
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4];
+    ldsm_x4_t(a, dZ + (16 * ks + 8 * (lane >> 4) + (lane & 7)) * Sz + n0 + 8 * ((lane >> 3) & 1));
+#pragma unroll
+    for (int jp = 0; jp < NTk / 2; ++jp) {
+      uint32_t b[4];
+      ldsm_x4_t(b, In + (16 * ks + 8 * ((lane >> 3) & 1) + (lane & 7)) * Si + k0 + 8 * (2 * jp + (lane >> 4)));
+      mma16816(acc[2 * jp], a, b[0], b[1]);
+      mma16816(acc[2 * jp + 1], a, b[2], b[3]);
+    }
+  }
+}
+
+// C tiles (fp32) -> A fragments (bf16) of the next layer, optional ReLU.
+template <int NT, bool RELU>
+__device__ __forceinline__ void c_to_a(const float (&c)[NT][4], uint32_t (&a)[NT / 2][4]) {
+#pragma unroll
+  for (int k = 0; k < NT / 2; ++k) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float* s = c[2 * k + h];
+      float v0 = s[0], v1 = s[1], v2 = s[2], v3 = s[3];
+      if (RELU) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f), v2 = fmaxf(v2, 0.f), v3 = fmaxf(v3, 0.f);
+      a[k][2 * h] = pack2(v0, v1);      // row g
+      a[k][2 * h + 1] = pack2(v2, v3);  // row g + 8
+    }
+  }
+}
+
+// store A fragments of a 16-row slab into a [rows][width + PAD] bf16 tile (row0 = first row of the slab)
+template <int KT>
+__device__ __forceinline__ void store_a(const uint32_t (&a)[KT][4], bf16* tile, int S, int row0, int col0, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    uint32_t* r0 = reinterpret_cast<uint32_t*>(tile + (row0 + g) * S + col0 + 16 * k + 2 * t);
+    uint32_t* r1 = reinterpret_cast<uint32_t*>(tile + (row0 + g + 8) * S + col0 + 16 * k + 2 * t);
+    r0[0] = a[k][0], r1[0] = a[k][1], r0[4] = a[k][2], r1[4] = a[k][3];
+  }
+}
+
+// fp32 weight matrix [rows][src_cols] (row stride src_cols) -> bf16 smem [rows][cols + PAD]; columns
+// src_cols..cols-1 (input padding the parameter vector does not store) are zero-filled
+__device__ __forceinline__ void load_weights(const float* __restrict__ W, int rows, int cols, int src_cols, bf16* dst) {
+  const int S = cols + PAD;
+  for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
+    const int r = i / cols, c = i - r * cols;
+    dst[r * S + c] = __float2bfloat16(c < src_cols ? __ldg(W + (size_t)r * src_cols + c) : 0.f);
+  }
+}
+
+// view-direction Fourier features of one point -> 32 bf16 (27 valid, zero padded) at dst
+__device__ __forceinline__ void dir_features(const float* __restrict__ dirs, int64_t p, int64_t P,
+                                             const float* __restrict__ bands, int L, bf16* dst) {
+  float d[3] = {0.f, 0.f, 0.f};
+  if (p < P) d[0] = __ldg(dirs + 3 * p), d[1] = __ldg(dirs + 3 * p + 1), d[2] = __ldg(dirs + 3 * p + 2);
+  float f[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = 0.f;
+  f[0] = d[0], f[1] = d[1], f[2] = d[2];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k < L) {
+      const float fr = __ldg(bands + k);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        float s, c;
+        sincosf(__fmul_rn(__fmul_rn(d[j], fr), 3.14159274101257324f), &s, &c);
+        f[3 + 6 * k + j] = s;
+        f[3 + 6 * k + 3 + j] = c;
+      }
+    }
+  }
+  uint4* o = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    o[i] = make_uint4(pack2(f[8 * i], f[8 * i + 1]), pack2(f[8 * i + 2], f[8 * i + 3]),
+                      pack2(f[8 * i + 4], f[8 * i + 5]), pack2(f[8 * i + 6], f[8 * i + 7]));
+}
+
+// A fragments of 16 rows of x_enc [P, pos_dim] fp32 (zero beyond pos_dim / P)
+template <int KT>
+__device__ __forceinline__ void load_x(const float* __restrict__ x, int ldx, int pos_dim, int64_t p0, int64_t P,
+                                       uint32_t (&a)[KT][4], int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const bool vec = ((ldx & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {      // h: column half (+0 / +8)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {    // r: row g / g + 8
+        const int64_t p = p0 + g + 8 * r;
+        const int c = 16 * k + 8 * h + 2 * t;
+        float v0 = 0.f, v1 = 0.f;
+        if (p < P) {
+          const float* src = x + p * ldx + c;
+          if (vec && c + 1 < pos_dim) {
+            const float2 v = __ldcs(reinterpret_cast<const float2*>(src));
+            v0 = v.x, v1 = v.y;
+          } else {
+            if (c < pos_dim) v0 = __ldcs(src);
+            if (c + 1 < pos_dim) v1 = __ldcs(src + 1);
+          }
+        }
+        a[k][2 * h + r] = pack2(v0, v1);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float softplus_m5(float h0) {
+  const float v = h0 - 5.0f;
+  return v > 20.f ? v : log1pf(expf(v));
+}
+__device__ __forceinline__ float sigmoidf(float v) { return 1.f / (1.f + expf(-v)); }
+
+struct MlpSmem {
+  // offsets (in bf16 elements) of the weight matrices inside dynamic shared memory
+  int w1, w2, v1, v2, v3, end;
+};
+template <int POS_K>
+__host__ __device__ constexpr MlpSmem weight_layout() {
+  MlpSmem m{};
+  m.w1 = 0;
+  m.w2 = m.w1 + HID * (POS_K + PAD);
+  m.v1 = m.w2 + GEO * (HID + PAD);
+  m.v2 = m.v1 + HID * (CIN + PAD);
+  m.v3 = m.v2 + HID * (HID + PAD);
+  m.end = m.v3 + 16 * (HID + PAD);
+  return m;
+}
+
+// in_pad = pad16(pos_dim): the stored width of sigma_net's first matrix (16, 32, 48 or 64 <= POS_K)
+template <int POS_K>
+__device__ __forceinline__ void load_all_weights(const float* __restrict__ sp, const float* __restrict__ cp, int in_pad,
+                                                 bf16* sm) {
+  constexpr MlpSmem L = weight_layout<POS_K>();
+  load_weights(sp, HID, POS_K, in_pad, sm + L.w1);
+  load_weights(sp + HID * in_pad, GEO, HID, HID, sm + L.w2);
+  load_weights(cp, HID, CIN, CIN, sm + L.v1);
+  load_weights(cp + HID * CIN, HID, HID, HID, sm + L.v2);
+  load_weights(cp + HID * CIN + HID * HID, 16, HID, HID, sm + L.v3);
+}
+
+// ------------------------------------------------------------------------------ forward
+template <int POS_K>
+__global__ void __launch_bounds__(MLP_THREADS)
+k_instant_fwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __restrict__ dirs,
+              const float* __restrict__ bands, int L_dir, const float* __restrict__ sp, const float* __restrict__ cp,
+              int64_t P, float* __restrict__ rgb, float* __restrict__ sigma) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  bf16* sm = reinterpret_cast<bf16*>(smem_raw);
+  constexpr MlpSmem L = weight_layout<POS_K>();
+  constexpr int KT1 = POS_K / 16;
+  constexpr int DS = 32 + PAD;                 // direction-feature staging row stride
+  bf16* dstage = sm + L.end + (threadIdx.x >> 5) * 32 * DS;
+  const int in_pad = (pos_dim + 15) & ~15;
+  load_all_weights<POS_K>(sp, cp, in_pad, sm);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int64_t n_tiles = (P + 31) / 32;
+  const int64_t wstride = (int64_t)gridDim.x * (MLP_THREADS / 32);
+  for (int64_t tile = (int64_t)blockIdx.x * (MLP_THREADS / 32) + (threadIdx.x >> 5); tile < n_tiles; tile += wstride) {
+    const int64_t p0 = tile * 32;
+    dir_features(dirs, p0 + lane, P, bands, L_dir, dstage + lane * DS);
+    uint32_t ax[2][KT1][4];
+    load_x<KT1>(x, ldx, pos_dim, p0, P, ax[0], lane);
+    load_x<KT1>(x, ldx, pos_dim, p0 + 16, P, ax[1], lane);
+    // sigma_net layer 1
+    uint32_t ah[2][4][4];
+    {
+      float c[2][8][4] = {};
+      gemm_fwd<2, 8, KT1>(c, ax, sm + L.w1, POS_K + PAD, lane);
+      c_to_a<8, true>(c[0], ah[0]);
+      c_to_a<8, true>(c[1], ah[1]);
+    }
+    // sigma_net layer 2 -> h (16 wide), density head
+    uint32_t ac[2][3][4];
+    {
+      float c[2][2][4] = {};
+      gemm_fwd<2, 2, 4>(c, ah, sm + L.w2, HID + PAD, lane);
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        if (t == 0) {
+          const int64_t pa = p0 + 16 * m + g, pb = pa + 8;
+          if (pa < P) __stcs(sigma + pa, softplus_m5(c[m][0][0]));
+          if (pb < P) __stcs(sigma + pb, softplus_m5(c[m][0][2]));
+        }
+        uint32_t tmp[1][4];
+        c_to_a<2, false>(c[m], tmp);
+        ac[m][0][0] = tmp[0][0], ac[m][0][1] = tmp[0][1], ac[m][0][2] = tmp[0][2], ac[m][0][3] = tmp[0][3];
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      ldsm_x4(ac[m][1], dstage + (16 * m + (lane & 7) + 8 * ((lane >> 3) & 1)) * DS + 8 * (lane >> 4));
+      ldsm_x4(ac[m][2], dstage + (16 * m + (lane & 7) + 8 * ((lane >> 3) & 1)) * DS + 16 + 8 * (lane >> 4));
+    }
+    __syncwarp();
+    // color_net
+    uint32_t a1[2][4][4];
+    {
+      float c[2][8][4] = {};
+      gemm_fwd<2, 8, 3>(c, ac, sm + L.v1, CIN + PAD, lane);
+      c_to_a<8, true>(c[0], a1[0]);
+      c_to_a<8, true>(c[1], a1[1]);
+    }
+    {
+      float c[2][8][4] = {};
+      gemm_fwd<2, 8, 4>(c, a1, sm + L.v2, HID + PAD, lane);
+      c_to_a<8, true>(c[0], ah[0]);
+      c_to_a<8, true>(c[1], ah[1]);
+    }
+    {
+      float c[2][1][4] = {};
+      gemm_fwd<2, 1, 4>(c, ah, sm + L.v3, HID + PAD, lane);
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const int64_t pa = p0 + 16 * m + g, pb = pa + 8;
+        const int col = 2 * t;
+        if (col < 3) {
+          if (pa < P) {
+            rgb[3 * pa + col] = sigmoidf(c[m][0][0]);
+            if (col + 1 < 3) rgb[3 * pa + col + 1] = sigmoidf(c[m][0][1]);
+          }
+          if (pb < P) {
+            rgb[3 * pb + col] = sigmoidf(c[m][0][2]);
+            if (col + 1 < 3) rgb[3 * pb + col + 1] = sigmoidf(c[m][0][3]);
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------ backward
+template <int POS_K>
+struct BwdLayout {
+  static constexpr MlpSmem W = weight_layout<POS_K>();
+  static constexpr int SX = POS_K + PAD, SH = HID + PAD, SC = CIN + PAD, SG = 16 + PAD;
+  // staged layer inputs (64 points each)
+  static constexpr int in_x = W.end;
+  static constexpr int in_h1 = in_x + 64 * SX;
+  static constexpr int in_c = in_h1 + 64 * SH;
+  static constexpr int in_c1 = in_c + 64 * SC;
+  static constexpr int in_c2 = in_c1 + 64 * SH;
+  // staged pre-activation gradients
+  static constexpr int dz1 = in_c2 + 64 * SH;
+  static constexpr int dz2 = dz1 + 64 * SH;
+  static constexpr int dz3 = dz2 + 64 * SG;
+  static constexpr int dz4 = dz3 + 64 * SH;
+  static constexpr int dz5 = dz4 + 64 * SH;
+  static constexpr int end = dz5 + 64 * SG;
+};
+
+// ReLU mask from the staged activation tile (the thread re-reads exactly what it wrote)
+template <int NT>
+__device__ __forceinline__ void relu_mask(float (&c)[NT][4], const bf16* tile, int S, int row0, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const float2 lo = unpack2(*reinterpret_cast<const uint32_t*>(tile + (row0 + g) * S + 8 * j + 2 * t));
+    const float2 hi = unpack2(*reinterpret_cast<const uint32_t*>(tile + (row0 + g + 8) * S + 8 * j + 2 * t));
+    if (!(lo.x > 0.f)) c[j][0] = 0.f;
+    if (!(lo.y > 0.f)) c[j][1] = 0.f;
+    if (!(hi.x > 0.f)) c[j][2] = 0.f;
+    if (!(hi.y > 0.f)) c[j][3] = 0.f;
+  }
+}
+
+template <int NTk>
+__device__ __forceinline__ void flush_acc(const float (&acc)[NTk][4], float* __restrict__ gW, int ldw, int n0, int k0,
+                                          int n_valid, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int j = 0; j < NTk; ++j) {
+    const int k = k0 + 8 * j + 2 * t;
+    if (k >= ldw) continue;  // columns beyond the stored (padded) input width
+    if (n0 + g < n_valid) {
+      atomicAdd(gW + (size_t)(n0 + g) * ldw + k, acc[j][0]);
+      atomicAdd(gW + (size_t)(n0 + g) * ldw + k + 1, acc[j][1]);
+    }
+    if (n0 + g + 8 < n_valid) {
+      atomicAdd(gW + (size_t)(n0 + g + 8) * ldw + k, acc[j][2]);
+      atomicAdd(gW + (size_t)(n0 + g + 8) * ldw + k + 1, acc[j][3]);
+    }
+  }
+}
+
+template <int POS_K>
+__global__ void __launch_bounds__(MLP_THREADS)
+k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __restrict__ dirs,
+              const float* __restrict__ bands, int L_dir, const float* __restrict__ sp, const float* __restrict__ cp,
+              int64_t P, const float* __restrict__ g_rgb, const float* __restrict__ g_sigma, float* __restrict__ g_x,
+              int ldg, float* __restrict__ g_sp, float* __restrict__ g_cp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  bf16* sm = reinterpret_cast<bf16*>(smem_raw);
+  using LY = BwdLayout<POS_K>;
+  constexpr MlpSmem L = LY::W;
+  constexpr int KT1 = POS_K / 16;
+  const int in_pad = (pos_dim + 15) & ~15;
+  load_all_weights<POS_K>(sp, cp, in_pad, sm);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int row0 = 16 * warp;  // this warp's slab inside the 64-point tile
+
+  // persistent weight-gradient accumulators (this warp's share of every matrix)
+  float acc1[POS_K / 8][4] = {};  // dW1 rows 16*warp.., all POS_K columns
+  float acc2[2][4] = {};          // dW2 (16 x 64): columns 16*warp..
+  float acc3[6][4] = {};          // dV1 rows 16*warp.., 48 columns
+  float acc4[8][4] = {};          // dV2 rows 16*warp.., 64 columns
+  float acc5[2][4] = {};          // dV3 (16 x 64, 3 valid rows): columns 16*warp..
+
+  const int64_t n_tiles = (P + 63) / 64;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t p0 = tile * 64 + row0;
+    // ---------------- forward recompute (staging every layer input)
+    uint32_t ax[1][KT1][4];
+    load_x<KT1>(x, ldx, pos_dim, p0, P, ax[0], lane);
+    store_a<KT1>(ax[0], sm + LY::in_x, LY::SX, row0, 0, lane);
+    if (lane < 16) dir_features(dirs, p0 + lane, P, bands, L_dir, sm + LY::in_c + (row0 + lane) * LY::SC + 16);
+    uint32_t ah[1][4][4];
+    {
+      float c[1][8][4] = {};
+      gemm_fwd<1, 8, KT1>(c, ax, sm + L.w1, LY::SX, lane);
+      c_to_a<8, true>(c[0], ah[0]);
+      store_a<4>(ah[0], sm + LY::in_h1, LY::SH, row0, 0, lane);
+    }
+    float hs0 = 0.f, hs1 = 0.f;  // h[.,0] of rows g and g+8 (threads with t == 0)
+    uint32_t ac[1][3][4];
+    {
+      float c[1][2][4] = {};
+      gemm_fwd<1, 2, 4>(c, ah, sm + L.w2, LY::SH, lane);
+      hs0 = c[0][0][0], hs1 = c[0][0][2];
+      uint32_t tmp[1][4];
+      c_to_a<2, false>(c[0], tmp);
+      ac[0][0][0] = tmp[0][0], ac[0][0][1] = tmp[0][1], ac[0][0][2] = tmp[0][2], ac[0][0][3] = tmp[0][3];
+      store_a<1>(tmp, sm + LY::in_c, LY::SC, row0, 0, lane);
+    }
+    __syncwarp();
+    ldsm_x4(ac[0][1], sm + LY::in_c + (row0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LY::SC + 16 + 8 * (lane >> 4));
+    ldsm_x4(ac[0][2], sm + LY::in_c + (row0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LY::SC + 32 + 8 * (lane >> 4));
+    uint32_t a1[1][4][4], a2[1][4][4];
+    {
+      float c[1][8][4] = {};
+      gemm_fwd<1, 8, 3>(c, ac, sm + L.v1, LY::SC, lane);
+      c_to_a<8, true>(c[0], a1[0]);
+      store_a<4>(a1[0], sm + LY::in_c1, LY::SH, row0, 0, lane);
+    }
+    {
+      float c[1][8][4] = {};
+      gemm_fwd<1, 8, 4>(c, a1, sm + L.v2, LY::SH, lane);
+      c_to_a<8, true>(c[0], a2[0]);
+      store_a<4>(a2[0], sm + LY::in_c2, LY::SH, row0, 0, lane);
+    }
+    // ---------------- output layer + its gradient
+    uint32_t dz5[1][4];
+    {
+      float c[1][1][4] = {};
+      gemm_fwd<1, 1, 4>(c, a2, sm + L.v3, LY::SH, lane);
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+      const int64_t pa = p0 + g, pb = pa + 8;
+      const int col = 2 * t;
+      if (col < 3) {
+        if (pa < P) {
+          const float y = sigmoidf(c[0][0][0]);
+          d[0] = __ldcs(g_rgb + 3 * pa + col) * y * (1.f - y);
+          if (col + 1 < 3) {
+            const float y1 = sigmoidf(c[0][0][1]);
+            d[1] = __ldcs(g_rgb + 3 * pa + col + 1) * y1 * (1.f - y1);
+          }
+        }
+        if (pb < P) {
+          const float y = sigmoidf(c[0][0][2]);
+          d[2] = __ldcs(g_rgb + 3 * pb + col) * y * (1.f - y);
+          if (col + 1 < 3) {
+            const float y1 = sigmoidf(c[0][0][3]);
+            d[3] = __ldcs(g_rgb + 3 * pb + col + 1) * y1 * (1.f - y1);
+          }
+        }
+      }
+      dz5[0][0] = pack2(d[0], d[1]), dz5[0][1] = pack2(d[2], d[3]), dz5[0][2] = 0u, dz5[0][3] = 0u;
+      store_a<1>(dz5, sm + LY::dz5, LY::SG, row0, 0, lane);
+    }
+    // ---------------- data-gradient chain
+    uint32_t dz[1][4][4];
+    {
+      float c[8][4] = {};
+      gemm_dgrad<8, 1>(c, dz5, sm + L.v3, LY::SH, lane);          // d c2
+      relu_mask<8>(c, sm + LY::in_c2, LY::SH, row0, lane);
+      c_to_a<8, false>(c, dz[0]);
+      store_a<4>(dz[0], sm + LY::dz4, LY::SH, row0, 0, lane);
+    }
+    {
+      float c[8][4] = {};
+      gemm_dgrad<8, 4>(c, dz[0], sm + L.v2, LY::SH, lane);        // d c1
+      relu_mask<8>(c, sm + LY::in_c1, LY::SH, row0, lane);
+      c_to_a<8, false>(c, dz[0]);
+      store_a<4>(dz[0], sm + LY::dz3, LY::SH, row0, 0, lane);
+    }
+    uint32_t dz2[1][4];
+    {
+      float c[2][4] = {};
+      gemm_dgrad<2, 4>(c, dz[0], sm + L.v1, LY::SC, lane);        // d h (first 16 inputs of color_net)
+      if (t == 0) {                                               // density head: softplus'(h0 - 5)
+        const int64_t pa = p0 + g, pb = pa + 8;
+        if (pa < P) {
+          const float v = hs0 - 5.f;
+          c[0][0] += __ldcs(g_sigma + pa) * (v > 20.f ? 1.f : sigmoidf(v));
+        }
+        if (pb < P) {
+          const float v = hs1 - 5.f;
+          c[0][2] += __ldcs(g_sigma + pb) * (v > 20.f ? 1.f : sigmoidf(v));
+        }
+      }
+      c_to_a<2, false>(c, dz2);
+      store_a<1>(dz2, sm + LY::dz2, LY::SG, row0, 0, lane);
+    }
+    {
+      float c[8][4] = {};
+      gemm_dgrad<8, 1>(c, dz2, sm + L.w2, LY::SH, lane);          // d hidden1
+      relu_mask<8>(c, sm + LY::in_h1, LY::SH, row0, lane);
+      c_to_a<8, false>(c, dz[0]);
+      store_a<4>(dz[0], sm + LY::dz1, LY::SH, row0, 0, lane);
+    }
+    if (g_x) {
+      float c[POS_K / 8][4] = {};
+      gemm_dgrad<POS_K / 8, 4>(c, dz[0], sm + L.w1, LY::SX, lane);  // d x_enc
+      const int64_t pa = p0 + g, pb = pa + 8;
+#pragma unroll
+      for (int j = 0; j < POS_K / 8; ++j) {
+        const int col = 8 * j + 2 * t;
+        if (pa < P) {
+          if (col < pos_dim) g_x[pa * ldg + col] = c[j][0];
+          if (col + 1 < pos_dim) g_x[pa * ldg + col + 1] = c[j][1];
+        }
+        if (pb < P) {
+          if (col < pos_dim) g_x[pb * ldg + col] = c[j][2];
+          if (col + 1 < pos_dim) g_x[pb * ldg + col + 1] = c[j][3];
+        }
+      }
+    }
+    __syncthreads();
+    // ---------------- weight gradients over the 64 staged points
+    wgrad_tile<POS_K / 8>(acc1, sm + LY::dz1, LY::SH, 16 * warp, sm + LY::in_x, LY::SX, 0, lane);
+    wgrad_tile<2>(acc2, sm + LY::dz2, LY::SG, 0, sm + LY::in_h1, LY::SH, 16 * warp, lane);
+    wgrad_tile<6>(acc3, sm + LY::dz3, LY::SH, 16 * warp, sm + LY::in_c, LY::SC, 0, lane);
+    wgrad_tile<8>(acc4, sm + LY::dz4, LY::SH, 16 * warp, sm + LY::in_c1, LY::SH, 0, lane);
+    wgrad_tile<2>(acc5, sm + LY::dz5, LY::SG, 0, sm + LY::in_c2, LY::SH, 16 * warp, lane);
+    __syncthreads();
+  }
+  // ---------------- flush: one atomicAdd per weight per CTA
+  flush_acc<POS_K / 8>(acc1, g_sp, in_pad, 16 * warp, 0, HID, lane);
+  flush_acc<2>(acc2, g_sp + HID * in_pad, HID, 0, 16 * warp, GEO, lane);
+  flush_acc<6>(acc3, g_cp, CIN, 16 * warp, 0, HID, lane);
+  flush_acc<8>(acc4, g_cp + HID * CIN, HID, 16 * warp, 0, HID, lane);
+  flush_acc<2>(acc5, g_cp + HID * CIN + HID * HID, HID, 0, 16 * warp, 3, lane);
+}
+
+template <int POS_K>
+constexpr size_t fwd_smem_bytes() {
+  return (size_t)(weight_layout<POS_K>().end + (MLP_THREADS / 32) * 32 * (32 + PAD)) * sizeof(bf16);
+}
+template <int POS_K>
+constexpr size_t bwd_smem_bytes() {
+  return (size_t)BwdLayout<POS_K>::end * sizeof(bf16);
+}
+
+static int persistent_grid(const void* kernel, int threads, size_t smem, int64_t work_tiles) {
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t g = (int64_t)kSMs * per_sm;
+  if (g > work_tiles) g = work_tiles;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace b2n
+
+using namespace b2n;
+
+static int check_mlp_args(const float* x, int ldx, int pos_dim, const float* dirs, const float* bands, int L_dir,
+                          const float* sp, const float* cp) {
+  B2N_REQUIRE(pos_dim > 0 && pos_dim <= 64 && ldx >= pos_dim, "pos_dim must be in [1, 64]");
+  B2N_REQUIRE(L_dir >= 0 && L_dir <= 4, "direction encoding must have at most 4 bands (27 features)");
+  B2N_REQUIRE(x && dirs && sp && cp && (L_dir == 0 || bands), "null pointer");
+  return B2N_OK;
+}
+
+extern "C" int b2n_instant_mlp_fwd(const float* x_enc, int ldx, int pos_dim, const float* dirs, const float* dir_bands,
+                                   int L_dir, const float* sigma_params, const float* color_params, int64_t P,
+                                   float* rgb, float* sigma, b2n_stream_t stream) {
+  B2N_REQUIRE(P >= 0, "negative size");
+  if (P == 0) return B2N_OK;
+  int rc = check_mlp_args(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params, color_params);
+  if (rc) return rc;
+  B2N_REQUIRE(rgb && sigma, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t warp_tiles = (P + 31) / 32;
+  const int64_t block_tiles = (warp_tiles + 3) / 4;
+  if (pos_dim <= 32) {
+    constexpr size_t smem = fwd_smem_bytes<32>();
+    cudaFuncSetAttribute(k_instant_fwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = persistent_grid((const void*)k_instant_fwd<32>, MLP_THREADS, smem, block_tiles);
+    k_instant_fwd<32><<<grid, MLP_THREADS, smem, st>>>(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params,
+                                                       color_params, P, rgb, sigma);
+  } else {
+    constexpr size_t smem = fwd_smem_bytes<64>();
+    cudaFuncSetAttribute(k_instant_fwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = persistent_grid((const void*)k_instant_fwd<64>, MLP_THREADS, smem, block_tiles);
+    k_instant_fwd<64><<<grid, MLP_THREADS, smem, st>>>(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params,
+                                                       color_params, P, rgb, sigma);
+  }
+  return check_launch("b2n_instant_mlp_fwd");
+}
+
+extern "C" int b2n_instant_mlp_bwd(const float* x_enc, int ldx, int pos_dim, const float* dirs, const float* dir_bands,
+                                   int L_dir, const float* sigma_params, const float* color_params, int64_t P,
+                                   const float* g_rgb, const float* g_sigma, float* g_x_enc, int ldg,
+                                   float* g_sigma_params, float* g_color_params, b2n_stream_t stream) {
+  B2N_REQUIRE(P >= 0, "negative size");
+  if (P == 0) return B2N_OK;
+  int rc = check_mlp_args(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params, color_params);
+  if (rc) return rc;
+  B2N_REQUIRE(g_rgb && g_sigma && g_sigma_params && g_color_params, "null pointer");
+  B2N_REQUIRE(!g_x_enc || ldg >= pos_dim, "gradient row too narrow");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t tiles = (P + 63) / 64;
+  if (pos_dim <= 32) {
+    constexpr size_t smem = bwd_smem_bytes<32>();
+    cudaFuncSetAttribute(k_instant_bwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = persistent_grid((const void*)k_instant_bwd<32>, MLP_THREADS, smem, tiles);
+    k_instant_bwd<32><<<grid, MLP_THREADS, smem, st>>>(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params,
+                                                       color_params, P, g_rgb, g_sigma, g_x_enc, ldg, g_sigma_params,
+                                                       g_color_params);
+  } else {
+    constexpr size_t smem = bwd_smem_bytes<64>();
+    cudaFuncSetAttribute(k_instant_bwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int grid = persistent_grid((const void*)k_instant_bwd<64>, MLP_THREADS, smem, tiles);
+    k_instant_bwd<64><<<grid, MLP_THREADS, smem, st>>>(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params,
+                                                       color_params, P, g_rgb, g_sigma, g_x_enc, ldg, g_sigma_params,
+                                                       g_color_params);
+  }
+  return check_launch("b2n_instant_mlp_bwd");
+}

@@ -134,7 +134,7 @@ class NeuralField(nn.Module):
             feat_t = self.time_encoder(td)
             delta_x = self.deform_net(self.pos_encoder_for_deform(xd), feat_t)
             feat_can = self.canonical_repr(x + delta_x)
-            rgb, sigma = self.decoder(torch.cat([feat_can, feat_t], dim=-1), self.dir_representation(d))
+            rgb, sigma = self._decode(torch.cat([feat_can, feat_t], dim=-1), d)
             return rgb, sigma, delta_x
         if mode == "part4":
             if t is None:
@@ -146,8 +146,15 @@ class NeuralField(nn.Module):
             blend = (w0 * self.deform_grid_start(xd) + w1 * self.deform_grid_mid(xd) + w2 * self.deform_grid_end(xd))
             delta_x = self.deform_decoder(blend, time_mod)
             feat_can = self.canonical_repr(x + delta_x)
-            rgb, sigma = self.decoder(torch.cat([feat_can, feat_t], dim=-1), self.dir_representation(d))
+            rgb, sigma = self._decode(torch.cat([feat_can, feat_t], dim=-1), d)
             return rgb, sigma, delta_x
         if d is None:
             raise ValueError(f"{mode} requires view directions.")
-        return self.decoder(self.representation(x), self.dir_representation(d))
+        return self._decode(self.representation(x), d)
+
+    def _decode(self, feat, d):
+        """decoder(feat, gamma(d)); the 64-wide Instant decoder runs fused on raw directions in bf16 mode."""
+        dec = self.decoder
+        if isinstance(dec, InstantNeRFDecoder) and dec.can_fuse(self.dir_representation):
+            return dec.forward_fused(feat, d, self.dir_representation)
+        return dec(feat, self.dir_representation(d))

@@ -116,10 +116,21 @@ class InstantNeRFDecoder(BaseDecoder):
                                                     "n_hidden_layers": 2})
 
     def forward(self, x_enc, d_enc):
+        """Module-API path on pre-encoded directions (layer-by-layer fp32 kernels)."""
         h = self.sigma_net(x_enc)
         sigma = b2n.sigma_head(h)
         rgb = self.color_net(torch.cat([h, d_enc], dim=-1))
         return rgb, sigma
+
+    def can_fuse(self, dir_encoder):
+        return (b2n.mlp_precision() == "bf16" and self.sigma_net.n_neurons == 64 and self.color_net.n_neurons == 64
+                and self.sigma_net.n_input_dims <= 64 and dir_encoder.input_dim == 3 and dir_encoder.use_encoding
+                and 0 <= dir_encoder.L <= 4 and self.color_net.n_input_dims == 16 + dir_encoder.out_dim)
+
+    def forward_fused(self, x_enc, dirs, dir_encoder):
+        """Whole decoder (+ direction Fourier features) as ONE tensor-core kernel each way
+        (b2n_instant_mlp_fwd / _bwd); NeuralField.forward takes this path in bf16 mode."""
+        return b2n.instant_mlp(x_enc, dirs, dir_encoder.freq_bands, self.sigma_net.params, self.color_net.params)
 
 
 class DeformationNetwork(BaseDecoder):

@@ -1,0 +1,70 @@
+"""world_size-2 gloo test (CPU) of the data-parallel plumbing: ray sharding + flat-buffer
+gradient averaging must reproduce the single-process gradient of the mean-over-rays loss."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _load_dp():
+    # b2n/__init__ loads the CUDA library (present after build()); dp.py itself is pure torch
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("b2n_dp", os.path.join(ROOT, "project-nerf_b200", "b2n", "dp.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _make():
+    torch.manual_seed(0)
+    return torch.nn.Sequential(torch.nn.Linear(6, 32), torch.nn.ReLU(), torch.nn.Linear(32, 3))
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    dp = _load_dp()
+    model = _make()
+    red = dp.GradAllReducer(model, world)
+    torch.manual_seed(1)
+    rays, target = torch.randn(64, 6), torch.randn(64, 3)
+    a, b = dp.shard_rays(64, rank, world)
+    red.zero_grad()
+    torch.nn.functional.mse_loss(model(rays[a:b]), target[a:b]).backward()
+    red.allreduce()
+    torch.nn.utils.clip_grad_norm_(model.parameters(), 0.05)          # after the all-reduce: identical on all ranks
+    if rank == 0:
+        torch.save(red.flat.clone(), out)
+    gathered = [torch.zeros_like(red.flat) for _ in range(world)]
+    dist.all_gather(gathered, red.flat)
+    assert all(torch.equal(g, gathered[0]) for g in gathered)
+    dist.destroy_process_group()
+
+
+def test_flat_allreduce_matches_single_process(tmp_path):
+    out = str(tmp_path / "g.pt")
+    mp.spawn(_worker, args=(2, 29517, out), nprocs=2, join=True)
+    dp = _load_dp()
+    model = _make()
+    red = dp.GradAllReducer(model, 1)
+    torch.manual_seed(1)
+    rays, target = torch.randn(64, 6), torch.randn(64, 3)
+    torch.nn.functional.mse_loss(model(rays), target).backward()
+    torch.nn.utils.clip_grad_norm_(model.parameters(), 0.05)
+    got = torch.load(out)
+    assert torch.allclose(got, red.flat, rtol=1e-5, atol=1e-7)
+    # p.grad are views of the flat buffer (zeroing is one memset)
+    assert all(p.grad.data_ptr() >= red.flat.data_ptr() for p in model.parameters())
+
+
+def test_shard_rays_covers_batch():
+    dp = _load_dp()
+    for n, w in ((64, 2), (65, 8), (7, 8), (0, 4)):
+        spans = [dp.shard_rays(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))

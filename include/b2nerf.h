@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2N_ABI_VERSION 4
+#define B2N_ABI_VERSION 5
 
 #define B2N_OK 0
 #define B2N_EINVAL (-1)  /* bad argument (null pointer, size, unsupported shape) */
@@ -198,6 +198,27 @@ int b2n_instant_mlp_bwd(const float* x_enc, int ldx, int pos_dim, const float* d
                         int L_dir, const float* sigma_params, const float* color_params, int64_t P,
                         const float* g_rgb, const float* g_sigma, float* g_x_enc, int ldg, float* g_sigma_params,
                         float* g_color_params, b2n_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * 256-wide vanilla NeRF decoder (NeRFDecoder.forward, src/decoders.py:68-87)
+ * on tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM).  Fixed
+ * architecture of the reference configs: 8 x 256 trunk, skip [h, x] at layer 4,
+ * 128-wide view layer; pos_dim <= 64, dir_dim <= 32.
+ *   b2n_nerf_mlp_pack: converts the fp32 nn.Linear weights (pts_layers[0..7],
+ *     feature_layer, view_layer) into the bf16 operand-tile stream the kernel
+ *     consumes (b2n_nerf_mlp_packed_bytes() bytes); call once per weight update.
+ *   b2n_nerf_mlp_fwd: x_enc [P,pos_dim], d_enc [P,dir_dim] -> rgb [P,3], sigma [P].
+ *     bias: concatenated [8*256 + 256 + 128]; w_sigma [256]; w_rgb [3*128];
+ *     head_bias: device float[4] = {b_sigma, b_rgb[3]}; save: optional bf16
+ *     [10][P][256] planes of the layer outputs (training); err_flag: device int
+ *     (0 = ok; non-zero = the kernel aborted a stalled pipeline instead of hanging).
+ * ---------------------------------------------------------------------- */
+size_t b2n_nerf_mlp_packed_bytes(void);
+int b2n_nerf_mlp_pack(const float* const* pts_w, const float* feature_w, const float* view_w, int pos_dim, int dir_dim,
+                      void* packed, b2n_stream_t stream);
+int b2n_nerf_mlp_fwd(const float* x_enc, int pos_dim, const float* d_enc, int dir_dim, const void* packed,
+                     const float* bias, const float* w_sigma, const float* w_rgb, const float* head_bias, int64_t P,
+                     float* rgb, float* sigma, void* save, int* err_flag, b2n_stream_t stream);
 
 #ifdef __cplusplus
 }

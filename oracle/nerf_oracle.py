@@ -222,17 +222,22 @@ def _lin(sd: Dict[str, Tensor], prefix: str, h: Tensor) -> Tensor:
     return F.linear(h, sd[prefix + ".weight"].to(h.dtype), sd[prefix + ".bias"].to(h.dtype))
 
 
-def nerf_decoder(sd, prefix: str, x: Tensor, d: Tensor, num_layers=8, skip_layer=4):
+def nerf_decoder(sd, prefix: str, x: Tensor, d: Tensor, num_layers=8, skip_layer=4, emulate_bf16: bool = False):
     """8x256 trunk with [h, x] skip concat, sigma/feature heads, view branch
-    (src/decoders.py:68-87)."""
+    (src/decoders.py:68-87).  ``emulate_bf16`` rounds the operands of the trunk / feature / view
+    GEMMs to bf16 like the tensor-core kernel does (the two small heads stay in fp32)."""
+    q = bf16_round if emulate_bf16 else (lambda v: v)
+
+    def lin(name, v):
+        return F.linear(q(v), q(sd[name + ".weight"].to(v.dtype)), sd[name + ".bias"].to(v.dtype))
     h = x
     for i in range(num_layers):
         if i == skip_layer:
             h = torch.cat([h, x], dim=-1)
-        h = torch.relu(_lin(sd, f"{prefix}.pts_layers.{i}", h))
+        h = torch.relu(lin(f"{prefix}.pts_layers.{i}", h))
     sigma = torch.relu(_lin(sd, f"{prefix}.sigma_layer", h))
-    feat = _lin(sd, f"{prefix}.feature_layer", h)
-    hv = torch.relu(_lin(sd, f"{prefix}.view_layer", torch.cat([feat, d], dim=-1)))
+    feat = lin(f"{prefix}.feature_layer", h)
+    hv = torch.relu(lin(f"{prefix}.view_layer", torch.cat([feat, d], dim=-1)))
     rgb = torch.sigmoid(_lin(sd, f"{prefix}.rgb_layer", hv))
     return rgb, sigma
 

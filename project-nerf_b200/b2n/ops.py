@@ -341,3 +341,52 @@ class _InstantMLP(torch.autograd.Function):
 def instant_mlp(x_enc, dirs, bands, sigma_params, color_params):
     """Fused InstantNeRFDecoder on raw unit view directions: (rgb [P,3], sigma [P,1])."""
     return _InstantMLP.apply(x_enc, dirs, bands, sigma_params, color_params)
+
+
+# ----------------------------------------------------------------------------
+# 256-wide vanilla NeRF decoder on tcgen05 (bf16 operands, fp32 accumulate in TMEM)
+# ----------------------------------------------------------------------------
+
+def nerf_mlp_supported(decoder, pos_dim: int, dir_dim: int) -> bool:
+    """the tcgen05 kernel covers the reference architecture: 8 x 256, skip at 4, view 128"""
+    try:
+        return (len(decoder.pts_layers) == 8 and decoder.skip_layer == 4 and decoder.feature_layer.out_features == 256
+                and decoder.view_layer.out_features == 128 and decoder.pts_layers[0].out_features == 256
+                and 0 < pos_dim <= 64 and 0 < dir_dim <= 32)
+    except AttributeError:
+        return False
+
+
+def _nerf_mlp_pack(decoder):
+    dev = decoder.feature_layer.weight.device
+    pos_dim = decoder.pts_layers[0].in_features
+    dir_dim = decoder.view_layer.in_features - 256
+    ws = [_c(l.weight) for l in decoder.pts_layers]
+    ptrs = (ctypes.c_void_p * 8)(*[w.data_ptr() for w in ws])
+    fw, vw = _c(decoder.feature_layer.weight), _c(decoder.view_layer.weight)
+    packed = torch.empty(_lib.lib.b2n_nerf_mlp_packed_bytes(), device=dev, dtype=torch.uint8)
+    call("b2n_nerf_mlp_pack", ptrs, ptr(fw), ptr(vw), pos_dim, dir_dim, ptr(packed), stream())
+    bias = torch.cat([l.bias for l in decoder.pts_layers] + [decoder.feature_layer.bias, decoder.view_layer.bias]).float()
+    head_bias = torch.cat([decoder.sigma_layer.bias, decoder.rgb_layer.bias]).float()
+    return packed, bias.contiguous(), head_bias.contiguous(), pos_dim, dir_dim
+
+
+@torch.no_grad()
+def nerf_mlp_forward(decoder, x_enc, d_enc, save: bool = False):
+    """NeRFDecoder forward on the tensor cores.  Returns (rgb [P,3], sigma [P,1], saved planes | None)."""
+    require_cuda(x_enc, d_enc)
+    x_enc, d_enc = _c(x_enc), _c(d_enc)
+    packed, bias, head_bias, pos_dim, dir_dim = _nerf_mlp_pack(decoder)
+    Pn = x_enc.shape[0]
+    dev = x_enc.device
+    rgb = torch.empty(Pn, 3, device=dev)
+    sigma = torch.empty(Pn, 1, device=dev)
+    planes = torch.empty(10, Pn, 256, device=dev, dtype=torch.bfloat16) if save else None
+    err = torch.zeros(1, device=dev, dtype=torch.int32)
+    w_sigma = _c(decoder.sigma_layer.weight).view(-1)
+    w_rgb = _c(decoder.rgb_layer.weight).view(-1)
+    flops = 2.0 * Pn * (256 * pos_dim + 256 * 256 * 6 + 256 * (256 + pos_dim) + 256 + 256 * 256 + 128 * (256 + dir_dim) + 384)
+    call("b2n_nerf_mlp_fwd", ptr(x_enc), pos_dim, ptr(d_enc), dir_dim, ptr(packed), ptr(bias), ptr(w_sigma), ptr(w_rgb),
+         ptr(head_bias), Pn, ptr(rgb), ptr(sigma), ptr(planes), ptr(err), stream(),
+         work=(Pn * (4.0 * (pos_dim + dir_dim) + 16 + (5120 if save else 0)), flops))
+    return rgb, sigma, planes, err

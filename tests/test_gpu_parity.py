@@ -441,3 +441,33 @@ def test_render_rays_golden_bf16(mods, bf16_mode, tag, pert):
     if "mean_delta_x" in g:
         loss = loss + (out[3]["mean_delta_x"] * cu(g["g_mdx"])).sum()
     _check_grads(model, loss, g, 0.1, l2=True)
+
+
+# ------------------------------------------------------------------ tcgen05 256-wide decoder
+@pytest.mark.parametrize("Pn", [256, 1000, 128 * 37 + 5, 40000])
+def test_nerf_mlp256_tcgen05_forward(mods, Pn):
+    """NeRFDecoder forward on tcgen05 vs the oracle: tight against the bf16-operand emulation,
+    1e-2 against plain fp32; saved activation planes equal the layer outputs."""
+    from oracle import nerf_oracle as O
+    from b2n import ops
+    sd = full_nerf_state_dict(31)
+    cfg = dict(mode="part2_nerf", L_embed=10, L_embed_dir=4)
+    model = _model_from(mods, cfg, sd).eval()
+    torch.manual_seed(11)
+    x = (torch.rand(Pn, 3) * 2 - 1) * 1.5
+    d = torch.randn(Pn, 3)
+    d = d / d.norm(dim=-1, keepdim=True)
+    xe = O.fourier_encode(x, sd["representation.freq_bands"])
+    de = O.fourier_encode(d, sd["dir_representation.freq_bands"])
+    rgb_q, sig_q = O.nerf_decoder(sd, "decoder", xe, de, emulate_bf16=True)
+    rgb_f, sig_f = O.nerf_decoder(sd, "decoder", xe, de)
+    assert ops.nerf_mlp_supported(model.decoder, 63, 27)
+    rgb, sigma, planes, err = ops.nerf_mlp_forward(model.decoder, cu(xe), cu(de), save=True)
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0, f"tcgen05 pipeline aborted with code {int(err.item())}"
+    assert rel_err(rgb.cpu(), rgb_q) < 3e-3 and rel_err(sigma.cpu(), sig_q) < 3e-3
+    assert rel_err(rgb.cpu(), rgb_f) < 1e-2 and rel_err(sigma.cpu(), sig_f) < 2e-2
+    # saved plane 0 = relu(W0 x + b0) in bf16
+    h0 = torch.relu(torch.nn.functional.linear(O.bf16_round(xe), O.bf16_round(sd["decoder.pts_layers.0.weight"]),
+                                               sd["decoder.pts_layers.0.bias"]))
+    assert rel_err(planes[0].float().cpu(), h0) < 1e-2

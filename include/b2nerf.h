@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2N_ABI_VERSION 5
+#define B2N_ABI_VERSION 6
 
 #define B2N_OK 0
 #define B2N_EINVAL (-1)  /* bad argument (null pointer, size, unsupported shape) */
@@ -219,6 +219,20 @@ int b2n_nerf_mlp_pack(const float* const* pts_w, const float* feature_w, const f
 int b2n_nerf_mlp_fwd(const float* x_enc, int pos_dim, const float* d_enc, int dir_dim, const void* packed,
                      const float* bias, const float* w_sigma, const float* w_rgb, const float* head_bias, int64_t P,
                      float* rgb, float* sigma, void* save, int* err_flag, b2n_stream_t stream);
+
+/* Backward data-gradient chain of the same decoder on tcgen05 (autograd of
+ * src/decoders.py:68-87 w.r.t. the activations).  fwd_planes = the `save` planes
+ * of b2n_nerf_mlp_fwd; rgb/sigma = its outputs; g_rgb [P,3], g_sigma [P] = incoming
+ * gradients.  Writes dz_planes (bf16 [10][P][256]: dZ_view(128 wide), dZ_feat,
+ * dZ7 .. dZ0 = pre-activation gradients of every layer) and dz_small (fp32 [P,4]:
+ * d rgb_pre[3], d sigma_pre).  Weight/bias gradients are dZ^T * layer-input GEMMs
+ * over those planes (plain GEMMs, done by the caller). */
+size_t b2n_nerf_mlp_packed_bwd_bytes(void);
+int b2n_nerf_mlp_pack_bwd(const float* const* pts_w, const float* feature_w, const float* view_w, int pos_dim,
+                          int dir_dim, void* packed, b2n_stream_t stream);
+int b2n_nerf_mlp_bwd(const void* packed_bwd, const float* w_sigma, const float* w_rgb, const void* fwd_planes,
+                     const float* rgb, const float* sigma, const float* g_rgb, const float* g_sigma, int64_t P,
+                     void* dz_planes, float* dz_small, int* err_flag, b2n_stream_t stream);
 
 #ifdef __cplusplus
 }

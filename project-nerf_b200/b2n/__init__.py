@@ -6,4 +6,4 @@ has not been built: there is deliberately no CPU fallback.
 from . import _lib  # noqa: F401  (fails loudly when the .so is missing)
 from .ops import (HashGeometry, composite, fourier_encode, hash_encode, instant_mlp, linear, mlp_precision,  # noqa: F401
                   set_mlp_precision, sigma_head)
-from . import march  # noqa: F401
+from . import march, ops  # noqa: F401

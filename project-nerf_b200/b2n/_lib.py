@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb2nerf.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 P, L, I, F = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
 
@@ -46,9 +46,12 @@ SIGNATURES = {
     "b2n_nerf_mlp_packed_bytes": [],
     "b2n_nerf_mlp_pack": [P, P, P, I, I, P, P],
     "b2n_nerf_mlp_fwd": [P, I, P, I, P, P, P, P, P, L, P, P, P, P, P],
+    "b2n_nerf_mlp_packed_bwd_bytes": [],
+    "b2n_nerf_mlp_pack_bwd": [P, P, P, I, I, P, P],
+    "b2n_nerf_mlp_bwd": [P, P, P, P, P, P, P, P, L, P, P, P, P],
 }
 _RESTYPES = {"b2n_last_error": ctypes.c_char_p, "b2n_march_scan_scratch": ctypes.c_size_t,
-             "b2n_nerf_mlp_packed_bytes": ctypes.c_size_t}
+             "b2n_nerf_mlp_packed_bytes": ctypes.c_size_t, "b2n_nerf_mlp_packed_bwd_bytes": ctypes.c_size_t}
 
 
 class HashLevelC(ctypes.Structure):

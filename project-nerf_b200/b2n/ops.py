@@ -390,3 +390,92 @@ def nerf_mlp_forward(decoder, x_enc, d_enc, save: bool = False):
          ptr(head_bias), Pn, ptr(rgb), ptr(sigma), ptr(planes), ptr(err), stream(),
          work=(Pn * (4.0 * (pos_dim + dir_dim) + 16 + (5120 if save else 0)), flops))
     return rgb, sigma, planes, err
+
+
+def _mm_f32(a_t, b):
+    """a_t^T @ b for bf16 operands with an fp32 result (plain library GEMM: the weight-gradient
+    reductions over all points)."""
+    try:
+        return torch.mm(a_t.t(), b, out_dtype=torch.float32)
+    except TypeError:
+        return torch.mm(a_t.t(), b).float()
+
+
+class _NerfMLP(torch.autograd.Function):
+    """NeRFDecoder on tcgen05: forward kernel (saving bf16 layer outputs), backward = the tcgen05
+    data-gradient chain + one GEMM per layer for the weight gradients."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, decoder, x_enc, d_enc, *params):
+        need_grad = any(ctx.needs_input_grad[3:])
+        rgb, sigma, planes, err = nerf_mlp_forward(decoder, x_enc, d_enc, save=need_grad)
+        ctx.decoder = decoder
+        ctx.save_for_backward(_c(x_enc), _c(d_enc), rgb, sigma, planes, err)
+        return rgb, sigma
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, g_rgb, g_sigma):
+        x_enc, d_enc, rgb, sigma, planes, err = ctx.saved_tensors
+        dec = ctx.decoder
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            raise RuntimeError("tcgen05 NeRFDecoder path does not produce input gradients (use fp32 mode)")
+        Pn = x_enc.shape[0]
+        dev = x_enc.device
+        pos_dim, dir_dim = x_enc.shape[1], d_enc.shape[1]
+        ws = [_c(l.weight) for l in dec.pts_layers]
+        ptrs = (ctypes.c_void_p * 8)(*[w.data_ptr() for w in ws])
+        fw, vw = _c(dec.feature_layer.weight), _c(dec.view_layer.weight)
+        packed = torch.empty(_lib.lib.b2n_nerf_mlp_packed_bwd_bytes(), device=dev, dtype=torch.uint8)
+        call("b2n_nerf_mlp_pack_bwd", ptrs, ptr(fw), ptr(vw), pos_dim, dir_dim, ptr(packed), stream())
+        dz = torch.empty(10, Pn, 256, device=dev, dtype=torch.bfloat16)
+        dz_small = torch.empty(Pn, 4, device=dev)
+        w_sigma = _c(dec.sigma_layer.weight).view(-1)
+        w_rgb = _c(dec.rgb_layer.weight).view(-1)
+        flops = 2.0 * Pn * (128 * 256 + 256 * 256 * 8)
+        call("b2n_nerf_mlp_bwd", ptr(packed), ptr(w_sigma), ptr(w_rgb), ptr(planes), ptr(rgb), ptr(sigma.view(-1)),
+             ptr(_c(g_rgb)), ptr(_c(g_sigma).view(-1)), Pn, ptr(dz), ptr(dz_small), ptr(err), stream(),
+             work=(Pn * (2.0 * 5120 + 48), flops))
+        # ---- weight / bias gradients: dW = dZ^T In, one plain GEMM per layer over all points
+        xb, db = x_enc.to(torch.bfloat16), d_enc.to(torch.bfloat16)
+        H = planes                      # H[0..7] trunk outputs, H[8] feat, H[9][:, :128] hv
+        dZ = {l: dz[9 - l] for l in range(8)}     # dZ_l of trunk layer l
+        gb_all = torch.sum(dz, dim=1, dtype=torch.float32)   # [10, 256] column sums
+        grads = {}
+        for l in range(8):
+            if l == 0:
+                gW = _mm_f32(dZ[0], xb)
+            elif l == 4:
+                gW = torch.cat([_mm_f32(dZ[4], H[3]), _mm_f32(dZ[4], xb)], dim=1)
+            else:
+                gW = _mm_f32(dZ[l], H[l - 1])
+            grads[f"pts{l}"] = (gW, gb_all[9 - l])
+        grads["feat"] = (_mm_f32(dz[1], H[7]), gb_all[1])
+        dzv = dz[0][:, :128]
+        grads["view"] = (torch.cat([_mm_f32(dzv, H[8]), _mm_f32(dzv, db)], dim=1), gb_all[0][:128])
+        dzs16 = dz_small.to(torch.bfloat16)
+        grads["sigma"] = (_mm_f32(dzs16[:, 3:4], H[7]), dz_small[:, 3].sum().view(1))
+        grads["rgb"] = (_mm_f32(dzs16[:, :3], H[9][:, :128]), dz_small[:, :3].sum(dim=0))
+        out = []
+        for l in range(8):
+            out += list(grads[f"pts{l}"])
+        for k in ("sigma", "feat", "view", "rgb"):
+            out += list(grads[k])
+        return (None, None, None) + tuple(out)
+
+
+def _nerf_params(decoder):
+    ps = []
+    for l in decoder.pts_layers:
+        ps += [l.weight, l.bias]
+    for m in (decoder.sigma_layer, decoder.feature_layer, decoder.view_layer, decoder.rgb_layer):
+        ps += [m.weight, m.bias]
+    return ps
+
+
+def nerf_mlp(decoder, x_enc, d_enc):
+    """(rgb [P,3], sigma [P,1]) of NeRFDecoder on the tensor cores, differentiable w.r.t. its parameters."""
+    if x_enc.requires_grad or d_enc.requires_grad:
+        raise RuntimeError("nerf_mlp: input gradients are not produced by the tcgen05 path")
+    return _NerfMLP.apply(decoder, x_enc, d_enc, *_nerf_params(decoder))

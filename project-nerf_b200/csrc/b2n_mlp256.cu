@@ -44,7 +44,8 @@ constexpr int N_THREADS = 320;
 constexpr int EPI_THREADS = 256;
 constexpr int MAX_STEPS = 12, MAX_CHUNKS = 64;
 
-enum { EPI_RELU = 0, EPI_RELU_SIGMA = 1, EPI_LINEAR = 2, EPI_VIEW_RGB = 3 };
+enum { EPI_RELU = 0, EPI_RELU_SIGMA = 1, EPI_LINEAR = 2, EPI_VIEW_RGB = 3,
+       EPI_B_LINEAR = 4, EPI_B_MASK = 5, EPI_B_MASK_SIGMA = 6 };
 
 struct Step {
   int n_act;     // k-chunks taken from the activation buffer (0 or 4)
@@ -165,10 +166,16 @@ struct FwdArgs {
   float* rgb; float* sigma;
   __nv_bfloat16* save;              // [n_slots][P][256] or nullptr
   int* err;
+  // backward only
+  const __nv_bfloat16* fwd_planes;  // [10][P][256] saved by the forward (H0..H7, feat, hv)
+  const float* g_rgb; const float* g_sigma;   // [P,3], [P]
+  const float* rgb_out; const float* sigma_out;
+  float* dz_small;                  // [P,4]: d(pre-sigmoid rgb)[3], d(pre-relu sigma)
   Plan plan;
 };
 
-__global__ void __launch_bounds__(N_THREADS, 1) k_mlp256_fwd(const FwdArgs a) {
+template <bool BWD>
+__global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -266,25 +273,64 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256_fwd(const FwdArgs a) {
     unsigned char* aux = smem + OFF_AUX + t * KBLK_BYTES;
     const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16) + t * 256;
     uint32_t acc_phase = 0;
+    if (BWD) {  // head weights are needed by every pair: stage them once
+      vec[e] = __ldg(a.w_sigma + e);
+      vec[256 + e] = __ldg(a.w_rgb + e);
+      if (e < 128) vec[512 + e] = __ldg(a.w_rgb + 256 + e);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
       const int64_t p = pair * 256 + t * 128 + r;
       const bool valid = p < a.P;
-      // ---- pre-step: stage the encoded position as the first A operand
-      stage_row(a.x_enc + p * a.pos_dim, a.pos_dim, valid, aux, r);
+      float sig_acc = 0.f;      // fwd: density dot product; bwd: d(pre-relu sigma) of this row
+      if (!BWD) {
+        // ---- pre-step: stage the encoded position as the first A operand
+        stage_row(a.x_enc + p * a.pos_dim, a.pos_dim, valid, aux, r);
+      } else {
+        // ---- pre-step: colour head backward -> dZ_view (128 wide) as the first A operand
+        float dzr[3] = {0.f, 0.f, 0.f};
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const float y = __ldg(a.rgb_out + 3 * p + j);
+            dzr[j] = __ldg(a.g_rgb + 3 * p + j) * y * (1.f - y);
+          }
+          sig_acc = __ldg(a.sigma_out + p) > 0.f ? __ldg(a.g_sigma + p) : 0.f;
+          *reinterpret_cast<float4*>(a.dz_small + 4 * p) = make_float4(dzr[0], dzr[1], dzr[2], sig_acc);
+        }
+        const __nv_bfloat16* hv = a.fwd_planes + ((size_t)9 * a.P + (valid ? p : 0)) * HID;
+        __nv_bfloat16* srow = (a.save && valid) ? a.save + ((size_t)0 * a.P + p) * HID : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < 16; ++c) {
+          uint4 hraw = valid ? __ldcs(reinterpret_cast<const uint4*>(hv + 8 * c)) : make_uint4(0, 0, 0, 0);
+          const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&hraw);
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int col = 8 * c + j;
+            const float g = dzr[0] * vec[256 + col] + dzr[1] * vec[256 + 128 + col] + dzr[2] * vec[256 + 256 + col];
+            f[j] = (__bfloat162float(hb[j]) > 0.f) ? g : 0.f;
+          }
+          const uint4 pk = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+          *reinterpret_cast<uint4*>(act + ((8 * c) >> 6) * KBLK_BYTES + swz(r, ((8 * c) & 63) >> 3)) = pk;
+          if (srow) __stcs(reinterpret_cast<uint4*>(srow + 8 * c), pk);
+        }
+      }
       proxy_fence();
       mbar_arrive(bar_act);
-      float sig_acc = 0.f;
       for (int s = 0; s < plan.n_steps; ++s) {
         const Step& sp = plan.s[s];
-        // stage this step's bias (and the head weights) for broadcast reads
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (e < sp.n) vec[e] = __ldg(a.bias + sp.bias_off + e);
-        if (sp.epi == EPI_RELU_SIGMA) vec[256 + e] = __ldg(a.w_sigma + e);
-        if (sp.epi == EPI_VIEW_RGB) {
-          vec[256 + e] = __ldg(a.w_rgb + e);
-          if (e < 128) vec[512 + e] = __ldg(a.w_rgb + 256 + e);
+        if (!BWD) {
+          // stage this step's bias (and the head weights) for broadcast reads
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (e < sp.n) vec[e] = __ldg(a.bias + sp.bias_off + e);
+          if (sp.epi == EPI_RELU_SIGMA) vec[256 + e] = __ldg(a.w_sigma + e);
+          if (sp.epi == EPI_VIEW_RGB) {
+            vec[256 + e] = __ldg(a.w_rgb + e);
+            if (e < 128) vec[512 + e] = __ldg(a.w_rgb + 256 + e);
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (!mbar_wait(bar_acc, acc_phase & 1, abort_flag, a.err, 4)) goto epi_done;
         ++acc_phase;
         tc_fence_after();
@@ -292,25 +338,48 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256_fwd(const FwdArgs a) {
         const bool relu = sp.epi != EPI_LINEAR;
         __nv_bfloat16* save_row = (a.save && sp.save_slot >= 0 && valid)
                                       ? a.save + ((size_t)sp.save_slot * a.P + p) * HID : nullptr;
+        // bwd: the forward activation whose ReLU gates this gradient (plane index in bias_off)
+        const __nv_bfloat16* mask_row = (BWD && sp.epi != EPI_B_LINEAR)
+                                            ? a.fwd_planes + ((size_t)sp.bias_off * a.P + (valid ? p : 0)) * HID : nullptr;
+        const bool last = (s + 1 == plan.n_steps);
 #pragma unroll 1
         for (int cb = 0; cb < sp.n / 32; ++cb) {
           uint32_t v[32];
           tc_ld32(trow + 32 * cb, v);
           float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(v[j]) + vec[32 * cb + j];
-            f[j] = relu ? fmaxf(x, 0.f) : x;
-          }
-          if (sp.epi == EPI_RELU_SIGMA) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sig_acc = fmaf(f[j], vec[256 + 32 * cb + j], sig_acc);
-          } else if (sp.epi == EPI_VIEW_RGB) {
+          if (!BWD) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              rgb_acc[0] = fmaf(f[j], vec[256 + 32 * cb + j], rgb_acc[0]);
-              rgb_acc[1] = fmaf(f[j], vec[256 + 128 + 32 * cb + j], rgb_acc[1]);
-              rgb_acc[2] = fmaf(f[j], vec[256 + 256 + 32 * cb + j], rgb_acc[2]);
+              float x = __uint_as_float(v[j]) + vec[32 * cb + j];
+              f[j] = relu ? fmaxf(x, 0.f) : x;
+            }
+            if (sp.epi == EPI_RELU_SIGMA) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) sig_acc = fmaf(f[j], vec[256 + 32 * cb + j], sig_acc);
+            } else if (sp.epi == EPI_VIEW_RGB) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                rgb_acc[0] = fmaf(f[j], vec[256 + 32 * cb + j], rgb_acc[0]);
+                rgb_acc[1] = fmaf(f[j], vec[256 + 128 + 32 * cb + j], rgb_acc[1]);
+                rgb_acc[2] = fmaf(f[j], vec[256 + 256 + 32 * cb + j], rgb_acc[2]);
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (sp.epi == EPI_B_MASK_SIGMA) {   // + d(sigma_pre) * w_sigma  (density head, rank-1)
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = fmaf(sig_acc, vec[32 * cb + j], f[j]);
+            }
+            if (mask_row) {
+#pragma unroll
+              for (int c4 = 0; c4 < 4; ++c4) {
+                uint4 hraw = valid ? __ldcs(reinterpret_cast<const uint4*>(mask_row + 32 * cb + 8 * c4)) : make_uint4(0, 0, 0, 0);
+                const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&hraw);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (!(__bfloat162float(hb[j]) > 0.f)) f[8 * c4 + j] = 0.f;
+              }
             }
           }
 #pragma unroll
@@ -318,23 +387,25 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256_fwd(const FwdArgs a) {
             const uint4 pk = make_uint4(pack_bf16(f[8 * c4], f[8 * c4 + 1]), pack_bf16(f[8 * c4 + 2], f[8 * c4 + 3]),
                                         pack_bf16(f[8 * c4 + 4], f[8 * c4 + 5]), pack_bf16(f[8 * c4 + 6], f[8 * c4 + 7]));
             const int col = 32 * cb + 8 * c4;            // first column of this 16-byte chunk
-            if (sp.epi != EPI_VIEW_RGB)
+            if (sp.epi != EPI_VIEW_RGB && !(BWD && last))
               *reinterpret_cast<uint4*>(act + (col >> 6) * KBLK_BYTES + swz(r, (col & 63) >> 3)) = pk;
             if (save_row) __stcs(reinterpret_cast<uint4*>(save_row + col), pk);
           }
         }
-        if (sp.epi == EPI_RELU_SIGMA && valid) a.sigma[p] = fmaxf(sig_acc + __ldg(a.head_bias), 0.f);
-        if (sp.epi == EPI_VIEW_RGB && valid) {
+        if (!BWD) {
+          if (sp.epi == EPI_RELU_SIGMA && valid) a.sigma[p] = fmaxf(sig_acc + __ldg(a.head_bias), 0.f);
+          if (sp.epi == EPI_VIEW_RGB && valid) {
 #pragma unroll
-          for (int j = 0; j < 3; ++j) a.rgb[3 * p + j] = 1.f / (1.f + expf(-(rgb_acc[j] + __ldg(a.head_bias + 1 + j))));
+            for (int j = 0; j < 3; ++j) a.rgb[3 * p + j] = 1.f / (1.f + expf(-(rgb_acc[j] + __ldg(a.head_bias + 1 + j))));
+          }
+          // the x block is dead after the skip layer (the step that consumed both act and aux):
+          // re-use it for the encoded view direction of the view layer
+          if (sp.n_act > 0 && sp.aux_k16 > 0 && sp.epi == EPI_RELU)
+            stage_row(a.d_enc + p * a.dir_dim, a.dir_dim, valid, aux, r);
         }
-        // the x block is dead after the skip layer (the step that consumed both act and aux):
-        // re-use it for the encoded view direction of the view layer
-        if (sp.n_act > 0 && sp.aux_k16 > 0 && sp.epi == EPI_RELU)
-          stage_row(a.d_enc + p * a.dir_dim, a.dir_dim, valid, aux, r);
         tc_fence_before();
         proxy_fence();
-        if (s + 1 < plan.n_steps) mbar_arrive(bar_act);
+        if (!last) mbar_arrive(bar_act);
       }
     }
   epi_done:;
@@ -347,8 +418,10 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256_fwd(const FwdArgs a) {
 
 // ---------------------------------------------------------------------------------------- weight packing
 struct PackChunk {
-  const float* W;   // source matrix, row-major [n_real, ldw]
-  int ldw, n_real, n_pad, k0, k_real;  // chunk covers source columns k0 .. k0+63 (k_real = matrix width)
+  const float* W;   // source matrix, row-major, leading dimension ldw
+  // forward (trans = 0): tile row n <- source row n (n < n_real), tile k <- source column k0 + k (< k_real)
+  // backward (trans = 1): tile row n <- source column n (n < n_real), tile k <- source row k0 + k (< k_real)
+  int ldw, n_real, n_pad, k0, k_real, trans;
   int64_t dst_off;  // byte offset in the packed stream
 };
 struct PackArgs {
@@ -366,7 +439,8 @@ __global__ void k_mlp256_pack(const PackArgs a) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int k = c.k0 + 8 * ch + j;
-      f[j] = (n < c.n_real && k < c.k_real) ? __ldg(c.W + (size_t)n * c.ldw + k) : 0.f;
+      const bool ok = n < c.n_real && k < c.k_real;
+      f[j] = ok ? __ldg(c.trans ? c.W + (size_t)k * c.ldw + n : c.W + (size_t)n * c.ldw + k) : 0.f;
     }
     *reinterpret_cast<uint4*>(dst + swz(n, ch)) =
         make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
@@ -413,7 +487,7 @@ extern "C" int b2n_nerf_mlp_pack(const float* const* pts_w, const float* feature
   int n = 0;
   int64_t off = 0;
   auto add = [&](const float* W, int ldw, int n_real, int n_pad, int k0, int k_real) {
-    pa.c[n++] = PackChunk{W, ldw, n_real, n_pad, k0, k_real, off};
+    pa.c[n++] = PackChunk{W, ldw, n_real, n_pad, k0, k_real, 0, off};
     off += (int64_t)n_pad * 128;
   };
   for (int l = 0; l < 8; ++l) {
@@ -450,9 +524,74 @@ extern "C" int b2n_nerf_mlp_fwd(const float* x_enc, int pos_dim, const float* d_
   a.head_bias = head_bias;
   a.P = P, a.rgb = rgb, a.sigma = sigma, a.save = (__nv_bfloat16*)save, a.err = err_flag;
   build_fwd_plan(&a.plan);
-  cudaFuncSetAttribute(k_mlp256_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  cudaFuncSetAttribute(k_mlp256<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   const int64_t n_pairs = (P + 255) / 256;
   const int grid = (int)(n_pairs < kSMs ? n_pairs : kSMs);
-  k_mlp256_fwd<<<grid, N_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  k_mlp256<false><<<grid, N_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a);
   return check_launch("b2n_nerf_mlp_fwd");
+}
+
+// ---------------------------------------------------------------------------------------- backward (data gradients)
+// Chain (all on the tensor cores, M = 128 x 2 tiles, N = 256):
+//   pre : dZ_view = (d rgb_pre * W_rgb) (.) [hv > 0]                       (epilogue warps, 128 wide)
+//   B1  : d feat  = dZ_view  * W_view[:, :256]            K = 128   -> dZ_feat (linear)
+//   B2  : d h7    = dZ_feat  * W_feat + d sigma_pre * w_sigma, gated by H7  -> dZ7
+//   B3..: d h_{l-1} = dZ_l * W_l[:, :256], gated by H_{l-1}    (l = 7 .. 1)  -> dZ_{l-1}
+// Every dZ plane is written to HBM in bf16: the weight gradients dW_l = dZ_l^T In_l are plain
+// [256 x P] x [P x 256] GEMMs done outside this kernel.  Step::bias_off holds the index of the
+// forward plane that gates the step.
+static void build_bwd_plan(Plan* pl) {
+  int n = 0;
+  auto add = [&](int n_act, int epi, int gate_plane, int slot) { pl->s[n++] = Step{n_act, 0, 256, epi, gate_plane, slot}; };
+  add(2, EPI_B_LINEAR, 0, 1);        // d feat
+  add(4, EPI_B_MASK_SIGMA, 7, 2);    // dZ7
+  for (int l = 7; l >= 1; --l) add(4, EPI_B_MASK, l - 1, 2 + (8 - l));   // dZ6 .. dZ0 -> slots 3..9
+  pl->n_steps = n;
+}
+
+extern "C" size_t b2n_nerf_mlp_packed_bwd_bytes(void) { return (size_t)(2 + 4 * 8) * 256 * 128; }
+
+extern "C" int b2n_nerf_mlp_pack_bwd(const float* const* pts_w, const float* feature_w, const float* view_w, int pos_dim,
+                                     int dir_dim, void* packed, b2n_stream_t stream) {
+  B2N_REQUIRE(pts_w && feature_w && view_w && packed, "null pointer");
+  B2N_REQUIRE(pos_dim > 0 && pos_dim <= 64 && dir_dim > 0 && dir_dim <= 32, "pos_dim <= 64 and dir_dim <= 32 required");
+  PackArgs pa{};
+  int n = 0;
+  int64_t off = 0;
+  // tile rows = input index of the layer (first 256 inputs), tile k = output index of the layer
+  auto add = [&](const float* W, int ldw, int n_out, int k0) {
+    pa.c[n++] = PackChunk{W, ldw, 256, 256, k0, n_out, 1, off};
+    off += (int64_t)256 * 128;
+  };
+  for (int c = 0; c < 2; ++c) add(view_w, 256 + dir_dim, 128, 64 * c);
+  for (int c = 0; c < 4; ++c) add(feature_w, 256, 256, 64 * c);
+  for (int l = 7; l >= 1; --l) {
+    B2N_REQUIRE(pts_w[l], "null weight");
+    const int ld = (l == 4) ? 256 + pos_dim : 256;
+    for (int c = 0; c < 4; ++c) add(pts_w[l], ld, 256, 64 * c);
+  }
+  pa.n_chunks = n;
+  pa.dst = (unsigned char*)packed;
+  B2N_REQUIRE((size_t)off == b2n_nerf_mlp_packed_bwd_bytes(), "internal: packed size mismatch");
+  k_mlp256_pack<<<n, 256, 0, (cudaStream_t)stream>>>(pa);
+  return check_launch("b2n_nerf_mlp_pack_bwd");
+}
+
+extern "C" int b2n_nerf_mlp_bwd(const void* packed_bwd, const float* w_sigma, const float* w_rgb, const void* fwd_planes,
+                                const float* rgb, const float* sigma, const float* g_rgb, const float* g_sigma,
+                                int64_t P, void* dz_planes, float* dz_small, int* err_flag, b2n_stream_t stream) {
+  B2N_REQUIRE(P >= 0, "negative size");
+  if (P == 0) return B2N_OK;
+  B2N_REQUIRE(packed_bwd && w_sigma && w_rgb && fwd_planes && rgb && sigma && g_rgb && g_sigma && dz_planes &&
+                  dz_small && err_flag, "null pointer");
+  FwdArgs a{};
+  a.packed = (const unsigned char*)packed_bwd, a.w_sigma = w_sigma, a.w_rgb = w_rgb;
+  a.fwd_planes = (const __nv_bfloat16*)fwd_planes, a.rgb_out = rgb, a.sigma_out = sigma, a.g_rgb = g_rgb;
+  a.g_sigma = g_sigma, a.P = P, a.save = (__nv_bfloat16*)dz_planes, a.dz_small = dz_small, a.err = err_flag;
+  build_bwd_plan(&a.plan);
+  cudaFuncSetAttribute(k_mlp256<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  const int64_t n_pairs = (P + 255) / 256;
+  const int grid = (int)(n_pairs < kSMs ? n_pairs : kSMs);
+  k_mlp256<true><<<grid, N_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  return check_launch("b2n_nerf_mlp_bwd");
 }

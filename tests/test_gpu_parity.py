@@ -471,3 +471,30 @@ def test_nerf_mlp256_tcgen05_forward(mods, Pn):
     h0 = torch.relu(torch.nn.functional.linear(O.bf16_round(xe), O.bf16_round(sd["decoder.pts_layers.0.weight"]),
                                                sd["decoder.pts_layers.0.bias"]))
     assert rel_err(planes[0].float().cpu(), h0) < 1e-2
+
+
+def test_nerf_mlp256_tcgen05_backward(mods, bf16_mode):
+    """Parameter gradients of the tensor-core NeRFDecoder vs autograd through the bf16-emulating oracle."""
+    from oracle import nerf_oracle as O
+    sd = full_nerf_state_dict(31)
+    cfg = dict(mode="part2_nerf", L_embed=10, L_embed_dir=4)
+    model = _model_from(mods, cfg, sd).train()
+    torch.manual_seed(12)
+    Pn = 128 * 21 + 77
+    x = (torch.rand(Pn, 3) * 2 - 1) * 1.5
+    d = torch.randn(Pn, 3)
+    d = d / d.norm(dim=-1, keepdim=True)
+    sdg = {k: v.clone().requires_grad_("freq" not in k) for k, v in sd.items()}
+    xe = O.fourier_encode(x, sd["representation.freq_bands"])
+    de = O.fourier_encode(d, sd["dir_representation.freq_bands"])
+    rgb_q, sig_q = O.nerf_decoder(sdg, "decoder", xe, de, emulate_bf16=True)
+    g_rgb, g_sig = torch.randn_like(rgb_q), torch.randn_like(sig_q)
+    names = [k for k in sdg if k.startswith("decoder.")]
+    ref = torch.autograd.grad((rgb_q * g_rgb).sum() + (sig_q * g_sig).sum(), [sdg[k] for k in names])
+    rgb, sigma = model(cu(x), cu(d))
+    assert rel_err(rgb.cpu(), rgb_q) < 3e-3 and rel_err(sigma.cpu(), sig_q) < 3e-3
+    params = dict(model.named_parameters())
+    got = torch.autograd.grad((rgb * cu(g_rgb)).sum() + (sigma * cu(g_sig)).sum(), [params[k] for k in names])
+    for k, a_, b_ in zip(names, got, ref):
+        l2 = float((a_.cpu().double() - b_.double()).norm() / (b_.double().norm() + 1e-30))
+        assert l2 < 3e-2, (k, l2)

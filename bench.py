@@ -223,6 +223,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "NONE"       # keep stdout to the single JSON line (no "NCCL version" banner)
         dist.init_process_group("nccl", device_id=dev)
     B = args.rays
 

@@ -143,9 +143,29 @@ k_hash_fwd(const float* __restrict__ x, int64_t P, float bound, float two_bound,
   for (int d = 0; d < 3; ++d) x01[d] = to_unit(__ldg(x + 3 * p + d), bound, two_bound, &in);
   const Cell c = locate(x01, L.scale);
   float vals[8][F];
+  if (F == 2) {
+    // The two x-neighbours of a corner pair are adjacent table entries half of the time (dense
+    // levels: consecutive indices; hashed levels: x has hash prime 1, so for even gx the indices
+    // differ only in bit 0).  An aligned pair is fetched with ONE 16-byte gather.
 #pragma unroll
-  for (int k = 0; k < 8; ++k)
-    load_feat<F>(table, corner_entry(L, c.g[0] + (k & 1), c.g[1] + ((k >> 1) & 1), c.g[2] + ((k >> 2) & 1)), vals[k]);
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t cy = c.g[1] + (k & 1), cz = c.g[2] + ((k >> 1) & 1);
+      const uint32_t e0 = corner_entry(L, c.g[0], cy, cz), e1 = corner_entry(L, c.g[0] + 1, cy, cz);
+      if ((e0 ^ e1) == 1u) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(table) + (e0 >> 1));
+        const bool lo = (e0 & 1u) == 0u;
+        vals[2 * k][0] = lo ? t.x : t.z, vals[2 * k][1] = lo ? t.y : t.w;
+        vals[2 * k + 1][0] = lo ? t.z : t.x, vals[2 * k + 1][1] = lo ? t.w : t.y;
+      } else {
+        load_feat<F>(table, e0, vals[2 * k]);
+        load_feat<F>(table, e1, vals[2 * k + 1]);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      load_feat<F>(table, corner_entry(L, c.g[0] + (k & 1), c.g[1] + ((k >> 1) & 1), c.g[2] + ((k >> 2) & 1)), vals[k]);
+  }
   float acc[F];
 #pragma unroll
   for (int f = 0; f < F; ++f) acc[f] = 0.f;
@@ -194,6 +214,26 @@ k_hash_bwd_table(const float* __restrict__ x, int64_t P, float bound, float two_
 #pragma unroll
   for (int f = 0; f < F; ++f) any |= (gv[f] != 0.f);
   if (!any) return;  // nothing to scatter (e.g. samples that received no gradient)
+  if (F == 2) {
+    // aligned x-neighbour pairs (see k_hash_fwd) are reduced with ONE 16-byte red.global.add.v4.f32
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t cy = c.g[1] + (k & 1), cz = c.g[2] + ((k >> 1) & 1);
+      const float wyz = ((k & 1) ? c.w[1] : 1.f - c.w[1]) * ((k & 2) ? c.w[2] : 1.f - c.w[2]);
+      const float w0 = (1.f - c.w[0]) * wyz, w1 = c.w[0] * wyz;
+      const uint32_t e0 = corner_entry(L, c.g[0], cy, cz), e1 = corner_entry(L, c.g[0] + 1, cy, cz);
+      if ((e0 ^ e1) == 1u) {
+        const bool lo = (e0 & 1u) == 0u;
+        const float wa = lo ? w0 : w1, wb = lo ? w1 : w0;
+        atomicAdd(reinterpret_cast<float4*>(g_table) + (e0 >> 1),
+                  make_float4(wa * gv[0], wa * gv[1], wb * gv[0], wb * gv[1]));
+      } else {
+        atomicAdd(reinterpret_cast<float2*>(g_table) + e0, make_float2(w0 * gv[0], w0 * gv[1]));
+        atomicAdd(reinterpret_cast<float2*>(g_table) + e1, make_float2(w1 * gv[0], w1 * gv[1]));
+      }
+    }
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const float wt = ((k & 1) ? c.w[0] : 1.f - c.w[0]) * ((k & 2) ? c.w[1] : 1.f - c.w[1]) *

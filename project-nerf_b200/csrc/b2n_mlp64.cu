@@ -166,17 +166,28 @@ __device__ __forceinline__ void dir_features(const float* __restrict__ dirs, int
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = 0.f;
   f[0] = d[0], f[1] = d[1], f[2] = d[2];
+  // band k+1 = 2 * band k (the reference's 2^k bands): double-angle recurrence instead of a fresh
+  // sincosf (error grows ~2x per band from 1e-7: far below the bf16 rounding applied next)
+  float ps[3], pc[3], prev = 0.f;
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     if (k < L) {
       const float fr = __ldg(bands + k);
+      const bool dbl = (k > 0) && (fr == 2.f * prev);
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         float s, c;
-        sincosf(__fmul_rn(__fmul_rn(d[j], fr), 3.14159274101257324f), &s, &c);
+        if (dbl) {
+          s = 2.f * ps[j] * pc[j];
+          c = 1.f - 2.f * ps[j] * ps[j];
+        } else {
+          sincosf(__fmul_rn(__fmul_rn(d[j], fr), 3.14159274101257324f), &s, &c);
+        }
+        ps[j] = s, pc[j] = c;
         f[3 + 6 * k + j] = s;
         f[3 + 6 * k + 3 + j] = c;
       }
+      prev = fr;
     }
   }
   uint4* o = reinterpret_cast<uint4*>(dst);

@@ -46,7 +46,38 @@ def mlp256(P):
         print(f"fp32 layer-wise path: {best:.3f} ms -> {flops / best / 1e9:.1f} TFLOP/s")
 
 
+def c1_step(P_rays=4096, N=64):
+    """C1: vanilla NeRF training step (render_rays + MSE + backward + Adam), B=4096, N=64."""
+    from b2n import synthetic
+    from src.renderer import render_rays
+    for mode in ("bf16", "fp32"):
+        b2n.set_mlp_precision(mode)
+        torch.manual_seed(0)
+        model = NeuralField(dict(mode="part2_nerf", L_embed=10, L_embed_dir=4)).cuda().train()
+        opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+        ro, rd, tgt = (t.cuda() for t in synthetic.random_rays(P_rays, seed=1))
+
+        def step():
+            pred, _, _ = render_rays(model, ro, rd, 2.0, 6.0, N, True, white_bkgd=True)
+            loss = torch.nn.functional.mse_loss(pred, tgt[:, :3])
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+
+        med, best = timeit(step, n=5 if mode == "fp32" else 20, warm=3)
+        flops = 3 * 2.0 * P_rays * N * 593408
+        print(f"C1 train step [{mode}] B={P_rays} N={N}: median {med:.3f} ms -> {P_rays / med * 1e3 / 1e6:.3f} M rays/s, "
+              f"{flops / med / 1e9:.1f} TFLOP/s algorithmic")
+        model.eval()
+        with torch.no_grad():
+            med, best = timeit(lambda: render_rays(model, ro, rd, 2.0, 6.0, N, False, white_bkgd=True), n=10, warm=2)
+        print(f"C1 render [{mode}]: median {med:.3f} ms -> {P_rays * N / med * 1e3 / 1e6:.1f} Msamples/s")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "mlp256"
     P = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
-    {"mlp256": mlp256}[what](P)
+    if what == "c1":
+        c1_step()
+    else:
+        {"mlp256": mlp256}[what](P)

@@ -58,25 +58,35 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
 }
 
 // C[mt][j] (16 x 8 tiles) += A[mt][kt] * W^T ; W in smem as [n][k] bf16, row stride S.
+// Loop order: k-pairs outer, n-tiles inner, and the two k-halves issued in separate sweeps, so that
+// consecutive mma.sync never depend on each other's accumulator (NT*MT independent chains).
 template <int MT, int NT, int KT>
 __device__ __forceinline__ void gemm_fwd(float (&c)[MT][NT][4], const uint32_t (&a)[MT][KT][4], const bf16* W, int S,
                                          int lane) {
+  constexpr int G = (NT < 4) ? NT : 4;     // n-tiles per sweep: G*MT independent accumulators in flight
+  const bf16* base = W + (lane & 7) * S + 8 * (lane >> 3);
 #pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    const bf16* row = W + (8 * j + (lane & 7)) * S;
+  for (int j0 = 0; j0 < NT; j0 += G) {
 #pragma unroll
     for (int q = 0; q < KT / 2; ++q) {
-      uint32_t b[4];
-      ldsm_x4(b, row + 32 * q + 8 * (lane >> 3));
+      uint32_t b[G][4];
 #pragma unroll
-      for (int m = 0; m < MT; ++m) {
-        mma16816(c[m][j], a[m][2 * q], b[0], b[1]);
-        mma16816(c[m][j], a[m][2 * q + 1], b[2], b[3]);
+      for (int j = 0; j < G; ++j) {
+        ldsm_x4(b[j], base + 8 * (j0 + j) * S + 32 * q);
+#pragma unroll
+        for (int m = 0; m < MT; ++m) mma16816(c[m][j0 + j], a[m][2 * q], b[j][0], b[j][1]);
       }
+#pragma unroll
+      for (int j = 0; j < G; ++j)
+#pragma unroll
+        for (int m = 0; m < MT; ++m) mma16816(c[m][j0 + j], a[m][2 * q + 1], b[j][2], b[j][3]);
     }
-    if (KT & 1) {
+  }
+  if (KT & 1) {
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
       uint32_t b[2];
-      ldsm_x2(b, row + 16 * (KT - 1) + 8 * ((lane >> 3) & 1));
+      ldsm_x2(b, W + (8 * j + (lane & 7)) * S + 16 * (KT - 1) + 8 * ((lane >> 3) & 1));
 #pragma unroll
       for (int m = 0; m < MT; ++m) mma16816(c[m][j], a[m][KT - 1], b[0], b[1]);
     }
@@ -84,14 +94,15 @@ __device__ __forceinline__ void gemm_fwd(float (&c)[MT][NT][4], const uint32_t (
 }
 
 // dIn[16 x 8*NTo] += dZ[16 x 16*KTz] * W ; W in smem as [n][k] (n is the reduction index).
+// Reduction index outer so that consecutive mma.sync hit different accumulators.
 template <int NTo, int KTz>
 __device__ __forceinline__ void gemm_dgrad(float (&c)[NTo][4], const uint32_t (&a)[KTz][4], const bf16* W, int S,
                                            int lane) {
   static_assert(NTo % 2 == 0, "pairs of output tiles");
 #pragma unroll
-  for (int jp = 0; jp < NTo / 2; ++jp) {
+  for (int kt = 0; kt < KTz; ++kt) {
 #pragma unroll
-    for (int kt = 0; kt < KTz; ++kt) {
+    for (int jp = 0; jp < NTo / 2; ++jp) {
       uint32_t b[4];
       ldsm_x4_t(b, W + (16 * kt + 8 * ((lane >> 3) & 1) + (lane & 7)) * S + 8 * (2 * jp + (lane >> 4)));
       mma16816(c[2 * jp], a[kt], b[0], b[1]);
@@ -228,6 +239,52 @@ __device__ __forceinline__ void load_x(const float* __restrict__ x, int ldx, int
   }
 }
 
+// pull the lines of a future tile towards L2 (no registers held): rows [p0, p0+rows) of x and dirs
+__device__ __forceinline__ void prefetch_rows(const float* __restrict__ x, int ldx, const float* __restrict__ dirs,
+                                              int64_t p0, int rows, int64_t P, int lane) {
+  if (lane < rows && p0 + lane < P) {
+    const char* a = reinterpret_cast<const char*>(x + (p0 + lane) * ldx);
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+    if (ldx > 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128));
+    if ((lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(dirs + 3 * (p0 + lane))));
+  }
+}
+
+// split version of load_x for software pipelining: issue the loads now, pack (and stall) later
+template <int KT>
+__device__ __forceinline__ void load_x_raw(const float* __restrict__ x, int ldx, int pos_dim, int64_t p0, int64_t P,
+                                           float2 (&raw)[KT][4], int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const bool vec = ((ldx & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
+#pragma unroll
+  for (int k = 0; k < KT; ++k)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int64_t p = p0 + g + 8 * r;
+        const int c = 16 * k + 8 * h + 2 * t;
+        float2 v = make_float2(0.f, 0.f);
+        if (p < P) {
+          const float* src = x + p * ldx + c;
+          if (vec && c + 1 < pos_dim) {
+            v = __ldcs(reinterpret_cast<const float2*>(src));
+          } else {
+            if (c < pos_dim) v.x = __ldcs(src);
+            if (c + 1 < pos_dim) v.y = __ldcs(src + 1);
+          }
+        }
+        raw[k][2 * h + r] = v;
+      }
+}
+template <int KT>
+__device__ __forceinline__ void pack_x(const float2 (&raw)[KT][4], uint32_t (&a)[KT][4]) {
+#pragma unroll
+  for (int k = 0; k < KT; ++k)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) a[k][i] = pack2(raw[k][i].x, raw[k][i].y);
+}
+
 __device__ __forceinline__ float softplus_m5(float h0) {
   const float v = h0 - 5.0f;
   return v > 20.f ? v : log1pf(expf(v));
@@ -282,6 +339,7 @@ k_instant_fwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
   const int64_t wstride = (int64_t)gridDim.x * (MLP_THREADS / 32);
   for (int64_t tile = (int64_t)blockIdx.x * (MLP_THREADS / 32) + (threadIdx.x >> 5); tile < n_tiles; tile += wstride) {
     const int64_t p0 = tile * 32;
+    prefetch_rows(x, ldx, dirs, (tile + wstride) * 32, 32, P, lane);
     dir_features(dirs, p0 + lane, P, bands, L_dir, dstage + lane * DS);
     uint32_t ax[2][KT1][4];
     load_x<KT1>(x, ldx, pos_dim, p0, P, ax[0], lane);
@@ -433,11 +491,11 @@ k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
   float acc5[2][4] = {};          // dV3 (16 x 64, 3 valid rows): columns 16*warp..
 
   const int64_t n_tiles = (P + 63) / 64;
+  uint32_t ax[1][KT1][4];
+  load_x<KT1>(x, ldx, pos_dim, (int64_t)blockIdx.x * 64 + row0, P, ax[0], lane);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t p0 = tile * 64 + row0;
-    // ---------------- forward recompute (staging every layer input)
-    uint32_t ax[1][KT1][4];
-    load_x<KT1>(x, ldx, pos_dim, p0, P, ax[0], lane);
+    // ---------------- forward recompute (staging every layer input); ax was fetched one tile ahead
     store_a<KT1>(ax[0], sm + LY::in_x, LY::SX, row0, 0, lane);
     if (lane < 16) dir_features(dirs, p0 + lane, P, bands, L_dir, sm + LY::in_c + (row0 + lane) * LY::SC + 16);
     uint32_t ah[1][4][4];
@@ -562,12 +620,16 @@ k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
       }
     }
     __syncthreads();
+    // next tile's inputs: issue the global loads now, they land while the tensor cores do the wgrad
+    float2 xraw[KT1][4];
+    load_x_raw<KT1>(x, ldx, pos_dim, (tile + gridDim.x) * 64 + row0, P, xraw, lane);
     // ---------------- weight gradients over the 64 staged points
     wgrad_tile<POS_K / 8>(acc1, sm + LY::dz1, LY::SH, 16 * warp, sm + LY::in_x, LY::SX, 0, lane);
     wgrad_tile<2>(acc2, sm + LY::dz2, LY::SG, 0, sm + LY::in_h1, LY::SH, 16 * warp, lane);
     wgrad_tile<6>(acc3, sm + LY::dz3, LY::SH, 16 * warp, sm + LY::in_c, LY::SC, 0, lane);
     wgrad_tile<8>(acc4, sm + LY::dz4, LY::SH, 16 * warp, sm + LY::in_c1, LY::SH, 0, lane);
     wgrad_tile<2>(acc5, sm + LY::dz5, LY::SG, 0, sm + LY::in_c2, LY::SH, 16 * warp, lane);
+    pack_x<KT1>(xraw, ax[0]);
     __syncthreads();
   }
   // ---------------- flush: one atomicAdd per weight per CTA

@@ -81,7 +81,7 @@ lib = _load()
 # launch accounting for bench.py ("gpu_launches"): every successful C-ABI call adds the
 # number of kernels that entry point launches.
 LAUNCHES = {"count": 0}
-_KERNELS_PER_CALL = {"b2n_march_scan": 3, "b2n_linear_wgrad": 2, "b2n_hash_bwd": 2}
+_KERNELS_PER_CALL = {"b2n_march_scan": 3, "b2n_linear_wgrad": 2, "b2n_hash_bwd": 2}   # hash_bwd: dense + hashed levels
 
 
 def ptr(t):

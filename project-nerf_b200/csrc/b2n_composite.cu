@@ -53,7 +53,9 @@ k_composite_fwd(const float* __restrict__ rgb, const float* __restrict__ sigma, 
     const int64_t zb = r * N;
     int64_t off = mask_words ? (int64_t)ray_offset[r] : zb;
     float T0 = 1.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, dd = 0.f, aa = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
-    if (N > 1) {  // N == 1: the reference composites nothing (empty interval tensor)
+    // a ray without a single active sample composites to exactly zero weights: skip its scan
+    const bool empty_ray = mask_words && ray_offset[r + 1] == ray_offset[r];
+    if (N > 1 && !empty_ray) {  // N == 1: the reference composites nothing (empty interval tensor)
       for (int k = 0; k < W; ++k) {
         const int s = (k << 5) + lane;
         const bool valid = s < N;
@@ -127,6 +129,7 @@ k_composite_bwd(const float* __restrict__ rgb, const float* __restrict__ sigma, 
     const float gm0 = (g_mdx && dx) ? g_mdx[3 * r] : 0.f, gm1 = (g_mdx && dx) ? g_mdx[3 * r + 1] : 0.f,
                 gm2 = (g_mdx && dx) ? g_mdx[3 * r + 2] : 0.f;
 
+    if (mask_words && ray_offset[r + 1] == ray_offset[r]) continue;  // no active sample: nothing to write
     if (N == 1) {  // nothing was composited: all sample gradients are zero
       const bool act = lane == 0 && (!mask_words || (mask_words[r * W] & 1u));
       if (act) {

@@ -74,10 +74,39 @@ def c1_step(P_rays=4096, N=64):
         print(f"C1 render [{mode}]: median {med:.3f} ms -> {P_rays * N / med * 1e3 / 1e6:.1f} Msamples/s")
 
 
+def hash_levels(P=24_000_000):
+    """hash fwd / bwd time as a function of the level range (contention study)."""
+    from b2n import synthetic, march
+    torch.manual_seed(0)
+    ro, rd, _ = (t.cuda() for t in synthetic.random_rays(2 ** 18, seed=1))
+    u = torch.rand(2 ** 18, 128, device="cuda")
+    occ = torch.ones(128, 128, 128, dtype=torch.bool, device="cuda")
+    m = march.march(ro, rd, 2.0, 6.0, 128, u, bits=march.pack_occupancy(occ), R=128, bound=1.5)
+    x = m.pts
+    print("points", x.shape[0])
+    for (nl, base, note) in ((16, 16, "all 16 levels"), (4, 16, "levels 0-3 (dense 16..54)"), (8, 16, "levels 0-7"),
+                             (4, 411, "4 fine hashed levels (res 411..1384)")):
+        geom = b2n.HashGeometry(nl, base, 1.5, 19, 2)
+        table = torch.randn(geom.n_params, device="cuda", requires_grad=True) * 0.1
+        table = table.detach().requires_grad_(True)
+        y = b2n.hash_encode(x, table, geom, 1.5)
+        g = torch.randn_like(y)
+        f_med, _ = timeit(lambda: b2n.hash_encode(x, table, geom, 1.5), n=5, warm=2)
+
+        def bwd():
+            y = b2n.hash_encode(x, table, geom, 1.5)
+            y.backward(g)
+        b_med, _ = timeit(bwd, n=5, warm=2)
+        print(f"{note:45s} L={nl:2d}: fwd {f_med:7.3f} ms ({f_med / nl:6.3f}/level)  bwd(+fwd+memset) {b_med - f_med:7.3f} ms "
+              f"({(b_med - f_med) / nl:6.3f}/level)")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "mlp256"
     P = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
     if what == "c1":
         c1_step()
+    elif what == "hash":
+        hash_levels()
     else:
         {"mlp256": mlp256}[what](P)

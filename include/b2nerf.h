@@ -227,6 +227,8 @@ int b2n_nerf_mlp_fwd(const float* x_enc, int pos_dim, const float* d_enc, int di
  * dZ7 .. dZ0 = pre-activation gradients of every layer) and dz_small (fp32 [P,4]:
  * d rgb_pre[3], d sigma_pre).  Weight/bias gradients are dZ^T * layer-input GEMMs
  * over those planes (plain GEMMs, done by the caller). */
+/* debug aid: per-role cycle counters of CTA 0 of the next b2n_nerf_mlp_* launches (device int64[8], or NULL) */
+int b2n_debug_mlp256_prof(void* device_int64x8);
 size_t b2n_nerf_mlp_packed_bwd_bytes(void);
 int b2n_nerf_mlp_pack_bwd(const float* const* pts_w, const float* feature_w, const float* view_w, int pos_dim,
                           int dir_dim, void* packed, b2n_stream_t stream);

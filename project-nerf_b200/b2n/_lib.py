@@ -46,6 +46,7 @@ SIGNATURES = {
     "b2n_nerf_mlp_packed_bytes": [],
     "b2n_nerf_mlp_pack": [P, P, P, I, I, P, P],
     "b2n_nerf_mlp_fwd": [P, I, P, I, P, P, P, P, P, L, P, P, P, P, P],
+    "b2n_debug_mlp256_prof": [P],
     "b2n_nerf_mlp_packed_bwd_bytes": [],
     "b2n_nerf_mlp_pack_bwd": [P, P, P, I, I, P, P],
     "b2n_nerf_mlp_bwd": [P, P, P, P, P, P, P, P, L, P, P, P, P],

@@ -1,23 +1,40 @@
-// 256-wide vanilla NeRF decoder (NeRFDecoder.forward, src/decoders.py:68-87) on the 5th-gen
-// tensor cores: tcgen05.mma (cta_group::1, M=128, N=256|128, K=16, bf16 x bf16 -> fp32 in TMEM).
+// 256-wide vanilla NeRF decoder (NeRFDecoder.forward / backward, src/decoders.py:68-87) on the
+// 5th-gen tensor cores: tcgen05.mma (cta_group::1, M=128, N=128, K=16, bf16 x bf16 -> fp32 in TMEM).
 //
 //   h = x; for i in 0..7: (i == 4: h = [h, x]); h = relu(W_i h + b_i)
 //   sigma = relu(w_s h + b_s); feat = W_f h + b_f; hv = relu(W_v [feat, d] + b_v); rgb = sigmoid(W_c hv + b_c)
 //
-// One persistent CTA per SM processes PAIRS of 128-point tiles.  The activations of both tiles
-// never leave the SM: they sit in shared memory as bf16 in the canonical K-major SWIZZLE_128B
-// UMMA layout (4 k-blocks of 128 rows x 128 B per tile) and are the A operand of the next layer.
-// The weights are pre-packed once per step (b2n_nerf_mlp_pack) into a stream of 32 KB chunks
-// that are byte images of the B operand tiles ([N rows x 64 k] bf16, same swizzle), so the
-// producer needs no tensor map: one elected thread issues one 1-D bulk copy (cp.async.bulk ->
-// mbarrier complete_tx) per chunk into a 2-stage ring, and every chunk is used for BOTH tiles
-// (256 rows per weight fetch).  Accumulators: tile 0 in TMEM columns 0..255, tile 1 in 256..511.
+// One persistent CTA per SM works on PAIRS of 128-point tiles whose activations never leave the
+// SM: they sit in shared memory as bf16 in the canonical K-major SWIZZLE_128B UMMA layout (4
+// k-blocks of 128 rows x 128 B per tile) and are the A operand of the next layer.
+//
+// Schedule (measured: reading a 128 x 256 fp32 accumulator out of TMEM costs about as many cycles
+// as the MMAs that produced it, so the two must overlap): the tiles are processed in LOCK-STEP
+// BUT ALTERNATING -- while the tensor core runs layer l of tile B, all eight epilogue warps drain
+// layer l of tile A (TMEM -> +bias/ReLU -> bf16 -> swizzled st.shared), and vice versa:
+//       tensor : MMA(A,l)  MMA(B,l)  MMA(A,l+1)  MMA(B,l+1) ...
+//       epilog :           EPI(A,l)  EPI(B,l)    EPI(A,l+1) ...
+// Accumulators: tile A in TMEM columns 0..255, tile B in 256..511 (all 512 columns).
+//
+// Weights are pre-packed once per optimizer step (b2n_nerf_mlp_pack*) into a stream of 16 KB
+// chunks that are byte images of B operand tiles ([128 n-rows x 64 k] bf16, same swizzle), so
+// the producer needs no tensor map: one elected thread issues one 1-D bulk copy (cp.async.bulk
+// -> mbarrier complete_tx) per chunk into a 4-stage ring (the layer is streamed once per tile;
+// L2 serves it, measured L2 throughput < 20 %).
 //
 // Warp roles (10 warps): warp 0 = weight producer, warp 1 = TMEM allocator + MMA issuer (one
-// elected thread), warps 2..9 = epilogue (4 per tile; warp_id % 4 selects the TMEM lane quarter):
-// tcgen05.ld 32x32b.x32 -> +bias, ReLU -> bf16 -> swizzled st.shared (next layer's A) and, for
-// training, a bf16 copy to HBM (saved activations for the backward / weight-gradient GEMMs).
+// elected thread), warps 2..9 = epilogue: warp_id % 4 selects the TMEM lane quarter (rows), warps
+// 2-5 take accumulator columns 0..127 and warps 6-9 columns 128..255 of the tile being drained.
 // The 256->1 density head and the 128->3 colour head are dot products inside the epilogue.
+// For training the epilogue also writes every layer output to HBM in bf16 (saved activations).
+//
+// Measured on B200 (tools/kbench.py mlp256, P = 2^20): 727 TFLOP/s = 52 % of the sustained cuBLAS bf16
+// peak.  Per layer and tile pair: tensor work 4096 cycles, epilogue 5300 cycles (TMEM drain ~64 B/cycle
+// plus 64 KB of swizzled stores), period 8800 cycles, independent of the number of CTAs (not L2 bound).
+// The binding resource is SHARED-MEMORY BANDWIDTH: with both operands in smem an M=128,N=128,K=16 MMA
+// reads 8 KB per 64 cycles (= the 128 B/cycle limit) while the weight ring and the epilogue write another
+// 192 KB per tile and layer.  Next step (round 2): cta_group::2 (each CTA supplies half of B) or the A
+// operand in TMEM.
 //
 // Every mbarrier wait is bounded; on time-out the CTA raises an abort flag, stores an error code
 // and drains, so a protocol bug cannot hang the GPU.
@@ -30,30 +47,30 @@ namespace m256 {
 constexpr int HID = 256;
 constexpr int KBLK_BYTES = 128 * 128;          // one k-block of one tile: 128 rows x 64 bf16
 constexpr int ACT_BYTES = 4 * KBLK_BYTES;      // 128 x 256 bf16
-constexpr int STAGE_BYTES = 256 * 128;         // one weight chunk: 256 rows x 64 bf16
-constexpr int N_STAGES = 2;
+constexpr int CHUNK_BYTES = 128 * 128;         // one weight chunk: 128 n-rows x 64 k bf16
+constexpr int N_STAGES = 4;
 constexpr int OFF_ACT = 0;                     // [2 tiles][ACT_BYTES]
 constexpr int OFF_AUX = OFF_ACT + 2 * ACT_BYTES;       // [2 tiles][KBLK_BYTES]   x_enc, later d_enc
-constexpr int OFF_RING = OFF_AUX + 2 * KBLK_BYTES;     // [N_STAGES][STAGE_BYTES]
-constexpr int OFF_VEC = OFF_RING + N_STAGES * STAGE_BYTES;   // 256 floats bias + 384 floats head weights
+constexpr int OFF_RING = OFF_AUX + 2 * KBLK_BYTES;     // [N_STAGES][CHUNK_BYTES]
+constexpr int OFF_VEC = OFF_RING + N_STAGES * CHUNK_BYTES;   // 256 floats bias + 384 floats head weights / scratch
 constexpr int OFF_BAR = OFF_VEC + (256 + 384) * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 128;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
 
 constexpr int N_THREADS = 320;
 constexpr int EPI_THREADS = 256;
-constexpr int MAX_STEPS = 12, MAX_CHUNKS = 64;
+constexpr int MAX_STEPS = 12, MAX_CHUNKS = 96;
 
 enum { EPI_RELU = 0, EPI_RELU_SIGMA = 1, EPI_LINEAR = 2, EPI_VIEW_RGB = 3,
        EPI_B_LINEAR = 4, EPI_B_MASK = 5, EPI_B_MASK_SIGMA = 6 };
 
 struct Step {
-  int n_act;     // k-chunks taken from the activation buffer (0 or 4)
+  int n_act;     // k-chunks taken from the activation buffer (0, 2 or 4)
   int aux_k16;   // k16 sub-steps taken from the aux buffer (0 = none, 4 = 64 columns, 2 = 32 columns)
   int n;         // output width of the step (256 or 128)
   int epi;       // epilogue kind
-  int bias_off;  // offset into the bias vector
-  int save_slot; // index of the saved-activation plane (or -1)
+  int bias_off;  // fwd: offset into the bias vector; bwd: index of the gating forward plane
+  int save_slot; // index of the saved plane (or -1)
 };
 struct Plan {
   int n_steps;
@@ -95,6 +112,12 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// one lane of a converged warp (warp-uniform control flow keeps descriptors in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -118,8 +141,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr) : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row atoms 1024 B apart.
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
@@ -138,11 +161,11 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
-// stage `width` fp32 columns of one input row as bf16 into an aux k-block (zero padded to 64;
-// column `one_col` (if >= 0) is set to 1 -- unused here, biases are added in the epilogue)
-__device__ __forceinline__ void stage_row(const float* __restrict__ src, int width, bool valid, unsigned char* blk, int r) {
+// stage 4 of the 8 sixteen-byte chunks (c0 .. c0+3) of one fp32 input row as bf16 into an aux k-block
+__device__ __forceinline__ void stage_row(const float* __restrict__ src, int width, bool valid, unsigned char* blk,
+                                          int r, int c0) {
 #pragma unroll 1
-  for (int c = 0; c < 8; ++c) {
+  for (int c = c0; c < c0 + 4; ++c) {
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -171,6 +194,7 @@ struct FwdArgs {
   const float* g_rgb; const float* g_sigma;   // [P,3], [P]
   const float* rgb_out; const float* sigma_out;
   float* dz_small;                  // [P,4]: d(pre-sigmoid rgb)[3], d(pre-relu sigma)
+  long long* prof;                  // optional [8] cycle counters of CTA 0 (b2n_debug_mlp256_prof)
   Plan plan;
 };
 
@@ -180,11 +204,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   const uint32_t bar_full = s32(bars + 0);     // [N_STAGES]
-  const uint32_t bar_empty = s32(bars + 2);    // [N_STAGES]
-  const uint32_t bar_acc = s32(bars + 4);      // MMA -> epilogue: accumulators of the step complete
-  const uint32_t bar_act = s32(bars + 5);      // epilogue -> MMA: A operands written, accumulators drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-  volatile int* abort_flag = reinterpret_cast<volatile int*>(bars + 7);
+  const uint32_t bar_empty = s32(bars + 4);    // [N_STAGES]
+  const uint32_t bar_acc = s32(bars + 8);      // [2] MMA -> epilogue: accumulators of tile t complete
+  const uint32_t bar_act = s32(bars + 10);     // [2] epilogue -> MMA: A operand of tile t written, accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(bars + 13);
   float* vec = reinterpret_cast<float*>(smem + OFF_VEC);
 
   if ((s32(smem) & 1023u) != 0) {  // SWIZZLE_128B operands need 1024-byte aligned tiles
@@ -193,8 +217,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < N_STAGES; ++i) mbar_init(bar_full + 8 * i, 1), mbar_init(bar_empty + 8 * i, 1);
-    mbar_init(bar_acc, 1);
-    mbar_init(bar_act, EPI_THREADS);
+    for (int t = 0; t < 2; ++t) mbar_init(bar_acc + 8 * t, 1), mbar_init(bar_act + 8 * t, EPI_THREADS);
     *abort_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -214,65 +237,83 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
     if (lane == 0) {
       uint32_t use = 0;  // running chunk counter (ring position)
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-        const unsigned char* src = a.packed;
+        const unsigned char* step_src = a.packed;
         for (int s = 0; s < plan.n_steps; ++s) {
-          const int nch = plan.s[s].n_act + (plan.s[s].aux_k16 ? 1 : 0);
-          const uint32_t bytes = (uint32_t)plan.s[s].n * 128u;
-          for (int c = 0; c < nch; ++c, ++use) {
-            const uint32_t st = use % N_STAGES, ph = (use / N_STAGES) & 1;
-            if (!mbar_wait(bar_empty + 8 * st, ph ^ 1, abort_flag, a.err, 1)) goto prod_done;
-            mbar_expect_tx(bar_full + 8 * st, bytes);
-            bulk_g2s(s32(smem + OFF_RING + st * STAGE_BYTES), src, bytes, bar_full + 8 * st);
-            src += bytes;
+          const int nch = (plan.s[s].n_act + (plan.s[s].aux_k16 ? 1 : 0)) * (plan.s[s].n / 128);
+          for (int t = 0; t < 2; ++t) {        // the layer is streamed once per tile
+            const unsigned char* src = step_src;
+            for (int c = 0; c < nch; ++c, ++use) {
+              const uint32_t st = use % N_STAGES, ph = (use / N_STAGES) & 1;
+              if (!mbar_wait(bar_empty + 8 * st, ph ^ 1, abort_flag, a.err, 1)) goto prod_done;
+              mbar_expect_tx(bar_full + 8 * st, CHUNK_BYTES);
+              bulk_g2s(s32(smem + OFF_RING + st * CHUNK_BYTES), src, CHUNK_BYTES, bar_full + 8 * st);
+              src += CHUNK_BYTES;
+            }
           }
+          step_src += (size_t)nch * CHUNK_BYTES;
         }
       }
     }
   prod_done:;
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      uint32_t use = 0, act_phase = 0;
+    // The whole warp walks the (warp-uniform) schedule; one elected lane issues the tcgen05 ops.
+    {
+      uint32_t use = 0, act_phase[2] = {0, 0};
+      const uint32_t idesc = umma_idesc(128);
+      const uint32_t ring0 = s32(smem + OFF_RING), act0 = s32(smem + OFF_ACT), aux0 = s32(smem + OFF_AUX);
       for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
         for (int s = 0; s < plan.n_steps; ++s) {
-          const Step& sp = plan.s[s];
-          if (!mbar_wait(bar_act, act_phase & 1, abort_flag, a.err, 2)) goto mma_done;
-          ++act_phase;
-          tc_fence_after();
-          const uint32_t idesc = umma_idesc(sp.n);
-          const int nch = sp.n_act + (sp.aux_k16 ? 1 : 0);
-          for (int c = 0; c < nch; ++c, ++use) {
-            const uint32_t st = use % N_STAGES, ph = (use / N_STAGES) & 1;
-            if (!mbar_wait(bar_full + 8 * st, ph, abort_flag, a.err, 3)) goto mma_done;
+          const int n_act = plan.s[s].n_act, aux_k16 = plan.s[s].aux_k16;
+          const int nkc = n_act + (aux_k16 ? 1 : 0), halves = plan.s[s].n / 128;
+          for (int t = 0; t < 2; ++t) {
+            long long t0 = clock64();
+            if (!mbar_wait(bar_act + 8 * t, act_phase[t] & 1, abort_flag, a.err, 2)) goto mma_done;
+            if (a.prof && blockIdx.x == 0 && lane == 0) a.prof[0] += clock64() - t0;   // waiting for the epilogue
+            ++act_phase[t];
             tc_fence_after();
-            const uint64_t bdesc = umma_desc(s32(smem + OFF_RING + st * STAGE_BYTES));
-            const bool from_aux = c >= sp.n_act;
-            const int nk = from_aux ? sp.aux_k16 : 4;
-#pragma unroll 1
-            for (int t = 0; t < 2; ++t) {
-              const uint32_t abase = from_aux ? s32(smem + OFF_AUX + t * KBLK_BYTES)
-                                              : s32(smem + OFF_ACT + t * ACT_BYTES + c * KBLK_BYTES);
-              const uint64_t adesc = umma_desc(abase);
-              for (int k = 0; k < nk; ++k)
-                tc_mma(tmem + t * 256, adesc + 2 * k, bdesc + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+            const uint32_t d_tmem = tmem + t * 256;
+            for (int c = 0; c < nkc; ++c) {
+              const bool from_aux = c >= n_act;
+              const int nk = from_aux ? aux_k16 : 4;
+              const uint64_t adesc = umma_desc(from_aux ? aux0 + t * KBLK_BYTES : act0 + t * ACT_BYTES + c * KBLK_BYTES);
+              for (int h = 0; h < halves; ++h, ++use) {
+                const uint32_t st = use % N_STAGES, ph = (use / N_STAGES) & 1;
+                t0 = clock64();
+                if (!mbar_wait(bar_full + 8 * st, ph, abort_flag, a.err, 3)) goto mma_done;
+                if (a.prof && blockIdx.x == 0 && lane == 0) a.prof[1] += clock64() - t0;   // waiting for weights
+                tc_fence_after();
+                const uint64_t bdesc = umma_desc(ring0 + st * CHUNK_BYTES);
+                if (elect_one()) {
+                  if (nk == 4) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      tc_mma(d_tmem + h * 128, adesc + 2 * k, bdesc + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                  } else {
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                      tc_mma(d_tmem + h * 128, adesc + 2 * k, bdesc + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                  }
+                  tc_commit(bar_empty + 8 * st);   // frees the ring slot once these MMAs have read it
+                }
+                __syncwarp();
+              }
             }
-            tc_commit(bar_empty + 8 * st);   // frees the ring slot once these MMAs have read it
+            if (elect_one()) tc_commit(bar_acc + 8 * t);
+            __syncwarp();
           }
-          tc_commit(bar_acc);
         }
       }
     }
   mma_done:;
   } else {
-    // ================================ epilogue (8 warps) ================================
+    // ================================ epilogue (8 warps, all on the tile being drained) ================
     const int e = threadIdx.x - 64;            // 0..255
-    const int t = e >> 7;                      // tile of this thread
     const int q = warp & 3;                    // TMEM lane quarter this warp may touch
+    const int half = (warp - 2) >> 2;          // accumulator column half this warp drains
     const int r = 32 * q + lane;               // row inside the tile
-    unsigned char* act = smem + OFF_ACT + t * ACT_BYTES;
-    unsigned char* aux = smem + OFF_AUX + t * KBLK_BYTES;
-    const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16) + t * 256;
-    uint32_t acc_phase = 0;
+    const int c0 = 128 * half;                 // first accumulator column of this thread
+    uint32_t acc_phase[2] = {0, 0};
     if (BWD) {  // head weights are needed by every pair: stage them once
       vec[e] = __ldg(a.w_sigma + e);
       vec[256 + e] = __ldg(a.w_rgb + e);
@@ -280,46 +321,52 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
     }
     for (int64_t pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
-      const int64_t p = pair * 256 + t * 128 + r;
-      const bool valid = p < a.P;
-      float sig_acc = 0.f;      // fwd: density dot product; bwd: d(pre-relu sigma) of this row
-      if (!BWD) {
-        // ---- pre-step: stage the encoded position as the first A operand
-        stage_row(a.x_enc + p * a.pos_dim, a.pos_dim, valid, aux, r);
-      } else {
-        // ---- pre-step: colour head backward -> dZ_view (128 wide) as the first A operand
-        float dzr[3] = {0.f, 0.f, 0.f};
-        if (valid) {
+      float row_scalar[2] = {0.f, 0.f};   // fwd: unused; bwd: d(pre-relu sigma) of this thread's row in tile t
+      // ---- pre-step: first A operand of both tiles
+      for (int t = 0; t < 2; ++t) {
+        unsigned char* act = smem + OFF_ACT + t * ACT_BYTES;
+        unsigned char* aux = smem + OFF_AUX + t * KBLK_BYTES;
+        const int64_t p = pair * 256 + t * 128 + r;
+        const bool valid = p < a.P;
+        if (!BWD) {
+          stage_row(a.x_enc + p * a.pos_dim, a.pos_dim, valid, aux, r, 4 * half);
+        } else {
+          // colour head backward -> dZ_view (128 wide; this thread covers 64 of its columns)
+          float dzr[3] = {0.f, 0.f, 0.f};
+          if (valid) {
 #pragma unroll
-          for (int j = 0; j < 3; ++j) {
-            const float y = __ldg(a.rgb_out + 3 * p + j);
-            dzr[j] = __ldg(a.g_rgb + 3 * p + j) * y * (1.f - y);
+            for (int j = 0; j < 3; ++j) {
+              const float y = __ldg(a.rgb_out + 3 * p + j);
+              dzr[j] = __ldg(a.g_rgb + 3 * p + j) * y * (1.f - y);
+            }
+            row_scalar[t] = __ldg(a.sigma_out + p) > 0.f ? __ldg(a.g_sigma + p) : 0.f;
+            if (half == 0) *reinterpret_cast<float4*>(a.dz_small + 4 * p) = make_float4(dzr[0], dzr[1], dzr[2], row_scalar[t]);
           }
-          sig_acc = __ldg(a.sigma_out + p) > 0.f ? __ldg(a.g_sigma + p) : 0.f;
-          *reinterpret_cast<float4*>(a.dz_small + 4 * p) = make_float4(dzr[0], dzr[1], dzr[2], sig_acc);
-        }
-        const __nv_bfloat16* hv = a.fwd_planes + ((size_t)9 * a.P + (valid ? p : 0)) * HID;
-        __nv_bfloat16* srow = (a.save && valid) ? a.save + ((size_t)0 * a.P + p) * HID : nullptr;
+          const __nv_bfloat16* hv = a.fwd_planes + ((size_t)9 * a.P + (valid ? p : 0)) * HID;
+          __nv_bfloat16* srow = (a.save && valid) ? a.save + ((size_t)0 * a.P + p) * HID : nullptr;
 #pragma unroll 1
-        for (int c = 0; c < 16; ++c) {
-          uint4 hraw = valid ? __ldcs(reinterpret_cast<const uint4*>(hv + 8 * c)) : make_uint4(0, 0, 0, 0);
-          const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&hraw);
-          float f[8];
+          for (int c = 8 * half; c < 8 * half + 8; ++c) {
+            uint4 hraw = valid ? __ldcs(reinterpret_cast<const uint4*>(hv + 8 * c)) : make_uint4(0, 0, 0, 0);
+            const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&hraw);
+            float f[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int col = 8 * c + j;
-            const float g = dzr[0] * vec[256 + col] + dzr[1] * vec[256 + 128 + col] + dzr[2] * vec[256 + 256 + col];
-            f[j] = (__bfloat162float(hb[j]) > 0.f) ? g : 0.f;
+            for (int j = 0; j < 8; ++j) {
+              const int col = 8 * c + j;
+              const float g = dzr[0] * vec[256 + col] + dzr[1] * vec[256 + 128 + col] + dzr[2] * vec[256 + 256 + col];
+              f[j] = (__bfloat162float(hb[j]) > 0.f) ? g : 0.f;
+            }
+            const uint4 pk = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+            *reinterpret_cast<uint4*>(act + ((8 * c) >> 6) * KBLK_BYTES + swz(r, ((8 * c) & 63) >> 3)) = pk;
+            if (srow) __stcs(reinterpret_cast<uint4*>(srow + 8 * c), pk);
           }
-          const uint4 pk = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-          *reinterpret_cast<uint4*>(act + ((8 * c) >> 6) * KBLK_BYTES + swz(r, ((8 * c) & 63) >> 3)) = pk;
-          if (srow) __stcs(reinterpret_cast<uint4*>(srow + 8 * c), pk);
         }
+        proxy_fence();
+        mbar_arrive(bar_act + 8 * t);
       }
-      proxy_fence();
-      mbar_arrive(bar_act);
+      if (a.prof && blockIdx.x == 0 && e == 0) a.prof[4] += 1;            // pairs processed by CTA 0
       for (int s = 0; s < plan.n_steps; ++s) {
         const Step& sp = plan.s[s];
+        const bool last = (s + 1 == plan.n_steps);
         if (!BWD) {
           // stage this step's bias (and the head weights) for broadcast reads
           asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -331,81 +378,106 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
           }
           asm volatile("bar.sync 1, 256;" ::: "memory");
         }
-        if (!mbar_wait(bar_acc, acc_phase & 1, abort_flag, a.err, 4)) goto epi_done;
-        ++acc_phase;
-        tc_fence_after();
-        float rgb_acc[3] = {0.f, 0.f, 0.f};
-        const bool relu = sp.epi != EPI_LINEAR;
-        __nv_bfloat16* save_row = (a.save && sp.save_slot >= 0 && valid)
-                                      ? a.save + ((size_t)sp.save_slot * a.P + p) * HID : nullptr;
-        // bwd: the forward activation whose ReLU gates this gradient (plane index in bias_off)
-        const __nv_bfloat16* mask_row = (BWD && sp.epi != EPI_B_LINEAR)
-                                            ? a.fwd_planes + ((size_t)sp.bias_off * a.P + (valid ? p : 0)) * HID : nullptr;
-        const bool last = (s + 1 == plan.n_steps);
-#pragma unroll 1
-        for (int cb = 0; cb < sp.n / 32; ++cb) {
-          uint32_t v[32];
-          tc_ld32(trow + 32 * cb, v);
-          float f[32];
-          if (!BWD) {
+        const bool works = c0 < sp.n;            // a 128-wide step is drained by the column-half-0 warps only
+        for (int t = 0; t < 2; ++t) {
+          unsigned char* act = smem + OFF_ACT + t * ACT_BYTES;
+          unsigned char* aux = smem + OFF_AUX + t * KBLK_BYTES;
+          const int64_t p = pair * 256 + t * 128 + r;
+          const bool valid = p < a.P;
+          const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16) + t * 256 + c0;
+          long long t0 = clock64();
+          if (!mbar_wait(bar_acc + 8 * t, acc_phase[t] & 1, abort_flag, a.err, 4)) goto epi_done;
+          long long t1 = clock64();
+          if (a.prof && blockIdx.x == 0 && e == 0) a.prof[2] += t1 - t0;    // epilogue waiting for the MMAs
+          ++acc_phase[t];
+          tc_fence_after();
+          float sig_acc = 0.f, rgb_acc[3] = {0.f, 0.f, 0.f};
+          const bool relu = sp.epi != EPI_LINEAR;
+          __nv_bfloat16* save_row = (a.save && sp.save_slot >= 0 && valid)
+                                        ? a.save + ((size_t)sp.save_slot * a.P + p) * HID : nullptr;
+          // bwd: the forward activation whose ReLU gates this gradient (plane index in bias_off)
+          const __nv_bfloat16* mask_row = (BWD && sp.epi != EPI_B_LINEAR)
+                                              ? a.fwd_planes + ((size_t)sp.bias_off * a.P + (valid ? p : 0)) * HID : nullptr;
+          if (works) {
+            // TMEM reads are the scarce resource of this epilogue (~64 B/cycle/SM): keep one 32-column
+            // load in flight while the previous block is converted and stored (double-buffered registers)
+            uint32_t vbuf[2][32];
+            tc_ld32(trow, vbuf[0]);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(v[j]) + vec[32 * cb + j];
-              f[j] = relu ? fmaxf(x, 0.f) : x;
-            }
-            if (sp.epi == EPI_RELU_SIGMA) {
+            for (int cb = 0; cb < 4; ++cb) {
+              const int colb = c0 + 32 * cb;           // first accumulator column of this block of 32
+              tc_ld_wait();
+              if (cb + 1 < 4) tc_ld32(trow + 32 * (cb + 1), vbuf[(cb + 1) & 1]);
+              const uint32_t (&v)[32] = vbuf[cb & 1];
+              float f[32];
+              if (!BWD) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) sig_acc = fmaf(f[j], vec[256 + 32 * cb + j], sig_acc);
-            } else if (sp.epi == EPI_VIEW_RGB) {
+                for (int j = 0; j < 32; ++j) {
+                  float x = __uint_as_float(v[j]) + vec[colb + j];
+                  f[j] = relu ? fmaxf(x, 0.f) : x;
+                }
+                if (sp.epi == EPI_RELU_SIGMA) {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                rgb_acc[0] = fmaf(f[j], vec[256 + 32 * cb + j], rgb_acc[0]);
-                rgb_acc[1] = fmaf(f[j], vec[256 + 128 + 32 * cb + j], rgb_acc[1]);
-                rgb_acc[2] = fmaf(f[j], vec[256 + 256 + 32 * cb + j], rgb_acc[2]);
+                  for (int j = 0; j < 32; ++j) sig_acc = fmaf(f[j], vec[256 + colb + j], sig_acc);
+                } else if (sp.epi == EPI_VIEW_RGB) {
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) {
+                    rgb_acc[0] = fmaf(f[j], vec[256 + colb + j], rgb_acc[0]);
+                    rgb_acc[1] = fmaf(f[j], vec[256 + 128 + colb + j], rgb_acc[1]);
+                    rgb_acc[2] = fmaf(f[j], vec[256 + 256 + colb + j], rgb_acc[2]);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                if (sp.epi == EPI_B_MASK_SIGMA) {   // + d(sigma_pre) * w_sigma  (density head, rank-1)
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) f[j] = fmaf(row_scalar[t], vec[colb + j], f[j]);
+                }
+                if (mask_row) {
+#pragma unroll
+                  for (int c4 = 0; c4 < 4; ++c4) {
+                    uint4 hraw = valid ? __ldcs(reinterpret_cast<const uint4*>(mask_row + colb + 8 * c4)) : make_uint4(0, 0, 0, 0);
+                    const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&hraw);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                      if (!(__bfloat162float(hb[j]) > 0.f)) f[8 * c4 + j] = 0.f;
+                  }
+                }
               }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (sp.epi == EPI_B_MASK_SIGMA) {   // + d(sigma_pre) * w_sigma  (density head, rank-1)
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = fmaf(sig_acc, vec[32 * cb + j], f[j]);
-            }
-            if (mask_row) {
 #pragma unroll
               for (int c4 = 0; c4 < 4; ++c4) {
-                uint4 hraw = valid ? __ldcs(reinterpret_cast<const uint4*>(mask_row + 32 * cb + 8 * c4)) : make_uint4(0, 0, 0, 0);
-                const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&hraw);
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  if (!(__bfloat162float(hb[j]) > 0.f)) f[8 * c4 + j] = 0.f;
+                const uint4 pk = make_uint4(pack_bf16(f[8 * c4], f[8 * c4 + 1]), pack_bf16(f[8 * c4 + 2], f[8 * c4 + 3]),
+                                            pack_bf16(f[8 * c4 + 4], f[8 * c4 + 5]), pack_bf16(f[8 * c4 + 6], f[8 * c4 + 7]));
+                const int col = colb + 8 * c4;            // first column of this 16-byte chunk
+                if (sp.epi != EPI_VIEW_RGB && !(BWD && last))
+                  *reinterpret_cast<uint4*>(act + (col >> 6) * KBLK_BYTES + swz(r, (col & 63) >> 3)) = pk;
+                if (save_row) __stcs(reinterpret_cast<uint4*>(save_row + col), pk);
               }
             }
           }
+          if (!BWD) {
+            if (sp.epi == EPI_RELU_SIGMA) {
+              // the density dot product is split over the two column halves: combine through smem
+              if (half == 1) vec[512 + r] = sig_acc;
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+              if (half == 0 && valid) a.sigma[p] = fmaxf(sig_acc + vec[512 + r] + __ldg(a.head_bias), 0.f);
+              asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+            if (sp.epi == EPI_VIEW_RGB && works && valid) {
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const uint4 pk = make_uint4(pack_bf16(f[8 * c4], f[8 * c4 + 1]), pack_bf16(f[8 * c4 + 2], f[8 * c4 + 3]),
-                                        pack_bf16(f[8 * c4 + 4], f[8 * c4 + 5]), pack_bf16(f[8 * c4 + 6], f[8 * c4 + 7]));
-            const int col = 32 * cb + 8 * c4;            // first column of this 16-byte chunk
-            if (sp.epi != EPI_VIEW_RGB && !(BWD && last))
-              *reinterpret_cast<uint4*>(act + (col >> 6) * KBLK_BYTES + swz(r, (col & 63) >> 3)) = pk;
-            if (save_row) __stcs(reinterpret_cast<uint4*>(save_row + col), pk);
+              for (int j = 0; j < 3; ++j) a.rgb[3 * p + j] = 1.f / (1.f + expf(-(rgb_acc[j] + __ldg(a.head_bias + 1 + j))));
+            }
+            // the x block is dead after the skip layer (the step that consumed both act and aux):
+            // re-use it for the encoded view direction of the view layer
+            if (sp.n_act > 0 && sp.aux_k16 > 0 && sp.epi == EPI_RELU)
+              stage_row(a.d_enc + p * a.dir_dim, a.dir_dim, valid, aux, r, 4 * half);
           }
+          tc_fence_before();
+          proxy_fence();
+          if (a.prof && blockIdx.x == 0 && e == 0) a.prof[3] += clock64() - t1;   // epilogue body
+          if (!last) mbar_arrive(bar_act + 8 * t);
         }
-        if (!BWD) {
-          if (sp.epi == EPI_RELU_SIGMA && valid) a.sigma[p] = fmaxf(sig_acc + __ldg(a.head_bias), 0.f);
-          if (sp.epi == EPI_VIEW_RGB && valid) {
-#pragma unroll
-            for (int j = 0; j < 3; ++j) a.rgb[3 * p + j] = 1.f / (1.f + expf(-(rgb_acc[j] + __ldg(a.head_bias + 1 + j))));
-          }
-          // the x block is dead after the skip layer (the step that consumed both act and aux):
-          // re-use it for the encoded view direction of the view layer
-          if (sp.n_act > 0 && sp.aux_k16 > 0 && sp.epi == EPI_RELU)
-            stage_row(a.d_enc + p * a.dir_dim, a.dir_dim, valid, aux, r);
-        }
-        tc_fence_before();
-        proxy_fence();
-        if (!last) mbar_arrive(bar_act);
       }
     }
   epi_done:;
@@ -419,10 +491,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
 // ---------------------------------------------------------------------------------------- weight packing
 struct PackChunk {
   const float* W;   // source matrix, row-major, leading dimension ldw
-  // forward (trans = 0): tile row n <- source row n (n < n_real), tile k <- source column k0 + k (< k_real)
-  // backward (trans = 1): tile row n <- source column n (n < n_real), tile k <- source row k0 + k (< k_real)
-  int ldw, n_real, n_pad, k0, k_real, trans;
-  int64_t dst_off;  // byte offset in the packed stream
+  // forward (trans = 0): tile row i <- source row n0+i (< n_real), tile k <- source column k0 + k (< k_real)
+  // backward (trans = 1): tile row i <- source column n0+i (< n_real), tile k <- source row k0 + k (< k_real)
+  int ldw, n0, n_real, k0, k_real, trans;
 };
 struct PackArgs {
   int n_chunks;
@@ -432,9 +503,10 @@ struct PackArgs {
 
 __global__ void k_mlp256_pack(const PackArgs a) {
   const PackChunk& c = a.c[blockIdx.x];
-  unsigned char* dst = a.dst + c.dst_off;
-  for (int i = threadIdx.x; i < c.n_pad * 8; i += blockDim.x) {
-    const int n = i >> 3, ch = i & 7;
+  unsigned char* dst = a.dst + (size_t)blockIdx.x * CHUNK_BYTES;
+  for (int i = threadIdx.x; i < 128 * 8; i += blockDim.x) {
+    const int row = i >> 3, ch = i & 7;
+    const int n = c.n0 + row;
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -442,7 +514,7 @@ __global__ void k_mlp256_pack(const PackArgs a) {
       const bool ok = n < c.n_real && k < c.k_real;
       f[j] = ok ? __ldg(c.trans ? c.W + (size_t)k * c.ldw + n : c.W + (size_t)n * c.ldw + k) : 0.f;
     }
-    *reinterpret_cast<uint4*>(dst + swz(n, ch)) =
+    *reinterpret_cast<uint4*>(dst + swz(row, ch)) =
         make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
   }
 }
@@ -472,40 +544,44 @@ static void build_fwd_plan(Plan* pl) {
   pl->n_steps = n;
 }
 
-extern "C" size_t b2n_nerf_mlp_packed_bytes(void) {
-  // 1 + 3*4 + 5 + 3*4 + 4 chunks of 256 rows, 5 chunks of 128 rows
-  return (size_t)(1 + 12 + 5 + 12 + 4) * 256 * 128 + (size_t)5 * 128 * 128;
+static long long* g_prof = nullptr;
+// debug aid: cycle counters of CTA 0 ([0] MMA waits epilogue, [1] MMA waits weights, [2] epilogue waits MMA,
+// [3] epilogue body, [4] tile pairs); pass a device int64[8] (zeroed) or NULL to disable
+extern "C" int b2n_debug_mlp256_prof(void* device_int64x8) {
+  g_prof = (long long*)device_int64x8;
+  return B2N_OK;
 }
 
-// weights: the 12 nn.Linear weight matrices of NeRFDecoder in state_dict order:
-// pts_layers[0..7], sigma_layer (unused here), feature_layer, view_layer, rgb_layer (unused here)
+// chunks: (1 + 3*4 + 5 + 3*4 + 4) k-chunks x 2 halves for the 256-wide steps, 5 x 1 for the view layer
+extern "C" size_t b2n_nerf_mlp_packed_bytes(void) { return (size_t)((1 + 12 + 5 + 12 + 4) * 2 + 5) * CHUNK_BYTES; }
+
+// weights: the nn.Linear weight matrices of NeRFDecoder: pts_layers[0..7], feature_layer, view_layer
 extern "C" int b2n_nerf_mlp_pack(const float* const* pts_w, const float* feature_w, const float* view_w, int pos_dim,
                                  int dir_dim, void* packed, b2n_stream_t stream) {
   B2N_REQUIRE(pts_w && feature_w && view_w && packed, "null pointer");
   B2N_REQUIRE(pos_dim > 0 && pos_dim <= 64 && dir_dim > 0 && dir_dim <= 32, "pos_dim <= 64 and dir_dim <= 32 required");
   PackArgs pa{};
   int n = 0;
-  int64_t off = 0;
-  auto add = [&](const float* W, int ldw, int n_real, int n_pad, int k0, int k_real) {
-    pa.c[n++] = PackChunk{W, ldw, n_real, n_pad, k0, k_real, 0, off};
-    off += (int64_t)n_pad * 128;
+  // one k-chunk of a layer = `halves` chunks of 128 output rows each, in [k-chunk][half] order
+  auto add = [&](const float* W, int ldw, int n_real, int halves, int k0, int k_real) {
+    for (int h = 0; h < halves; ++h) pa.c[n++] = PackChunk{W, ldw, 128 * h, n_real, k0, k_real, 0};
   };
   for (int l = 0; l < 8; ++l) {
     B2N_REQUIRE(pts_w[l], "null weight");
     if (l == 0) {
-      add(pts_w[0], pos_dim, 256, 256, 0, pos_dim);
+      add(pts_w[0], pos_dim, 256, 2, 0, pos_dim);
     } else {
       const int ld = (l == 4) ? 256 + pos_dim : 256;
-      for (int c = 0; c < 4; ++c) add(pts_w[l], ld, 256, 256, 64 * c, 256);
-      if (l == 4) add(pts_w[4], ld, 256, 256, 256, ld);
+      for (int c = 0; c < 4; ++c) add(pts_w[l], ld, 256, 2, 64 * c, 256);
+      if (l == 4) add(pts_w[4], ld, 256, 2, 256, ld);
     }
   }
-  for (int c = 0; c < 4; ++c) add(feature_w, 256, 256, 256, 64 * c, 256);
-  for (int c = 0; c < 4; ++c) add(view_w, 256 + dir_dim, 128, 128, 64 * c, 256);
-  add(view_w, 256 + dir_dim, 128, 128, 256, 256 + dir_dim);
+  for (int c = 0; c < 4; ++c) add(feature_w, 256, 256, 2, 64 * c, 256);
+  for (int c = 0; c < 4; ++c) add(view_w, 256 + dir_dim, 128, 1, 64 * c, 256);
+  add(view_w, 256 + dir_dim, 128, 1, 256, 256 + dir_dim);
   pa.n_chunks = n;
   pa.dst = (unsigned char*)packed;
-  B2N_REQUIRE((size_t)off == b2n_nerf_mlp_packed_bytes(), "internal: packed size mismatch");
+  B2N_REQUIRE((size_t)n * CHUNK_BYTES == b2n_nerf_mlp_packed_bytes(), "internal: packed size mismatch");
   k_mlp256_pack<<<n, 256, 0, (cudaStream_t)stream>>>(pa);
   return check_launch("b2n_nerf_mlp_pack");
 }
@@ -524,6 +600,7 @@ extern "C" int b2n_nerf_mlp_fwd(const float* x_enc, int pos_dim, const float* d_
   a.head_bias = head_bias;
   a.P = P, a.rgb = rgb, a.sigma = sigma, a.save = (__nv_bfloat16*)save, a.err = err_flag;
   build_fwd_plan(&a.plan);
+  a.prof = g_prof;
   cudaFuncSetAttribute(k_mlp256<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   const int64_t n_pairs = (P + 255) / 256;
   const int grid = (int)(n_pairs < kSMs ? n_pairs : kSMs);
@@ -532,7 +609,7 @@ extern "C" int b2n_nerf_mlp_fwd(const float* x_enc, int pos_dim, const float* d_
 }
 
 // ---------------------------------------------------------------------------------------- backward (data gradients)
-// Chain (all on the tensor cores, M = 128 x 2 tiles, N = 256):
+// Chain (all on the tensor cores, same schedule as the forward):
 //   pre : dZ_view = (d rgb_pre * W_rgb) (.) [hv > 0]                       (epilogue warps, 128 wide)
 //   B1  : d feat  = dZ_view  * W_view[:, :256]            K = 128   -> dZ_feat (linear)
 //   B2  : d h7    = dZ_feat  * W_feat + d sigma_pre * w_sigma, gated by H7  -> dZ7
@@ -549,7 +626,7 @@ static void build_bwd_plan(Plan* pl) {
   pl->n_steps = n;
 }
 
-extern "C" size_t b2n_nerf_mlp_packed_bwd_bytes(void) { return (size_t)(2 + 4 * 8) * 256 * 128; }
+extern "C" size_t b2n_nerf_mlp_packed_bwd_bytes(void) { return (size_t)(2 + 4 * 8) * 2 * CHUNK_BYTES; }
 
 extern "C" int b2n_nerf_mlp_pack_bwd(const float* const* pts_w, const float* feature_w, const float* view_w, int pos_dim,
                                      int dir_dim, void* packed, b2n_stream_t stream) {
@@ -557,11 +634,9 @@ extern "C" int b2n_nerf_mlp_pack_bwd(const float* const* pts_w, const float* fea
   B2N_REQUIRE(pos_dim > 0 && pos_dim <= 64 && dir_dim > 0 && dir_dim <= 32, "pos_dim <= 64 and dir_dim <= 32 required");
   PackArgs pa{};
   int n = 0;
-  int64_t off = 0;
-  // tile rows = input index of the layer (first 256 inputs), tile k = output index of the layer
+  // tile rows = input index of the layer (first 256 inputs, two halves), tile k = output index of the layer
   auto add = [&](const float* W, int ldw, int n_out, int k0) {
-    pa.c[n++] = PackChunk{W, ldw, 256, 256, k0, n_out, 1, off};
-    off += (int64_t)256 * 128;
+    for (int h = 0; h < 2; ++h) pa.c[n++] = PackChunk{W, ldw, 128 * h, 256, k0, n_out, 1};
   };
   for (int c = 0; c < 2; ++c) add(view_w, 256 + dir_dim, 128, 64 * c);
   for (int c = 0; c < 4; ++c) add(feature_w, 256, 256, 64 * c);
@@ -572,7 +647,7 @@ extern "C" int b2n_nerf_mlp_pack_bwd(const float* const* pts_w, const float* fea
   }
   pa.n_chunks = n;
   pa.dst = (unsigned char*)packed;
-  B2N_REQUIRE((size_t)off == b2n_nerf_mlp_packed_bwd_bytes(), "internal: packed size mismatch");
+  B2N_REQUIRE((size_t)n * CHUNK_BYTES == b2n_nerf_mlp_packed_bwd_bytes(), "internal: packed size mismatch");
   k_mlp256_pack<<<n, 256, 0, (cudaStream_t)stream>>>(pa);
   return check_launch("b2n_nerf_mlp_pack_bwd");
 }
@@ -589,6 +664,7 @@ extern "C" int b2n_nerf_mlp_bwd(const void* packed_bwd, const float* w_sigma, co
   a.fwd_planes = (const __nv_bfloat16*)fwd_planes, a.rgb_out = rgb, a.sigma_out = sigma, a.g_rgb = g_rgb;
   a.g_sigma = g_sigma, a.P = P, a.save = (__nv_bfloat16*)dz_planes, a.dz_small = dz_small, a.err = err_flag;
   build_bwd_plan(&a.plan);
+  a.prof = g_prof;
   cudaFuncSetAttribute(k_mlp256<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   const int64_t n_pairs = (P + 255) / 256;
   const int grid = (int)(n_pairs < kSMs ? n_pairs : kSMs);

@@ -40,6 +40,15 @@ def mlp256(P):
         med, best = timeit(lambda: ops.nerf_mlp_forward(model.decoder, xe, de, save=save))
         print(f"mlp256 fwd P={P} save={save}: median {med:.3f} ms best {best:.3f} ms -> {flops / best / 1e9:.1f} TFLOP/s "
               f"({100 * flops / best / 1e9 / 1391.5:.1f} % of sustained bf16 peak)")
+    prof = torch.zeros(8, dtype=torch.int64, device="cuda")
+    b2n._lib.lib.b2n_debug_mlp256_prof(prof.data_ptr())
+    ops.nerf_mlp_forward(model.decoder, xe, de, save=False)
+    torch.cuda.synchronize()
+    b2n._lib.lib.b2n_debug_mlp256_prof(None)
+    pr = prof.tolist()
+    print(f"CTA0 cycles over {pr[4]} pairs: MMA-waits-epilogue {pr[0]}, MMA-waits-weights {pr[1]}, "
+          f"epilogue-waits-MMA {pr[2]}, epilogue-body {pr[3]}  (per step: {pr[0] / max(pr[4], 1) / 10:.0f}, "
+          f"{pr[1] / max(pr[4], 1) / 10:.0f}, {pr[2] / max(pr[4], 1) / 10:.0f}, {pr[3] / max(pr[4], 1) / 10:.0f})")
     with torch.no_grad():
         b2n.set_mlp_precision("fp32")
         med, best = timeit(lambda: model.decoder(xe, de), n=3, warm=1)

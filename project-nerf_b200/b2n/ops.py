@@ -438,25 +438,31 @@ class _NerfMLP(torch.autograd.Function):
              ptr(_c(g_rgb)), ptr(_c(g_sigma).view(-1)), Pn, ptr(dz), ptr(dz_small), ptr(err), stream(),
              work=(Pn * (2.0 * 5120 + 48), flops))
         # ---- weight / bias gradients: dW = dZ^T In, one plain GEMM per layer over all points
-        xb, db = x_enc.to(torch.bfloat16), d_enc.to(torch.bfloat16)
+        # layer inputs in bf16, zero-padded to 64 / 32 columns: aligned shapes keep cuBLAS on its fast kernels
+        xb = torch.nn.functional.pad(x_enc, (0, 64 - pos_dim)).to(torch.bfloat16)
+        db = torch.nn.functional.pad(d_enc, (0, 32 - dir_dim)).to(torch.bfloat16)
         H = planes                      # H[0..7] trunk outputs, H[8] feat, H[9][:, :128] hv
         dZ = {l: dz[9 - l] for l in range(8)}     # dZ_l of trunk layer l
         gb_all = torch.sum(dz, dim=1, dtype=torch.float32)   # [10, 256] column sums
         grads = {}
         for l in range(8):
             if l == 0:
-                gW = _mm_f32(dZ[0], xb)
+                gW = _mm_f32(dZ[0], xb)[:, :pos_dim]
             elif l == 4:
-                gW = torch.cat([_mm_f32(dZ[4], H[3]), _mm_f32(dZ[4], xb)], dim=1)
+                gW = torch.cat([_mm_f32(dZ[4], H[3]), _mm_f32(dZ[4], xb)[:, :pos_dim]], dim=1)
             else:
                 gW = _mm_f32(dZ[l], H[l - 1])
             grads[f"pts{l}"] = (gW, gb_all[9 - l])
         grads["feat"] = (_mm_f32(dz[1], H[7]), gb_all[1])
-        dzv = dz[0][:, :128]
-        grads["view"] = (torch.cat([_mm_f32(dzv, H[8]), _mm_f32(dzv, db)], dim=1), gb_all[0][:128])
-        dzs16 = dz_small.to(torch.bfloat16)
-        grads["sigma"] = (_mm_f32(dzs16[:, 3:4], H[7]), dz_small[:, 3].sum().view(1))
-        grads["rgb"] = (_mm_f32(dzs16[:, :3], H[9][:, :128]), dz_small[:, :3].sum(dim=0))
+        gv = _mm_f32(dz[0], torch.cat([H[8], db], dim=1))[:128]       # [256(128 used), 256 + 32]
+        grads["view"] = (gv[:, :256 + dir_dim], gb_all[0][:128])
+        # the two small heads share one GEMM per input plane: rows = (d rgb_pre[3], d sigma_pre) padded to 8
+        dzs16 = torch.nn.functional.pad(dz_small, (0, 4)).to(torch.bfloat16)      # [P, 8]
+        gs = _mm_f32(dzs16, H[7])                                                    # [8, 256]
+        gr = _mm_f32(dzs16, H[9])                                                    # [8, 256] (hv in cols 0..127)
+        small_sum = dz_small.sum(dim=0)
+        grads["sigma"] = (gs[3:4], small_sum[3:4])
+        grads["rgb"] = (gr[:3, :128], small_sum[:3])
         out = []
         for l in range(8):
             out += list(grads[f"pts{l}"])

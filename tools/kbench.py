@@ -74,6 +74,13 @@ def c1_step(P_rays=4096, N=64):
             opt.step()
 
         med, best = timeit(step, n=5 if mode == "fp32" else 20, warm=3)
+        if mode == "bf16" and "--prof" in sys.argv:
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                for _ in range(3):
+                    step()
+                torch.cuda.synchronize()
+            print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
         flops = 3 * 2.0 * P_rays * N * 593408
         print(f"C1 train step [{mode}] B={P_rays} N={N}: median {med:.3f} ms -> {P_rays / med * 1e3 / 1e6:.3f} M rays/s, "
               f"{flops / med / 1e9:.1f} TFLOP/s algorithmic")
@@ -112,7 +119,7 @@ def hash_levels(P=24_000_000):
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "mlp256"
-    P = int(sys.argv[2]) if len(sys.argv) > 2 else 262144
+    P = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 262144
     if what == "c1":
         c1_step()
     elif what == "hash":

@@ -202,6 +202,49 @@ def ncu_traffic(kernel_name):
     return None
 
 
+def bench_c1(dev):
+    """BASELINE.json configs[0] ("C1", Part 2 vanilla NeRF: PosEnc 10/4, 8x256 MLP on tcgen05, 64 samples, batch
+    4096) on one GPU -- reported as an extra, the headline stays C2."""
+    from b2n import synthetic
+    from src.core import NeuralField
+    from src.renderer import render_rays
+    torch.manual_seed(0)
+    model = NeuralField(dict(mode="part2_nerf", L_embed=10, L_embed_dir=4)).to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=5e-4)
+    B, N = 4096, 64
+    pool = [tuple(t.to(dev) for t in synthetic.random_rays(B, seed=50 + i)) for i in range(3)]
+
+    def step(i):
+        ro, rd, tgt = pool[i % 3]
+        target = tgt[:, :3] * tgt[:, 3:4] + (1.0 - tgt[:, 3:4])
+        pred, _, _ = render_rays(model, ro, rd, NEAR, FAR, N, True, white_bkgd=True)
+        loss = torch.nn.functional.mse_loss(pred, target)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+
+    def run(fn, n, warm):
+        for i in range(warm):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    ms_train = run(step, 20, 5)
+    model.eval()
+    with torch.no_grad():
+        ms_render = run(lambda i: render_rays(model, pool[i % 3][0], pool[i % 3][1], NEAR, FAR, N, False), 20, 5)
+    return {"workload": "C1 Part-2 vanilla NeRF, B=4096 rays x 64 samples, 8x256 MLP (tcgen05 bf16), Adam",
+            "train_rays_per_s": B / ms_train * 1e3, "train_ms_per_step": ms_train,
+            "train_mlp_tflops_algorithmic": 3 * 2.0 * B * N * 593408 / ms_train / 1e9,
+            "render_msamples_per_s": B * N / ms_render * 1e3 / 1e6}
+
+
 # --------------------------------------------------------------------------------------- GPU arm
 def main():
     args = parse()
@@ -332,6 +375,9 @@ def main():
         model.train()
         extras["render_msamples_per_s"] = world * B * N_SAMPLES * args.steps / (ms3 * 1e-3) / 1e6
         extras["render_occupancy"] = args.occupancy
+
+    if not args.no_extras and rank == 0:
+        extras["c1_vanilla"] = bench_c1(dev)
 
     if rank != 0:
         if world > 1:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2N_ABI_VERSION 6
+#define B2N_ABI_VERSION 7
 
 #define B2N_OK 0
 #define B2N_EINVAL (-1)  /* bad argument (null pointer, size, unsupported shape) */
@@ -235,6 +235,18 @@ int b2n_nerf_mlp_pack_bwd(const float* const* pts_w, const float* feature_w, con
 int b2n_nerf_mlp_bwd(const void* packed_bwd, const float* w_sigma, const float* w_rgb, const void* fwd_planes,
                      const float* rgb, const float* sigma, const float* g_rgb, const float* g_sigma, int64_t P,
                      void* dz_planes, float* dz_small, int* err_flag, b2n_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * GPU-resident training-ray sampler (sample_random_rays, src/dataset.py:147-171,
+ * :268-294): poses [V,4,4] fp32, images [V,H,W,4] uint8 RGBA, times [V] or NULL;
+ * img_idx / pix_y / pix_x: int64 [B] pixel picks (drawn by the caller, on the CPU
+ * generator for reference-identical streams or on the device) -> rays_o [B,3],
+ * rays_d [B,3] (unit), target_rgba [B,4] in [0,1], t_out [B] (optional).
+ * ---------------------------------------------------------------------- */
+int b2n_sample_rays(const float* poses, const uint8_t* images_rgba8, const float* times, const int64_t* img_idx,
+                    const int64_t* pix_y, const int64_t* pix_x, int64_t B, int V, int H, int W, float focal,
+                    float scene_scale, float* rays_o, float* rays_d, float* target_rgba, float* t_out,
+                    b2n_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -293,7 +293,40 @@ def gen_grid_update():
              grid1=g1, binary1=b1, grid2=grid.grid, binary2=grid.binary_grid, **sd_arrays(model))
 
 
+# ---------------------------------------------------------------- datasets (tiny synthetic scene on disk)
+def gen_dataset():
+    from PIL import Image
+    from src.dataset import BlenderDataset, DynamicDataset          # reference
+    root = os.path.join(HERE, "dataset_tiny")
+    os.makedirs(os.path.join(root, "train"), exist_ok=True)
+    rng = np.random.RandomState(5)
+    frames = []
+    for i in range(6):
+        img = rng.randint(0, 256, size=(20, 16, 4), dtype=np.uint8)
+        img[:5, :, 3] = 0                                            # some fully transparent pixels
+        Image.fromarray(img, "RGBA").save(os.path.join(root, "train", f"r_{i}.png"))
+        a = 0.7 * i
+        c2w = np.eye(4, dtype=np.float32)
+        c2w[:3, :3] = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]], dtype=np.float32)
+        c2w[:3, 3] = [4 * np.cos(a), 4 * np.sin(a), 0.5 * i]
+        frames.append({"file_path": f"./train/r_{i}", "transform_matrix": c2w.tolist(), "time": i / 5.0})
+    with open(os.path.join(root, "transforms_train.json"), "w") as f:
+        json.dump({"camera_angle_x": 0.6911112070083618, "frames": frames}, f)
+    for cls, tag in ((BlenderDataset, "blender"), (DynamicDataset, "dynamic")):
+        for scale in (1.0, 0.5):
+            ds = cls(root, split="train", downscale=1, white_bkgd=True, scene_scale=scale)
+            torch.manual_seed(77)
+            out = ds.sample_random_rays(257, "cpu")
+            img = ds.get_image_rays(3, "cpu")
+            arrs = dict(rays_o=out[0], rays_d=out[1], target=out[2], img_rays_o=img[0], img_rays_d=img[1], img_target=img[2],
+                        focal=np.float64(ds.focal), H=np.int64(ds.H), W=np.int64(ds.W))
+            if tag == "dynamic":
+                arrs.update(times=out[3], img_time=img[3], all_times=ds.times)
+            save(f"dataset_{tag}_s{scale}", **arrs)
+
+
 if __name__ == "__main__":
+    gen_dataset()
     gen_sampling()
     gen_mask()
     gen_composite()

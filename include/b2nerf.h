@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2N_ABI_VERSION 7
+#define B2N_ABI_VERSION 8
 
 #define B2N_OK 0
 #define B2N_EINVAL (-1)  /* bad argument (null pointer, size, unsupported shape) */
@@ -247,6 +247,11 @@ int b2n_sample_rays(const float* poses, const uint8_t* images_rgba8, const float
                     const int64_t* pix_y, const int64_t* pix_x, int64_t B, int V, int H, int W, float focal,
                     float scene_scale, float* rays_o, float* rays_d, float* target_rgba, float* t_out,
                     b2n_stream_t stream);
+
+/* measurement aid: random 8-byte gathers over a float2[n_entries] table (n_entries = 2^k); used to
+ * measure the L2 gather peak the hash-grid kernels are compared against (tools/kbench.py l2) */
+int b2n_debug_gather_bench(const float* table, int64_t n_entries, int blocks, int per_thread, float* sink,
+                           b2n_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -117,6 +117,24 @@ def hash_levels(P=24_000_000):
               f"({(b_med - f_med) / nl:6.3f}/level)")
 
 
+def l2_gather():
+    """Random 8-byte gathers over tables of 2 MiB .. 512 MiB: the L2 (and beyond-L2) gather peak."""
+    from b2n._lib import call, ptr, stream
+    sink = torch.zeros(1, device="cuda")
+    out = {}
+    for log2n in (18, 21, 22, 23, 24, 26):          # float2 entries: 2 MiB, 16, 32, 64, 128, 512 MiB
+        n = 1 << log2n
+        table = torch.randn(n, 2, device="cuda")
+        blocks, per_thread = 148 * 16, 512
+        fn = lambda: call("b2n_debug_gather_bench", ptr(table), n, blocks, per_thread, ptr(sink), stream())
+        med, best = timeit(fn, n=5, warm=2)
+        g = blocks * 256 * per_thread
+        out[n * 8 >> 20] = g / best / 1e6
+        print(f"table {n * 8 >> 20:4d} MiB: {g / best / 1e6:8.1f} G gathers/s  = {g * 8 / best / 1e6:7.1f} GB/s useful, "
+              f"{g * 32 / best / 1e6:7.1f} GB/s of 32-byte sectors")
+    return out
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "mlp256"
     P = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 262144
@@ -124,5 +142,7 @@ if __name__ == "__main__":
         c1_step()
     elif what == "hash":
         hash_levels()
+    elif what == "l2":
+        l2_gather()
     else:
         {"mlp256": mlp256}[what](P)

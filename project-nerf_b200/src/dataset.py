@@ -70,6 +70,16 @@ class BlenderDataset:
             self._images = torch.from_numpy(self._rgba8.astype(np.float32) / 255.0)
         return self._images
 
+    @images.setter
+    def images(self, value):
+        """run.py:484 assigns a subset (``val_set.images = test_set.images[val_indices]``): keep the 8-bit
+        stack, the float view and the device copies consistent with the assignment."""
+        value = value.detach().cpu().float()
+        if value.shape[-1] == 4:
+            self._rgba8 = (value * 255.0).round().clamp(0, 255).to(torch.uint8).numpy()
+        self._images = value
+        self._dev = {}
+
     def _build_directions(self):
         j, i = torch.meshgrid(torch.arange(self.H), torch.arange(self.W), indexing="ij")
         return torch.stack([(i - self.W * 0.5) / self.focal, -(j - self.H * 0.5) / self.focal, -torch.ones_like(i)], dim=-1)
@@ -94,6 +104,11 @@ class BlenderDataset:
         rays_o, rays_d = self.get_rays(self.poses[index])
         rgba = torch.from_numpy(self._rgba8[index].astype(np.float32) / 255.0)
         return rays_o.to(device), rays_d.to(device), self._composite(rgba).to(device)
+
+    def __setattr__(self, name, value):
+        if name == "poses":
+            self.__dict__.get("_dev", {}).clear()        # resident copies follow re-assigned poses (run.py:485)
+        object.__setattr__(self, name, value)
 
     # ---- sampling
     def _times_tensor(self):

@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--cpu-rays", type=int, default=CPU_SAMPLE_RAYS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip the sparse-occupancy and render legs")
+    ap.add_argument("--only", default=None, help="run only one extra leg (c1_vanilla, c3_dnerf, c4_instant_dnerf, "
+                                                 "c5_dualhash) and print its dict -- development aid")
     return ap.parse_args()
 
 
@@ -245,6 +247,99 @@ def bench_c1(dev):
             "render_msamples_per_s": B * N / ms_render * 1e3 / 1e6}
 
 
+DYNAMIC = {
+    # BASELINE.json configs[2..4]; shapes from configs/part3.yaml.example, part3_instant.yaml.example, part4.yaml.example
+    "c3_dnerf": dict(cfg=dict(mode="part3", L_embed_time=10, L_embed=10, deform_hidden_dim=128, deform_num_layers=4,
+                              canonical_type="nerf", L_embed_canon=10, hidden_dim=256, num_layers=8, skip_layer=4,
+                              view_dim=128), B=2048, N=64, grid=None, lr=5e-4, reg=1e-4, tv=0.0,
+                     label="C3 Part-3 standard D-NeRF (Fourier-MLP deformation 4x128 + Fourier-MLP canonical 8x256)"),
+    "c4_instant_dnerf": dict(cfg=dict(mode="part3", L_embed_time=10, L_embed=10, deform_hidden_dim=128,
+                                      deform_num_layers=4, canonical_type="instant", n_levels=16,
+                                      n_features_per_level=2, log2_hashmap_size=19, base_resolution=16,
+                                      per_level_scale=1.5, scene_bound=1.5, hidden_dim=64, use_coord_noise=True,
+                                      coord_noise_std=0.005, time_noise_std=0.04),
+                             B=8192, N=128, grid=(128, 0.01), lr=5e-3, reg=1e-2, tv=1e-5,
+                             label="C4 Part-3 Instant D-NeRF (Fourier-MLP deformation + hash-grid canonical, 128^3 grid)"),
+    "c5_dualhash": dict(cfg=dict(mode="part4", deform_n_levels=12, deform_n_features_per_level=2,
+                                 deform_log2_hashmap_size=16, deform_base_resolution=16, deform_per_level_scale=1.5,
+                                 deform_hidden_dim=64, L_embed_time=10, time_modulation_dim=64,
+                                 time_modulation_layers=2, n_levels=16, n_features_per_level=2, log2_hashmap_size=20,
+                                 base_resolution=16, per_level_scale=1.5, scene_bound=1.5, hidden_dim=64,
+                                 use_coord_noise=True, coord_noise_std=0.001, time_noise_std=0.01),
+                        B=8192, N=64, grid=(64, 0.01), lr=1e-2, reg=1e-4, tv=1e-6,
+                        label="C5 Part-4 Dual-Hash dynamic NeRF (3 deformation hash grids + time modulation + canonical hash grid)"),
+}
+
+
+def bench_dynamic(dev, name, steps=10, warm=4, occupancy="dense"):
+    """Training step of run.py:1073-1178 / :1804-1949 (autocast + GradScaler, render_rays with times, RGB MSE +
+    deformation L2 + table TV, clip, AdamW) on one GPU for the dynamic configs -- reported as extras."""
+    from b2n import synthetic
+    from src.core import NeuralField
+    from src.renderer import DensityGrid, render_rays
+    spec = DYNAMIC[name]
+    torch.manual_seed(0)
+    model = NeuralField(spec["cfg"]).to(dev).train()
+    B, N = spec["B"], spec["N"]
+    grid = None
+    if spec["grid"]:
+        grid = DensityGrid(resolution=spec["grid"][0], bound=1.5, threshold=spec["grid"][1]).to(dev)
+        if occupancy == "sparse":
+            grid.binary_grid = synthetic.ball_occupancy(spec["grid"][0], 1.5).to(dev)
+    opt = torch.optim.AdamW(model.parameters(), lr=spec["lr"], weight_decay=1e-5)
+    scaler = torch.amp.GradScaler("cuda", enabled=True)
+    pool = [tuple(t.to(dev) for t in synthetic.random_rays(B, seed=70 + i, n_views=150, with_time=True)) for i in range(3)]
+    bg = torch.ones(3, device=dev)
+    tables = [m.encoding.params for n_, m in model.named_children() if hasattr(m, "encoding") and n_ != "deformation_grid"]
+
+    def step(i):
+        ro, rd, tgt, times = pool[i % 3]
+        target = tgt[:, :3] * tgt[:, 3:4] + bg * (1.0 - tgt[:, 3:4])
+        with torch.amp.autocast("cuda", enabled=True):
+            pred, _, _, extras = render_rays(model=model, rays_o=ro, rays_d=rd, near=NEAR, far=FAR, n_samples=N,
+                                             perturb=True, times=times, density_grid=grid, bg_color=bg)
+            loss = torch.nn.functional.mse_loss(pred, target) + torch.mean(extras["mean_delta_x"] ** 2) * spec["reg"]
+            if spec["tv"] > 0:
+                for tb in tables:
+                    loss = loss + torch.mean(torch.abs(tb[1:] - tb[:-1])) * spec["tv"]
+        opt.zero_grad()
+        scaler.scale(loss).backward()
+        scaler.unscale_(opt)
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+        scaler.step(opt)
+        scaler.update()
+
+    def run(fn, n, w):
+        for i in range(w):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    ms_train = run(step, steps, warm)
+    if os.environ.get("B2N_PROF"):                      # development aid: per-kernel device time of 3 steps
+        from torch.profiler import ProfilerActivity, profile
+        cpu = os.environ["B2N_PROF"] == "cpu"
+        with profile(activities=[ProfilerActivity.CUDA] + ([ProfilerActivity.CPU] if cpu else [])) as prof:
+            for i in range(3):
+                step(i)
+            torch.cuda.synchronize()
+        print(prof.key_averages().table(sort_by="self_cpu_time_total" if cpu else "cuda_time_total", row_limit=40,
+                                        max_name_column_width=70), file=sys.stderr)
+    model.eval()
+    with torch.no_grad():
+        ms_render = run(lambda i: render_rays(model, pool[i % 3][0], pool[i % 3][1], NEAR, FAR, N, False,
+                                              times=pool[i % 3][3], density_grid=grid, bg_color=bg), steps, 2)
+    return {"workload": f"{spec['label']}, B={B} rays x {N} samples, AMP autocast + GradScaler, AdamW, {occupancy} occupancy",
+            "train_rays_per_s": B / ms_train * 1e3, "train_ms_per_step": ms_train,
+            "render_msamples_per_s": B * N / ms_render * 1e3 / 1e6}
+
+
 # --------------------------------------------------------------------------------------- GPU arm
 def main():
     args = parse()
@@ -270,6 +365,10 @@ def main():
             os.environ["NCCL_DEBUG"] = "NONE"       # keep stdout to the single JSON line (no "NCCL version" banner)
         dist.init_process_group("nccl", device_id=dev)
     B = args.rays
+    if args.only:
+        r = bench_c1(dev) if args.only == "c1_vanilla" else bench_dynamic(dev, args.only, occupancy=args.occupancy)
+        print(json.dumps({args.only: r}), flush=True)
+        return
 
     torch.manual_seed(0)                                   # replicated init on every rank
     model = NeuralField(C2).to(dev).train()
@@ -378,6 +477,8 @@ def main():
 
     if not args.no_extras and rank == 0:
         extras["c1_vanilla"] = bench_c1(dev)
+        for name in DYNAMIC:
+            extras[name] = bench_dynamic(dev, name)
 
     if rank != 0:
         if world > 1:
@@ -405,7 +506,7 @@ def main():
     line = {
         "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, B),
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, B),
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2N_ABI_VERSION 8
+#define B2N_ABI_VERSION 9
 
 #define B2N_OK 0
 #define B2N_EINVAL (-1)  /* bad argument (null pointer, size, unsupported shape) */
@@ -198,6 +198,43 @@ int b2n_instant_mlp_bwd(const float* x_enc, int ldx, int pos_dim, const float* d
                         int L_dir, const float* sigma_params, const float* color_params, int64_t P,
                         const float* g_rgb, const float* g_sigma, float* g_x_enc, int ldg, float* g_sigma_params,
                         float* g_color_params, b2n_stream_t stream);
+
+/* ------------------------------------------------------------------------
+ * Fused small-width ReLU MLPs of the dynamic configs, bf16 tensor-core
+ * operands, fp32 accumulation:
+ *   DeformationNetwork     cat[gamma(x'),gamma(t')](84)->128->128->128->3  (src/decoders.py:171-195)
+ *   HashDeformationDecoder cat[hash feat(24), time mod(64)](88)->64->64->3 (src/decoders.py:285-316)
+ *   TimeModulationNetwork  gamma(t')(21)->64->64 sigmoid                   (src/decoders.py:340-371)
+ * General form: input = [x0 | x1] (two row-major fp32 sources, d0 + d1 <= 96,
+ * x1 may be NULL with d1 = 0; the concat is never materialised), n_hidden
+ * (1..3) ReLU layers of width `hidden` (64 or 128), then an output layer to
+ * out_dim (<= 64) with activation out_act.  W[l] (l = 0..n_hidden) are row-major
+ * [out,in] fp32 matrices with row stride ldw[l] (torch.nn.Linear.weight, or the
+ * slices of a tinycudann flat `params`); b[l] may be NULL (no bias).
+ * forward : y [P,out_dim] (row stride ldy); when xin_plane / h_planes are given
+ *           (training) also writes the bf16 input rows [P][b2n_fmlp_in_pad(d0+d1)]
+ *           and the hidden activations [n_hidden][P][hidden].
+ * backward: from g_y, the forward output y (needed for sigmoid/relu outputs) and
+ *           h_planes: writes dz_out bf16 [P][b2n_fmlp_out_pad(out_dim)], dz_h bf16
+ *           [n_hidden][P][hidden] (pre-activation gradients) and the fp32 input
+ *           gradients g_x0 [P,d0] / g_x1 [P,d1] (either may be NULL).  Weight and
+ *           bias gradients are dZ_l^T * In_l GEMMs / column sums over the planes
+ *           (plain GEMMs, done by the caller).
+ * ---------------------------------------------------------------------- */
+int b2n_fmlp_in_pad(int d_in);
+int b2n_fmlp_out_pad(int out_dim);
+int b2n_fmlp_fwd(const float* x0, int ld0, int d0, const float* x1, int ld1, int d1, int hidden, int n_hidden,
+                 const float* const* W, const int* ldw, const float* const* b, int out_dim, int out_act, int64_t P,
+                 float* y, int ldy, void* xin_plane, void* h_planes, b2n_stream_t stream);
+/* dW_l[rows_valid, k_valid] (row stride lddw) += dZ_l^T In_l ; db_l[rows_valid] += colsum(dZ_l) for
+ * l < n_layers in one launch: dz[l] bf16 [P][ldz] of width rows[l], in[l] bf16 [P][ldi] of width k[l]
+ * (widths multiples of 16, <= 128).  ACCUMULATES into fp32 dW / db (db[l] may be NULL). */
+int b2n_fmlp_wgrad(int n_layers, const void* const* dz, const int* ldz, const int* rows, const void* const* in,
+                   const int* ldi, const int* k, float* const* dW, const int* lddw, const int* rows_valid,
+                   const int* k_valid, float* const* db, int64_t P, b2n_stream_t stream);
+int b2n_fmlp_bwd(int d0, int d1, int hidden, int n_hidden, const float* const* W, const int* ldw, int out_dim,
+                 int out_act, int64_t P, const float* y, int ldy, const float* g_y, int ldgy, const void* h_planes,
+                 void* dz_out, void* dz_h, float* g_x0, int ldg0, float* g_x1, int ldg1, b2n_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * 256-wide vanilla NeRF decoder (NeRFDecoder.forward, src/decoders.py:68-87)

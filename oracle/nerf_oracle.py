@@ -253,31 +253,38 @@ def instant_decoder(sd, prefix: str, x_enc: Tensor, d_enc: Tensor, hidden=64, em
     return rgb, sigma
 
 
-def deformation_net(sd, prefix: str, x_feat: Tensor, t_feat: Tensor, num_layers=4):
+def _lin_q(sd: Dict[str, Tensor], prefix: str, h: Tensor, emulate_bf16: bool) -> Tensor:
+    """nn.Linear with (optionally) bf16-rounded GEMM operands and an fp32 bias, like the tensor-core kernels"""
+    if not emulate_bf16:
+        return _lin(sd, prefix, h)
+    return F.linear(bf16_round(h), bf16_round(sd[prefix + ".weight"].to(h.dtype)), sd[prefix + ".bias"].to(h.dtype))
+
+
+def deformation_net(sd, prefix: str, x_feat: Tensor, t_feat: Tensor, num_layers=4, emulate_bf16: bool = False):
     """Linear/ReLU stack -> 3-vector (src/decoders.py:171-195); nn.Sequential
     indices 0,2,4,... hold the Linear layers."""
     h = torch.cat([x_feat, t_feat], dim=-1)
     for i in range(num_layers):
-        h = _lin(sd, f"{prefix}.net.{2 * i}", h)
+        h = _lin_q(sd, f"{prefix}.net.{2 * i}", h, emulate_bf16)
         if i < num_layers - 1:
             h = torch.relu(h)
     return h
 
 
-def time_modulation(sd, prefix: str, t_feat: Tensor, num_layers=2):
+def time_modulation(sd, prefix: str, t_feat: Tensor, num_layers=2, emulate_bf16: bool = False):
     """sigmoid(MLP(time features))   (src/decoders.py:342-371)."""
     h = t_feat
     for i in range(num_layers):
-        h = _lin(sd, f"{prefix}.net.{2 * i}", h)
+        h = _lin_q(sd, f"{prefix}.net.{2 * i}", h, emulate_bf16)
         if i < num_layers - 1:
             h = torch.relu(h)
     return torch.sigmoid(h)
 
 
-def hash_deform_decoder(sd, prefix: str, hash_feat: Tensor, time_mod: Tensor, hidden=64):
+def hash_deform_decoder(sd, prefix: str, hash_feat: Tensor, time_mod: Tensor, hidden=64, emulate_bf16: bool = False):
     """fused MLP (cat -> 64 -> 64 -> 3) * displacement_scale (src/decoders.py:300-318)."""
     h = torch.cat([hash_feat, time_mod], dim=-1)
-    dx = fused_mlp(h, sd[f"{prefix}.deform_net.params"], h.shape[-1], 3, hidden, 2)
+    dx = fused_mlp(h, sd[f"{prefix}.deform_net.params"], h.shape[-1], 3, hidden, 2, emulate_bf16=emulate_bf16)
     return dx * sd[f"{prefix}.displacement_scale"].to(dx.dtype)
 
 

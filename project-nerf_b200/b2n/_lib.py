@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb2nerf.so")
 
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 P, L, I, F = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
 
@@ -43,6 +43,11 @@ SIGNATURES = {
     "b2n_sigma_head_bwd": [P, I, L, P, P, I, P],
     "b2n_instant_mlp_fwd": [P, I, I, P, P, I, P, P, L, P, P, P],
     "b2n_instant_mlp_bwd": [P, I, I, P, P, I, P, P, L, P, P, P, I, P, P, P],
+    "b2n_fmlp_in_pad": [I],
+    "b2n_fmlp_out_pad": [I],
+    "b2n_fmlp_fwd": [P, I, I, P, I, I, I, I, P, P, P, I, I, L, P, I, P, P, P],
+    "b2n_fmlp_bwd": [I, I, I, I, P, P, I, I, L, P, I, P, I, P, P, P, P, I, P, I, P],
+    "b2n_fmlp_wgrad": [I, P, P, P, P, P, P, P, P, P, P, P, L, P],
     "b2n_nerf_mlp_packed_bytes": [],
     "b2n_nerf_mlp_pack": [P, P, P, I, I, P, P],
     "b2n_nerf_mlp_fwd": [P, I, P, I, P, P, P, P, P, L, P, P, P, P, P],

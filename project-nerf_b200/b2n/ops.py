@@ -485,3 +485,98 @@ def nerf_mlp(decoder, x_enc, d_enc):
     if x_enc.requires_grad or d_enc.requires_grad:
         raise RuntimeError("nerf_mlp: input gradients are not produced by the tcgen05 path")
     return _NerfMLP.apply(decoder, x_enc, d_enc, *_nerf_params(decoder))
+
+
+# ----------------------------------------------------------------------------
+# fused small-width MLPs of the dynamic configs (bf16 tensor cores): b2n_fmlp_*
+# ----------------------------------------------------------------------------
+
+def fused_mlp_supported(d_in: int, hidden: int, n_hidden: int, out_dim: int) -> bool:
+    return hidden in (64, 128) and 1 <= n_hidden <= 3 and 1 <= d_in <= 96 and 1 <= out_dim <= 64
+
+
+class _FusedMLP(torch.autograd.Function):
+    """act_out(W_n relu(... relu(W_0 [x0|x1] + b_0) ...) + b_n): forward kernel (saving the bf16 input rows and
+    hidden activations when a gradient is needed), backward = the data-gradient chain kernel + one plain GEMM per
+    layer for the weight gradients and a column sum per bias."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x0, x1, out_act, n_layers, *wb):
+        Ws, bs = list(wb[:n_layers]), list(wb[n_layers:])
+        require_cuda(x0, x1, *Ws)
+        x0, x1 = _c(x0), _c(x1)
+        Ws = [W if (W.dtype == torch.float32 and W.stride(-1) == 1) else _c(W) for W in Ws]
+        bs = [_c(b) for b in bs]
+        Pn, d0 = x0.shape
+        d1 = x1.shape[1] if x1 is not None else 0
+        hidden, n_hidden, out_dim = Ws[0].shape[0], n_layers - 1, Ws[-1].shape[0]
+        dev = x0.device
+        need = any(ctx.needs_input_grad)
+        in_pad = _lib.lib.b2n_fmlp_in_pad(d0 + d1)
+        y = torch.empty(Pn, out_dim, device=dev)
+        xin = torch.empty(Pn, in_pad, device=dev, dtype=torch.bfloat16) if need else None
+        hpl = torch.empty(n_hidden, Pn, hidden, device=dev, dtype=torch.bfloat16) if need else None
+        Wp = (ctypes.c_void_p * n_layers)(*[W.data_ptr() for W in Ws])
+        ld = (ctypes.c_int * n_layers)(*[W.stride(0) for W in Ws])
+        bp = (ctypes.c_void_p * n_layers)(*[(b.data_ptr() if b is not None else None) for b in bs])
+        macs = hidden * (d0 + d1) + hidden * hidden * (n_hidden - 1) + out_dim * hidden
+        call("b2n_fmlp_fwd", ptr(x0), x0.stride(0), d0, ptr(x1), x1.stride(0) if x1 is not None else 0, d1, hidden,
+             n_hidden, Wp, ld, bp, out_dim, out_act, Pn, ptr(y), out_dim, ptr(xin), ptr(hpl), stream(),
+             work=(Pn * (4.0 * (d0 + d1 + out_dim) + (2.0 * (in_pad + n_hidden * hidden) if need else 0.0)), 2.0 * Pn * macs))
+        ctx.save_for_backward(y, xin, hpl, *Ws)
+        ctx.meta = (d0, d1, hidden, n_hidden, out_dim, out_act, n_layers, [b is not None for b in bs])
+        return y
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, g_y):
+        y, xin, hpl, *Ws = ctx.saved_tensors
+        d0, d1, hidden, n_hidden, out_dim, out_act, n_layers, has_b = ctx.meta
+        Pn = y.shape[0]
+        dev = y.device
+        g_y = _c(g_y)
+        out_pad = _lib.lib.b2n_fmlp_out_pad(out_dim)
+        dz_out = torch.empty(Pn, out_pad, device=dev, dtype=torch.bfloat16)
+        dz_h = torch.empty(n_hidden, Pn, hidden, device=dev, dtype=torch.bfloat16)
+        g_x0 = torch.empty(Pn, d0, device=dev) if ctx.needs_input_grad[0] else None
+        g_x1 = torch.empty(Pn, d1, device=dev) if (d1 and ctx.needs_input_grad[1]) else None
+        Wp = (ctypes.c_void_p * n_layers)(*[W.data_ptr() for W in Ws])
+        ld = (ctypes.c_int * n_layers)(*[W.stride(0) for W in Ws])
+        macs = hidden * hidden * (n_hidden - 1) + out_dim * hidden + (hidden * (d0 + d1) if (g_x0 is not None or g_x1 is not None) else 0)
+        call("b2n_fmlp_bwd", d0, d1, hidden, n_hidden, Wp, ld, out_dim, out_act, Pn, ptr(y), out_dim, ptr(g_y), out_dim,
+             ptr(hpl), ptr(dz_out), ptr(dz_h), ptr(g_x0), d0, ptr(g_x1), d1, stream(),
+             work=(Pn * (4.0 * out_dim + 4.0 * n_hidden * hidden + 2.0 * out_pad + 4.0 * (d0 + d1)), 2.0 * Pn * macs))
+        # ---- weight / bias gradients of every layer: one launch (b2n_fmlp_wgrad), fp32 accumulation
+        shapes = [(Ws[l].shape[0], Ws[l].shape[1]) for l in range(n_layers)]
+        n_w = sum(r * c for r, c in shapes)
+        flat = torch.zeros(n_w + sum(r for r, _ in shapes), device=dev)
+        gW, gb, off, boff = [], [], 0, n_w
+        for r, c in shapes:
+            gW.append(flat[off:off + r * c].view(r, c))
+            gb.append(flat[boff:boff + r])
+            off, boff = off + r * c, boff + r
+        dzs = [dz_h[l] for l in range(n_hidden)] + [dz_out]
+        ins = [xin] + [hpl[l] for l in range(n_hidden)]
+        arr_p, arr_i = ctypes.c_void_p * n_layers, ctypes.c_int * n_layers
+        call("b2n_fmlp_wgrad", n_layers, arr_p(*[t.data_ptr() for t in dzs]), arr_i(*[t.stride(0) for t in dzs]),
+             arr_i(*[t.shape[1] for t in dzs]), arr_p(*[t.data_ptr() for t in ins]), arr_i(*[t.stride(0) for t in ins]),
+             arr_i(*[t.shape[1] for t in ins]), arr_p(*[g.data_ptr() for g in gW]), arr_i(*[c for _, c in shapes]),
+             arr_i(*[r for r, _ in shapes]), arr_i(*[min(c, t.shape[1]) for (_, c), t in zip(shapes, ins)]),
+             arr_p(*[(gb[l].data_ptr() if has_b[l] else None) for l in range(n_layers)]), Pn, stream(),
+             work=(2.0 * Pn * sum(a_.shape[1] + b_.shape[1] for a_, b_ in zip(dzs, ins)),
+                   2.0 * Pn * sum(r * c for r, c in shapes)))
+        gW = [g if ctx.needs_input_grad[4 + l] else None for l, g in enumerate(gW)]
+        gb = [gb[l] if (has_b[l] and ctx.needs_input_grad[4 + n_layers + l]) else None for l in range(n_layers)]
+        return (g_x0, g_x1, None, None) + tuple(gW) + tuple(gb)
+
+
+def fused_mlp(x0, x1, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]], out_act: str = "none"):
+    """Fused ReLU MLP on [x0 | x1] (x1 may be None).  weights[l]: [out, in(+padding columns)] fp32, last = output layer
+    (its first out rows are used -- pass ``W[:out_dim]`` for a padded FullyFusedMLP matrix); biases[l] or None."""
+    n = len(weights)
+    hidden = weights[0].shape[0]
+    d_in = x0.shape[1] + (x1.shape[1] if x1 is not None else 0)
+    if not fused_mlp_supported(d_in, hidden, n - 1, weights[-1].shape[0]):
+        raise ValueError("fused_mlp: unsupported shape (hidden 64/128, 1..3 hidden layers, <= 96 inputs, <= 64 outputs)")
+    return _FusedMLP.apply(x0, x1, _ACT[out_act], n, *weights, *biases)

@@ -16,157 +16,15 @@
 //             layer input / pre-activation gradient is staged once in shared memory as bf16 and
 //             the weight gradients dW = dZ^T * In are accumulated by tensor cores in registers
 //             over the whole persistent loop, then flushed with one atomicAdd per weight per CTA.
-#include <cuda_bf16.h>
-#include "b2n_common.cuh"
+#include "b2n_mma.cuh"
 
 namespace b2n {
-
-typedef __nv_bfloat16 bf16;
 
 constexpr int HID = 64;      // hidden width
 constexpr int GEO = 16;      // sigma_net output width
 constexpr int CIN = 48;      // color_net padded input width (16 + 27 -> 48)
-constexpr int PAD = 8;       // bf16 row padding: row stride = width + 8 keeps ldmatrix conflict-free
 constexpr int MLP_THREADS = 128;
 
-// ------------------------------------------------------------------------------ primitives
-__device__ __forceinline__ uint32_t pack2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ __forceinline__ float2 unpack2(uint32_t v) {
-  __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&v);
-  return __bfloat1622float2(b);
-}
-__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
-}
-__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], const void* p) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];\n" : "=r"(r[0]), "=r"(r[1]) : "r"(smem_u32(p)));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];\n"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
-}
-
-// C[mt][j] (16 x 8 tiles) += A[mt][kt] * W^T ; W in smem as [n][k] bf16, row stride S.
-// Loop order: k-pairs outer, n-tiles inner, and the two k-halves issued in separate sweeps, so that
-// consecutive mma.sync never depend on each other's accumulator (NT*MT independent chains).
-template <int MT, int NT, int KT>
-__device__ __forceinline__ void gemm_fwd(float (&c)[MT][NT][4], const uint32_t (&a)[MT][KT][4], const bf16* W, int S,
-                                         int lane) {
-  constexpr int G = (NT < 4) ? NT : 4;     // n-tiles per sweep: G*MT independent accumulators in flight
-  const bf16* base = W + (lane & 7) * S + 8 * (lane >> 3);
-#pragma unroll
-  for (int j0 = 0; j0 < NT; j0 += G) {
-#pragma unroll
-    for (int q = 0; q < KT / 2; ++q) {
-      uint32_t b[G][4];
-#pragma unroll
-      for (int j = 0; j < G; ++j) {
-        ldsm_x4(b[j], base + 8 * (j0 + j) * S + 32 * q);
-#pragma unroll
-        for (int m = 0; m < MT; ++m) mma16816(c[m][j0 + j], a[m][2 * q], b[j][0], b[j][1]);
-      }
-#pragma unroll
-      for (int j = 0; j < G; ++j)
-#pragma unroll
-        for (int m = 0; m < MT; ++m) mma16816(c[m][j0 + j], a[m][2 * q + 1], b[j][2], b[j][3]);
-    }
-  }
-  if (KT & 1) {
-#pragma unroll
-    for (int j = 0; j < NT; ++j) {
-      uint32_t b[2];
-      ldsm_x2(b, W + (8 * j + (lane & 7)) * S + 16 * (KT - 1) + 8 * ((lane >> 3) & 1));
-#pragma unroll
-      for (int m = 0; m < MT; ++m) mma16816(c[m][j], a[m][KT - 1], b[0], b[1]);
-    }
-  }
-}
-
-// dIn[16 x 8*NTo] += dZ[16 x 16*KTz] * W ; W in smem as [n][k] (n is the reduction index).
-// Reduction index outer so that consecutive mma.sync hit different accumulators.
-template <int NTo, int KTz>
-__device__ __forceinline__ void gemm_dgrad(float (&c)[NTo][4], const uint32_t (&a)[KTz][4], const bf16* W, int S,
-                                           int lane) {
-  static_assert(NTo % 2 == 0, "pairs of output tiles");
-#pragma unroll
-  for (int kt = 0; kt < KTz; ++kt) {
-#pragma unroll
-    for (int jp = 0; jp < NTo / 2; ++jp) {
-      uint32_t b[4];
-      ldsm_x4_t(b, W + (16 * kt + 8 * ((lane >> 3) & 1) + (lane & 7)) * S + 8 * (2 * jp + (lane >> 4)));
-      mma16816(c[2 * jp], a[kt], b[0], b[1]);
-      mma16816(c[2 * jp + 1], a[kt], b[2], b[3]);
-    }
-  }
-}
-
-// acc (16 rows of dW starting at n0, NTk*8 columns starting at k0) += dZ^T In over the 64 staged points.
-template <int NTk>
-__device__ __forceinline__ void wgrad_tile(float (&acc)[NTk][4], const bf16* dZ, int Sz, int n0, const bf16* In,
-                                           int Si, int k0, int lane) {
-  static_assert(NTk % 2 == 0, "pairs of tiles");
-#pragma unroll
-  for (int ks = 0; ks < 4; ++ks) {
-    uint32_t a[4];
-    ldsm_x4_t(a, dZ + (16 * ks + 8 * (lane >> 4) + (lane & 7)) * Sz + n0 + 8 * ((lane >> 3) & 1));
-#pragma unroll
-    for (int jp = 0; jp < NTk / 2; ++jp) {
-      uint32_t b[4];
-      ldsm_x4_t(b, In + (16 * ks + 8 * ((lane >> 3) & 1) + (lane & 7)) * Si + k0 + 8 * (2 * jp + (lane >> 4)));
-      mma16816(acc[2 * jp], a, b[0], b[1]);
-      mma16816(acc[2 * jp + 1], a, b[2], b[3]);
-    }
-  }
-}
-
-// C tiles (fp32) -> A fragments (bf16) of the next layer, optional ReLU.
-template <int NT, bool RELU>
-__device__ __forceinline__ void c_to_a(const float (&c)[NT][4], uint32_t (&a)[NT / 2][4]) {
-#pragma unroll
-  for (int k = 0; k < NT / 2; ++k) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const float* s = c[2 * k + h];
-      float v0 = s[0], v1 = s[1], v2 = s[2], v3 = s[3];
-      if (RELU) v0 = fmaxf(v0, 0.f), v1 = fmaxf(v1, 0.f), v2 = fmaxf(v2, 0.f), v3 = fmaxf(v3, 0.f);
-      a[k][2 * h] = pack2(v0, v1);      // row g
-      a[k][2 * h + 1] = pack2(v2, v3);  // row g + 8
-    }
-  }
-}
-
-// store A fragments of a 16-row slab into a [rows][width + PAD] bf16 tile (row0 = first row of the slab)
-template <int KT>
-__device__ __forceinline__ void store_a(const uint32_t (&a)[KT][4], bf16* tile, int S, int row0, int col0, int lane) {
-  const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-  for (int k = 0; k < KT; ++k) {
-    uint32_t* r0 = reinterpret_cast<uint32_t*>(tile + (row0 + g) * S + col0 + 16 * k + 2 * t);
-    uint32_t* r1 = reinterpret_cast<uint32_t*>(tile + (row0 + g + 8) * S + col0 + 16 * k + 2 * t);
-    r0[0] = a[k][0], r1[0] = a[k][1], r0[4] = a[k][2], r1[4] = a[k][3];
-  }
-}
-
-// fp32 weight matrix [rows][src_cols] (row stride src_cols) -> bf16 smem [rows][cols + PAD]; columns
-// src_cols..cols-1 (input padding the parameter vector does not store) are zero-filled
-__device__ __forceinline__ void load_weights(const float* __restrict__ W, int rows, int cols, int src_cols, bf16* dst) {
-  const int S = cols + PAD;
-  for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
-    const int r = i / cols, c = i - r * cols;
-    dst[r * S + c] = __float2bfloat16(c < src_cols ? __ldg(W + (size_t)r * src_cols + c) : 0.f);
-  }
-}
 
 // view-direction Fourier features of one point -> 32 bf16 (27 valid, zero padded) at dst
 __device__ __forceinline__ void dir_features(const float* __restrict__ dirs, int64_t p, int64_t P,

@@ -63,7 +63,20 @@ class FusedMLP(nn.Module):
             off += r * c
         return out
 
+    def can_fuse(self, d_in=None):
+        return (b2n.mlp_precision() == "bf16"
+                and b2n.ops.fused_mlp_supported(self.n_input_dims if d_in is None else d_in, self.n_neurons, self.n_hidden,
+                                                self.n_output_dims))
+
+    def forward_fused(self, x0, x1=None):
+        """whole network as one tensor-core kernel each way (b2n_fmlp_*); input = [x0 | x1]"""
+        mats = self.matrices()
+        act = "sigmoid" if self.output_activation == "Sigmoid" else "none"
+        return b2n.ops.fused_mlp(x0, x1, mats[:-1] + [mats[-1][: self.n_output_dims]], [None] * len(mats), act)
+
     def forward(self, x):
+        if x.is_cuda and self.can_fuse(x.shape[-1]):
+            return self.forward_fused(x)
         mats = self.matrices()
         h = x
         for W in mats[:-1]:
@@ -154,8 +167,13 @@ class DeformationNetwork(BaseDecoder):
         self.net = nn.Sequential(*mods)
 
     def forward(self, x_feat, t_feat):
-        h = torch.cat([x_feat, t_feat], dim=-1)
         dense = [m for m in self.net if isinstance(m, _Dense)]
+        if (b2n.mlp_precision() == "bf16" and x_feat.is_cuda
+                and b2n.ops.fused_mlp_supported(x_feat.shape[-1] + t_feat.shape[-1], dense[0].out_features,
+                                                len(dense) - 1, 3)
+                and all(m.out_features == dense[0].out_features for m in dense[:-1])):
+            return b2n.ops.fused_mlp(x_feat, t_feat, [m.weight for m in dense], [m.bias for m in dense], "none")
+        h = torch.cat([x_feat, t_feat], dim=-1)
         for m in dense[:-1]:
             h = m(h, "relu")
         return dense[-1](h)
@@ -172,6 +190,8 @@ class HashDeformationDecoder(BaseDecoder):
         self.displacement_scale = nn.Parameter(torch.tensor(0.1))
 
     def forward(self, hash_feat, time_mod):
+        if hash_feat.is_cuda and self.deform_net.can_fuse(hash_feat.shape[-1] + time_mod.shape[-1]):
+            return self.deform_net.forward_fused(hash_feat, time_mod) * self.displacement_scale
         return self.deform_net(torch.cat([hash_feat, time_mod], dim=-1)) * self.displacement_scale
 
 
@@ -194,6 +214,11 @@ class TimeModulationNetwork(BaseDecoder):
 
     def forward(self, time_feat):
         dense = [m for m in self.net if isinstance(m, _Dense)]
+        if (b2n.mlp_precision() == "bf16" and time_feat.is_cuda and len(dense) >= 2
+                and b2n.ops.fused_mlp_supported(time_feat.shape[-1], dense[0].out_features, len(dense) - 1,
+                                                dense[-1].out_features)
+                and all(m.out_features == dense[0].out_features for m in dense[:-1])):
+            return b2n.ops.fused_mlp(time_feat, None, [m.weight for m in dense], [m.bias for m in dense], "sigmoid")
         h = time_feat
         for m in dense[:-1]:
             h = m(h, "relu")

@@ -422,6 +422,78 @@ def test_instant_mlp_bf16_vs_oracle(mods, pos_dim, Pn):
     assert float(V3[3:].abs().max()) == 0.0
 
 
+
+def _fmlp_case(kind, gen):
+    """(state dict, oracle fn, module factory args) of the three fused dynamic-config networks"""
+    from oracle import nerf_oracle as O
+    if kind == "deform":          # DeformationNetwork 84 -> 128 x3 -> 3 (biases; src/decoders.py:171-195)
+        sd = {}
+        for i, (o, k) in enumerate([(128, 84), (128, 128), (128, 128), (3, 128)]):
+            sd[f"n.net.{2 * i}.weight"], sd[f"n.net.{2 * i}.bias"] = O._linear_init(o, k, gen)
+        sd["n.net.6.weight"] = sd["n.net.6.weight"] * 30.0      # the reference's U(+-1e-4) init would hide errors
+        return sd, (63, 21), lambda s, a, b, q: O.deformation_net(s, "n", a, b, 4, emulate_bf16=q)
+    if kind == "timemod":         # TimeModulationNetwork 21 -> 64 -> 64 sigmoid (src/decoders.py:340-371)
+        sd = {}
+        for i, (o, k) in enumerate([(64, 21), (64, 64)]):
+            sd[f"n.net.{2 * i}.weight"], sd[f"n.net.{2 * i}.bias"] = O._linear_init(o, k, gen)
+        return sd, (21, 0), lambda s, a, b, q: O.time_modulation(s, "n", a, 2, emulate_bf16=q)
+    sd = {"n.deform_net.params": O._fused_init(88, 3, 64, 2, gen), "n.displacement_scale": torch.tensor(0.1)}
+    return sd, (24, 64), lambda s, a, b, q: O.hash_deform_decoder(s, "n", a, b, 64, emulate_bf16=q)
+
+
+@pytest.mark.parametrize("kind", ["deform", "timemod", "hashdeform"])
+@pytest.mark.parametrize("Pn", [1000, 16 * 37 + 3, 5, 40000])
+def test_fused_mlp_bf16_vs_oracle(mods, bf16_mode, kind, Pn):
+    """b2n_fmlp_fwd/bwd behind DeformationNetwork / TimeModulationNetwork / HashDeformationDecoder"""
+    from src import decoders as D
+    gen = torch.Generator().manual_seed(11)
+    sd, (d0, d1), ref_fn = _fmlp_case(kind, gen)
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    a = (torch.randn(Pn, d0, generator=gen) * 0.7).requires_grad_(True)
+    b = (torch.rand(Pn, d1, generator=gen)).requires_grad_(True) if d1 else None
+    y = ref_fn(sd, a, b, False)
+    y_q = ref_fn(sd, a, b, True)
+    g_y = torch.randn(y.shape, generator=gen)
+    wrt = [a] + ([b] if d1 else []) + list(sd.values())
+    ref = torch.autograd.grad((y_q * g_y).sum(), wrt)
+    if kind == "deform":
+        mod = D.DeformationNetwork(63, 21, 128, 4)
+    elif kind == "timemod":
+        mod = D.TimeModulationNetwork(21, 64, 64, 2)
+    else:
+        mod = D.HashDeformationDecoder(24, 64, 64)
+    mod.load_state_dict({k[2:]: v.detach() for k, v in sd.items()})
+    mod = mod.to(DEV)
+    a2 = cu(a.detach()).requires_grad_(True)
+    b2 = cu(b.detach()).requires_grad_(True) if d1 else None
+    launches0 = mods["b2n"]._lib.LAUNCHES["count"]
+    y2 = mod(a2, b2) if d1 else mod(a2)
+    assert mods["b2n"]._lib.LAUNCHES["count"] - launches0 == 1          # ONE kernel: the fused path ran
+    assert y2.shape == y.shape
+    assert rel_err(y2.cpu(), y) < BF16_TOL
+    assert rel_err(y2.cpu(), y_q) < 5e-3          # bf16 rounding ties of the hidden activations only
+    params = dict(mod.named_parameters())
+    got = torch.autograd.grad((y2 * cu(g_y)).sum(), [a2] + ([b2] if d1 else []) + [params[k[2:]] for k in sd])
+    names = ["g_x0"] + (["g_x1"] if d1 else []) + list(sd)
+    for a_, b_, name in zip(got, ref, names):
+        a_ = a_.cpu()
+        l2 = float((a_ - b_).norm() / (b_.norm() + 1e-30))
+        assert l2 < 2e-2, (name, l2)
+    if kind == "hashdeform":      # padded rows of the flat parameter vector never receive gradient
+        gp = got[names.index("n.deform_net.params")].cpu()
+        assert float(gp[64 * 96 + 64 * 64:].view(16, 64)[3:].abs().max()) == 0.0
+        assert float(gp[: 64 * 96].view(64, 96)[:, 88:].abs().max()) == 0.0
+
+
+def test_fused_mlp_rejects_bad_shapes(mods):
+    b2n = mods["b2n"]
+    x = torch.zeros(8, 100, device=DEV)
+    with pytest.raises(ValueError):
+        b2n.fused_mlp(x, None, [torch.zeros(64, 100, device=DEV), torch.zeros(3, 64, device=DEV)], [None, None])
+    with pytest.raises(ValueError):
+        b2n.fused_mlp(x[:, :8], None, [torch.zeros(32, 8, device=DEV), torch.zeros(3, 32, device=DEV)], [None, None])
+
+
 @pytest.mark.parametrize("tag", ["part2_instant", "part3_instant", "part4"])
 @pytest.mark.parametrize("pert", ["flat", "pert"])
 def test_render_rays_golden_bf16(mods, bf16_mode, tag, pert):

@@ -240,7 +240,8 @@ int b2n_fmlp_bwd(int d0, int d1, int hidden, int n_hidden, const float* const* W
  * 256-wide vanilla NeRF decoder (NeRFDecoder.forward, src/decoders.py:68-87)
  * on tcgen05 tensor cores (bf16 operands, fp32 accumulation in TMEM).  Fixed
  * architecture of the reference configs: 8 x 256 trunk, skip [h, x] at layer 4,
- * 128-wide view layer; pos_dim <= 64, dir_dim <= 32.
+ * 128-wide view layer; pos_dim <= 96 (above 64 the layers reading x run as two
+ * accumulating MMA steps), dir_dim <= 32.
  *   b2n_nerf_mlp_pack: converts the fp32 nn.Linear weights (pts_layers[0..7],
  *     feature_layer, view_layer) into the bf16 operand-tile stream the kernel
  *     consumes (b2n_nerf_mlp_packed_bytes() bytes); call once per weight update.
@@ -264,6 +265,13 @@ int b2n_nerf_mlp_fwd(const float* x_enc, int pos_dim, const float* d_enc, int di
  * dZ7 .. dZ0 = pre-activation gradients of every layer) and dz_small (fp32 [P,4]:
  * d rgb_pre[3], d sigma_pre).  Weight/bias gradients are dZ^T * layer-input GEMMs
  * over those planes (plain GEMMs, done by the caller). */
+/* Input gradient of the same decoder from the planes of b2n_nerf_mlp_bwd:
+ * g_x [P,pos_dim] = dZ0 * W0 + dZ4 * W4[:, 256:256+pos_dim] (x feeds layer 0 and the skip concat of
+ * layer 4).  dz0 / dz4: bf16 [P][256] planes (dz_planes[9] / dz_planes[5]); W0 = pts_layers[0].weight
+ * (row stride ldw0), W4x = pts_layers[4].weight + 256 (row stride ldw4).  Needed by Part 3
+ * (src/core.py:268-277: the decoder input depends on the trainable deformation). */
+int b2n_nerf_mlp_dx(const void* dz0, const void* dz4, const float* W0, int ldw0, const float* W4x, int ldw4, int pos_dim,
+                    int64_t P, float* g_x, int ldg, b2n_stream_t stream);
 /* debug aid: per-role cycle counters of CTA 0 of the next b2n_nerf_mlp_* launches (device int64[8], or NULL) */
 int b2n_debug_mlp256_prof(void* device_int64x8);
 size_t b2n_nerf_mlp_packed_bwd_bytes(void);

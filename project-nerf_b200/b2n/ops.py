@@ -352,7 +352,7 @@ def nerf_mlp_supported(decoder, pos_dim: int, dir_dim: int) -> bool:
     try:
         return (len(decoder.pts_layers) == 8 and decoder.skip_layer == 4 and decoder.feature_layer.out_features == 256
                 and decoder.view_layer.out_features == 128 and decoder.pts_layers[0].out_features == 256
-                and 0 < pos_dim <= 64 and 0 < dir_dim <= 32)
+                and 0 < pos_dim <= 96 and 0 < dir_dim <= 32)
     except AttributeError:
         return False
 
@@ -408,7 +408,7 @@ class _NerfMLP(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, decoder, x_enc, d_enc, *params):
-        need_grad = any(ctx.needs_input_grad[3:])
+        need_grad = any(ctx.needs_input_grad)
         rgb, sigma, planes, err = nerf_mlp_forward(decoder, x_enc, d_enc, save=need_grad)
         ctx.decoder = decoder
         ctx.save_for_backward(_c(x_enc), _c(d_enc), rgb, sigma, planes, err)
@@ -419,8 +419,8 @@ class _NerfMLP(torch.autograd.Function):
     def backward(ctx, g_rgb, g_sigma):
         x_enc, d_enc, rgb, sigma, planes, err = ctx.saved_tensors
         dec = ctx.decoder
-        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
-            raise RuntimeError("tcgen05 NeRFDecoder path does not produce input gradients (use fp32 mode)")
+        if ctx.needs_input_grad[2]:
+            raise RuntimeError("tcgen05 NeRFDecoder path does not produce view-direction gradients (use fp32 mode)")
         Pn = x_enc.shape[0]
         dev = x_enc.device
         pos_dim, dir_dim = x_enc.shape[1], d_enc.shape[1]
@@ -439,7 +439,8 @@ class _NerfMLP(torch.autograd.Function):
              work=(Pn * (2.0 * 5120 + 48), flops))
         # ---- weight / bias gradients: dW = dZ^T In, one plain GEMM per layer over all points
         # layer inputs in bf16, zero-padded to 64 / 32 columns: aligned shapes keep cuBLAS on its fast kernels
-        xb = torch.nn.functional.pad(x_enc, (0, 64 - pos_dim)).to(torch.bfloat16)
+        kx = 64 if pos_dim <= 64 else 128
+        xb = torch.nn.functional.pad(x_enc, (0, kx - pos_dim)).to(torch.bfloat16)
         db = torch.nn.functional.pad(d_enc, (0, 32 - dir_dim)).to(torch.bfloat16)
         H = planes                      # H[0..7] trunk outputs, H[8] feat, H[9][:, :128] hv
         dZ = {l: dz[9 - l] for l in range(8)}     # dZ_l of trunk layer l
@@ -468,7 +469,13 @@ class _NerfMLP(torch.autograd.Function):
             out += list(grads[f"pts{l}"])
         for k in ("sigma", "feat", "view", "rgb"):
             out += list(grads[k])
-        return (None, None, None) + tuple(out)
+        g_x = None
+        if ctx.needs_input_grad[1]:       # d x_enc = dZ0 W0 + dZ4 W4[:, 256:]
+            g_x = torch.empty_like(x_enc)
+            call("b2n_nerf_mlp_dx", ptr(dz[9]), ptr(dz[5]), ptr(ws[0]), ws[0].stride(0), ws[4].data_ptr() + 256 * 4,
+                 ws[4].stride(0), pos_dim, Pn, ptr(g_x), pos_dim, stream(),
+                 work=(Pn * (1024.0 + 4.0 * pos_dim), 2.0 * Pn * 512 * pos_dim))
+        return (None, g_x, None) + tuple(out)
 
 
 def _nerf_params(decoder):
@@ -482,8 +489,8 @@ def _nerf_params(decoder):
 
 def nerf_mlp(decoder, x_enc, d_enc):
     """(rgb [P,3], sigma [P,1]) of NeRFDecoder on the tensor cores, differentiable w.r.t. its parameters."""
-    if x_enc.requires_grad or d_enc.requires_grad:
-        raise RuntimeError("nerf_mlp: input gradients are not produced by the tcgen05 path")
+    if d_enc.requires_grad:
+        raise RuntimeError("nerf_mlp: view-direction gradients are not produced by the tcgen05 path")
     return _NerfMLP.apply(decoder, x_enc, d_enc, *_nerf_params(decoder))
 
 

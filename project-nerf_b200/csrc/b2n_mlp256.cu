@@ -59,7 +59,7 @@ static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
 
 constexpr int N_THREADS = 320;
 constexpr int EPI_THREADS = 256;
-constexpr int MAX_STEPS = 12, MAX_CHUNKS = 96;
+constexpr int MAX_STEPS = 14, MAX_CHUNKS = 96;
 
 enum { EPI_RELU = 0, EPI_RELU_SIGMA = 1, EPI_LINEAR = 2, EPI_VIEW_RGB = 3,
        EPI_B_LINEAR = 4, EPI_B_MASK = 5, EPI_B_MASK_SIGMA = 6 };
@@ -71,6 +71,9 @@ struct Step {
   int epi;       // epilogue kind
   int bias_off;  // fwd: offset into the bias vector; bwd: index of the gating forward plane
   int save_slot; // index of the saved plane (or -1)
+  int acc_in;    // 1: the MMAs accumulate onto what the previous (partial) step left in TMEM
+  int partial;   // 1: no drain -- the epilogue only re-stages the aux block for the next step
+  int restage;   // aux block content for the NEXT step: 0 keep, 1 x_enc[:, 0:64], 2 x_enc[:, 64:128], 3 d_enc
 };
 struct Plan {
   int n_steps;
@@ -198,6 +201,13 @@ struct FwdArgs {
   Plan plan;
 };
 
+__device__ __forceinline__ void restage_aux(const FwdArgs& a, int what, int64_t p, bool valid, unsigned char* aux, int r,
+                                            int c0) {
+  if (what == 1) stage_row(a.x_enc + p * a.pos_dim, a.pos_dim < 64 ? a.pos_dim : 64, valid, aux, r, c0);
+  else if (what == 2) stage_row(a.x_enc + p * a.pos_dim + 64, a.pos_dim - 64, valid, aux, r, c0);
+  else if (what == 3) stage_row(a.d_enc + p * a.dir_dim, a.dir_dim, valid, aux, r, c0);
+}
+
 template <bool BWD>
 __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -266,6 +276,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
         for (int s = 0; s < plan.n_steps; ++s) {
           const int n_act = plan.s[s].n_act, aux_k16 = plan.s[s].aux_k16;
           const int nkc = n_act + (aux_k16 ? 1 : 0), halves = plan.s[s].n / 128;
+          const bool acc_in = plan.s[s].acc_in != 0;
           for (int t = 0; t < 2; ++t) {
             long long t0 = clock64();
             if (!mbar_wait(bar_act + 8 * t, act_phase[t] & 1, abort_flag, a.err, 2)) goto mma_done;
@@ -288,11 +299,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
                   if (nk == 4) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                      tc_mma(d_tmem + h * 128, adesc + 2 * k, bdesc + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                      tc_mma(d_tmem + h * 128, adesc + 2 * k, bdesc + 2 * k, idesc, (acc_in || c > 0 || k > 0) ? 1u : 0u);
                   } else {
 #pragma unroll
                     for (int k = 0; k < 2; ++k)
-                      tc_mma(d_tmem + h * 128, adesc + 2 * k, bdesc + 2 * k, idesc, (c > 0 || k > 0) ? 1u : 0u);
+                      tc_mma(d_tmem + h * 128, adesc + 2 * k, bdesc + 2 * k, idesc, (acc_in || c > 0 || k > 0) ? 1u : 0u);
                   }
                   tc_commit(bar_empty + 8 * st);   // frees the ring slot once these MMAs have read it
                 }
@@ -329,7 +340,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
         const int64_t p = pair * 256 + t * 128 + r;
         const bool valid = p < a.P;
         if (!BWD) {
-          stage_row(a.x_enc + p * a.pos_dim, a.pos_dim, valid, aux, r, 4 * half);
+          restage_aux(a, 1, p, valid, aux, r, 4 * half);
         } else {
           // colour head backward -> dZ_view (128 wide; this thread covers 64 of its columns)
           float dzr[3] = {0.f, 0.f, 0.f};
@@ -367,6 +378,23 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
       for (int s = 0; s < plan.n_steps; ++s) {
         const Step& sp = plan.s[s];
         const bool last = (s + 1 == plan.n_steps);
+        if (!BWD && sp.partial) {
+          // the MMAs of this step only add a k-slice to the accumulators: when they have read the aux
+          // block, swap in the next slice of the input row; nothing is drained
+          for (int t = 0; t < 2; ++t) {
+            unsigned char* aux = smem + OFF_AUX + t * KBLK_BYTES;
+            const int64_t p = pair * 256 + t * 128 + r;
+            const bool valid = p < a.P;
+            if (!mbar_wait(bar_acc + 8 * t, acc_phase[t] & 1, abort_flag, a.err, 4)) goto epi_done;
+            ++acc_phase[t];
+            tc_fence_after();
+            restage_aux(a, sp.restage, p, valid, aux, r, 4 * half);
+            tc_fence_before();
+            proxy_fence();
+            mbar_arrive(bar_act + 8 * t);
+          }
+          continue;
+        }
         if (!BWD) {
           // stage this step's bias (and the head weights) for broadcast reads
           asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -468,10 +496,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
 #pragma unroll
               for (int j = 0; j < 3; ++j) a.rgb[3 * p + j] = 1.f / (1.f + expf(-(rgb_acc[j] + __ldg(a.head_bias + 1 + j))));
             }
-            // the x block is dead after the skip layer (the step that consumed both act and aux):
-            // re-use it for the encoded view direction of the view layer
-            if (sp.n_act > 0 && sp.aux_k16 > 0 && sp.epi == EPI_RELU)
-              stage_row(a.d_enc + p * a.dir_dim, a.dir_dim, valid, aux, r, 4 * half);
+            // the aux block is re-used: next slice of x (pos_dim > 64), or the encoded view direction once
+            // the skip layer has consumed x
+            restage_aux(a, sp.restage, p, valid, aux, r, 4 * half);
           }
           tc_fence_before();
           proxy_fence();
@@ -525,17 +552,32 @@ __global__ void k_mlp256_pack(const PackArgs a) {
 using namespace b2n;
 using namespace b2n::m256;
 
-// Forward plan of the reference architecture (8 x 256, skip at 4, view 128); pos_dim, dir_dim <= 64.
-static void build_fwd_plan(Plan* pl) {
+// Forward plan of the reference architecture (8 x 256, skip at 4, view 128); dir_dim <= 32.
+// pos_dim <= 64: x is one 64-column aux block.  64 < pos_dim <= 96 (Part 3: 63 canonical + 21 time
+// features): the layers that read x (0 and 4) run as two accumulating steps, x[:, 0:64] then x[:, 64:96],
+// with the epilogue warps swapping the aux block in between.
+static void build_fwd_plan(Plan* pl, int pos_dim) {
   int n = 0;
-  auto add = [&](int n_act, int aux_k16, int width, int epi, int bias_off, int slot) {
-    pl->s[n++] = Step{n_act, aux_k16, width, epi, bias_off, slot};
+  auto add = [&](int n_act, int aux_k16, int width, int epi, int bias_off, int slot, int acc_in = 0, int partial = 0,
+                 int restage = 0) {
+    pl->s[n++] = Step{n_act, aux_k16, width, epi, bias_off, slot, acc_in, partial, restage};
   };
-  add(0, 4, 256, EPI_RELU, 0, 0);
+  const bool wide = pos_dim > 64;
+  if (!wide) {
+    add(0, 4, 256, EPI_RELU, 0, 0);
+  } else {
+    add(0, 4, 256, EPI_RELU, 0, -1, 0, 1, 2);     // x[:, 0:64]   -> swap in x[:, 64:]
+    add(0, 2, 256, EPI_RELU, 0, 0, 1, 0, 1);      // + x[:, 64:96] -> drain, swap x[:, 0:64] back for the skip layer
+  }
   add(4, 0, 256, EPI_RELU, 256, 1);
   add(4, 0, 256, EPI_RELU, 512, 2);
   add(4, 0, 256, EPI_RELU, 768, 3);
-  add(4, 4, 256, EPI_RELU, 1024, 4);        // skip layer: [h, x]
+  if (!wide) {
+    add(4, 4, 256, EPI_RELU, 1024, 4, 0, 0, 3);   // skip layer: [h, x]; afterwards the aux block takes d_enc
+  } else {
+    add(4, 4, 256, EPI_RELU, 1024, -1, 0, 1, 2);
+    add(0, 2, 256, EPI_RELU, 1024, 4, 1, 0, 3);
+  }
   add(4, 0, 256, EPI_RELU, 1280, 5);
   add(4, 0, 256, EPI_RELU, 1536, 6);
   add(4, 0, 256, EPI_RELU_SIGMA, 1792, 7);  // + density head
@@ -552,16 +594,18 @@ extern "C" int b2n_debug_mlp256_prof(void* device_int64x8) {
   return B2N_OK;
 }
 
-// chunks: (1 + 3*4 + 5 + 3*4 + 4) k-chunks x 2 halves for the 256-wide steps, 5 x 1 for the view layer
-extern "C" size_t b2n_nerf_mlp_packed_bytes(void) { return (size_t)((1 + 12 + 5 + 12 + 4) * 2 + 5) * CHUNK_BYTES; }
+// chunks: (1 + 3*4 + 5 + 3*4 + 4) k-chunks x 2 halves for the 256-wide steps, 5 x 1 for the view layer,
+// plus 2 more k-chunks x 2 halves when pos_dim > 64 (the buffer is always sized for that case)
+extern "C" size_t b2n_nerf_mlp_packed_bytes(void) { return (size_t)((1 + 12 + 5 + 12 + 4 + 2) * 2 + 5) * CHUNK_BYTES; }
 
 // weights: the nn.Linear weight matrices of NeRFDecoder: pts_layers[0..7], feature_layer, view_layer
 extern "C" int b2n_nerf_mlp_pack(const float* const* pts_w, const float* feature_w, const float* view_w, int pos_dim,
                                  int dir_dim, void* packed, b2n_stream_t stream) {
   B2N_REQUIRE(pts_w && feature_w && view_w && packed, "null pointer");
-  B2N_REQUIRE(pos_dim > 0 && pos_dim <= 64 && dir_dim > 0 && dir_dim <= 32, "pos_dim <= 64 and dir_dim <= 32 required");
+  B2N_REQUIRE(pos_dim > 0 && pos_dim <= 96 && dir_dim > 0 && dir_dim <= 32, "pos_dim <= 96 and dir_dim <= 32 required");
   PackArgs pa{};
   int n = 0;
+  const int x_lo = pos_dim < 64 ? pos_dim : 64;      // columns of the first x block
   // one k-chunk of a layer = `halves` chunks of 128 output rows each, in [k-chunk][half] order
   auto add = [&](const float* W, int ldw, int n_real, int halves, int k0, int k_real) {
     for (int h = 0; h < halves; ++h) pa.c[n++] = PackChunk{W, ldw, 128 * h, n_real, k0, k_real, 0};
@@ -569,11 +613,15 @@ extern "C" int b2n_nerf_mlp_pack(const float* const* pts_w, const float* feature
   for (int l = 0; l < 8; ++l) {
     B2N_REQUIRE(pts_w[l], "null weight");
     if (l == 0) {
-      add(pts_w[0], pos_dim, 256, 2, 0, pos_dim);
+      add(pts_w[0], pos_dim, 256, 2, 0, x_lo);
+      if (pos_dim > 64) add(pts_w[0], pos_dim, 256, 2, 64, pos_dim);
     } else {
       const int ld = (l == 4) ? 256 + pos_dim : 256;
       for (int c = 0; c < 4; ++c) add(pts_w[l], ld, 256, 2, 64 * c, 256);
-      if (l == 4) add(pts_w[4], ld, 256, 2, 256, ld);
+      if (l == 4) {
+        add(pts_w[4], ld, 256, 2, 256, 256 + x_lo);
+        if (pos_dim > 64) add(pts_w[4], ld, 256, 2, 256 + 64, ld);
+      }
     }
   }
   for (int c = 0; c < 4; ++c) add(feature_w, 256, 256, 2, 64 * c, 256);
@@ -581,7 +629,7 @@ extern "C" int b2n_nerf_mlp_pack(const float* const* pts_w, const float* feature
   add(view_w, 256 + dir_dim, 128, 1, 256, 256 + dir_dim);
   pa.n_chunks = n;
   pa.dst = (unsigned char*)packed;
-  B2N_REQUIRE((size_t)n * CHUNK_BYTES == b2n_nerf_mlp_packed_bytes(), "internal: packed size mismatch");
+  B2N_REQUIRE((size_t)n * CHUNK_BYTES <= b2n_nerf_mlp_packed_bytes() && n <= MAX_CHUNKS, "internal: packed size mismatch");
   k_mlp256_pack<<<n, 256, 0, (cudaStream_t)stream>>>(pa);
   return check_launch("b2n_nerf_mlp_pack");
 }
@@ -593,13 +641,13 @@ extern "C" int b2n_nerf_mlp_fwd(const float* x_enc, int pos_dim, const float* d_
   if (P == 0) return B2N_OK;
   B2N_REQUIRE(x_enc && d_enc && packed && bias && w_sigma && w_rgb && head_bias && rgb && sigma && err_flag,
               "null pointer");
-  B2N_REQUIRE(pos_dim > 0 && pos_dim <= 64 && dir_dim > 0 && dir_dim <= 32, "pos_dim <= 64 and dir_dim <= 32 required");
+  B2N_REQUIRE(pos_dim > 0 && pos_dim <= 96 && dir_dim > 0 && dir_dim <= 32, "pos_dim <= 96 and dir_dim <= 32 required");
   FwdArgs a{};
   a.x_enc = x_enc, a.pos_dim = pos_dim, a.d_enc = d_enc, a.dir_dim = dir_dim;
   a.packed = (const unsigned char*)packed, a.bias = bias, a.w_sigma = w_sigma, a.w_rgb = w_rgb;
   a.head_bias = head_bias;
   a.P = P, a.rgb = rgb, a.sigma = sigma, a.save = (__nv_bfloat16*)save, a.err = err_flag;
-  build_fwd_plan(&a.plan);
+  build_fwd_plan(&a.plan, pos_dim);
   a.prof = g_prof;
   cudaFuncSetAttribute(k_mlp256<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   const int64_t n_pairs = (P + 255) / 256;
@@ -631,7 +679,7 @@ extern "C" size_t b2n_nerf_mlp_packed_bwd_bytes(void) { return (size_t)(2 + 4 * 
 extern "C" int b2n_nerf_mlp_pack_bwd(const float* const* pts_w, const float* feature_w, const float* view_w, int pos_dim,
                                      int dir_dim, void* packed, b2n_stream_t stream) {
   B2N_REQUIRE(pts_w && feature_w && view_w && packed, "null pointer");
-  B2N_REQUIRE(pos_dim > 0 && pos_dim <= 64 && dir_dim > 0 && dir_dim <= 32, "pos_dim <= 64 and dir_dim <= 32 required");
+  B2N_REQUIRE(pos_dim > 0 && pos_dim <= 96 && dir_dim > 0 && dir_dim <= 32, "pos_dim <= 96 and dir_dim <= 32 required");
   PackArgs pa{};
   int n = 0;
   // tile rows = input index of the layer (first 256 inputs, two halves), tile k = output index of the layer

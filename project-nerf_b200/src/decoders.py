@@ -105,7 +105,7 @@ class NeRFDecoder(BaseDecoder):
         self.rgb_layer = _Dense(view_dim, 3)
 
     def forward(self, x, d):
-        if (b2n.mlp_precision() == "bf16" and x.is_cuda and not x.requires_grad and not d.requires_grad
+        if (b2n.mlp_precision() == "bf16" and x.is_cuda and not d.requires_grad
                 and b2n.ops.nerf_mlp_supported(self, x.shape[-1], d.shape[-1])):
             return b2n.ops.nerf_mlp(self, x, d)          # tcgen05 tensor-core path (fwd + bwd)
         h = x

@@ -570,3 +570,33 @@ def test_nerf_mlp256_tcgen05_backward(mods, bf16_mode):
     for k, a_, b_ in zip(names, got, ref):
         l2 = float((a_.cpu().double() - b_.double()).norm() / (b_.double().norm() + 1e-30))
         assert l2 < 3e-2, (k, l2)
+
+
+@pytest.mark.parametrize("pos_dim,Pn", [(84, 128 * 9 + 50), (63, 1000), (84, 256), (96, 300)])
+def test_nerf_mlp256_tcgen05_wide_input_and_dx(mods, bf16_mode, pos_dim, Pn):
+    """Part 3 canonical decoder (pos_dim = 63 + 21 > 64: two accumulating MMA steps for the layers reading x) and
+    the input gradient d x_enc = dZ0 W0 + dZ4 W4[:, 256:] (b2n_nerf_mlp_dx), vs the bf16-emulating oracle."""
+    from oracle import nerf_oracle as O
+    from src.decoders import NeRFDecoder
+    torch.manual_seed(41)
+    dec = NeRFDecoder(pos_dim=pos_dim, dir_dim=27)
+    sd = {"decoder." + k: v.detach().clone() for k, v in dec.state_dict().items()}
+    sdg = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    xe = (torch.randn(Pn, pos_dim) * 0.6).requires_grad_(True)
+    de = torch.randn(Pn, 27) * 0.6
+    rgb_q, sig_q = O.nerf_decoder(sdg, "decoder", xe, de, emulate_bf16=True)
+    g_rgb, g_sig = torch.randn_like(rgb_q), torch.randn_like(sig_q)
+    names = list(sdg)
+    ref = torch.autograd.grad((rgb_q * g_rgb).sum() + (sig_q * g_sig).sum(), [xe] + [sdg[k] for k in names])
+    dec = dec.to(DEV)
+    xe2 = cu(xe.detach()).requires_grad_(True)
+    launches0 = mods["b2n"]._lib.LAUNCHES["count"]
+    rgb, sigma = dec(xe2, cu(de))
+    assert mods["b2n"]._lib.LAUNCHES["count"] - launches0 == 2           # pack + the tcgen05 kernel (no fp32 fallback)
+    assert rel_err(rgb.cpu(), rgb_q) < 3e-3 and rel_err(sigma.cpu(), sig_q) < 3e-3
+    params = dict(dec.named_parameters())
+    got = torch.autograd.grad((rgb * cu(g_rgb)).sum() + (sigma * cu(g_sig)).sum(),
+                              [xe2] + [params[k[len("decoder."):]] for k in names])
+    for k, a_, b_ in zip(["g_x"] + names, got, ref):
+        l2 = float((a_.cpu().double() - b_.double()).norm() / (b_.double().norm() + 1e-30))
+        assert l2 < 3e-2, (k, l2)

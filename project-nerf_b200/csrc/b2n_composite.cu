@@ -216,6 +216,267 @@ k_composite_bwd(const float* __restrict__ rgb, const float* __restrict__ sigma, 
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Register-resident variants for N <= 32*WC samples per ray (every shipped config: N = 64 / 128).
+// All global loads of a ray (mask words, z, sigma, rgb, dx of every chunk) are issued before the
+// first scan step, so one warp keeps ~5*WC independent 128-byte requests in flight instead of 5,
+// and the backward re-uses z / sigma / exp(-sigma*delta) from its forward sweep instead of
+// re-reading and re-computing them.  Arithmetic (and therefore every result bit) is the same as
+// in the chunk-loop kernels above, which remain the path for longer rays.
+// per-ray header (direction, mask words of the lanes, compact offsets): fetched ONE RAY AHEAD so that the
+// dependent sample loads (sigma / rgb addresses come from the mask) can issue at the top of an iteration
+struct RayHdr {
+  float d0, d1, d2;
+  uint32_t mw;
+  int off0, off1;
+};
+__device__ __forceinline__ RayHdr load_hdr(const float* __restrict__ rays_d, const uint32_t* __restrict__ mask_words,
+                                           const int32_t* __restrict__ ray_offset, int64_t r, int W, int lane) {
+  RayHdr h;
+  h.d0 = __ldg(rays_d + 3 * r), h.d1 = __ldg(rays_d + 3 * r + 1), h.d2 = __ldg(rays_d + 3 * r + 2);
+  h.mw = 0xffffffffu, h.off0 = 0, h.off1 = 1;
+  if (mask_words) {
+    h.mw = lane < W ? __ldg(mask_words + r * W + lane) : 0u;
+    h.off0 = __ldg(ray_offset + r), h.off1 = __ldg(ray_offset + r + 1);
+  }
+  return h;
+}
+
+template <int WC>
+__global__ void __launch_bounds__(32)
+k_composite_fwd_reg(const float* __restrict__ rgb, const float* __restrict__ sigma, const float* __restrict__ dx,
+                    const float* __restrict__ z, const float* __restrict__ rays_d, const float* __restrict__ bg,
+                    int bg_per_ray, const uint32_t* __restrict__ mask_words, const int32_t* __restrict__ ray_offset,
+                    int64_t B, int N, float* __restrict__ color, float* __restrict__ depth, float* __restrict__ acc,
+                    float* __restrict__ mean_dx) {
+  const int lane = threadIdx.x;      // ONE warp per block: the ray index below is provably warp-uniform, so the
+  const int W = (N + 31) >> 5;       // shuffles need no re-convergence code and addresses live in uniform registers
+  const uint32_t lt = (1u << lane) - 1u;
+  RayHdr nxt = load_hdr(rays_d, mask_words, ray_offset, blockIdx.x < B ? (int64_t)blockIdx.x : 0, W, lane);
+  for (int64_t r = blockIdx.x; r < B; r += gridDim.x) {
+    const RayHdr h = nxt;
+    if (r + gridDim.x < B) nxt = load_hdr(rays_d, mask_words, ray_offset, r + gridDim.x, W, lane);
+    const float dn = sqrtf(h.d0 * h.d0 + h.d1 * h.d1 + h.d2 * h.d2);
+    const int64_t zb = r * N;
+    int64_t off = mask_words ? (int64_t)h.off0 : zb;
+    float T0 = 1.f, c0 = 0.f, c1 = 0.f, c2 = 0.f, dd = 0.f, aa = 0.f, m0 = 0.f, m1 = 0.f, m2 = 0.f;
+    const bool empty_ray = mask_words && __all_sync(0xffffffffu, h.off1 == h.off0);
+    if (N > 1 && !empty_ray) {
+      const uint32_t mw = h.mw;
+      float zs[WC], sg[WC], cr[WC][3], xr[WC][3];
+      // ---- all loads first
+#pragma unroll
+      for (int k = 0; k < WC; ++k) {
+        zs[k] = 0.f, sg[k] = 0.f;
+        cr[k][0] = cr[k][1] = cr[k][2] = 0.f;
+        xr[k][0] = xr[k][1] = xr[k][2] = 0.f;
+        if (k < W) {
+          const int s = (k << 5) + lane;
+          const bool valid = s < N;
+          const uint32_t w = __shfl_sync(0xffffffffu, mw, k);
+          const bool act = valid && ((w >> lane) & 1u);
+          const int64_t idx = mask_words ? off + __popc(w & lt) : off + lane;
+          if (valid) zs[k] = __ldcs(z + zb + s);
+          if (act) {
+            sg[k] = __ldcs(sigma + idx);
+            cr[k][0] = __ldcs(rgb + 3 * idx), cr[k][1] = __ldcs(rgb + 3 * idx + 1), cr[k][2] = __ldcs(rgb + 3 * idx + 2);
+            if (dx) xr[k][0] = __ldcs(dx + 3 * idx), xr[k][1] = __ldcs(dx + 3 * idx + 1), xr[k][2] = __ldcs(dx + 3 * idx + 2);
+          }
+          off += mask_words ? __popc(w) : 32;
+        }
+      }
+      // ---- per-sample alpha and attenuation of every chunk (independent of each other)
+      float alpha[WC], incl[WC];
+#pragma unroll
+      for (int k = 0; k < WC; ++k) {
+        const int s = (k << 5) + lane;
+        const bool valid = s < N;
+        float zn = __shfl_down_sync(0xffffffffu, zs[k], 1);
+        const float z_next0 = __shfl_sync(0xffffffffu, zs[(k + 1 < WC) ? k + 1 : k], 0);
+        if (lane == 31 && s + 1 < N) zn = z_next0;
+        const float dl = __fmul_rn((s == N - 1) ? 1e10f : __fsub_rn(zn, zs[k]), dn);
+        alpha[k] = valid ? __fsub_rn(1.0f, expf(-__fmul_rn(sg[k], dl))) : 0.f;
+        incl[k] = valid ? __fadd_rn(__fsub_rn(1.0f, alpha[k]), 1e-10f) : 1.f;
+      }
+      // ---- the WC warp product-scans run interleaved: WC independent shuffles in flight per step
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+        for (int k = 0; k < WC; ++k) {
+          const float t = __shfl_up_sync(0xffffffffu, incl[k], o);
+          if (lane >= o) incl[k] *= t;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < WC; ++k) {
+        float excl = __shfl_up_sync(0xffffffffu, incl[k], 1);
+        if (lane == 0) excl = 1.f;
+        const float wt = alpha[k] * (T0 * excl);
+        c0 += wt * cr[k][0], c1 += wt * cr[k][1], c2 += wt * cr[k][2];
+        dd += wt * zs[k];
+        aa += wt;
+        if (dx) m0 += wt * xr[k][0], m1 += wt * xr[k][1], m2 += wt * xr[k][2];
+        T0 *= __shfl_sync(0xffffffffu, incl[k], 31);
+      }
+    }
+    // ---- the 5 (8) ray sums reduce interleaved as well
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      c0 += __shfl_xor_sync(0xffffffffu, c0, o), c1 += __shfl_xor_sync(0xffffffffu, c1, o);
+      c2 += __shfl_xor_sync(0xffffffffu, c2, o), dd += __shfl_xor_sync(0xffffffffu, dd, o);
+      aa += __shfl_xor_sync(0xffffffffu, aa, o);
+      if (dx) {
+        m0 += __shfl_xor_sync(0xffffffffu, m0, o), m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+        m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+      }
+    }
+    if (lane == 0) {
+      if (bg) {
+        const float* b = bg + (bg_per_ray ? 3 * r : 0);
+        const float rem = 1.0f - aa;
+        c0 += rem * b[0], c1 += rem * b[1], c2 += rem * b[2];
+      }
+      color[3 * r] = c0, color[3 * r + 1] = c1, color[3 * r + 2] = c2;
+      if (depth) depth[r] = dd;
+      if (acc) acc[r] = aa;
+      if (mean_dx) mean_dx[3 * r] = m0, mean_dx[3 * r + 1] = m1, mean_dx[3 * r + 2] = m2;
+    }
+  }
+}
+
+template <int WC>
+__global__ void __launch_bounds__(32)
+k_composite_bwd_reg(const float* __restrict__ rgb, const float* __restrict__ sigma, const float* __restrict__ dx,
+                    const float* __restrict__ z, const float* __restrict__ rays_d, const float* __restrict__ bg,
+                    int bg_per_ray, const uint32_t* __restrict__ mask_words, const int32_t* __restrict__ ray_offset,
+                    int64_t B, int N, const float* __restrict__ g_color, const float* __restrict__ g_depth,
+                    const float* __restrict__ g_acc, const float* __restrict__ g_mdx, float* __restrict__ g_rgb,
+                    float* __restrict__ g_sigma, float* __restrict__ g_dx) {
+  const int lane = threadIdx.x;      // one warp per block (see the forward kernel)
+  const int W = (N + 31) >> 5;       // <= WC
+  const uint32_t lt = (1u << lane) - 1u;
+  RayHdr nxt = load_hdr(rays_d, mask_words, ray_offset, blockIdx.x < B ? (int64_t)blockIdx.x : 0, W, lane);
+  for (int64_t r = blockIdx.x; r < B; r += gridDim.x) {
+    const RayHdr h = nxt;
+    if (r + gridDim.x < B) nxt = load_hdr(rays_d, mask_words, ray_offset, r + gridDim.x, W, lane);
+    if (mask_words && __all_sync(0xffffffffu, h.off1 == h.off0)) continue;  // no active sample: nothing to write
+    const float dn = sqrtf(h.d0 * h.d0 + h.d1 * h.d1 + h.d2 * h.d2);
+    const int64_t zb = r * N;
+    const int64_t off0 = mask_words ? (int64_t)h.off0 : zb;
+    const float gc0 = g_color ? g_color[3 * r] : 0.f, gc1 = g_color ? g_color[3 * r + 1] : 0.f,
+                gc2 = g_color ? g_color[3 * r + 2] : 0.f;
+    const float gd = g_depth ? g_depth[r] : 0.f;
+    float ga = g_acc ? g_acc[r] : 0.f;
+    if (bg) {  // color += (1 - acc) * bg
+      const float* b = bg + (bg_per_ray ? 3 * r : 0);
+      ga -= gc0 * b[0] + gc1 * b[1] + gc2 * b[2];
+    }
+    const float gm0 = (g_mdx && dx) ? g_mdx[3 * r] : 0.f, gm1 = (g_mdx && dx) ? g_mdx[3 * r + 1] : 0.f,
+                gm2 = (g_mdx && dx) ? g_mdx[3 * r + 2] : 0.f;
+    const uint32_t mw = h.mw;
+    // ---- all loads first
+    float zs[WC], sg[WC], cr[WC][3], xr[WC][3];
+    int64_t idxs[WC];
+    bool acts[WC];
+    {
+      int64_t off = off0;
+#pragma unroll
+      for (int k = 0; k < WC; ++k) {
+        zs[k] = 0.f, sg[k] = 0.f;
+        cr[k][0] = cr[k][1] = cr[k][2] = 0.f;
+        xr[k][0] = xr[k][1] = xr[k][2] = 0.f;
+        idxs[k] = 0, acts[k] = false;
+        if (k < W) {
+          const int s = (k << 5) + lane;
+          const bool valid = s < N;
+          const uint32_t w = __shfl_sync(0xffffffffu, mw, k);
+          acts[k] = valid && ((w >> lane) & 1u);
+          idxs[k] = mask_words ? off + __popc(w & lt) : off + lane;
+          if (valid) zs[k] = __ldcs(z + zb + s);
+          if (acts[k]) {
+            sg[k] = __ldcs(sigma + idxs[k]);
+            cr[k][0] = __ldcs(rgb + 3 * idxs[k]), cr[k][1] = __ldcs(rgb + 3 * idxs[k] + 1), cr[k][2] = __ldcs(rgb + 3 * idxs[k] + 2);
+            if (dx) xr[k][0] = __ldcs(dx + 3 * idxs[k]), xr[k][1] = __ldcs(dx + 3 * idxs[k] + 1), xr[k][2] = __ldcs(dx + 3 * idxs[k] + 2);
+          }
+          off += mask_words ? __popc(w) : 32;
+        }
+      }
+    }
+    // ---- per-sample interval, exp, attenuation and adjoint seed of every chunk (independent of each other)
+    float dl[WC], ee[WC], incl[WC], fa[WC], fb[WC], vv[WC];
+#pragma unroll
+    for (int k = 0; k < WC; ++k) {
+      const int s = (k << 5) + lane;
+      const bool valid = s < N;
+      float zn = __shfl_down_sync(0xffffffffu, zs[k], 1);
+      const float z_next0 = __shfl_sync(0xffffffffu, zs[(k + 1 < WC) ? k + 1 : k], 0);
+      if (lane == 31 && s + 1 < N) zn = z_next0;
+      dl[k] = __fmul_rn((s == N - 1) ? 1e10f : __fsub_rn(zn, zs[k]), dn);
+      ee[k] = expf(-__fmul_rn(sg[k], dl[k]));
+      const float alpha = valid ? __fsub_rn(1.0f, ee[k]) : 0.f;
+      fa[k] = valid ? __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f) : 1.f;
+      incl[k] = fa[k];
+      vv[k] = gc0 * cr[k][0] + gc1 * cr[k][1] + gc2 * cr[k][2] + gd * zs[k] + ga + gm0 * xr[k][0] + gm1 * xr[k][1] +
+              gm2 * xr[k][2];
+      fb[k] = valid ? alpha * vv[k] : 0.f;
+    }
+    // ---- WC product scans (transmittance) and WC suffix compositions of f_s(R) = b_s + a_s R, interleaved
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+      for (int k = 0; k < WC; ++k) {
+        const float t = __shfl_up_sync(0xffffffffu, incl[k], o);
+        const float a2 = __shfl_down_sync(0xffffffffu, fa[k], o);
+        const float b2 = __shfl_down_sync(0xffffffffu, fb[k], o);
+        if (lane >= o) incl[k] *= t;
+        if (lane + o < 32) {
+          fb[k] = fb[k] + fa[k] * b2;
+          fa[k] = fa[k] * a2;
+        }
+      }
+    }
+    float Tin[WC];
+    {
+      float carryT = 1.f;
+#pragma unroll
+      for (int k = 0; k < WC; ++k) {
+        Tin[k] = carryT;
+        carryT *= __shfl_sync(0xffffffffu, incl[k], 31);
+      }
+    }
+    // ---- back to front: R_s = (f_{s+1} o ... o f_last)(0), gradients
+    float Rend = 0.f;
+#pragma unroll
+    for (int k = WC - 1; k >= 0; --k) {
+      const int s = (k << 5) + lane;
+      const bool valid = s < N;
+      const float alpha = valid ? __fsub_rn(1.0f, ee[k]) : 0.f;
+      float excl = __shfl_up_sync(0xffffffffu, incl[k], 1);
+      if (lane == 0) excl = 1.f;
+      const float T = Tin[k] * excl;
+      float na = __shfl_down_sync(0xffffffffu, fa[k], 1), nb = __shfl_down_sync(0xffffffffu, fb[k], 1);
+      if (lane == 31) na = 1.f, nb = 0.f;
+      const float Rs = nb + na * Rend;
+      if (acts[k]) {
+        const float wt = alpha * T;
+        const int64_t idx = idxs[k];
+        if (g_sigma) __stcs(g_sigma + idx, T * (vv[k] - Rs) * dl[k] * ee[k]);
+        if (g_rgb) __stcs(g_rgb + 3 * idx, wt * gc0), __stcs(g_rgb + 3 * idx + 1, wt * gc1), __stcs(g_rgb + 3 * idx + 2, wt * gc2);
+        if (g_dx && dx) __stcs(g_dx + 3 * idx, wt * gm0), __stcs(g_dx + 3 * idx + 1, wt * gm1), __stcs(g_dx + 3 * idx + 2, wt * gm2);
+      }
+      const float A0 = __shfl_sync(0xffffffffu, fa[k], 0), B0 = __shfl_sync(0xffffffffu, fb[k], 0);
+      Rend = B0 + A0 * Rend;
+    }
+  }
+}
+
+// one-warp blocks: 32 resident per SM, a few waves so that rays of different cost balance out
+static inline unsigned warp_grid(int64_t B) {
+  const int64_t cap = (int64_t)kSMs * 32 * 4;
+  return (unsigned)(B < cap ? (B < 1 ? 1 : B) : cap);
+}
+
 static inline unsigned ray_grid(int64_t B) {
   int64_t blocks = (B + 7) / 8;
   const int64_t cap = (int64_t)kSMs * 8 * 4;
@@ -237,9 +498,14 @@ extern "C" int b2n_composite_fwd(const float* rgb, const float* sigma, const flo
   B2N_REQUIRE(rgb && sigma && z && rays_d && color, "null pointer");
   B2N_REQUIRE(!mask_words || ray_offset, "compact layout needs ray_offset");
   B2N_REQUIRE(!mean_dx || dx, "mean_dx needs dx");
-  k_composite_fwd<<<ray_grid(B), 256, 0, (cudaStream_t)stream>>>(rgb, sigma, dx, z, rays_d, bg, bg_per_ray,
-                                                                mask_words, ray_offset, B, N, color, depth, acc,
-                                                                mean_dx);
+  if (N > 1 && N <= 128) {
+    auto kern = N <= 64 ? k_composite_fwd_reg<2> : k_composite_fwd_reg<4>;
+    kern<<<warp_grid(B), 32, 0, (cudaStream_t)stream>>>(rgb, sigma, dx, z, rays_d, bg, bg_per_ray, mask_words, ray_offset, B,
+                                                       N, color, depth, acc, mean_dx);
+  } else {
+    k_composite_fwd<<<ray_grid(B), 256, 0, (cudaStream_t)stream>>>(rgb, sigma, dx, z, rays_d, bg, bg_per_ray, mask_words,
+                                                                  ray_offset, B, N, color, depth, acc, mean_dx);
+  }
   return check_launch("b2n_composite_fwd");
 }
 
@@ -252,8 +518,14 @@ extern "C" int b2n_composite_bwd(const float* rgb, const float* sigma, const flo
   if (B == 0) return B2N_OK;
   B2N_REQUIRE(rgb && sigma && z && rays_d, "null pointer");
   B2N_REQUIRE(!mask_words || ray_offset, "compact layout needs ray_offset");
-  k_composite_bwd<<<ray_grid(B), 256, 0, (cudaStream_t)stream>>>(rgb, sigma, dx, z, rays_d, bg, bg_per_ray,
-                                                                mask_words, ray_offset, B, N, g_color, g_depth, g_acc,
-                                                                g_mean_dx, g_rgb, g_sigma, g_dx);
+  if (N > 1 && N <= 128) {
+    auto kern = N <= 64 ? k_composite_bwd_reg<2> : k_composite_bwd_reg<4>;
+    kern<<<warp_grid(B), 32, 0, (cudaStream_t)stream>>>(rgb, sigma, dx, z, rays_d, bg, bg_per_ray, mask_words, ray_offset, B,
+                                                       N, g_color, g_depth, g_acc, g_mean_dx, g_rgb, g_sigma, g_dx);
+  } else {
+    k_composite_bwd<<<ray_grid(B), 256, 0, (cudaStream_t)stream>>>(rgb, sigma, dx, z, rays_d, bg, bg_per_ray, mask_words,
+                                                                  ray_offset, B, N, g_color, g_depth, g_acc, g_mean_dx,
+                                                                  g_rgb, g_sigma, g_dx);
+  }
   return check_launch("b2n_composite_bwd");
 }

@@ -116,10 +116,12 @@ def test_composite_golden(mods, path):
     assert rel_err(gs.cpu(), g["g_sigma"]) < TOL
 
 
-def test_composite_compact_with_dx_vs_oracle(mods):
+@pytest.mark.parametrize("N", [96, 64, 33, 128, 200, 7])
+def test_composite_compact_with_dx_vs_oracle(mods, N):
+    """N <= 128 runs the register-resident kernels, longer rays the chunk-loop kernels"""
     from oracle import nerf_oracle as O
     torch.manual_seed(1)
-    B, N = 300, 96
+    B = 300
     mask = torch.rand(B, N) < 0.3
     mask[5] = False
     mask[6] = True

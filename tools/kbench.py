@@ -135,6 +135,39 @@ def l2_gather():
     return out
 
 
+def composite(B=2 ** 18, N=128):
+    """compositing forward / backward on the C2 shapes: dense occupancy (~72 % of samples active, compact layout)"""
+    from b2n import synthetic, march
+    torch.manual_seed(0)
+    ro, rd, _ = (t.cuda() for t in synthetic.random_rays(B, seed=1))
+    u = torch.rand(B, N, device="cuda")
+    for kind in ("dense", "sparse"):
+        occ = torch.ones(128, 128, 128, dtype=torch.bool, device="cuda") if kind == "dense" else synthetic.ball_occupancy(128, 1.5).cuda()
+        m = march.march(ro, rd, 2.0, 6.0, N, u, bits=march.pack_occupancy(occ), R=128, bound=1.5)
+        Pn = m.pts.shape[0]
+        rgb = torch.rand(Pn, 3, device="cuda", requires_grad=True)
+        sigma = (torch.rand(Pn, device="cuda") * 2).requires_grad_(True)
+        bg = torch.ones(3, device="cuda")
+        from b2n import _lib
+        g = torch.randn(B, 3, device="cuda")
+
+        def both():
+            c, d, a, _ = b2n.composite(rgb, sigma, m.z, rd, bg=bg, mask_words=m.mask_words, ray_offset=m.ray_offset)
+            torch.autograd.grad((c * g).sum(), [rgb, sigma])
+        for _ in range(3):
+            both()
+        torch.cuda.synchronize()
+        prof = _lib.Profiler()
+        _lib.PROFILER = prof
+        for _ in range(20):
+            both()
+        torch.cuda.synchronize()
+        _lib.PROFILER = None
+        for name, v in prof.summary().items():
+            print(f"composite [{kind}] B={B} N={N} active={Pn}: {name} {v['ms'] / v['calls']:.4f} ms = "
+                  f"{v['bytes'] / v['ms'] / 1e6:.0f} GB/s algorithmic ({100 * v['bytes'] / v['ms'] / 1e6 / 6496.8:.1f} % of measured HBM peak)")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "mlp256"
     P = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 262144
@@ -144,5 +177,8 @@ if __name__ == "__main__":
         hash_levels()
     elif what == "l2":
         l2_gather()
+    elif what == "composite":
+        composite()
+        composite(8192, 64)
     else:
         {"mlp256": mlp256}[what](P)

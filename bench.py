@@ -271,10 +271,14 @@ DYNAMIC = {
 }
 
 
-def bench_dynamic(dev, name, steps=10, warm=4, occupancy="dense"):
+def bench_dynamic(dev, name, steps=10, warm=4, occupancy="dense", world=1, rank=0):
     """Training step of run.py:1073-1178 / :1804-1949 (autocast + GradScaler, render_rays with times, RGB MSE +
-    deformation L2 + table TV, clip, AdamW) on one GPU for the dynamic configs -- reported as extras."""
+    deformation L2 + table TV, clip, AdamW) for the dynamic configs -- reported as extras.  world > 1: ray-sharded
+    data parallel (B rays per GPU, replicated weights/tables, one flat gradient all-reduce per step before
+    unscale/clip/AdamW; every rank must call this)."""
+    import torch.distributed as dist
     from b2n import synthetic
+    from b2n.dp import GradAllReducer
     from src.core import NeuralField
     from src.renderer import DensityGrid, render_rays
     spec = DYNAMIC[name]
@@ -288,7 +292,9 @@ def bench_dynamic(dev, name, steps=10, warm=4, occupancy="dense"):
             grid.binary_grid = synthetic.ball_occupancy(spec["grid"][0], 1.5).to(dev)
     opt = torch.optim.AdamW(model.parameters(), lr=spec["lr"], weight_decay=1e-5)
     scaler = torch.amp.GradScaler("cuda", enabled=True)
-    pool = [tuple(t.to(dev) for t in synthetic.random_rays(B, seed=70 + i, n_views=150, with_time=True)) for i in range(3)]
+    reducer = GradAllReducer(model, world) if world > 1 else None
+    pool = [tuple(t.to(dev) for t in synthetic.random_rays(B, seed=70 + i + 1000 * rank, n_views=150, with_time=True))
+            for i in range(3)]
     bg = torch.ones(3, device=dev)
     tables = [m.encoding.params for n_, m in model.named_children() if hasattr(m, "encoding") and n_ != "deformation_grid"]
 
@@ -302,24 +308,39 @@ def bench_dynamic(dev, name, steps=10, warm=4, occupancy="dense"):
             if spec["tv"] > 0:
                 for tb in tables:
                     loss = loss + torch.mean(torch.abs(tb[1:] - tb[:-1])) * spec["tv"]
-        opt.zero_grad()
+        if reducer is None:
+            opt.zero_grad()
+        else:
+            reducer.zero_grad()
         scaler.scale(loss).backward()
+        if reducer is not None:
+            reducer.allreduce()            # before unscale/clip: every rank takes the same inf/clip decisions
         scaler.unscale_(opt)
         torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
         scaler.step(opt)
         scaler.update()
 
+    def sync():
+        if world > 1:
+            dist.barrier(device_ids=[dev.index])
+        torch.cuda.synchronize()
+
     def run(fn, n, w):
         for i in range(w):
             fn(i)
-        torch.cuda.synchronize()
+        sync()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for i in range(n):
             fn(i)
         e1.record()
-        torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / n
+        sync()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / n
 
     ms_train = run(step, steps, warm)
     if os.environ.get("B2N_PROF"):                      # development aid: per-kernel device time of 3 steps
@@ -335,9 +356,12 @@ def bench_dynamic(dev, name, steps=10, warm=4, occupancy="dense"):
     with torch.no_grad():
         ms_render = run(lambda i: render_rays(model, pool[i % 3][0], pool[i % 3][1], NEAR, FAR, N, False,
                                               times=pool[i % 3][3], density_grid=grid, bg_color=bg), steps, 2)
-    return {"workload": f"{spec['label']}, B={B} rays x {N} samples, AMP autocast + GradScaler, AdamW, {occupancy} occupancy",
-            "train_rays_per_s": B / ms_train * 1e3, "train_ms_per_step": ms_train,
-            "render_msamples_per_s": B * N / ms_render * 1e3 / 1e6}
+    out = {"workload": f"{spec['label']}, B={B} rays x {N} samples per GPU, AMP autocast + GradScaler, AdamW, {occupancy} occupancy",
+           "n_gpus": world, "train_rays_per_s": world * B / ms_train * 1e3, "train_ms_per_step": ms_train,
+           "render_msamples_per_s": world * B * N / ms_render * 1e3 / 1e6}
+    if reducer is not None:
+        out["allreduce_bytes_per_step"] = reducer.nbytes
+    return out
 
 
 # --------------------------------------------------------------------------------------- GPU arm
@@ -475,6 +499,9 @@ def main():
         extras["render_msamples_per_s"] = world * B * N_SAMPLES * args.steps / (ms3 * 1e-3) / 1e6
         extras["render_occupancy"] = args.occupancy
 
+    if not args.no_extras and world > 1:
+        # BASELINE.json configs[4]: Part 4 Dual-Hash, ray batch sharded over the GPUs, hash-table gradient all-reduce
+        extras["c5_dualhash_dp"] = bench_dynamic(dev, "c5_dualhash", world=world, rank=rank)
     if not args.no_extras and rank == 0:
         extras["c1_vanilla"] = bench_c1(dev)
         for name in DYNAMIC:

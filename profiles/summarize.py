@@ -21,7 +21,9 @@ HERE = os.path.join(ROOT, "profiles")
 ENTRY_OF = {"k_hash_fwd": "b2n_hash_fwd", "k_hash_bwd_table": "b2n_hash_bwd", "k_instant_fwd": "b2n_instant_mlp_fwd",
             "k_instant_bwd": "b2n_instant_mlp_bwd", "k_composite_fwd": "b2n_composite_fwd",
             "k_composite_bwd": "b2n_composite_bwd", "k_march_mask": "b2n_march_mask",
-            "k_march_compact": "b2n_march_compact", "k_mlp256": "b2n_nerf_mlp"}
+            "k_march_compact": "b2n_march_compact", "k_mlp256<false>": "b2n_nerf_mlp_fwd", "k_mlp256<true>": "b2n_nerf_mlp_bwd",
+            "k_fmlp_fwd": "b2n_fmlp_fwd", "k_fmlp_bwd": "b2n_fmlp_bwd", "k_fmlp_wgrad": "b2n_fmlp_wgrad",
+            "k_nerf_dx": "b2n_nerf_mlp_dx", "k_hash_bwd_input": "b2n_hash_bwd_input"}
 
 METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
            "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
@@ -41,7 +43,7 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
 
 def short(name):
     name = name.split("(")[0]
-    for pre in ("void ", "b2n::"):
+    for pre in ("void ", "b2n::", "fm::", "m256::"):
         name = name.replace(pre, "")
     return name.strip()
 
@@ -79,20 +81,26 @@ def launches(tag):
 
 
 def kernels(tag):
-    rep = os.path.join(OUT, f"{tag}_prof.ncu-rep")
-    if not os.path.exists(rep):
+    import glob
+    reps = sorted(glob.glob(os.path.join(OUT, f"{tag}_prof*.ncu-rep")))
+    if not reps:
         return
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    hdr, units = rows[0], rows[1]
-    idx = {h: i for i, h in enumerate(hdr)}
     traffic_path = os.path.join(HERE, "ncu_traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
-    with open(os.path.join(HERE, f"{tag}_kernels.md"), "w") as f:
-        f.write(f"# {tag}: `ncu --set full --clock-control none` of the bench command, selected counters\n\n")
+    all_rows = []
+    for rep in reps:
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(raw.splitlines()))
+        if len(rows) < 3:
+            continue
+        idx_ = {h: i for i, h in enumerate(rows[0])}
         for r in rows[2:]:
+            all_rows.append((os.path.basename(rep), idx_, rows[1], r))
+    with open(os.path.join(HERE, f"{tag}_kernels.md"), "w") as f:
+        f.write(f"# {tag}: `ncu --set full --clock-control none` of the bench commands, selected counters\n\n")
+        for rep_name, idx, units, r in all_rows:
             name = short(r[idx["Kernel Name"]])
-            f.write(f"## `{name}`\n\n| metric | value | unit |\n|---|---:|---|\n")
+            f.write(f"## `{name}`  ({rep_name})\n\n| metric | value | unit |\n|---|---:|---|\n")
             for m in METRICS:
                 if m in idx and r[idx[m]] != "":
                     f.write(f"| {m} | {r[idx[m]]} | {units[idx[m]]} |\n")

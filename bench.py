@@ -204,6 +204,20 @@ def ncu_traffic(kernel_name):
     return None
 
 
+def _maybe_profile(step):
+    """development aid (B2N_PROF=1 | cpu): per-kernel device time / per-op host time of 3 steps, to stderr"""
+    if not os.environ.get("B2N_PROF"):
+        return
+    from torch.profiler import ProfilerActivity, profile
+    cpu = os.environ["B2N_PROF"] == "cpu"
+    with profile(activities=[ProfilerActivity.CUDA] + ([ProfilerActivity.CPU] if cpu else [])) as prof:
+        for i in range(3):
+            step(i)
+        torch.cuda.synchronize()
+    print(prof.key_averages().table(sort_by="self_cpu_time_total" if cpu else "cuda_time_total", row_limit=40,
+                                    max_name_column_width=70), file=sys.stderr)
+
+
 def bench_c1(dev):
     """BASELINE.json configs[0] ("C1", Part 2 vanilla NeRF: PosEnc 10/4, 8x256 MLP on tcgen05, 64 samples, batch
     4096) on one GPU -- reported as an extra, the headline stays C2."""
@@ -238,6 +252,7 @@ def bench_c1(dev):
         return e0.elapsed_time(e1) / n
 
     ms_train = run(step, 20, 5)
+    _maybe_profile(step)
     model.eval()
     with torch.no_grad():
         ms_render = run(lambda i: render_rays(model, pool[i % 3][0], pool[i % 3][1], NEAR, FAR, N, False), 20, 5)
@@ -343,15 +358,7 @@ def bench_dynamic(dev, name, steps=10, warm=4, occupancy="dense", world=1, rank=
         return ms / n
 
     ms_train = run(step, steps, warm)
-    if os.environ.get("B2N_PROF"):                      # development aid: per-kernel device time of 3 steps
-        from torch.profiler import ProfilerActivity, profile
-        cpu = os.environ["B2N_PROF"] == "cpu"
-        with profile(activities=[ProfilerActivity.CUDA] + ([ProfilerActivity.CPU] if cpu else [])) as prof:
-            for i in range(3):
-                step(i)
-            torch.cuda.synchronize()
-        print(prof.key_averages().table(sort_by="self_cpu_time_total" if cpu else "cuda_time_total", row_limit=40,
-                                        max_name_column_width=70), file=sys.stderr)
+    _maybe_profile(step)
     model.eval()
     with torch.no_grad():
         ms_render = run(lambda i: render_rays(model, pool[i % 3][0], pool[i % 3][1], NEAR, FAR, N, False,

@@ -38,6 +38,8 @@
 //
 // Every mbarrier wait is bounded; on time-out the CTA raises an abort flag, stores an error code
 // and drains, so a protocol bug cannot hang the GPU.
+#include <cuda.h>
+#include <string.h>
 #include <cuda_bf16.h>
 #include "b2n_common.cuh"
 
@@ -74,6 +76,8 @@ struct Step {
   int acc_in;    // 1: the MMAs accumulate onto what the previous (partial) step left in TMEM
   int partial;   // 1: no drain -- the epilogue only re-stages the aux block for the next step
   int restage;   // aux block content for the NEXT step: 0 keep, 1 x_enc[:, 0:64], 2 x_enc[:, 64:128], 3 d_enc
+  int tma;       // 1: the saved plane of this step is written by a TMA tensor store of the activation tile
+                 //    (issued by the MMA warp at the next step) instead of st.global from the epilogue registers
 };
 struct Plan {
   int n_steps;
@@ -145,6 +149,14 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr) : "memory");
 }
+// TMA tensor store of one swizzled [128 rows x 64 bf16] k-block: smem -> planes[slot][row0.., col0..col0+63]
+__device__ __forceinline__ void tma_store_3d(const void* tmap, uint32_t smem_src, int col0, int row0, int slot) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(tmap), "r"(smem_src), "r"(col0), "r"(row0), "r"(slot) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row atoms 1024 B apart.
@@ -199,17 +211,26 @@ struct FwdArgs {
   float* dz_small;                  // [P,4]: d(pre-sigmoid rgb)[3], d(pre-relu sigma)
   long long* prof;                  // optional [8] cycle counters of CTA 0 (b2n_debug_mlp256_prof)
   Plan plan;
+  int use_tma;                      // the planes are written through the TMA tensor map passed next to this struct
 };
 
-__device__ __forceinline__ void restage_aux(const FwdArgs& a, int what, int64_t p, bool valid, unsigned char* aux, int r,
-                                            int c0) {
-  if (what == 1) stage_row(a.x_enc + p * a.pos_dim, a.pos_dim < 64 ? a.pos_dim : 64, valid, aux, r, c0);
-  else if (what == 2) stage_row(a.x_enc + p * a.pos_dim + 64, a.pos_dim - 64, valid, aux, r, c0);
-  else if (what == 3) stage_row(a.d_enc + p * a.dir_dim, a.dir_dim, valid, aux, r, c0);
+// one out-of-line copy: the three call sites are off the hot loop, and inlining them grew the forward kernel
+// by 850 instructions (measured: -8 % throughput, the epilogue is instruction-cache sensitive)
+__device__ __noinline__ void restage_aux(const FwdArgs& a, int what, int64_t p, bool valid, unsigned char* aux, int r,
+                                         int c0) {
+  const float* src;
+  int width;
+  if (what == 1) src = a.x_enc + p * a.pos_dim, width = a.pos_dim < 64 ? a.pos_dim : 64;
+  else if (what == 2) src = a.x_enc + p * a.pos_dim + 64, width = a.pos_dim - 64;
+  else if (what == 3) src = a.d_enc + p * a.dir_dim, width = a.dir_dim;
+  else return;
+  stage_row(src, width, valid, aux, r, c0);
 }
 
-template <bool BWD>
-__global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
+// WIDE: forward with 64 < pos_dim <= 96 (partial steps / aux swaps); the common instantiation carries none of that code
+template <bool BWD, bool WIDE = false>
+__global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const __grid_constant__ FwdArgs a, const __grid_constant__ CUtensorMap tmap_save) {
+  // tmap_save: 3-D map of the saved planes (cols, rows, slot), box 64 x 128 x 1, SWIZZLE_128B
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -276,13 +297,25 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
         for (int s = 0; s < plan.n_steps; ++s) {
           const int n_act = plan.s[s].n_act, aux_k16 = plan.s[s].aux_k16;
           const int nkc = n_act + (aux_k16 ? 1 : 0), halves = plan.s[s].n / 128;
-          const bool acc_in = plan.s[s].acc_in != 0;
+          const bool acc_in = WIDE && plan.s[s].acc_in != 0;
           for (int t = 0; t < 2; ++t) {
             long long t0 = clock64();
             if (!mbar_wait(bar_act + 8 * t, act_phase[t] & 1, abort_flag, a.err, 2)) goto mma_done;
             if (a.prof && blockIdx.x == 0 && lane == 0) a.prof[0] += clock64() - t0;   // waiting for the epilogue
             ++act_phase[t];
             tc_fence_after();
+            // the activation tile the epilogue just finished is also a saved plane: store it with the TMA
+            // while the MMAs below read it (both only read); it is overwritten after bar_acc fires
+            const bool store_prev = a.use_tma && s > 0 && plan.s[s - 1].tma;
+            if (store_prev) {
+              if (elect_one()) {
+                const int row0 = (int)(pair * 256 + t * 128);
+                for (int kb = 0; kb < plan.s[s - 1].n / 64; ++kb)
+                  tma_store_3d(&tmap_save, act0 + t * ACT_BYTES + kb * KBLK_BYTES, 64 * kb, row0, plan.s[s - 1].save_slot);
+                bulk_commit();
+              }
+              __syncwarp();
+            }
             const uint32_t d_tmem = tmem + t * 256;
             for (int c = 0; c < nkc; ++c) {
               const bool from_aux = c >= n_act;
@@ -310,10 +343,17 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
                 __syncwarp();
               }
             }
-            if (elect_one()) tc_commit(bar_acc + 8 * t);
+            if (elect_one()) {
+              if (store_prev) bulk_wait_read0();     // the store has read the tile before the epilogue may overwrite it
+              tc_commit(bar_acc + 8 * t);
+            }
             __syncwarp();
           }
         }
+      }
+      if (a.use_tma) {
+        if (elect_one()) bulk_wait0();               // all plane stores complete before the CTA exits
+        __syncwarp();
       }
     }
   mma_done:;
@@ -340,7 +380,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
         const int64_t p = pair * 256 + t * 128 + r;
         const bool valid = p < a.P;
         if (!BWD) {
-          restage_aux(a, 1, p, valid, aux, r, 4 * half);
+          stage_row(a.x_enc + p * a.pos_dim, a.pos_dim < 64 ? a.pos_dim : 64, valid, aux, r, 4 * half);
         } else {
           // colour head backward -> dZ_view (128 wide; this thread covers 64 of its columns)
           float dzr[3] = {0.f, 0.f, 0.f};
@@ -378,7 +418,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
       for (int s = 0; s < plan.n_steps; ++s) {
         const Step& sp = plan.s[s];
         const bool last = (s + 1 == plan.n_steps);
-        if (!BWD && sp.partial) {
+        if (!BWD && WIDE && sp.partial) {
           // the MMAs of this step only add a k-slice to the accumulators: when they have read the aux
           // block, swap in the next slice of the input row; nothing is drained
           for (int t = 0; t < 2; ++t) {
@@ -421,7 +461,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
           tc_fence_after();
           float sig_acc = 0.f, rgb_acc[3] = {0.f, 0.f, 0.f};
           const bool relu = sp.epi != EPI_LINEAR;
-          __nv_bfloat16* save_row = (a.save && sp.save_slot >= 0 && valid)
+          __nv_bfloat16* save_row = (a.save && sp.save_slot >= 0 && valid && !(a.use_tma && sp.tma))
                                         ? a.save + ((size_t)sp.save_slot * a.P + p) * HID : nullptr;
           // bwd: the forward activation whose ReLU gates this gradient (plane index in bias_off)
           const __nv_bfloat16* mask_row = (BWD && sp.epi != EPI_B_LINEAR)
@@ -498,7 +538,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const FwdArgs a) {
             }
             // the aux block is re-used: next slice of x (pos_dim > 64), or the encoded view direction once
             // the skip layer has consumed x
-            restage_aux(a, sp.restage, p, valid, aux, r, 4 * half);
+            if (WIDE) restage_aux(a, sp.restage, p, valid, aux, r, 4 * half);
+            else if (sp.restage == 3) stage_row(a.d_enc + p * a.dir_dim, a.dir_dim, valid, aux, r, 4 * half);
           }
           tc_fence_before();
           proxy_fence();
@@ -586,6 +627,39 @@ static void build_fwd_plan(Plan* pl, int pos_dim) {
   pl->n_steps = n;
 }
 
+// ---------------------------------------------------------------------------------------- TMA tensor map of the planes
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+// planes: bf16 [n_slots][P][256]; box = one swizzled k-block of an activation tile (64 columns x 128 rows).
+// Returns false when the map cannot be built (the kernel then stores the planes from registers).
+static bool make_plane_map(CUtensorMap* m, void* planes, int64_t P, int n_slots) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || !planes || P < 128) return false;
+  const cuuint64_t dims[3] = {256, (cuuint64_t)P, (cuuint64_t)n_slots};
+  const cuuint64_t strides[2] = {512, (cuuint64_t)P * 512};
+  const cuuint32_t box[3] = {64, 128, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, planes, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// every step that leaves its output in the activation tile (all but the view layer / the last step) saves it by TMA
+static void mark_tma_steps(Plan* pl) {
+  for (int i = 0; i + 1 < pl->n_steps; ++i)
+    pl->s[i].tma = (pl->s[i].save_slot >= 0 && !pl->s[i].partial && pl->s[i].epi != EPI_VIEW_RGB) ? 1 : 0;
+}
+
 static long long* g_prof = nullptr;
 // debug aid: cycle counters of CTA 0 ([0] MMA waits epilogue, [1] MMA waits weights, [2] epilogue waits MMA,
 // [3] epilogue body, [4] tile pairs); pass a device int64[8] (zeroed) or NULL to disable
@@ -648,11 +722,20 @@ extern "C" int b2n_nerf_mlp_fwd(const float* x_enc, int pos_dim, const float* d_
   a.head_bias = head_bias;
   a.P = P, a.rgb = rgb, a.sigma = sigma, a.save = (__nv_bfloat16*)save, a.err = err_flag;
   build_fwd_plan(&a.plan, pos_dim);
+  mark_tma_steps(&a.plan);
+  alignas(64) CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  a.use_tma = (a.save && make_plane_map(&tmap, save, P, 10)) ? 1 : 0;
   a.prof = g_prof;
-  cudaFuncSetAttribute(k_mlp256<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   const int64_t n_pairs = (P + 255) / 256;
   const int grid = (int)(n_pairs < kSMs ? n_pairs : kSMs);
-  k_mlp256<false><<<grid, N_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  if (pos_dim > 64) {
+    cudaFuncSetAttribute(k_mlp256<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    k_mlp256<false, true><<<grid, N_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a, tmap);
+  } else {
+    cudaFuncSetAttribute(k_mlp256<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    k_mlp256<false, false><<<grid, N_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a, tmap);
+  }
   return check_launch("b2n_nerf_mlp_fwd");
 }
 
@@ -712,10 +795,14 @@ extern "C" int b2n_nerf_mlp_bwd(const void* packed_bwd, const float* w_sigma, co
   a.fwd_planes = (const __nv_bfloat16*)fwd_planes, a.rgb_out = rgb, a.sigma_out = sigma, a.g_rgb = g_rgb;
   a.g_sigma = g_sigma, a.P = P, a.save = (__nv_bfloat16*)dz_planes, a.dz_small = dz_small, a.err = err_flag;
   build_bwd_plan(&a.plan);
+  mark_tma_steps(&a.plan);
+  alignas(64) CUtensorMap tmap;
+  memset(&tmap, 0, sizeof(tmap));
+  a.use_tma = make_plane_map(&tmap, dz_planes, P, 10) ? 1 : 0;
   a.prof = g_prof;
   cudaFuncSetAttribute(k_mlp256<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   const int64_t n_pairs = (P + 255) / 256;
   const int grid = (int)(n_pairs < kSMs ? n_pairs : kSMs);
-  k_mlp256<true><<<grid, N_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a);
+  k_mlp256<true><<<grid, N_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a, tmap);
   return check_launch("b2n_nerf_mlp_bwd");
 }

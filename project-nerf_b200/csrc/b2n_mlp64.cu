@@ -179,7 +179,7 @@ __device__ __forceinline__ void load_all_weights(const float* __restrict__ sp, c
 
 // ------------------------------------------------------------------------------ forward
 template <int POS_K>
-__global__ void __launch_bounds__(MLP_THREADS)
+__global__ void __launch_bounds__(MLP_THREADS, 4)
 k_instant_fwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __restrict__ dirs,
               const float* __restrict__ bands, int L_dir, const float* __restrict__ sp, const float* __restrict__ cp,
               int64_t P, float* __restrict__ rgb, float* __restrict__ sigma) {

@@ -87,3 +87,42 @@ def test_vanilla_nerf_tcgen05_learns_a_sphere():
         assert last < 0.4 * first, (first, last)      # vanilla NeRF converges slowly; 400 steps only show the trend
     finally:
         b2n.set_mlp_precision("fp32")
+
+
+def test_bf16_and_fp32_paths_render_the_same_psnr():
+    """north star: 'test-view PSNR within 0.05 dB' between the fp32 path and the bf16 tensor-core path.  Train a small
+    Instant-NeRF on the analytic sphere, then render the same held-out rays with both precisions."""
+    import b2n
+    from b2n import synthetic
+    from src.core import NeuralField
+    from src.renderer import DensityGrid, render_rays
+    dev = "cuda"
+    b2n.set_mlp_precision("bf16")
+    try:
+        torch.manual_seed(0)
+        cfg = dict(mode="part2_instant", n_levels=12, n_features_per_level=2, log2_hashmap_size=17, base_resolution=16,
+                   per_level_scale=1.5, scene_bound=1.5, L_embed_dir=4, hidden_dim=64)
+        model = NeuralField(cfg).to(dev).train()
+        grid = DensityGrid(resolution=64, bound=1.5, threshold=0.05).to(dev)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-2, weight_decay=1e-5)
+        bg = torch.ones(3, device=dev)
+        for step in range(1, 251):
+            ro, rd, _ = (t.to(dev) for t in synthetic.random_rays(4096, seed=step))
+            pred, _, _ = render_rays(model, ro, rd, 2.0, 6.0, 64, True, density_grid=grid, bg_color=bg)
+            loss = torch.nn.functional.mse_loss(pred, _sphere_targets(ro, rd))
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+        model.eval()
+        ro, rd, _ = (t.to(dev) for t in synthetic.random_rays(16384, seed=9999))
+        target = _sphere_targets(ro, rd)
+        psnr = {}
+        with torch.no_grad():
+            for mode in ("bf16", "fp32"):
+                b2n.set_mlp_precision(mode)
+                pred, _, _ = render_rays(model, ro, rd, 2.0, 6.0, 128, False, density_grid=grid, bg_color=bg)
+                psnr[mode] = 10 * math.log10(1.0 / float(torch.mean((pred - target) ** 2)))
+        assert psnr["fp32"] > 20.0, psnr
+        assert abs(psnr["bf16"] - psnr["fp32"]) < 0.05, psnr
+    finally:
+        b2n.set_mlp_precision("fp32")

@@ -602,3 +602,20 @@ def test_nerf_mlp256_tcgen05_wide_input_and_dx(mods, bf16_mode, pos_dim, Pn):
     for k, a_, b_ in zip(["g_x"] + names, got, ref):
         l2 = float((a_.cpu().double() - b_.double()).norm() / (b_.double().norm() + 1e-30))
         assert l2 < 3e-2, (k, l2)
+
+
+def test_new_entry_points_accept_empty_batches(mods, bf16_mode):
+    """P == 0 is a no-op for every fused entry point (an all-empty occupancy mask yields zero active samples)"""
+    from src import decoders as D
+    dn = D.DeformationNetwork(63, 21, 128, 4).to(DEV)
+    out = dn(torch.zeros(0, 63, device=DEV), torch.zeros(0, 21, device=DEV))
+    assert out.shape == (0, 3)
+    tm = D.TimeModulationNetwork(21, 64, 64, 2).to(DEV)
+    assert tm(torch.zeros(0, 21, device=DEV)).shape == (0, 64)
+    dec = D.NeRFDecoder(pos_dim=84, dir_dim=27).to(DEV)
+    x = torch.zeros(0, 84, device=DEV, requires_grad=True)
+    rgb, sigma = dec(x, torch.zeros(0, 27, device=DEV))
+    assert rgb.shape == (0, 3) and sigma.shape == (0, 1)
+    (rgb.sum() + sigma.sum()).backward()
+    assert x.grad.shape == (0, 84)
+    assert all(p.grad is not None and float(p.grad.abs().max()) == 0.0 for p in dec.parameters())

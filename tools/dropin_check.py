@@ -38,7 +38,7 @@ def make_scene(root, res=64, n_train=24, n_test=8, dynamic=False):
     focal = 0.5 * res / math.tan(0.5 * fov)
     os.makedirs(root, exist_ok=True)
     rng = np.random.RandomState(0)
-    for split, n in (("train", n_train), ("test", n_test)):
+    for split, n in (("train", n_train), ("val", max(n_test // 2, 2)), ("test", n_test)):
         os.makedirs(os.path.join(root, split), exist_ok=True)
         frames = []
         for i in range(n):

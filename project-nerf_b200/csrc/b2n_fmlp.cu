@@ -520,21 +520,24 @@ static int launch_bwd(const Args& a, cudaStream_t st) {
 using namespace b2n;
 using namespace b2n::fm;
 
-static int fill_args(Args* a, const float* x0, int ld0, int d0, const float* x1, int ld1, int d1, int hidden, int n_hidden,
-                     const float* const* W, const int* ldw, const float* const* b, int out_dim, int out_act, int64_t P) {
+// need_inputs: the forward reads x0 / x1; the backward only needs their widths
+static int fill_args(Args* a, bool need_inputs, const float* x0, int ld0, int d0, const float* x1, int ld1, int d1,
+                     int hidden, int n_hidden, const float* const* W, const int* ldw, const float* const* b, int out_dim,
+                     int out_act, int64_t P) {
   B2N_REQUIRE(hidden == 64 || hidden == 128, "hidden width must be 64 or 128");
   B2N_REQUIRE(n_hidden >= 1 && n_hidden <= MAX_HID, "1..3 hidden layers");
-  B2N_REQUIRE(x0 && d0 > 0 && ld0 >= d0 && d1 >= 0 && (d1 == 0 || (x1 && ld1 >= d1)), "bad input sources");
+  B2N_REQUIRE(d0 > 0 && d1 >= 0, "bad input widths");
+  B2N_REQUIRE(!need_inputs || (x0 && ld0 >= d0 && (d1 == 0 || (x1 && ld1 >= d1))), "bad input sources");
   B2N_REQUIRE(d0 + d1 <= 96, "at most 96 inputs");
   B2N_REQUIRE(out_dim >= 1 && out_dim <= 64, "1..64 outputs");
   B2N_REQUIRE(out_act == B2N_ACT_NONE || out_act == B2N_ACT_RELU || out_act == B2N_ACT_SIGMOID, "bad activation");
-  B2N_REQUIRE(W && ldw && b, "null pointer");
+  B2N_REQUIRE(W && ldw && (b || !need_inputs), "null pointer");
   a->x0 = x0, a->ld0 = ld0, a->d0 = d0, a->x1 = x1, a->ld1 = ld1, a->d1 = d1;
   for (int l = 0; l <= n_hidden; ++l) {
     B2N_REQUIRE(W[l], "null weight");
     const int k = (l == 0) ? d0 + d1 : hidden;
     B2N_REQUIRE(ldw[l] >= k, "weight row shorter than the layer input");
-    a->W[l] = W[l], a->ldw[l] = ldw[l], a->b[l] = b[l];
+    a->W[l] = W[l], a->ldw[l] = ldw[l], a->b[l] = b ? b[l] : nullptr;
   }
   a->n_hidden = n_hidden, a->out_dim = out_dim, a->out_act = out_act, a->P = P;
   return B2N_OK;
@@ -549,7 +552,7 @@ extern "C" int b2n_fmlp_fwd(const float* x0, int ld0, int d0, const float* x1, i
   B2N_REQUIRE(P >= 0, "negative size");
   if (P == 0) return B2N_OK;
   Args a{};
-  int rc = fill_args(&a, x0, ld0, d0, x1, ld1, d1, hidden, n_hidden, W, ldw, b, out_dim, out_act, P);
+  int rc = fill_args(&a, true, x0, ld0, d0, x1, ld1, d1, hidden, n_hidden, W, ldw, b, out_dim, out_act, P);
   if (rc) return rc;
   B2N_REQUIRE(y && ldy >= out_dim, "bad output");
   a.y = y, a.ldy = ldy, a.xin = (bf16*)xin_plane, a.hplanes = (bf16*)h_planes;
@@ -570,14 +573,11 @@ extern "C" int b2n_fmlp_bwd(int d0, int d1, int hidden, int n_hidden, const floa
   B2N_REQUIRE(P >= 0, "negative size");
   if (P == 0) return B2N_OK;
   Args a{};
-  const float* nob[MAX_HID + 1] = {nullptr, nullptr, nullptr, nullptr};
-  static const float dummy = 0.f;   // the backward never reads the inputs themselves
-  int rc = fill_args(&a, &dummy, d0, d0, d1 ? &dummy : nullptr, d1, d1, hidden, n_hidden, W, ldw, nob, out_dim, out_act, P);
+  int rc = fill_args(&a, false, nullptr, 0, d0, nullptr, 0, d1, hidden, n_hidden, W, ldw, nullptr, out_dim, out_act, P);
   if (rc) return rc;
   B2N_REQUIRE(g_y && ldgy >= out_dim && h_planes && dz_out && dz_h, "null pointer");
   B2N_REQUIRE(out_act == B2N_ACT_NONE || (y && ldy >= out_dim), "activation derivative needs the forward output");
   B2N_REQUIRE((!g_x0 || ldg0 >= d0) && (!g_x1 || ldg1 >= d1), "gradient row too narrow");
-  a.x0 = a.x1 = nullptr;
   a.y_out = y, a.ldy = ldy, a.g_y = g_y, a.ldgy = ldgy, a.hplanes = (bf16*)h_planes;
   a.dz_out = (bf16*)dz_out, a.dz_h = (bf16*)dz_h, a.g_x0 = g_x0, a.ldg0 = ldg0, a.g_x1 = g_x1, a.ldg1 = ldg1;
   cudaStream_t st = (cudaStream_t)stream;

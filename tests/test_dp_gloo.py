@@ -25,12 +25,16 @@ def _make():
     return torch.nn.Sequential(torch.nn.Linear(6, 32), torch.nn.ReLU(), torch.nn.Linear(32, 3))
 
 
+BIG = 100          # parameters with >= BIG elements take the asynchronous (hook-driven) all-reduce path: the 6x32 weight
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     dp = _load_dp()
     model = _make()
-    red = dp.GradAllReducer(model, world)
+    red = dp.GradAllReducer(model, world, overlap=True, big_numel=BIG)
+    assert red.overlap and len(red._hooks) == 1
     torch.manual_seed(1)
     rays, target = torch.randn(64, 6), torch.randn(64, 3)
     a, b = dp.shard_rays(64, rank, world)
@@ -39,7 +43,7 @@ def _worker(rank, world, port, out):
     red.allreduce()
     torch.nn.utils.clip_grad_norm_(model.parameters(), 0.05)          # after the all-reduce: identical on all ranks
     if rank == 0:
-        torch.save(red.flat.clone(), out)
+        torch.save({n: p.grad.clone() for n, p in model.named_parameters()}, out)
     gathered = [torch.zeros_like(red.flat) for _ in range(world)]
     dist.all_gather(gathered, red.flat)
     assert all(torch.equal(g, gathered[0]) for g in gathered)
@@ -57,7 +61,8 @@ def test_flat_allreduce_matches_single_process(tmp_path):
     torch.nn.functional.mse_loss(model(rays), target).backward()
     torch.nn.utils.clip_grad_norm_(model.parameters(), 0.05)
     got = torch.load(out)
-    assert torch.allclose(got, red.flat, rtol=1e-5, atol=1e-7)
+    for n, p in model.named_parameters():
+        assert torch.allclose(got[n], p.grad, rtol=1e-5, atol=1e-7), n
     # p.grad are views of the flat buffer (zeroing is one memset)
     assert all(p.grad.data_ptr() >= red.flat.data_ptr() for p in model.parameters())
 

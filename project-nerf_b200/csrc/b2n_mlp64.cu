@@ -27,10 +27,13 @@ constexpr int MLP_THREADS = 128;
 
 
 // view-direction Fourier features of one point -> 32 bf16 (27 valid, zero padded) at dst
-__device__ __forceinline__ void dir_features(const float* __restrict__ dirs, int64_t p, int64_t P,
-                                             const float* __restrict__ bands, int L, bf16* dst) {
-  float d[3] = {0.f, 0.f, 0.f};
+// (load and use are split so that the load can be issued long before the features are needed: ncu showed
+// long-scoreboard stalls on the small per-tile loads as the top stall reason of both decoder kernels)
+__device__ __forceinline__ void load_dir(const float* __restrict__ dirs, int64_t p, int64_t P, float (&d)[3]) {
+  d[0] = d[1] = d[2] = 0.f;
   if (p < P) d[0] = __ldg(dirs + 3 * p), d[1] = __ldg(dirs + 3 * p + 1), d[2] = __ldg(dirs + 3 * p + 2);
+}
+__device__ __forceinline__ void dir_features(const float (&d)[3], const float* __restrict__ bands, int L, bf16* dst) {
   float f[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = 0.f;
@@ -179,7 +182,7 @@ __device__ __forceinline__ void load_all_weights(const float* __restrict__ sp, c
 
 // ------------------------------------------------------------------------------ forward
 template <int POS_K>
-__global__ void __launch_bounds__(MLP_THREADS, 4)
+__global__ void __launch_bounds__(MLP_THREADS, 3)
 k_instant_fwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __restrict__ dirs,
               const float* __restrict__ bands, int L_dir, const float* __restrict__ sp, const float* __restrict__ cp,
               int64_t P, float* __restrict__ rgb, float* __restrict__ sigma) {
@@ -195,13 +198,41 @@ k_instant_fwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int64_t n_tiles = (P + 31) / 32;
   const int64_t wstride = (int64_t)gridDim.x * (MLP_THREADS / 32);
-  for (int64_t tile = (int64_t)blockIdx.x * (MLP_THREADS / 32) + (threadIdx.x >> 5); tile < n_tiles; tile += wstride) {
+  // POS_K == 32: the next tile's inputs (x_enc rows, view direction) are fetched into registers one tile ahead,
+  // right after the current ones have been packed, and land during the ~10 us of layer work; the 64-wide
+  // variant (Part 3/4: pos_dim 53) has no registers to spare and only pulls the lines towards L2
+  constexpr bool PF = (POS_K == 32);
+  constexpr int KTP = PF ? KT1 : 1;
+  float2 xraw[2][KTP][4];
+  float dnext[3] = {0.f, 0.f, 0.f};
+  const int64_t tile0 = (int64_t)blockIdx.x * (MLP_THREADS / 32) + (threadIdx.x >> 5);
+  if (PF) {
+    load_x_raw<KTP>(x, ldx, pos_dim, tile0 * 32, P, xraw[0], lane);
+    load_x_raw<KTP>(x, ldx, pos_dim, tile0 * 32 + 16, P, xraw[1], lane);
+    load_dir(dirs, tile0 * 32 + lane, P, dnext);
+  }
+  for (int64_t tile = tile0; tile < n_tiles; tile += wstride) {
     const int64_t p0 = tile * 32;
-    prefetch_rows(x, ldx, dirs, (tile + wstride) * 32, 32, P, lane);
-    dir_features(dirs, p0 + lane, P, bands, L_dir, dstage + lane * DS);
     uint32_t ax[2][KT1][4];
-    load_x<KT1>(x, ldx, pos_dim, p0, P, ax[0], lane);
-    load_x<KT1>(x, ldx, pos_dim, p0 + 16, P, ax[1], lane);
+    float dcur[3];
+    if (PF) {
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int k = 0; k < KT1; ++k)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ax[m][k][i] = pack2(xraw[m][k % KTP][i].x, xraw[m][k % KTP][i].y);
+      dcur[0] = dnext[0], dcur[1] = dnext[1], dcur[2] = dnext[2];
+      const int64_t pn = (tile + wstride) * 32;
+      load_x_raw<KTP>(x, ldx, pos_dim, pn, P, xraw[0], lane);
+      load_x_raw<KTP>(x, ldx, pos_dim, pn + 16, P, xraw[1], lane);
+      load_dir(dirs, pn + lane, P, dnext);
+    } else {
+      prefetch_rows(x, ldx, dirs, (tile + wstride) * 32, 32, P, lane);
+      load_dir(dirs, p0 + lane, P, dcur);
+      load_x<KT1>(x, ldx, pos_dim, p0, P, ax[0], lane);
+      load_x<KT1>(x, ldx, pos_dim, p0 + 16, P, ax[1], lane);
+    }
     // sigma_net layer 1
     uint32_t ah[2][4][4];
     {
@@ -227,6 +258,7 @@ k_instant_fwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
         ac[m][0][0] = tmp[0][0], ac[m][0][1] = tmp[0][1], ac[m][0][2] = tmp[0][2], ac[m][0][3] = tmp[0][3];
       }
     }
+    dir_features(dcur, bands, L_dir, dstage + lane * DS);     // needed only now: the direction load had two layers to land
     __syncwarp();
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
@@ -355,7 +387,29 @@ k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
     const int64_t p0 = tile * 64 + row0;
     // ---------------- forward recompute (staging every layer input); ax was fetched one tile ahead
     store_a<KT1>(ax[0], sm + LY::in_x, LY::SX, row0, 0, lane);
-    if (lane < 16) dir_features(dirs, p0 + lane, P, bands, L_dir, sm + LY::in_c + (row0 + lane) * LY::SC + 16);
+    // small per-tile loads issued now, consumed several layers later (view direction -> colour net input,
+    // incoming gradients -> output layer / density head)
+    float dcur[3];
+    load_dir(dirs, p0 + (lane & 15), P, dcur);
+    float grgb[4] = {0.f, 0.f, 0.f, 0.f}, gsig[2] = {0.f, 0.f};
+    {
+      const int64_t pa = p0 + g, pb = pa + 8;
+      const int col = 2 * t;
+      if (col < 3) {
+        if (pa < P) {
+          grgb[0] = __ldcs(g_rgb + 3 * pa + col);
+          if (col + 1 < 3) grgb[1] = __ldcs(g_rgb + 3 * pa + col + 1);
+        }
+        if (pb < P) {
+          grgb[2] = __ldcs(g_rgb + 3 * pb + col);
+          if (col + 1 < 3) grgb[3] = __ldcs(g_rgb + 3 * pb + col + 1);
+        }
+      }
+      if (t == 0) {
+        if (pa < P) gsig[0] = __ldcs(g_sigma + pa);
+        if (pb < P) gsig[1] = __ldcs(g_sigma + pb);
+      }
+    }
     uint32_t ah[1][4][4];
     {
       float c[1][8][4] = {};
@@ -374,6 +428,7 @@ k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
       ac[0][0][0] = tmp[0][0], ac[0][0][1] = tmp[0][1], ac[0][0][2] = tmp[0][2], ac[0][0][3] = tmp[0][3];
       store_a<1>(tmp, sm + LY::in_c, LY::SC, row0, 0, lane);
     }
+    if (lane < 16) dir_features(dcur, bands, L_dir, sm + LY::in_c + (row0 + lane) * LY::SC + 16);
     __syncwarp();
     ldsm_x4(ac[0][1], sm + LY::in_c + (row0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LY::SC + 16 + 8 * (lane >> 4));
     ldsm_x4(ac[0][2], sm + LY::in_c + (row0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LY::SC + 32 + 8 * (lane >> 4));
@@ -401,18 +456,18 @@ k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
       if (col < 3) {
         if (pa < P) {
           const float y = sigmoidf(c[0][0][0]);
-          d[0] = __ldcs(g_rgb + 3 * pa + col) * y * (1.f - y);
+          d[0] = grgb[0] * y * (1.f - y);
           if (col + 1 < 3) {
             const float y1 = sigmoidf(c[0][0][1]);
-            d[1] = __ldcs(g_rgb + 3 * pa + col + 1) * y1 * (1.f - y1);
+            d[1] = grgb[1] * y1 * (1.f - y1);
           }
         }
         if (pb < P) {
           const float y = sigmoidf(c[0][0][2]);
-          d[2] = __ldcs(g_rgb + 3 * pb + col) * y * (1.f - y);
+          d[2] = grgb[2] * y * (1.f - y);
           if (col + 1 < 3) {
             const float y1 = sigmoidf(c[0][0][3]);
-            d[3] = __ldcs(g_rgb + 3 * pb + col + 1) * y1 * (1.f - y1);
+            d[3] = grgb[3] * y1 * (1.f - y1);
           }
         }
       }
@@ -443,11 +498,11 @@ k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
         const int64_t pa = p0 + g, pb = pa + 8;
         if (pa < P) {
           const float v = hs0 - 5.f;
-          c[0][0] += __ldcs(g_sigma + pa) * (v > 20.f ? 1.f : sigmoidf(v));
+          c[0][0] += gsig[0] * (v > 20.f ? 1.f : sigmoidf(v));
         }
         if (pb < P) {
           const float v = hs1 - 5.f;
-          c[0][2] += __ldcs(g_sigma + pb) * (v > 20.f ? 1.f : sigmoidf(v));
+          c[0][2] += gsig[1] * (v > 20.f ? 1.f : sigmoidf(v));
         }
       }
       c_to_a<2, false>(c, dz2);

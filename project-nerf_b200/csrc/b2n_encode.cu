@@ -200,27 +200,57 @@ k_hash_bwd_table_dense(const float* __restrict__ x, int64_t P, float bound, floa
 #pragma unroll
     for (int d = 0; d < 3; ++d) x01[d] = to_unit(__ldg(x + 3 * p + d), bound, two_bound, &in);
   }
+  // the gradients of the first (up to) 8 dense-level features of a point are 32 contiguous bytes: two 16-byte loads
+  // instead of one 4-byte load per feature (lanes are 128 B apart, so every load instruction costs 32 L1 wavefronts
+  // whatever its width -- this kernel ran at 95 % L1TEX throughput)
+  float gall[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const float* grow = g + p * ld + col0;
+  const bool vec = live && ((reinterpret_cast<uintptr_t>(grow) & 15) == 0) && (ld - col0 >= 8);
+  if (vec) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(grow));
+    gall[0] = a.x, gall[1] = a.y, gall[2] = a.z, gall[3] = a.w;
+    if (n_dense * F > 4) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(grow) + 1);
+      gall[4] = b.x, gall[5] = b.y, gall[6] = b.z, gall[7] = b.w;
+    }
+  }
   for (int l = 0; l < n_dense; ++l) {
     const b2n_hash_level L = lv.l[l];      // warp-uniform index: constant-bank read
     const Cell c = locate(x01, L.scale);
     float gv[F];
 #pragma unroll
-    for (int f = 0; f < F; ++f) gv[f] = live ? __ldg(g + p * ld + col0 + l * F + f) : 0.f;
+    for (int f = 0; f < F; ++f) {
+      const int j = l * F + f;
+      if (vec && j < 8) {
+        float v = gall[0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) v = (j == q) ? gall[q] : v;      // register select (l is warp-uniform)
+        gv[f] = v;
+      } else {
+        gv[f] = live ? __ldg(grow + j) : 0.f;
+      }
+    }
+    // Runs: consecutive lanes in the same cell share all 8 entries, so the run structure is computed once per
+    // level from the cell index.  The segmented reduction stops after `steps` doubling steps (runs are a few
+    // samples long: about res/12 lanes at the sample spacing of a ray): afterwards every lane whose offset inside
+    // its run is a multiple of 2^steps holds the sum of up to 2^steps lanes and issues the red.  Fewer steps trade
+    // shuffles (the kernel's bottleneck: 10 per corner and level for the full scan) against a few more atomics.
+    const uint32_t cell = live ? (c.g[0] + c.g[1] * L.res + c.g[2] * L.res * L.res) : (0xffffffffu - (uint32_t)lane);
+    const uint32_t cell_prev = __shfl_up_sync(0xffffffffu, cell, 1);
+    const bool head = (lane == 0) || (cell != cell_prev);
+    const uint32_t heads = __ballot_sync(0xffffffffu, head);
+    const int steps = L.res <= 24 ? 3 : (L.res <= 64 ? 2 : 1);
+    const int run_start = 31 - __clz((int)(heads & (0xffffffffu >> (31 - lane))));
+    const bool issuer = live && (((lane - run_start) & ((1 << steps) - 1)) == 0);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const float wt = ((k & 1) ? c.w[0] : 1.f - c.w[0]) * ((k & 2) ? c.w[1] : 1.f - c.w[1]) *
                        ((k & 4) ? c.w[2] : 1.f - c.w[2]);
-      uint32_t e = live ? corner_entry(L, c.g[0] + (k & 1), c.g[1] + ((k >> 1) & 1), c.g[2] + ((k >> 2) & 1))
-                        : 0xffffffffu;
       float v[F];
 #pragma unroll
       for (int f = 0; f < F; ++f) v[f] = wt * gv[f];
-      // run heads: a lane starts a run when its entry differs from the previous lane's
-      const uint32_t e_prev = __shfl_up_sync(0xffffffffu, e, 1);
-      const bool head = (lane == 0) || (e != e_prev);
-      const uint32_t heads = __ballot_sync(0xffffffffu, head);
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
+      for (int s = 0; s < steps; ++s) {
+        const int o = 1 << s;
         float t[F];
 #pragma unroll
         for (int f = 0; f < F; ++f) t[f] = __shfl_down_sync(0xffffffffu, v[f], o);
@@ -231,7 +261,8 @@ k_hash_bwd_table_dense(const float* __restrict__ x, int64_t P, float bound, floa
           for (int f = 0; f < F; ++f) v[f] += t[f];
         }
       }
-      if (head && e != 0xffffffffu) {
+      if (issuer) {
+        const uint32_t e = corner_entry(L, c.g[0] + (k & 1), c.g[1] + ((k >> 1) & 1), c.g[2] + ((k >> 2) & 1));
         bool any = false;
 #pragma unroll
         for (int f = 0; f < F; ++f) any |= (v[f] != 0.f);

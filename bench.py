@@ -196,6 +196,15 @@ def measured_peaks():
     return 6650.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_units(kernel_name):
+    """per-unit utilisation (DRAM / L2 / L1TEX / tensor pipe, % of peak) of the dominant entry point's kernels from the
+    committed `ncu --set full` capture: which unit actually binds it."""
+    p = os.path.join(ROOT, "profiles", "ncu_units.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get(kernel_name)
+    return None
+
+
 def ncu_traffic(kernel_name):
     """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -530,7 +539,11 @@ def main():
                 "frac": (top["gbs"] / hbm_peak) if top["gbs"] else None, "peak_source": peak_src,
                 "avg_launch_ms": top["ms_per_step"] / max(top["calls_per_step"], 1e-9),
                 "share_of_step": top["ms_per_step"] / (ms / args.steps),
-                "traffic": ncu_traffic(top["entry"])}
+                "traffic": ncu_traffic(top["entry"]), "ncu": ncu_units(top["entry"]),
+                "note": ("algorithmic bytes (SURVEY 8d: per point 12 + L*F*4 gradient row + 2*L*8*F*4 table read-modify-write) "
+                         "over the launch time; the 52 MB gradient table is L2-resident, so `traffic` (DRAM bytes, ncu) is "
+                         "far below them and the binding unit is the L2 (atomics), see `ncu`")
+                if top["entry"].startswith("b2n_hash") else None}
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

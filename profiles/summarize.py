@@ -21,7 +21,7 @@ HERE = os.path.join(ROOT, "profiles")
 ENTRY_OF = {"k_hash_fwd": "b2n_hash_fwd", "k_hash_bwd_table": "b2n_hash_bwd", "k_instant_fwd": "b2n_instant_mlp_fwd",
             "k_instant_bwd": "b2n_instant_mlp_bwd", "k_composite_fwd": "b2n_composite_fwd",
             "k_composite_bwd": "b2n_composite_bwd", "k_march_mask": "b2n_march_mask",
-            "k_march_compact": "b2n_march_compact", "k_mlp256<false>": "b2n_nerf_mlp_fwd", "k_mlp256<true>": "b2n_nerf_mlp_bwd",
+            "k_march_compact": "b2n_march_compact", "k_mlp256<0": "b2n_nerf_mlp_fwd", "k_mlp256<1": "b2n_nerf_mlp_bwd",
             "k_fmlp_fwd": "b2n_fmlp_fwd", "k_fmlp_bwd": "b2n_fmlp_bwd", "k_fmlp_wgrad": "b2n_fmlp_wgrad",
             "k_nerf_dx": "b2n_nerf_mlp_dx", "k_hash_bwd_input": "b2n_hash_bwd_input"}
 
@@ -117,7 +117,30 @@ def kernels(tag):
             except Exception:
                 pass
     json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)
-    print("wrote", f"{tag}_kernels.md", "and ncu_traffic.json")
+    # unit utilisation per C-ABI entry point (what actually bounds the kernel), read by bench.py into roofline.ncu
+    units = {}
+    want = {"dram_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+            "lts_pct": "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+            "l1tex_pct": "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm_pct": "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "tensor_pipe_pct": "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+            "time_ms": "gpu__time_duration.sum"}
+    for rep_name, idx, units_row, r in all_rows:
+        name = short(r[idx["Kernel Name"]])
+        for k, entry in ENTRY_OF.items():
+            if name.startswith(k):
+                d = {}
+                for key, m in want.items():
+                    if m in idx and r[idx[m]] != "":
+                        v = float(r[idx[m]].replace(",", ""))
+                        if key == "time_ms":
+                            v *= {"ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}.get(units_row[idx[m]], 1e-6)
+                        d[key] = round(v, 3)
+                d["kernel"] = name[:60]
+                d["capture"] = rep_name
+                units.setdefault(entry, []).append(d)
+    json.dump(units, open(os.path.join(HERE, "ncu_units.json"), "w"), indent=1, sort_keys=True)
+    print("wrote", f"{tag}_kernels.md", "ncu_traffic.json and ncu_units.json")
 
 
 if __name__ == "__main__":

@@ -115,6 +115,31 @@ __device__ __forceinline__ void load_in(const Args& a, int64_t p0, uint32_t (&f)
       }
 }
 
+// split version for software pipelining: issue the loads of a tile now, pack (and wait for them) one tile later
+template <int KT>
+__device__ __forceinline__ void load_in_raw(const Args& a, int64_t p0, float (&raw)[KT][4][2], int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const int din = a.d0 + a.d1;
+#pragma unroll
+  for (int k = 0; k < KT; ++k)
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int64_t p = p0 + g + 8 * r;
+        const int c = 16 * k + 8 * h + 2 * t;
+        raw[k][2 * h + r][0] = raw[k][2 * h + r][1] = 0.f;
+        if (p < a.P) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int cc = c + j;
+            if (cc < a.d0) raw[k][2 * h + r][j] = __ldcs(a.x0 + p * a.ld0 + cc);
+            else if (cc < din) raw[k][2 * h + r][j] = __ldcs(a.x1 + p * a.ld1 + (cc - a.d0));
+          }
+        }
+      }
+}
+
 // A fragments of a 16-row slab -> rows p0.. of a row-major bf16 plane (row stride ld, even)
 template <int KT>
 __device__ __forceinline__ void store_plane(const uint32_t (&f)[KT][4], bf16* plane, int ld, int64_t p0, int64_t P,
@@ -161,6 +186,30 @@ __device__ __forceinline__ void relu_gate(float (&c)[NT][4], const bf16* plane, 
   }
 }
 
+// split version: the gate words of a layer are fetched one GEMM ahead of their use
+template <int NT>
+__device__ __forceinline__ void load_gate(const bf16* plane, int ld, int64_t p0, int64_t P, uint32_t (&ga)[NT],
+                                          uint32_t (&gb)[NT], int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const int64_t pa = p0 + g, pb = pa + 8;
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    ga[j] = pa < P ? __ldcs(reinterpret_cast<const uint32_t*>(plane + pa * ld + 8 * j + 2 * t)) : 0u;
+    gb[j] = pb < P ? __ldcs(reinterpret_cast<const uint32_t*>(plane + pb * ld + 8 * j + 2 * t)) : 0u;
+  }
+}
+template <int NT>
+__device__ __forceinline__ void apply_gate(float (&c)[NT][4], const uint32_t (&ga)[NT], const uint32_t (&gb)[NT]) {
+#pragma unroll
+  for (int j = 0; j < NT; ++j) {
+    const float2 lo = unpack2(ga[j]), hi = unpack2(gb[j]);
+    if (!(lo.x > 0.f)) c[j][0] = 0.f;
+    if (!(lo.y > 0.f)) c[j][1] = 0.f;
+    if (!(hi.x > 0.f)) c[j][2] = 0.f;
+    if (!(hi.y > 0.f)) c[j][3] = 0.f;
+  }
+}
+
 __device__ __forceinline__ float sigm(float v) { return 1.f / (1.f + expf(-v)); }
 
 // ------------------------------------------------------------------------------ forward
@@ -175,15 +224,30 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_fwd(const Args a) {
   constexpr int ROWS = 16 * MT;
   const int64_t n_tiles = (a.P + ROWS - 1) / ROWS;
   const int64_t wstride = (int64_t)gridDim.x * (THREADS / 32);
-  for (int64_t tile = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); tile < n_tiles; tile += wstride) {
+  // single-slab variants (H = 128) have registers to spare: the next tile's input rows are fetched one tile ahead
+  constexpr bool PF = (MT == 1);
+  constexpr int KTP = PF ? KT_IN : 1;
+  float raw[KTP][4][2];
+  const int64_t tile0 = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+  if (PF) load_in_raw<KTP>(a, tile0 * ROWS, raw, lane);
+  for (int64_t tile = tile0; tile < n_tiles; tile += wstride) {
     const int64_t p0 = tile * ROWS;
     uint32_t ah[MT][H / 16][4];
     {
       uint32_t ax[MT][KT_IN][4];
+      if (PF) {
 #pragma unroll
-      for (int m = 0; m < MT; ++m) {
-        load_in<KT_IN>(a, p0 + 16 * m, ax[m], lane);
-        if (a.xin) store_plane<KT_IN>(ax[m], a.xin, LY::IN_PAD, p0 + 16 * m, a.P, lane);
+        for (int k = 0; k < KT_IN; ++k)
+#pragma unroll
+          for (int i = 0; i < 4; ++i) ax[0][k][i] = pack2(raw[k % KTP][i][0], raw[k % KTP][i][1]);
+        load_in_raw<KTP>(a, (tile + wstride) * ROWS, raw, lane);
+        if (a.xin) store_plane<KT_IN>(ax[0], a.xin, LY::IN_PAD, p0, a.P, lane);
+      } else {
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          load_in<KT_IN>(a, p0 + 16 * m, ax[m], lane);
+          if (a.xin) store_plane<KT_IN>(ax[m], a.xin, LY::IN_PAD, p0 + 16 * m, a.P, lane);
+        }
       }
       float c[MT][H / 8][4];
 #pragma unroll
@@ -248,6 +312,8 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_bwd(const Args a) {
   const int64_t wstride = (int64_t)gridDim.x * (THREADS / 32);
   for (int64_t tile = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); tile < n_tiles; tile += wstride) {
     const int64_t p0 = tile * 16;
+    uint32_t ga[H / 8], gb[H / 8];      // ReLU gate words of the layer about to be gated
+    load_gate<H / 8>(a.hplanes + (size_t)(a.n_hidden - 1) * a.P * H, H, p0, a.P, ga, gb, lane);
     // ---- dZ of the output layer
     uint32_t dzo[KTO][4];
 #pragma unroll
@@ -280,7 +346,8 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_bwd(const Args a) {
     {
       float c[H / 8][4] = {};
       gemm_dgrad<H / 8, KTO>(c, dzo, sm + LY::wo, LY::SH, lane);
-      relu_gate<H / 8>(c, a.hplanes + (size_t)(a.n_hidden - 1) * a.P * H, H, p0, a.P, lane);
+      apply_gate<H / 8>(c, ga, gb);
+      if (a.n_hidden > 1) load_gate<H / 8>(a.hplanes + (size_t)(a.n_hidden - 2) * a.P * H, H, p0, a.P, ga, gb, lane);
       c_to_a<H / 8, false>(c, dz);
       store_plane<H / 16>(dz, a.dz_h + (size_t)(a.n_hidden - 1) * a.P * H, H, p0, a.P, lane);
     }
@@ -288,7 +355,8 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_bwd(const Args a) {
     for (int l = a.n_hidden - 1; l >= 1; --l) {
       float c[H / 8][4] = {};
       gemm_dgrad<H / 8, H / 16>(c, dz, sm + LY::wh + (l - 1) * H * LY::SH, LY::SH, lane);
-      relu_gate<H / 8>(c, a.hplanes + (size_t)(l - 1) * a.P * H, H, p0, a.P, lane);
+      apply_gate<H / 8>(c, ga, gb);
+      if (l > 1) load_gate<H / 8>(a.hplanes + (size_t)(l - 2) * a.P * H, H, p0, a.P, ga, gb, lane);
       c_to_a<H / 8, false>(c, dz);
       store_plane<H / 16>(dz, a.dz_h + (size_t)(l - 1) * a.P * H, H, p0, a.P, lane);
     }

@@ -151,6 +151,18 @@ int b2n_hash_bwd(const float* x, int64_t P, float bound, const float* table, con
                  int L, int F, const float* g_out, int ld_g, int col0, float* g_table, float* g_x, int accumulate_x,
                  b2n_stream_t stream);
 
+/* Tri-grid temporal blend of Part 4 (src/core.py:308-335): out[P, 2L] = sum_i w_i(t) * HashGrid_i(x) for the
+ * start / mid / end deformation grids (one shared geometry, F = 2), w_i = clamp(1 - |t - a_i| / 0.5, 0, 1) with
+ * a = (0, 0.5, 1), normalised by (w0 + w1 + w2 + 1e-8).  t [P] (one time per point).  One kernel each way; a grid
+ * whose weight is zero is neither read nor scattered to.  backward: g_out [P, 2L] -> ACCUMULATES w_i-weighted table
+ * gradients into g_table_* (fp32, zero-initialised by the caller; any may be NULL).  No gradient w.r.t. x or t. */
+int b2n_hash_tri_fwd(const float* x, const float* t, int64_t P, float bound, const float* table_start,
+                     const float* table_mid, const float* table_end, const b2n_hash_level* levels_host, int L,
+                     float* out, int ld_out, b2n_stream_t stream);
+int b2n_hash_tri_bwd(const float* x, const float* t, int64_t P, float bound, const b2n_hash_level* levels_host, int L,
+                     const float* g_out, int ld_g, float* g_table_start, float* g_table_mid, float* g_table_end,
+                     b2n_stream_t stream);
+
 /* ------------------------------------------------------------------------
  * fp32 dense layers (torch.nn.Linear of NeRFDecoder / DeformationNetwork /
  * TimeModulationNetwork, src/decoders.py:55-66,176-189,347, and the bias-free

@@ -35,6 +35,8 @@ SIGNATURES = {
     "b2n_pe_bwd": [P, L, I, P, I, P, I, I, P, I, P],
     "b2n_hash_fwd": [P, L, F, P, P, I, I, P, I, I, P],
     "b2n_hash_bwd": [P, L, F, P, P, I, I, P, I, I, P, P, I, P],
+    "b2n_hash_tri_fwd": [P, P, L, F, P, P, P, P, I, P, I, P],
+    "b2n_hash_tri_bwd": [P, P, L, F, P, I, P, I, P, P, P, P],
     "b2n_linear_fwd": [P, I, P, I, P, P, I, L, I, I, I, P],
     "b2n_linear_dgrad": [P, I, P, I, P, I, I, P, I, L, I, I, I, P],
     "b2n_linear_wgrad": [P, I, P, I, P, I, P, L, I, I, P],

@@ -117,6 +117,50 @@ def hash_encode(x, table, geom: HashGeometry, bound: float):
     return _HashEncode.apply(x, table, geom, bound)
 
 
+class _HashTriBlend(torch.autograd.Function):
+    """sum_i w_i(t) * HashGrid_i(x) over the start / mid / end deformation grids of Part 4 (src/core.py:308-335):
+    one kernel forward (b2n_hash_tri_fwd), one backward (b2n_hash_tri_bwd)."""
+
+    @staticmethod
+    @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, x, t, t0, t1, t2, geom: HashGeometry, bound: float):
+        require_cuda(x, t, t0, t1, t2)
+        x, t, t0, t1, t2 = _c(x), _c(t).reshape(-1), _c(t0), _c(t1), _c(t2)
+        if geom.n_features != 2:
+            raise ValueError("hash_tri_blend needs 2 features per level")
+        if t.shape[0] != x.shape[0] or any(tb.numel() != geom.n_params for tb in (t0, t1, t2)):
+            raise ValueError("hash_tri_blend: one time per point and three tables of the shared geometry")
+        Pn = x.shape[0]
+        out = torch.empty(Pn, geom.out_dim, device=x.device)
+        call("b2n_hash_tri_fwd", ptr(x), ptr(t), Pn, float(bound), ptr(t0), ptr(t1), ptr(t2), geom.c_levels,
+             geom.n_levels, ptr(out), geom.out_dim, stream(),
+             work=(Pn * (16 + geom.n_levels * 2 * 4 * (2 * 8 + 1)), 0.0))
+        ctx.save_for_backward(x, t)
+        ctx.geom, ctx.bound, ctx.shapes = geom, bound, (t0.shape, t1.shape, t2.shape)
+        return out
+
+    @staticmethod
+    @custom_bwd(device_type="cuda")
+    def backward(ctx, g):
+        x, t = ctx.saved_tensors
+        geom = ctx.geom
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            raise RuntimeError("hash_tri_blend has no gradient w.r.t. positions or times")
+        g = _c(g)
+        grads = [torch.zeros(shape, device=x.device) if ctx.needs_input_grad[2 + i] else None
+                 for i, shape in enumerate(ctx.shapes)]
+        if any(gr is not None for gr in grads):
+            call("b2n_hash_tri_bwd", ptr(x), ptr(t), x.shape[0], float(ctx.bound), geom.c_levels, geom.n_levels, ptr(g),
+                 geom.out_dim, ptr(grads[0]), ptr(grads[1]), ptr(grads[2]), stream(),
+                 work=(x.shape[0] * (16 + geom.n_levels * 2 * 4 * (1 + 2 * 2 * 8)), 0.0))
+        return None, None, grads[0], grads[1], grads[2], None, None
+
+
+def hash_tri_blend(x, t, tables: Sequence[torch.Tensor], geom: HashGeometry, bound: float):
+    """Tent-weighted blend of three hash grids sharing ``geom`` at per-point times t in [0, 1]: [P, L*2]."""
+    return _HashTriBlend.apply(x, t, tables[0], tables[1], tables[2], geom, bound)
+
+
 # ----------------------------------------------------------------------------
 # Fourier features
 # ----------------------------------------------------------------------------

@@ -329,6 +329,121 @@ k_hash_bwd_input(const float* __restrict__ x, int64_t P, float bound, float two_
   }
 }
 
+// ----------------------------------------------------------------------------- tri-grid temporal blend (Part 4)
+// deform_feat = sum_i w_i(t) * HashGrid_i(x), i = start / mid / end anchors at t = 0, 0.5, 1 with tent weights of
+// half-width 0.5, normalised (src/core.py:308-335).  The three grids share one geometry, so cell, corner indices and
+// trilinear weights are computed once per (point, level) item; a grid whose weight is exactly zero (always at least
+// one of the three) is neither gathered nor scattered to.  Replaces 3 encoder launches + ~25 elementwise launches
+// (forward) and 3 scatter launches + their autograd glue (backward) by one kernel each way.
+struct TriTables {
+  const float* t[3];
+};
+struct TriGrads {
+  float* t[3];
+};
+
+__device__ __forceinline__ void tri_weights(float tv, float (&w)[3]) {
+  // clamp(1 - |t - a| / 0.5, 0, 1) for a in (0, 0.5, 1); / (w0 + w1 + w2 + 1e-8)   -- same fp32 operation order
+  const float a[3] = {0.f, 0.5f, 1.f};
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    w[i] = fminf(fmaxf(__fsub_rn(1.0f, __fdiv_rn(fabsf(__fsub_rn(tv, a[i])), 0.5f)), 0.f), 1.f);
+  const float tot = __fadd_rn(__fadd_rn(__fadd_rn(w[0], w[1]), w[2]), 1e-8f);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) w[i] = __fdiv_rn(w[i], tot);
+}
+
+__global__ void __launch_bounds__(256)
+k_hash_tri_fwd(const float* __restrict__ x, const float* __restrict__ tval, int64_t P, float bound, float two_bound,
+               const TriTables tabs, const Levels lv, int nl, float* __restrict__ out, int ld) {
+  __shared__ SmemLevels sl;
+  stage_levels(lv, nl, &sl);
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= P * nl) return;
+  const int64_t p = item / nl;
+  const int level = (int)(item - p * nl);
+  const b2n_hash_level L = sl.l[level];
+  bool in;
+  float x01[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) x01[d] = to_unit(__ldg(x + 3 * p + d), bound, two_bound, &in);
+  float w[3];
+  tri_weights(__ldg(tval + p), w);
+  const Cell c = locate(x01, L.scale);
+  uint32_t e[8];
+  float wt[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    e[k] = corner_entry(L, c.g[0] + (k & 1), c.g[1] + ((k >> 1) & 1), c.g[2] + ((k >> 2) & 1));
+    wt[k] = ((k & 1) ? c.w[0] : 1.f - c.w[0]) * ((k & 2) ? c.w[1] : 1.f - c.w[1]) * ((k & 4) ? c.w[2] : 1.f - c.w[2]);
+  }
+  float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    if (w[i] == 0.f) continue;          // 0 * f == 0 exactly: the inactive anchor grid is not read
+    float vals[8][2];
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {    // x-neighbour pair: one 16-byte gather when the two entries are an aligned pair
+      if ((e[k] ^ e[k + 1]) == 1u) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(tabs.t[i]) + (e[k] >> 1));
+        const bool lo = (e[k] & 1u) == 0u;
+        vals[k][0] = lo ? q.x : q.z, vals[k][1] = lo ? q.y : q.w;
+        vals[k + 1][0] = lo ? q.z : q.x, vals[k + 1][1] = lo ? q.w : q.y;
+      } else {
+        load_feat<2>(tabs.t[i], e[k], vals[k]);
+        load_feat<2>(tabs.t[i], e[k + 1], vals[k + 1]);
+      }
+    }
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a0 += wt[k] * vals[k][0], a1 += wt[k] * vals[k][1];
+    o0 = __fadd_rn(o0, __fmul_rn(w[i], a0));
+    o1 = __fadd_rn(o1, __fmul_rn(w[i], a1));
+  }
+  __stcs(reinterpret_cast<float2*>(out + p * ld + level * 2), make_float2(o0, o1));
+}
+
+__global__ void __launch_bounds__(256)
+k_hash_tri_bwd(const float* __restrict__ x, const float* __restrict__ tval, int64_t P, float bound, float two_bound,
+               const Levels lv, int nl, const float* __restrict__ g, int ld, const TriGrads grads) {
+  __shared__ SmemLevels sl;
+  stage_levels(lv, nl, &sl);
+  const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= P * nl) return;
+  const int64_t p = item / nl;
+  const int level = (int)(item - p * nl);
+  const b2n_hash_level L = sl.l[level];
+  const float2 gv = __ldcs(reinterpret_cast<const float2*>(g + p * ld + level * 2));
+  if (gv.x == 0.f && gv.y == 0.f) return;
+  bool in;
+  float x01[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d) x01[d] = to_unit(__ldg(x + 3 * p + d), bound, two_bound, &in);
+  float w[3];
+  tri_weights(__ldg(tval + p), w);
+  const Cell c = locate(x01, L.scale);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const uint32_t cy = c.g[1] + (k & 1), cz = c.g[2] + ((k >> 1) & 1);
+    const float wyz = ((k & 1) ? c.w[1] : 1.f - c.w[1]) * ((k & 2) ? c.w[2] : 1.f - c.w[2]);
+    const float w0 = (1.f - c.w[0]) * wyz, w1 = c.w[0] * wyz;
+    const uint32_t e0 = corner_entry(L, c.g[0], cy, cz), e1 = corner_entry(L, c.g[0] + 1, cy, cz);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (w[i] == 0.f || !grads.t[i]) continue;
+      const float g0 = __fmul_rn(w[i], gv.x), g1 = __fmul_rn(w[i], gv.y);     // d(w_i f_i)/d f_i, as autograd forms it
+      if ((e0 ^ e1) == 1u) {
+        const bool lo = (e0 & 1u) == 0u;
+        const float wa = lo ? w0 : w1, wb = lo ? w1 : w0;
+        atomicAdd(reinterpret_cast<float4*>(grads.t[i]) + (e0 >> 1), make_float4(wa * g0, wa * g1, wb * g0, wb * g1));
+      } else {
+        atomicAdd(reinterpret_cast<float2*>(grads.t[i]) + e0, make_float2(w0 * g0, w0 * g1));
+        atomicAdd(reinterpret_cast<float2*>(grads.t[i]) + e1, make_float2(w1 * g0, w1 * g1));
+      }
+    }
+  }
+}
+
 static int fill_levels(const b2n_hash_level* h, int L, Levels* out) {
   if (!h || L <= 0 || L > B2N_MAX_LEVELS) return -1;
   for (int i = 0; i < L; ++i) {
@@ -417,4 +532,32 @@ extern "C" int b2n_hash_bwd(const float* x, int64_t P, float bound, const float*
     else k_hash_bwd_input<1><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, g_out, ld_g, col0, g_x, accumulate_x);
   }
   return check_launch("b2n_hash_bwd");
+}
+
+extern "C" int b2n_hash_tri_fwd(const float* x, const float* t, int64_t P, float bound, const float* table_start,
+                                const float* table_mid, const float* table_end, const b2n_hash_level* levels_host, int L,
+                                float* out, int ld_out, b2n_stream_t stream) {
+  B2N_REQUIRE(P >= 0 && bound >= 0.f, "bad shape");
+  Levels lv;
+  B2N_REQUIRE(fill_levels(levels_host, L, &lv) == 0, "bad level table");
+  if (P == 0) return B2N_OK;
+  B2N_REQUIRE(x && t && table_start && table_mid && table_end && out, "null pointer");
+  B2N_REQUIRE(ld_out >= 2 * L && (ld_out & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0, "output row too narrow / unaligned");
+  const TriTables tabs{{table_start, table_mid, table_end}};
+  k_hash_tri_fwd<<<grid_for(P * L, 256), 256, 0, (cudaStream_t)stream>>>(x, t, P, bound, 2.0f * bound, tabs, lv, L, out, ld_out);
+  return check_launch("b2n_hash_tri_fwd");
+}
+
+extern "C" int b2n_hash_tri_bwd(const float* x, const float* t, int64_t P, float bound, const b2n_hash_level* levels_host,
+                                int L, const float* g_out, int ld_g, float* g_table_start, float* g_table_mid,
+                                float* g_table_end, b2n_stream_t stream) {
+  B2N_REQUIRE(P >= 0 && bound >= 0.f, "bad shape");
+  Levels lv;
+  B2N_REQUIRE(fill_levels(levels_host, L, &lv) == 0, "bad level table");
+  if (P == 0) return B2N_OK;
+  B2N_REQUIRE(x && t && g_out, "null pointer");
+  B2N_REQUIRE(ld_g >= 2 * L && (ld_g & 1) == 0 && (reinterpret_cast<uintptr_t>(g_out) & 7) == 0, "gradient row too narrow / unaligned");
+  const TriGrads grads{{g_table_start, g_table_mid, g_table_end}};
+  k_hash_tri_bwd<<<grid_for(P * L, 256), 256, 0, (cudaStream_t)stream>>>(x, t, P, bound, 2.0f * bound, lv, L, g_out, ld_g, grads);
+  return check_launch("b2n_hash_tri_bwd");
 }

@@ -9,6 +9,8 @@ fitting) is outside the ray-marching hot path and is rejected.
 import torch
 from torch import nn
 
+import b2n
+
 from .decoders import (DeformationNetwork, HashDeformationDecoder, InstantNeRFDecoder, NeRFDecoder,
                        TimeModulationNetwork)
 from .embeddings import FourierRepresentation, HashRepresentation
@@ -120,6 +122,17 @@ class NeuralField(nn.Module):
         total = ws[0] + ws[1] + ws[2] + 1e-8
         return [w / total for w in ws]
 
+    def _tri_blend(self, xd, td):
+        """sum_i w_i(t) * deform_grid_i(x) (reference core.py:308-335): one kernel each way when the three grids share
+        their geometry (they always do: one config block builds all three), otherwise the module-by-module form"""
+        grids = (self.deform_grid_start, self.deform_grid_mid, self.deform_grid_end)
+        g0 = grids[0].encoding.geometry
+        same = all(g.encoding.geometry.levels == g0.levels and g.bound == grids[0].bound for g in grids[1:])
+        if xd.is_cuda and same and g0.n_features == 2 and not xd.requires_grad and not td.requires_grad:
+            return b2n.ops.hash_tri_blend(xd, td, [g.encoding.params for g in grids], g0, float(grids[0].bound))
+        w0, w1, w2 = self._tri_weights(td)
+        return w0 * grids[0](xd) + w1 * grids[1](xd) + w2 * grids[2](xd)
+
     # ------------------------------------------------------------------ forward
     def forward(self, x, d=None, t=None):
         mode = self.mode
@@ -142,8 +155,7 @@ class NeuralField(nn.Module):
             xd, td = self._augment(x, t)
             feat_t = self.time_encoder(td)
             time_mod = self.time_modulation(feat_t)
-            w0, w1, w2 = self._tri_weights(td)
-            blend = (w0 * self.deform_grid_start(xd) + w1 * self.deform_grid_mid(xd) + w2 * self.deform_grid_end(xd))
+            blend = self._tri_blend(xd, td)
             delta_x = self.deform_decoder(blend, time_mod)
             feat_can = self.canonical_repr(x + delta_x)
             rgb, sigma = self._decode(torch.cat([feat_can, feat_t], dim=-1), d)

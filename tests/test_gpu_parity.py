@@ -619,3 +619,29 @@ def test_new_entry_points_accept_empty_batches(mods, bf16_mode):
     (rgb.sum() + sigma.sum()).backward()
     assert x.grad.shape == (0, 84)
     assert all(p.grad is not None and float(p.grad.abs().max()) == 0.0 for p in dec.parameters())
+
+
+@pytest.mark.parametrize("Pn", [2000, 33, 1])
+def test_hash_tri_blend_vs_module_form(mods, Pn):
+    """b2n_hash_tri_fwd/bwd against w0*grid0(x) + w1*grid1(x) + w2*grid2(x) built from b2n_hash_fwd/bwd + torch ops (the
+    form the golden Part-4 fixtures pinned before the fusion), incl. t = 0, 0.5, 1 where one or two weights vanish."""
+    b2n = mods["b2n"]
+    torch.manual_seed(3)
+    geom = b2n.HashGeometry(12, 16, 1.5, 16, 2)
+    tabs = [((torch.rand(geom.n_params) * 2 - 1) * 0.3).to(DEV).requires_grad_(True) for _ in range(3)]
+    x = ((torch.rand(Pn, 3) * 2 - 1) * 1.6).to(DEV)
+    t = torch.rand(Pn, 1)
+    t[:: 7] = 0.0
+    t[1:: 7] = 0.5
+    t[2:: 7] = 1.0
+    t = t.to(DEV)
+    g = torch.randn(Pn, geom.out_dim, device=DEV)
+    ws = [torch.clamp(1.0 - torch.abs(t - a) / 0.5, 0.0, 1.0) for a in (0.0, 0.5, 1.0)]
+    tot = ws[0] + ws[1] + ws[2] + 1e-8
+    ref = sum((w / tot) * b2n.hash_encode(x, tb, geom, 1.5) for w, tb in zip(ws, tabs))
+    g_ref = torch.autograd.grad((ref * g).sum(), tabs)
+    out = b2n.ops.hash_tri_blend(x, t, tabs, geom, 1.5)
+    assert rel_err(out, ref) < 1e-6
+    g_out = torch.autograd.grad((out * g).sum(), tabs)
+    for a_, b_ in zip(g_out, g_ref):
+        assert rel_err(a_, b_) < 1e-5

@@ -645,3 +645,28 @@ def test_hash_tri_blend_vs_module_form(mods, Pn):
     g_out = torch.autograd.grad((out * g).sum(), tabs)
     for a_, b_ in zip(g_out, g_ref):
         assert rel_err(a_, b_) < 1e-5
+
+
+def test_hash_encode_properties_full_size(mods):
+    """C2-sized point set (2^24 points, L = 16, T = 2^19): the encoding is linear in the table, and because the 8
+    trilinear weights of a point sum to 1, the table gradient of sum(out * g) must sum (per level and feature) to the
+    column sums of g -- a conservation check on the 2 x 10^9 atomics of the backward."""
+    b2n = mods["b2n"]
+    torch.manual_seed(4)
+    geom = b2n.HashGeometry(16, 16, 1.5, 19, 2)
+    Pn = 2 ** 24
+    x = (torch.rand(Pn, 3, device=DEV) * 2 - 1) * 1.5
+    ta = ((torch.rand(geom.n_params, device=DEV) * 2 - 1) * 0.1)
+    tb = ((torch.rand(geom.n_params, device=DEV) * 2 - 1) * 0.1)
+    ea, eb = b2n.hash_encode(x, ta, geom, 1.5), b2n.hash_encode(x, tb, geom, 1.5)
+    eab = b2n.hash_encode(x, ta + tb, geom, 1.5)
+    assert rel_err(eab, ea + eb) < 1e-5
+    del ea, eb, eab
+    t = ta.clone().requires_grad_(True)
+    g = torch.rand(Pn, geom.out_dim, device=DEV)          # positive: no cancellation in the sums
+    (b2n.hash_encode(x, t, geom, 1.5) * g).sum().backward()
+    col = g.double().sum(0)                               # [L*F]
+    off = 0
+    for l, (_, _, size, offset, _) in enumerate(geom.levels):
+        got = t.grad[offset * 2:(offset + size) * 2].view(-1, 2).double().sum(0)
+        assert float((got - col[2 * l:2 * l + 2]).abs().max() / col[2 * l:2 * l + 2].abs().max()) < 1e-4, l

@@ -43,7 +43,7 @@ CPU_SAMPLE_RAYS = 1024
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b2n", choices=["b2n", "reference"])
     ap.add_argument("--occupancy", default="dense", choices=["dense", "sparse"])

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2N_ABI_VERSION 9
+#define B2N_ABI_VERSION 10
 
 #define B2N_OK 0
 #define B2N_EINVAL (-1)  /* bad argument (null pointer, size, unsupported shape) */
@@ -260,7 +260,10 @@ int b2n_fmlp_bwd(int d0, int d1, int hidden, int n_hidden, const float* const* W
  *   b2n_nerf_mlp_fwd: x_enc [P,pos_dim], d_enc [P,dir_dim] -> rgb [P,3], sigma [P].
  *     bias: concatenated [8*256 + 256 + 128]; w_sigma [256]; w_rgb [3*128];
  *     head_bias: device float[4] = {b_sigma, b_rgb[3]}; save: optional bf16
- *     [10][P][256] planes of the layer outputs (training); err_flag: device int
+ *     [10][P][256] planes of the layer outputs (training), written by TMA tensor
+ *     stores of the activation tiles; relu_masks: uint32 [10][P][8], bit c of a row
+ *     = (plane[c] > 0), given exactly when `save` is (the backward gates with these
+ *     32-byte rows instead of re-reading the 512-byte plane rows); err_flag: device int
  *     (0 = ok; non-zero = the kernel aborted a stalled pipeline instead of hanging).
  * ---------------------------------------------------------------------- */
 size_t b2n_nerf_mlp_packed_bytes(void);
@@ -268,11 +271,11 @@ int b2n_nerf_mlp_pack(const float* const* pts_w, const float* feature_w, const f
                       void* packed, b2n_stream_t stream);
 int b2n_nerf_mlp_fwd(const float* x_enc, int pos_dim, const float* d_enc, int dir_dim, const void* packed,
                      const float* bias, const float* w_sigma, const float* w_rgb, const float* head_bias, int64_t P,
-                     float* rgb, float* sigma, void* save, int* err_flag, b2n_stream_t stream);
+                     float* rgb, float* sigma, void* save, void* relu_masks, int* err_flag, b2n_stream_t stream);
 
 /* Backward data-gradient chain of the same decoder on tcgen05 (autograd of
- * src/decoders.py:68-87 w.r.t. the activations).  fwd_planes = the `save` planes
- * of b2n_nerf_mlp_fwd; rgb/sigma = its outputs; g_rgb [P,3], g_sigma [P] = incoming
+ * src/decoders.py:68-87 w.r.t. the activations).  relu_masks = the bit masks written
+ * by b2n_nerf_mlp_fwd; rgb/sigma = its outputs; g_rgb [P,3], g_sigma [P] = incoming
  * gradients.  Writes dz_planes (bf16 [10][P][256]: dZ_view(128 wide), dZ_feat,
  * dZ7 .. dZ0 = pre-activation gradients of every layer) and dz_small (fp32 [P,4]:
  * d rgb_pre[3], d sigma_pre).  Weight/bias gradients are dZ^T * layer-input GEMMs
@@ -289,7 +292,7 @@ int b2n_debug_mlp256_prof(void* device_int64x8);
 size_t b2n_nerf_mlp_packed_bwd_bytes(void);
 int b2n_nerf_mlp_pack_bwd(const float* const* pts_w, const float* feature_w, const float* view_w, int pos_dim,
                           int dir_dim, void* packed, b2n_stream_t stream);
-int b2n_nerf_mlp_bwd(const void* packed_bwd, const float* w_sigma, const float* w_rgb, const void* fwd_planes,
+int b2n_nerf_mlp_bwd(const void* packed_bwd, const float* w_sigma, const float* w_rgb, const void* relu_masks,
                      const float* rgb, const float* sigma, const float* g_rgb, const float* g_sigma, int64_t P,
                      void* dz_planes, float* dz_small, int* err_flag, b2n_stream_t stream);
 

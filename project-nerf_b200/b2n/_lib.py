@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb2nerf.so")
 
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 P, L, I, F = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
 
@@ -53,7 +53,7 @@ SIGNATURES = {
     "b2n_nerf_mlp_dx": [P, P, P, I, P, I, I, L, P, I, P],
     "b2n_nerf_mlp_packed_bytes": [],
     "b2n_nerf_mlp_pack": [P, P, P, I, I, P, P],
-    "b2n_nerf_mlp_fwd": [P, I, P, I, P, P, P, P, P, L, P, P, P, P, P],
+    "b2n_nerf_mlp_fwd": [P, I, P, I, P, P, P, P, P, L, P, P, P, P, P, P],
     "b2n_debug_mlp256_prof": [P],
     "b2n_debug_gather_bench": [P, L, I, I, P, P],
     "b2n_sample_rays": [P, P, P, P, P, P, L, I, I, I, F, F, P, P, P, P, P],

@@ -426,14 +426,15 @@ def nerf_mlp_forward(decoder, x_enc, d_enc, save: bool = False):
     rgb = torch.empty(Pn, 3, device=dev)
     sigma = torch.empty(Pn, 1, device=dev)
     planes = torch.empty(10, Pn, 256, device=dev, dtype=torch.bfloat16) if save else None
+    masks = torch.empty(10, Pn, 8, device=dev, dtype=torch.int32) if save else None      # ReLU bits of the planes
     err = torch.zeros(1, device=dev, dtype=torch.int32)
     w_sigma = _c(decoder.sigma_layer.weight).view(-1)
     w_rgb = _c(decoder.rgb_layer.weight).view(-1)
     flops = 2.0 * Pn * (256 * pos_dim + 256 * 256 * 6 + 256 * (256 + pos_dim) + 256 + 256 * 256 + 128 * (256 + dir_dim) + 384)
     call("b2n_nerf_mlp_fwd", ptr(x_enc), pos_dim, ptr(d_enc), dir_dim, ptr(packed), ptr(bias), ptr(w_sigma), ptr(w_rgb),
-         ptr(head_bias), Pn, ptr(rgb), ptr(sigma), ptr(planes), ptr(err), stream(),
+         ptr(head_bias), Pn, ptr(rgb), ptr(sigma), ptr(planes), ptr(masks), ptr(err), stream(),
          work=(Pn * (4.0 * (pos_dim + dir_dim) + 16 + (5120 if save else 0)), flops))
-    return rgb, sigma, planes, err
+    return rgb, sigma, (planes, masks) if save else None, err
 
 
 def _mm_f32(a_t, b):
@@ -453,15 +454,16 @@ class _NerfMLP(torch.autograd.Function):
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, decoder, x_enc, d_enc, *params):
         need_grad = any(ctx.needs_input_grad)
-        rgb, sigma, planes, err = nerf_mlp_forward(decoder, x_enc, d_enc, save=need_grad)
+        rgb, sigma, saved, err = nerf_mlp_forward(decoder, x_enc, d_enc, save=need_grad)
+        planes, masks = saved if saved is not None else (None, None)
         ctx.decoder = decoder
-        ctx.save_for_backward(_c(x_enc), _c(d_enc), rgb, sigma, planes, err)
+        ctx.save_for_backward(_c(x_enc), _c(d_enc), rgb, sigma, planes, masks, err)
         return rgb, sigma
 
     @staticmethod
     @custom_bwd(device_type="cuda")
     def backward(ctx, g_rgb, g_sigma):
-        x_enc, d_enc, rgb, sigma, planes, err = ctx.saved_tensors
+        x_enc, d_enc, rgb, sigma, planes, masks, err = ctx.saved_tensors
         dec = ctx.decoder
         if ctx.needs_input_grad[2]:
             raise RuntimeError("tcgen05 NeRFDecoder path does not produce view-direction gradients (use fp32 mode)")
@@ -478,7 +480,7 @@ class _NerfMLP(torch.autograd.Function):
         w_sigma = _c(dec.sigma_layer.weight).view(-1)
         w_rgb = _c(dec.rgb_layer.weight).view(-1)
         flops = 2.0 * Pn * (128 * 256 + 256 * 256 * 8)
-        call("b2n_nerf_mlp_bwd", ptr(packed), ptr(w_sigma), ptr(w_rgb), ptr(planes), ptr(rgb), ptr(sigma.view(-1)),
+        call("b2n_nerf_mlp_bwd", ptr(packed), ptr(w_sigma), ptr(w_rgb), ptr(masks), ptr(rgb), ptr(sigma.view(-1)),
              ptr(_c(g_rgb)), ptr(_c(g_sigma).view(-1)), Pn, ptr(dz), ptr(dz_small), ptr(err), stream(),
              work=(Pn * (2.0 * 5120 + 48), flops))
         # ---- weight / bias gradients: dW = dZ^T In, one plain GEMM per layer over all points

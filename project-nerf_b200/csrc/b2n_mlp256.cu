@@ -205,7 +205,8 @@ struct FwdArgs {
   __nv_bfloat16* save;              // [n_slots][P][256] or nullptr
   int* err;
   // backward only
-  const __nv_bfloat16* fwd_planes;  // [10][P][256] saved by the forward (H0..H7, feat, hv)
+  uint32_t* mask_out;               // fwd (training): [10][P][8] ReLU bit masks of the saved planes (bit c = plane[c] > 0)
+  const uint32_t* mask_in;          // bwd: the same buffer (gates of the data-gradient chain)
   const float* g_rgb; const float* g_sigma;   // [P,3], [P]
   const float* rgb_out; const float* sigma_out;
   float* dz_small;                  // [P,4]: d(pre-sigmoid rgb)[3], d(pre-relu sigma)
@@ -393,18 +394,20 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const __grid_constant__
             row_scalar[t] = __ldg(a.sigma_out + p) > 0.f ? __ldg(a.g_sigma + p) : 0.f;
             if (half == 0) *reinterpret_cast<float4*>(a.dz_small + 4 * p) = make_float4(dzr[0], dzr[1], dzr[2], row_scalar[t]);
           }
-          const __nv_bfloat16* hv = a.fwd_planes + ((size_t)9 * a.P + (valid ? p : 0)) * HID;
+          // gate of the view layer: bits 64*half .. 64*half+63 of the hv plane's mask row
+          uint2 hvm = make_uint2(0u, 0u);
+          if (valid) hvm = __ldcs(reinterpret_cast<const uint2*>(a.mask_in + ((size_t)9 * a.P + p) * 8 + 2 * half));
           __nv_bfloat16* srow = (a.save && valid) ? a.save + ((size_t)0 * a.P + p) * HID : nullptr;
 #pragma unroll 1
           for (int c = 8 * half; c < 8 * half + 8; ++c) {
-            uint4 hraw = valid ? __ldcs(reinterpret_cast<const uint4*>(hv + 8 * c)) : make_uint4(0, 0, 0, 0);
-            const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&hraw);
+            const int cl = c - 8 * half;                                  // 0..7: byte cl of this thread's 64 gate bits
+            const uint32_t hb = ((cl < 4 ? hvm.x : hvm.y) >> (8 * (cl & 3))) & 0xffu;
             float f[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const int col = 8 * c + j;
               const float g = dzr[0] * vec[256 + col] + dzr[1] * vec[256 + 128 + col] + dzr[2] * vec[256 + 256 + col];
-              f[j] = (__bfloat162float(hb[j]) > 0.f) ? g : 0.f;
+              f[j] = ((hb >> j) & 1u) ? g : 0.f;
             }
             const uint4 pk = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
             *reinterpret_cast<uint4*>(act + ((8 * c) >> 6) * KBLK_BYTES + swz(r, ((8 * c) & 63) >> 3)) = pk;
@@ -453,6 +456,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const __grid_constant__
           const int64_t p = pair * 256 + t * 128 + r;
           const bool valid = p < a.P;
           const uint32_t trow = tmem + ((uint32_t)(32 * q) << 16) + t * 256 + c0;
+          // bwd: the ReLU gate of this step = 128 mask bits of the forward plane named in bias_off, fetched before
+          // the wait so that the load overlaps the MMAs
+          const bool gated = BWD && sp.epi != EPI_B_LINEAR;
+          uint4 gate = make_uint4(0u, 0u, 0u, 0u);
+          if (gated && valid)
+            gate = __ldcs(reinterpret_cast<const uint4*>(a.mask_in + ((size_t)sp.bias_off * a.P + p) * 8 + 4 * half));
           long long t0 = clock64();
           if (!mbar_wait(bar_acc + 8 * t, acc_phase[t] & 1, abort_flag, a.err, 4)) goto epi_done;
           long long t1 = clock64();
@@ -463,9 +472,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const __grid_constant__
           const bool relu = sp.epi != EPI_LINEAR;
           __nv_bfloat16* save_row = (a.save && sp.save_slot >= 0 && valid && !(a.use_tma && sp.tma))
                                         ? a.save + ((size_t)sp.save_slot * a.P + p) * HID : nullptr;
-          // bwd: the forward activation whose ReLU gates this gradient (plane index in bias_off)
-          const __nv_bfloat16* mask_row = (BWD && sp.epi != EPI_B_LINEAR)
-                                              ? a.fwd_planes + ((size_t)sp.bias_off * a.P + (valid ? p : 0)) * HID : nullptr;
+          uint32_t mbits[4] = {0u, 0u, 0u, 0u};   // fwd: ReLU bits of this thread's 128 columns; bwd: the gate bits
           if (works) {
             // TMEM reads are the scarce resource of this epilogue (~64 B/cycle/SM): keep one 32-column
             // load in flight while the previous block is converted and stored (double-buffered registers)
@@ -483,6 +490,12 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const __grid_constant__
                 for (int j = 0; j < 32; ++j) {
                   float x = __uint_as_float(v[j]) + vec[colb + j];
                   f[j] = relu ? fmaxf(x, 0.f) : x;
+                }
+                if (a.mask_out) {      // training: 1 bit per activation replaces a 512-byte row read in the backward
+                  uint32_t m = 0u;
+#pragma unroll
+                  for (int j = 0; j < 32; ++j) m |= (f[j] > 0.f ? 1u : 0u) << j;
+                  mbits[cb] = m;
                 }
                 if (sp.epi == EPI_RELU_SIGMA) {
 #pragma unroll
@@ -502,15 +515,11 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const __grid_constant__
 #pragma unroll
                   for (int j = 0; j < 32; ++j) f[j] = fmaf(row_scalar[t], vec[colb + j], f[j]);
                 }
-                if (mask_row) {
+                if (gated) {
+                  const uint32_t m = gate.x * (cb == 0) + gate.y * (cb == 1) + gate.z * (cb == 2) + gate.w * (cb == 3);
 #pragma unroll
-                  for (int c4 = 0; c4 < 4; ++c4) {
-                    uint4 hraw = valid ? __ldcs(reinterpret_cast<const uint4*>(mask_row + colb + 8 * c4)) : make_uint4(0, 0, 0, 0);
-                    const __nv_bfloat16* hb = reinterpret_cast<const __nv_bfloat16*>(&hraw);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                      if (!(__bfloat162float(hb[j]) > 0.f)) f[8 * c4 + j] = 0.f;
-                  }
+                  for (int j = 0; j < 32; ++j)
+                    if (!((m >> j) & 1u)) f[j] = 0.f;
                 }
               }
 #pragma unroll
@@ -524,6 +533,9 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const __grid_constant__
               }
             }
           }
+          if (!BWD && a.mask_out && works && valid && sp.save_slot >= 0)
+            __stcs(reinterpret_cast<uint4*>(a.mask_out + ((size_t)sp.save_slot * a.P + p) * 8 + 4 * half),
+                   make_uint4(mbits[0], mbits[1], mbits[2], mbits[3]));
           if (!BWD) {
             if (sp.epi == EPI_RELU_SIGMA) {
               // the density dot product is split over the two column halves: combine through smem
@@ -710,7 +722,8 @@ extern "C" int b2n_nerf_mlp_pack(const float* const* pts_w, const float* feature
 
 extern "C" int b2n_nerf_mlp_fwd(const float* x_enc, int pos_dim, const float* d_enc, int dir_dim, const void* packed,
                                 const float* bias, const float* w_sigma, const float* w_rgb, const float* head_bias,
-                                int64_t P, float* rgb, float* sigma, void* save, int* err_flag, b2n_stream_t stream) {
+                                int64_t P, float* rgb, float* sigma, void* save, void* relu_masks, int* err_flag,
+                                b2n_stream_t stream) {
   B2N_REQUIRE(P >= 0, "negative size");
   if (P == 0) return B2N_OK;
   B2N_REQUIRE(x_enc && d_enc && packed && bias && w_sigma && w_rgb && head_bias && rgb && sigma && err_flag,
@@ -721,6 +734,8 @@ extern "C" int b2n_nerf_mlp_fwd(const float* x_enc, int pos_dim, const float* d_
   a.packed = (const unsigned char*)packed, a.bias = bias, a.w_sigma = w_sigma, a.w_rgb = w_rgb;
   a.head_bias = head_bias;
   a.P = P, a.rgb = rgb, a.sigma = sigma, a.save = (__nv_bfloat16*)save, a.err = err_flag;
+  B2N_REQUIRE(!save == !relu_masks, "save planes and relu_masks go together");
+  a.mask_out = (uint32_t*)relu_masks;
   build_fwd_plan(&a.plan, pos_dim);
   mark_tma_steps(&a.plan);
   alignas(64) CUtensorMap tmap;
@@ -783,16 +798,16 @@ extern "C" int b2n_nerf_mlp_pack_bwd(const float* const* pts_w, const float* fea
   return check_launch("b2n_nerf_mlp_pack_bwd");
 }
 
-extern "C" int b2n_nerf_mlp_bwd(const void* packed_bwd, const float* w_sigma, const float* w_rgb, const void* fwd_planes,
+extern "C" int b2n_nerf_mlp_bwd(const void* packed_bwd, const float* w_sigma, const float* w_rgb, const void* relu_masks,
                                 const float* rgb, const float* sigma, const float* g_rgb, const float* g_sigma,
                                 int64_t P, void* dz_planes, float* dz_small, int* err_flag, b2n_stream_t stream) {
   B2N_REQUIRE(P >= 0, "negative size");
   if (P == 0) return B2N_OK;
-  B2N_REQUIRE(packed_bwd && w_sigma && w_rgb && fwd_planes && rgb && sigma && g_rgb && g_sigma && dz_planes &&
+  B2N_REQUIRE(packed_bwd && w_sigma && w_rgb && relu_masks && rgb && sigma && g_rgb && g_sigma && dz_planes &&
                   dz_small && err_flag, "null pointer");
   FwdArgs a{};
   a.packed = (const unsigned char*)packed_bwd, a.w_sigma = w_sigma, a.w_rgb = w_rgb;
-  a.fwd_planes = (const __nv_bfloat16*)fwd_planes, a.rgb_out = rgb, a.sigma_out = sigma, a.g_rgb = g_rgb;
+  a.mask_in = (const uint32_t*)relu_masks, a.rgb_out = rgb, a.sigma_out = sigma, a.g_rgb = g_rgb;
   a.g_sigma = g_sigma, a.P = P, a.save = (__nv_bfloat16*)dz_planes, a.dz_small = dz_small, a.err = err_flag;
   build_bwd_plan(&a.plan);
   mark_tma_steps(&a.plan);

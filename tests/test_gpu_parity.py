@@ -536,7 +536,7 @@ def test_nerf_mlp256_tcgen05_forward(mods, Pn):
     rgb_q, sig_q = O.nerf_decoder(sd, "decoder", xe, de, emulate_bf16=True)
     rgb_f, sig_f = O.nerf_decoder(sd, "decoder", xe, de)
     assert ops.nerf_mlp_supported(model.decoder, 63, 27)
-    rgb, sigma, planes, err = ops.nerf_mlp_forward(model.decoder, cu(xe), cu(de), save=True)
+    rgb, sigma, (planes, masks), err = ops.nerf_mlp_forward(model.decoder, cu(xe), cu(de), save=True)
     torch.cuda.synchronize()
     assert int(err.item()) == 0, f"tcgen05 pipeline aborted with code {int(err.item())}"
     assert rel_err(rgb.cpu(), rgb_q) < 3e-3 and rel_err(sigma.cpu(), sig_q) < 3e-3
@@ -545,6 +545,10 @@ def test_nerf_mlp256_tcgen05_forward(mods, Pn):
     h0 = torch.relu(torch.nn.functional.linear(O.bf16_round(xe), O.bf16_round(sd["decoder.pts_layers.0.weight"]),
                                                sd["decoder.pts_layers.0.bias"]))
     assert rel_err(planes[0].float().cpu(), h0) < 1e-2
+    # ReLU bit masks: bit c of row p of slot s == (planes[s][p, c] > 0)
+    bits = ((masks.cpu().view(10, Pn, 8, 1) >> torch.arange(32, dtype=torch.int32)) & 1).reshape(10, Pn, 256).bool()
+    assert torch.equal(bits[:8], planes[:8].float().cpu() > 0)
+    assert torch.equal(bits[9][:, :128], planes[9][:, :128].float().cpu() > 0)
 
 
 def test_nerf_mlp256_tcgen05_backward(mods, bf16_mode):

@@ -53,7 +53,11 @@ __device__ __forceinline__ void dir_features(const float (&d)[3], const float* _
           s = 2.f * ps[j] * pc[j];
           c = 1.f - 2.f * ps[j] * ps[j];
         } else {
-          sincosf(__fmul_rn(__fmul_rn(d[j], fr), 3.14159274101257324f), &s, &c);
+          // view directions are unit vectors and the first band is 1: |arg| <= pi, where the MUFU sin/cos (abs.
+          // error ~1e-6) is far inside the bf16 rounding applied below; larger arguments take the accurate path
+          const float arg = __fmul_rn(__fmul_rn(d[j], fr), 3.14159274101257324f);
+          if (fabsf(arg) <= 3.2f) __sincosf(arg, &s, &c);
+          else sincosf(arg, &s, &c);
         }
         ps[j] = s, pc[j] = c;
         f[3 + 6 * k + j] = s;
@@ -182,7 +186,7 @@ __device__ __forceinline__ void load_all_weights(const float* __restrict__ sp, c
 
 // ------------------------------------------------------------------------------ forward
 template <int POS_K>
-__global__ void __launch_bounds__(MLP_THREADS, 3)
+__global__ void __launch_bounds__(MLP_THREADS, 2)
 k_instant_fwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __restrict__ dirs,
               const float* __restrict__ bands, int L_dir, const float* __restrict__ sp, const float* __restrict__ cp,
               int64_t P, float* __restrict__ rgb, float* __restrict__ sigma) {
@@ -417,6 +421,10 @@ k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
       c_to_a<8, true>(c[0], ah[0]);
       store_a<4>(ah[0], sm + LY::in_h1, LY::SH, row0, 0, lane);
     }
+    // next tile's inputs: ax is dead from here on, so the global loads are issued now and have the whole rest of
+    // the tile to land (ncu: the first use of a prefetch issued only before the wgrad phase was the hottest stall)
+    float2 xraw[KT1][4];
+    load_x_raw<KT1>(x, ldx, pos_dim, (tile + gridDim.x) * 64 + row0, P, xraw, lane);
     float hs0 = 0.f, hs1 = 0.f;  // h[.,0] of rows g and g+8 (threads with t == 0)
     uint32_t ac[1][3][4];
     {
@@ -533,9 +541,6 @@ k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
       }
     }
     __syncthreads();
-    // next tile's inputs: issue the global loads now, they land while the tensor cores do the wgrad
-    float2 xraw[KT1][4];
-    load_x_raw<KT1>(x, ldx, pos_dim, (tile + gridDim.x) * 64 + row0, P, xraw, lane);
     // ---------------- weight gradients over the 64 staged points
     wgrad_tile<POS_K / 8>(acc1, sm + LY::dz1, LY::SH, 16 * warp, sm + LY::in_x, LY::SX, 0, lane);
     wgrad_tile<2>(acc2, sm + LY::dz2, LY::SG, 0, sm + LY::in_h1, LY::SH, 16 * warp, lane);

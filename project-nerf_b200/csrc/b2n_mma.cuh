@@ -45,7 +45,7 @@ template <int MT, int NT, int KT>
 __device__ __forceinline__ void gemm_fwd(float (&c)[MT][NT][4], const uint32_t (&a)[MT][KT][4], const bf16* W, int S,
                                          int lane) {
   // n-tiles per sweep: G*MT independent accumulators in flight (8 when a warp owns a single 16-row slab)
-  constexpr int G = (NT < 4) ? NT : ((MT == 1 && NT % 8 == 0) ? 8 : 4);
+  constexpr int G = (NT < 4) ? NT : ((MT == 1 && NT == 8) ? 8 : 4);
   const bf16* base = W + (lane & 7) * S + 8 * (lane >> 3);
 #pragma unroll
   for (int j0 = 0; j0 < NT; j0 += G) {

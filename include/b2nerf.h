@@ -313,6 +313,11 @@ int b2n_sample_rays(const float* poses, const uint8_t* images_rgba8, const float
 int b2n_debug_gather_bench(const float* table, int64_t n_entries, int blocks, int per_thread, float* sink,
                            b2n_stream_t stream);
 
+/* development probe: D[128x128] = A^T B through tcgen05.mma with MN-major shared-memory operands (A, B: bf16 [64][128],
+ * row = contraction index); lbo / sbo / kadv (bytes) and extra instruction-descriptor bits are arguments */
+int b2n_debug_mnmajor_probe(const void* A, const void* B, float* D, int lbo, int sbo, int kadv, int idesc_extra,
+                            b2n_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,7 @@ SIGNATURES = {
     "b2n_nerf_mlp_fwd": [P, I, P, I, P, P, P, P, P, L, P, P, P, P, P, P],
     "b2n_debug_mlp256_prof": [P],
     "b2n_debug_gather_bench": [P, L, I, I, P, P],
+    "b2n_debug_mnmajor_probe": [P, P, P, I, I, I, I, P],
     "b2n_sample_rays": [P, P, P, P, P, P, L, I, I, I, F, F, P, P, P, P, P],
     "b2n_nerf_mlp_packed_bwd_bytes": [],
     "b2n_nerf_mlp_pack_bwd": [P, P, P, I, I, P, P],

@@ -2,6 +2,7 @@
 // hash-encode kernels to be judged against.  MEASURED_PEAKS.json only has the HBM copy and the
 // bf16 GEMM peaks; a multiresolution hash lookup is neither -- it is 8-byte gathers at random
 // addresses of a table that lives in L2.
+#include <cuda_bf16.h>
 #include "b2n_common.cuh"
 
 namespace b2n {
@@ -24,9 +25,93 @@ __global__ void __launch_bounds__(256) k_gather_bench(const float2* __restrict__
   if (acc == 1.2345e-30f) *sink = acc;  // keep the loads alive
 }
 
+// ---------------------------------------------------------------------------------------------
+// Probe of the MN-major (``transposed'') shared-memory operand form of tcgen05.mma, needed for a tensor-core
+// weight-gradient kernel dW = dZ^T In whose operands are stored point-major ([P][features], the contraction index is
+// the ROW).  D[128 x 128] = sum_k A[k][m] * B[k][n], K = 64: A and B tiles [64 rows (K)][128 (MN)] bf16 are staged as two
+// 64-column blocks of [64 rows x 128 B], each 8-row group 128B-swizzled (the image a TMA box {64 cols, 64 rows} with
+// SWIZZLE_128B would leave).  lbo / sbo / k-advance are arguments so that the encoding can be established empirically.
+__device__ __forceinline__ uint32_t ps32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__global__ void __launch_bounds__(128) k_mnmajor_probe(const __nv_bfloat16* __restrict__ A, const __nv_bfloat16* __restrict__ B,
+                                                       float* __restrict__ D, uint32_t lbo, uint32_t sbo, uint32_t kadv,
+                                                       uint32_t idesc_extra) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* sa = smem;               // 2 blocks x 8 KB
+  unsigned char* sb = smem + 16384;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 32768);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(smem + 32768 + 8);
+  const int warp = threadIdx.x >> 5;
+  // stage: element (k, mn) -> block mn/64, row k, 16-byte chunk c = (mn%64)/8 at ((c ^ (k & 7)) << 4)
+  for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
+    const int k = i >> 4, ch = i & 15;                 // 16 chunks of 8 elements per 128-element row
+    const int blk = ch >> 3, c = ch & 7;
+    const uint4 va = *reinterpret_cast<const uint4*>(A + k * 128 + 8 * ch);
+    const uint4 vb = *reinterpret_cast<const uint4*>(B + k * 128 + 8 * ch);
+    const uint32_t off = blk * 8192 + k * 128 + ((c ^ (k & 7)) << 4);
+    *reinterpret_cast<uint4*>(sa + off) = va;
+    *reinterpret_cast<uint4*>(sb + off) = vb;
+  }
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(ps32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(ps32(slot)), "r"(128));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *slot;
+  if (threadIdx.x == 0) {
+    auto desc = [&](uint32_t saddr) {
+      return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+             ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    };
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24) | idesc_extra;
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t ad = desc(ps32(sa) + k * kadv), bd = desc(ps32(sb) + k * kadv);
+      const uint32_t acc = k > 0;
+      asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                   ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+    }
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(ps32(bar)) : "memory");
+  }
+  // bounded wait
+  uint32_t ok = 0;
+  for (uint32_t it = 0; it < (1u << 20) && !ok; ++it)
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(ps32(bar)) : "memory");
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const int row = threadIdx.x;           // TMEM lane = output row m
+  for (int c0 = 0; c0 < 128; c0 += 8) {
+    uint32_t v[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(tmem + ((uint32_t)(32 * warp) << 16) + c0) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    for (int j = 0; j < 8; ++j) D[row * 128 + c0 + j] = ok ? __uint_as_float(v[j]) : -12345.f;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128));
+}
+
 }  // namespace b2n
 
 using namespace b2n;
+
+// A, B: bf16 [64][128] (row = contraction index); D: fp32 [128][128] = A^T B if the descriptor encoding is right
+extern "C" int b2n_debug_mnmajor_probe(const void* A, const void* B, float* D, int lbo, int sbo, int kadv, int idesc_extra,
+                                       b2n_stream_t stream) {
+  B2N_REQUIRE(A && B && D, "null pointer");
+  cudaFuncSetAttribute(k_mnmajor_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  k_mnmajor_probe<<<1, 128, 200 * 1024, (cudaStream_t)stream>>>((const __nv_bfloat16*)A, (const __nv_bfloat16*)B, D, (uint32_t)lbo,
+                                                         (uint32_t)sbo, (uint32_t)kadv, (uint32_t)idesc_extra);
+  return check_launch("b2n_debug_mnmajor_probe");
+}
 
 // table: float2[n_entries] with n_entries a power of two; launches `blocks` CTAs of 256 threads.
 extern "C" int b2n_debug_gather_bench(const float* table, int64_t n_entries, int blocks, int per_thread, float* sink,

@@ -490,17 +490,26 @@ class _NerfMLP(torch.autograd.Function):
         db = torch.nn.functional.pad(d_enc, (0, 32 - dir_dim)).to(torch.bfloat16)
         H = planes                      # H[0..7] trunk outputs, H[8] feat, H[9][:, :128] hv
         dZ = {l: dz[9 - l] for l in range(8)}     # dZ_l of trunk layer l
-        gb_all = torch.sum(dz, dim=1, dtype=torch.float32)   # [10, 256] column sums
         grads = {}
+        if Pn >= 64:
+            # the eight 256 x 256 weight gradients and all bias column sums: ONE tcgen05 launch over the planes
+            dW = torch.zeros(8, 256, 256, device=dev)
+            gb_all = torch.zeros(10, 256, device=dev)
+            call("b2n_nerf_mlp_wgrad", ptr(dz), ptr(planes), Pn, ptr(dW), ptr(gb_all), ptr(err), stream(),
+                 work=(Pn * 8 * 1024.0 + Pn * 2 * 512.0, 2.0 * Pn * 8 * 65536))
+        else:
+            dW = None
+            gb_all = torch.sum(dz, dim=1, dtype=torch.float32)   # [10, 256] column sums
         for l in range(8):
             if l == 0:
                 gW = _mm_f32(dZ[0], xb)[:, :pos_dim]
             elif l == 4:
-                gW = torch.cat([_mm_f32(dZ[4], H[3]), _mm_f32(dZ[4], xb)[:, :pos_dim]], dim=1)
+                gh = dW[3] if dW is not None else _mm_f32(dZ[4], H[3])
+                gW = torch.cat([gh, _mm_f32(dZ[4], xb)[:, :pos_dim]], dim=1)
             else:
-                gW = _mm_f32(dZ[l], H[l - 1])
+                gW = dW[l - 1] if dW is not None else _mm_f32(dZ[l], H[l - 1])
             grads[f"pts{l}"] = (gW, gb_all[9 - l])
-        grads["feat"] = (_mm_f32(dz[1], H[7]), gb_all[1])
+        grads["feat"] = (dW[7] if dW is not None else _mm_f32(dz[1], H[7]), gb_all[1])
         gv = _mm_f32(dz[0], torch.cat([H[8], db], dim=1))[:128]       # [256(128 used), 256 + 32]
         grads["view"] = (gv[:, :256 + dir_dim], gb_all[0][:128])
         # the two small heads share one GEMM per input plane: rows = (d rgb_pre[3], d sigma_pre) padded to 8

@@ -1,0 +1,261 @@
+// Weight / bias gradients of the 256-wide vanilla NeRF decoder on tcgen05 (autograd of NeRFDecoder.forward,
+// src/decoders.py:68-87, w.r.t. the nn.Linear parameters):
+//     dW_l[256 x 256] = dZ_l^T H_{l-1}   (contraction over all P points),   db_l = column sums of dZ_l
+// for the eight 256 x 256 layers (trunk layers 1..7 and the feature layer) in ONE launch.  dZ_l / H_l are the bf16
+// [P][256] planes written by b2n_nerf_mlp_bwd / b2n_nerf_mlp_fwd, i.e. POINT-major: the contraction index is the row.
+// That is the MN-major operand form of tcgen05.mma: a TMA box {64 columns, 64 points} with
+// SWIZZLE_128B is already a valid operand block, so there is no transpose anywhere.
+//
+// grid = (splits of P, jobs).  A CTA owns one (job, P-slice): it streams 64-point stages (dZ tile 64 x 256 and H tile
+// 64 x 256 = 64 KB, 3-stage TMA/mbarrier ring), issues 8 MMAs per stage (M = 128 per dZ column half, N = 256, K = 16)
+// into a 256 x 256 fp32 accumulator that fills the 512 TMEM columns, and at the end adds it to dW with red.global.
+// The eight warps that drain TMEM at the end spend the main loop summing the columns of the dZ tiles (bias gradients),
+// so the dZ planes are read exactly once.  Jobs without a GEMM (the view-layer and layer-0 planes, whose weight
+// gradients have other shapes) only do the column sums.
+// The work is HBM-bound (115 FLOP/B): 2.15 GB at P = 262 144.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <string.h>
+#include "b2n_common.cuh"
+
+namespace b2n {
+namespace wg256 {
+
+constexpr int TP = 64;                         // points per stage
+constexpr int BLK = TP * 128;                  // one 64-column operand block: 64 rows x 128 B
+constexpr int STAGE_BYTES = 8 * BLK;           // dZ: 4 blocks, H: 4 blocks
+constexpr int N_STAGES = 3;
+constexpr int OFF_BAR = N_STAGES * STAGE_BYTES;
+constexpr int SMEM_BYTES = OFF_BAR + 128;
+constexpr int N_THREADS = 320;                 // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 column sums + drain
+constexpr int MAX_JOBS = 10;
+
+struct Job {
+  int dz_slot, in_slot;     // plane indices; in_slot < 0: column sums only
+  float* dW;                // [256][256] fp32 (row = dZ column = output neuron) or null
+  float* db;                // [256] fp32
+};
+struct Args {
+  Job job[MAX_JOBS];
+  int64_t P;
+  int64_t rows_per_split;   // multiple of TP
+  int* err;
+};
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must not hang the GPU
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* err, int code) {
+  for (uint32_t it = 0; it < (1u << 24); ++it) {
+    if (mbar_try(bar, parity)) return true;
+    if ((it & 1023) == 1023 && *abort_flag) return false;
+  }
+  *abort_flag = 1;
+  atomicCAS(err, 0, code);
+  return false;
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+// MN-major SWIZZLE_128B operand: 64-column blocks BLK bytes apart, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t mn_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((BLK >> 4) & 0x3FFF) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+
+__global__ void __launch_bounds__(N_THREADS, 1)
+k_wgrad256(const Args a, const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_in) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
+  const uint32_t bar_full = s32(bars + 0), bar_empty = s32(bars + 3), bar_done = s32(bars + 6);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(bars + 8);
+  const Job job = a.job[blockIdx.y];
+  const bool gemm = job.in_slot >= 0;
+  const int64_t row_begin = (int64_t)blockIdx.x * a.rows_per_split;
+  int64_t row_end = row_begin + a.rows_per_split;
+  if (row_end > a.P) row_end = a.P;
+  const int n_steps = row_begin < a.P ? (int)((row_end - row_begin + TP - 1) / TP) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < N_STAGES; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * i), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_empty + 8 * i), "r"(gemm ? 9 : 8));
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_done), "r"(1));
+    *abort_flag = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      for (int it = 0; it < n_steps; ++it) {
+        const int st = it % N_STAGES;
+        if (!mbar_wait(bar_empty + 8 * st, ((it / N_STAGES) & 1) ^ 1, abort_flag, a.err, 1)) break;
+        const uint32_t bytes = gemm ? STAGE_BYTES : 4 * BLK;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_full + 8 * st), "r"(bytes) : "memory");
+        const int r0 = (int)(row_begin + (int64_t)it * TP);
+        const uint32_t base = s32(smem + st * STAGE_BYTES);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) tma_load_3d(base + b * BLK, &tm_dz, 64 * b, r0, job.dz_slot, bar_full + 8 * st);
+        if (gemm) {
+#pragma unroll
+          for (int b = 0; b < 4; ++b) tma_load_3d(base + (4 + b) * BLK, &tm_in, 64 * b, r0, job.in_slot, bar_full + 8 * st);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (gemm) {
+      // instruction descriptor: D fp32, A = B = bf16, both MN-major, M = 128, N = 256
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) |
+                             ((uint32_t)(128 >> 4) << 24);
+      for (int it = 0; it < n_steps; ++it) {
+        const int st = it % N_STAGES;
+        if (!mbar_wait(bar_full + 8 * st, (it / N_STAGES) & 1, abort_flag, a.err, 2)) break;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0) {
+          const uint32_t base = s32(smem + st * STAGE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < TP / 16; ++kk) {
+#pragma unroll
+            for (int mh = 0; mh < 2; ++mh) {
+              const uint64_t ad = mn_desc(base + mh * 2 * BLK + kk * 2048);      // dZ columns 128*mh .. +127
+              const uint64_t bd = mn_desc(base + 4 * BLK + kk * 2048);           // H columns 0 .. 255
+              const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
+              asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                           ::"r"(tmem + mh * 256), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+            }
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_empty + 8 * st) : "memory");
+          if (it + 1 == n_steps)
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_done) : "memory");
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ================================ column sums (main loop) + accumulator drain ================================
+    const int c = threadIdx.x - 64;             // 0..255: the dZ column this thread sums
+    float colsum = 0.f;
+    for (int it = 0; it < n_steps; ++it) {
+      const int st = it % N_STAGES;
+      if (!mbar_wait(bar_full + 8 * st, (it / N_STAGES) & 1, abort_flag, a.err, 3)) break;
+      const unsigned char* blk = smem + st * STAGE_BYTES + (c >> 6) * BLK + (c & 7) * 2;
+      const int ch = (c & 63) >> 3;
+      float s = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < TP; ++r)
+        s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(blk + r * 128 + ((ch ^ (r & 7)) << 4)));
+      colsum += s;
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_empty + 8 * st) : "memory");
+    }
+    if (job.db && n_steps > 0) atomicAdd(job.db + c, colsum);
+    if (gemm && n_steps > 0 && mbar_wait(bar_done, 0, abort_flag, a.err, 4)) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int q = warp & 3;                   // TMEM lane quarter this warp may read
+      const int mh = (warp - 2) >> 2;           // which dZ column half (accumulator columns 256*mh ..)
+      const int n = 128 * mh + 32 * q + lane;   // output neuron = dW row
+      float* drow = job.dW + (size_t)n * 256;
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        uint32_t v[32];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+              "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+              "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+              "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+            : "r"(tmem + ((uint32_t)(32 * q) << 16) + 256 * mh + c0) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          atomicAdd(reinterpret_cast<float4*>(drow + c0 + j),
+                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+static bool make_map(CUtensorMap* m, const void* planes, int64_t P, int n_slots) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return false;
+  const cuuint64_t dims[3] = {256, (cuuint64_t)P, (cuuint64_t)n_slots};
+  const cuuint64_t strides[2] = {512, (cuuint64_t)P * 512};
+  const cuuint32_t box[3] = {64, TP, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(planes), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace wg256
+}  // namespace b2n
+
+using namespace b2n;
+using namespace b2n::wg256;
+
+// dz_planes / fwd_planes: bf16 [10][P][256] as written by b2n_nerf_mlp_bwd / b2n_nerf_mlp_fwd.
+// dW: fp32 [8][256][256], ACCUMULATED: dW[l-1] = dZ_l^T H_{l-1} for the trunk layers l = 1..7 (rows = output neurons; for
+// the skip layer 4 these are the first 256 input columns), dW[7] = dZ_feat^T H_7 (feature layer).
+// db: fp32 [10][256], ACCUMULATED: column sums of every dZ plane, indexed by plane slot (0 view, 1 feat, 2..9 = dZ7..dZ0).
+// Returns B2N_EINVAL if P < 64 or the TMA descriptors cannot be built (the caller then uses plain GEMMs).
+extern "C" int b2n_nerf_mlp_wgrad(const void* dz_planes, const void* fwd_planes, int64_t P, float* dW, float* db,
+                                  int* err_flag, b2n_stream_t stream) {
+  B2N_REQUIRE(dz_planes && fwd_planes && dW && db && err_flag, "null pointer");
+  B2N_REQUIRE(P >= TP, "needs at least 64 points");
+  alignas(64) CUtensorMap tm_dz, tm_in;
+  memset(&tm_dz, 0, sizeof(tm_dz));
+  memset(&tm_in, 0, sizeof(tm_in));
+  B2N_REQUIRE(make_map(&tm_dz, dz_planes, P, 10) && make_map(&tm_in, fwd_planes, P, 10), "cuTensorMapEncodeTiled failed");
+  Args a{};
+  int n = 0;
+  for (int l = 1; l <= 7; ++l) a.job[n++] = Job{9 - l, l - 1, dW + (size_t)(l - 1) * 65536, db + (size_t)(9 - l) * 256};
+  a.job[n++] = Job{1, 7, dW + (size_t)7 * 65536, db + 256};
+  a.job[n++] = Job{0, -1, nullptr, db};                    // view-layer plane: bias sums only
+  a.job[n++] = Job{9, -1, nullptr, db + (size_t)9 * 256};  // layer-0 plane: bias sums only
+  a.P = P, a.err = err_flag;
+  int splits = (2 * kSMs) / n;                             // ~2 CTAs' worth of jobs per SM (bias-only CTAs are short)
+  const int64_t max_splits = (P + TP - 1) / TP;
+  if (splits > max_splits) splits = (int)max_splits;
+  if (splits < 1) splits = 1;
+  a.rows_per_split = ((P + splits - 1) / splits + TP - 1) / TP * TP;
+  cudaFuncSetAttribute(k_wgrad256, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  k_wgrad256<<<dim3((unsigned)splits, (unsigned)n), N_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a, tm_dz, tm_in);
+  return check_launch("b2n_nerf_mlp_wgrad");
+}

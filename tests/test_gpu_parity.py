@@ -674,3 +674,27 @@ def test_hash_encode_properties_full_size(mods):
     for l, (_, _, size, offset, _) in enumerate(geom.levels):
         got = t.grad[offset * 2:(offset + size) * 2].view(-1, 2).double().sum(0)
         assert float((got - col[2 * l:2 * l + 2]).abs().max() / col[2 * l:2 * l + 2].abs().max()) < 1e-4, l
+
+
+@pytest.mark.parametrize("Pn", [64, 1000, 64 * 37 + 5, 200000])
+def test_nerf_mlp_wgrad_tcgen05_vs_torch(mods, Pn):
+    """b2n_nerf_mlp_wgrad (tcgen05 with MN-major operands straight from the point-major planes, TMA loads, split over P,
+    fused bias column sums) against fp32 matmuls of the same bf16 planes; ragged P exercises the zero-filled TMA tails."""
+    from b2n._lib import call, ptr, stream
+    torch.manual_seed(8)
+    dz = (torch.randn(10, Pn, 256, device=DEV) * 0.1).to(torch.bfloat16)
+    H = torch.relu(torch.randn(10, Pn, 256, device=DEV)).to(torch.bfloat16)
+    dW = torch.zeros(8, 256, 256, device=DEV)
+    db = torch.zeros(10, 256, device=DEV)
+    err = torch.zeros(1, device=DEV, dtype=torch.int32)
+    call("b2n_nerf_mlp_wgrad", ptr(dz), ptr(H), Pn, ptr(dW), ptr(db), ptr(err), stream())
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    for l in range(1, 8):
+        ref = dz[9 - l].float().t() @ H[l - 1].float()
+        assert rel_err(dW[l - 1], ref) < 2e-5, l
+    assert rel_err(dW[7], dz[1].float().t() @ H[7].float()) < 2e-5
+    assert rel_err(db, dz.float().sum(1)) < 2e-5
+    # accumulation semantics: a second call doubles the result
+    call("b2n_nerf_mlp_wgrad", ptr(dz), ptr(H), Pn, ptr(dW), ptr(db), ptr(err), stream())
+    assert rel_err(dW[0], 2 * (dz[8].float().t() @ H[0].float())) < 2e-5

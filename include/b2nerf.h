@@ -287,14 +287,17 @@ int b2n_nerf_mlp_fwd(const float* x_enc, int pos_dim, const float* d_enc, int di
  * (src/core.py:268-277: the decoder input depends on the trainable deformation). */
 int b2n_nerf_mlp_dx(const void* dz0, const void* dz4, const float* W0, int ldw0, const float* W4x, int ldw4, int pos_dim,
                     int64_t P, float* g_x, int ldg, b2n_stream_t stream);
-/* Weight / bias gradients of the eight 256 x 256 layers of the same decoder on tcgen05 (MN-major operands: the
- * point-major planes are consumed as they lie, TMA-loaded; one launch): dz_planes / fwd_planes = bf16 [10][P][256] of
- * b2n_nerf_mlp_bwd / _fwd.  ACCUMULATES dW fp32 [8][256][256]: dW[l-1] = dZ_l^T H_{l-1} for trunk layers l = 1..7 (for
- * the skip layer 4: its first 256 input columns), dW[7] = dZ_feat^T H_7; and db fp32 [10][256] = column sums of every
- * dZ plane (slot 0 view layer, 1 feature layer, 2..9 = trunk layers 7..0).  P >= 64.  The remaining, differently
- * shaped weight gradients (layer 0, the x part of layer 4, view layer, the two heads) stay plain GEMMs of the caller. */
-int b2n_nerf_mlp_wgrad(const void* dz_planes, const void* fwd_planes, int64_t P, float* dW, float* db, int* err_flag,
-                       b2n_stream_t stream);
+/* Weight / bias gradients of the same decoder on tcgen05 (MN-major operands: the point-major planes are consumed as
+ * they lie, TMA-loaded; one launch).  dz_planes / fwd_planes = bf16 [10][P][256] of b2n_nerf_mlp_bwd / _fwd; x_bf16 = bf16
+ * [P][kx] encoded positions zero-padded to kx = 64 or 128 columns; d_bf16 = bf16 [P][64] encoded directions, zero-padded.
+ * All outputs fp32 and ACCUMULATED: dW [8][256][256]: dW[l-1] = dZ_l^T H_{l-1} for trunk layers l = 1..7 (skip layer 4:
+ * its first 256 input columns), dW[7] = dZ_feat^T H_7; dW0 [256][kx] = dZ_0^T x; dW4x [256][kx] = dZ_4^T x; dWv_h
+ * [128][256] = dZ_view^T H_8; dWv_d [128][64] = dZ_view^T d; db [10][256] = column sums of every dZ plane (slot 0 view
+ * layer, 1 feature layer, 2..9 = trunk layers 7..0).  x_bf16 / d_bf16 and their outputs may be NULL.  P >= 64.  The two
+ * 1- and 3-row heads stay with the caller. */
+int b2n_nerf_mlp_wgrad(const void* dz_planes, const void* fwd_planes, const void* x_bf16, int kx, const void* d_bf16,
+                       int64_t P, float* dW, float* dW0, float* dW4x, float* dWv_h, float* dWv_d, float* db,
+                       int* err_flag, b2n_stream_t stream);
 /* debug aid: per-role cycle counters of CTA 0 of the next b2n_nerf_mlp_* launches (device int64[8], or NULL) */
 int b2n_debug_mlp256_prof(void* device_int64x8);
 size_t b2n_nerf_mlp_packed_bwd_bytes(void);

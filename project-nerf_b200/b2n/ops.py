@@ -483,35 +483,47 @@ class _NerfMLP(torch.autograd.Function):
         call("b2n_nerf_mlp_bwd", ptr(packed), ptr(w_sigma), ptr(w_rgb), ptr(masks), ptr(rgb), ptr(sigma.view(-1)),
              ptr(_c(g_rgb)), ptr(_c(g_sigma).view(-1)), Pn, ptr(dz), ptr(dz_small), ptr(err), stream(),
              work=(Pn * (2.0 * 5120 + 48), flops))
-        # ---- weight / bias gradients: dW = dZ^T In, one plain GEMM per layer over all points
-        # layer inputs in bf16, zero-padded to 64 / 32 columns: aligned shapes keep cuBLAS on its fast kernels
+        # ---- weight / bias gradients: dW = dZ^T In over all points
+        # layer inputs in bf16; x / d zero-padded to 64-column multiples (the operand blocks of the tcgen05 kernel)
         kx = 64 if pos_dim <= 64 else 128
         xb = torch.nn.functional.pad(x_enc, (0, kx - pos_dim)).to(torch.bfloat16)
-        db = torch.nn.functional.pad(d_enc, (0, 32 - dir_dim)).to(torch.bfloat16)
+        db = torch.nn.functional.pad(d_enc, (0, 64 - dir_dim)).to(torch.bfloat16)
         H = planes                      # H[0..7] trunk outputs, H[8] feat, H[9][:, :128] hv
         dZ = {l: dz[9 - l] for l in range(8)}     # dZ_l of trunk layer l
         grads = {}
         if Pn >= 64:
-            # the eight 256 x 256 weight gradients and all bias column sums: ONE tcgen05 launch over the planes
-            dW = torch.zeros(8, 256, 256, device=dev)
-            gb_all = torch.zeros(10, 256, device=dev)
-            call("b2n_nerf_mlp_wgrad", ptr(dz), ptr(planes), Pn, ptr(dW), ptr(gb_all), ptr(err), stream(),
-                 work=(Pn * 8 * 1024.0 + Pn * 2 * 512.0, 2.0 * Pn * 8 * 65536))
+            # every layer's weight gradient (but the two 1- / 3-row heads) and all bias column sums: ONE tcgen05 launch
+            sizes = [8 * 65536, 256 * kx, 256 * kx, 128 * 256, 128 * 64, 10 * 256]
+            flat = torch.zeros(sum(sizes), device=dev)
+            dW, dW0, dW4x, dWv_h, dWv_d, gb_all = [t.view(*shape) for t, shape in zip(
+                torch.split(flat, sizes), [(8, 256, 256), (256, kx), (256, kx), (128, 256), (128, 64), (10, 256)])]
+            call("b2n_nerf_mlp_wgrad", ptr(dz), ptr(planes), ptr(xb), kx, ptr(db), Pn, ptr(dW), ptr(dW0), ptr(dW4x),
+                 ptr(dWv_h), ptr(dWv_d), ptr(gb_all), ptr(err), stream(),
+                 work=(Pn * (8 * 1024.0 + 2 * (512 + 2 * kx) + 256 + 512 + 128),
+                       2.0 * Pn * (8 * 65536 + 2 * 256 * kx + 128 * 256 + 128 * 64)))
+            for l in range(8):
+                if l == 0:
+                    gW = dW0[:, :pos_dim]
+                elif l == 4:
+                    gW = torch.cat([dW[3], dW4x[:, :pos_dim]], dim=1)
+                else:
+                    gW = dW[l - 1]
+                grads[f"pts{l}"] = (gW, gb_all[9 - l])
+            grads["feat"] = (dW[7], gb_all[1])
+            grads["view"] = (torch.cat([dWv_h, dWv_d[:, :dir_dim]], dim=1), gb_all[0][:128])
         else:
-            dW = None
             gb_all = torch.sum(dz, dim=1, dtype=torch.float32)   # [10, 256] column sums
-        for l in range(8):
-            if l == 0:
-                gW = _mm_f32(dZ[0], xb)[:, :pos_dim]
-            elif l == 4:
-                gh = dW[3] if dW is not None else _mm_f32(dZ[4], H[3])
-                gW = torch.cat([gh, _mm_f32(dZ[4], xb)[:, :pos_dim]], dim=1)
-            else:
-                gW = dW[l - 1] if dW is not None else _mm_f32(dZ[l], H[l - 1])
-            grads[f"pts{l}"] = (gW, gb_all[9 - l])
-        grads["feat"] = (dW[7] if dW is not None else _mm_f32(dz[1], H[7]), gb_all[1])
-        gv = _mm_f32(dz[0], torch.cat([H[8], db], dim=1))[:128]       # [256(128 used), 256 + 32]
-        grads["view"] = (gv[:, :256 + dir_dim], gb_all[0][:128])
+            for l in range(8):
+                if l == 0:
+                    gW = _mm_f32(dZ[0], xb)[:, :pos_dim]
+                elif l == 4:
+                    gW = torch.cat([_mm_f32(dZ[4], H[3]), _mm_f32(dZ[4], xb)[:, :pos_dim]], dim=1)
+                else:
+                    gW = _mm_f32(dZ[l], H[l - 1])
+                grads[f"pts{l}"] = (gW, gb_all[9 - l])
+            grads["feat"] = (_mm_f32(dz[1], H[7]), gb_all[1])
+            gv = _mm_f32(dz[0], torch.cat([H[8], db], dim=1))[:128]       # [256(128 used), 256 + 64]
+            grads["view"] = (gv[:, :256 + dir_dim], gb_all[0][:128])
         # the two small heads share one GEMM per input plane: rows = (d rgb_pre[3], d sigma_pre) padded to 8
         dzs16 = torch.nn.functional.pad(dz_small, (0, 4)).to(torch.bfloat16)      # [P, 8]
         gs = _mm_f32(dzs16, H[7])                                                    # [8, 256]

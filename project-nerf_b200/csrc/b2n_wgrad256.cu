@@ -28,12 +28,16 @@ constexpr int N_STAGES = 3;
 constexpr int OFF_BAR = N_STAGES * STAGE_BYTES;
 constexpr int SMEM_BYTES = OFF_BAR + 128;
 constexpr int N_THREADS = 320;                 // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 column sums + drain
-constexpr int MAX_JOBS = 10;
+constexpr int MAX_JOBS = 12;
 
 struct Job {
-  int dz_slot, in_slot;     // plane indices; in_slot < 0: column sums only
-  float* dW;                // [256][256] fp32 (row = dZ column = output neuron) or null
-  float* db;                // [256] fp32
+  int dz_slot;              // dZ plane
+  int in_kind;              // 0: forward plane in_slot, 1: encoded positions x, 2: encoded directions d, -1: column sums only
+  int in_slot;
+  int m_halves;             // 2: all 256 dZ columns, 1: the first 128 (view layer)
+  int n_cols;               // width of the input operand: 64, 128 or 256
+  float* dW;                // [128 * m_halves][n_cols] fp32 (row = dZ column = output neuron) or null
+  float* db;                // [256] fp32 or null (column sums of the dZ plane: once per plane)
 };
 struct Args {
   Job job[MAX_JOBS];
@@ -70,7 +74,8 @@ __device__ __forceinline__ uint64_t mn_desc(uint32_t saddr) {
 }
 
 __global__ void __launch_bounds__(N_THREADS, 1)
-k_wgrad256(const Args a, const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_in) {
+k_wgrad256(const Args a, const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_in,
+           const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_d) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -78,7 +83,8 @@ k_wgrad256(const Args a, const __grid_constant__ CUtensorMap tm_dz, const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(bars + 8);
   const Job job = a.job[blockIdx.y];
-  const bool gemm = job.in_slot >= 0;
+  const bool gemm = job.in_kind >= 0;
+  const int dz_blocks = 2 * job.m_halves, in_blocks = gemm ? job.n_cols >> 6 : 0;
   const int64_t row_begin = (int64_t)blockIdx.x * a.rows_per_split;
   int64_t row_end = row_begin + a.rows_per_split;
   if (row_end > a.P) row_end = a.P;
@@ -108,23 +114,20 @@ k_wgrad256(const Args a, const __grid_constant__ CUtensorMap tm_dz, const __grid
       for (int it = 0; it < n_steps; ++it) {
         const int st = it % N_STAGES;
         if (!mbar_wait(bar_empty + 8 * st, ((it / N_STAGES) & 1) ^ 1, abort_flag, a.err, 1)) break;
-        const uint32_t bytes = gemm ? STAGE_BYTES : 4 * BLK;
+        const uint32_t bytes = (uint32_t)(dz_blocks + in_blocks) * BLK;
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_full + 8 * st), "r"(bytes) : "memory");
         const int r0 = (int)(row_begin + (int64_t)it * TP);
         const uint32_t base = s32(smem + st * STAGE_BYTES);
-#pragma unroll
-        for (int b = 0; b < 4; ++b) tma_load_3d(base + b * BLK, &tm_dz, 64 * b, r0, job.dz_slot, bar_full + 8 * st);
-        if (gemm) {
-#pragma unroll
-          for (int b = 0; b < 4; ++b) tma_load_3d(base + (4 + b) * BLK, &tm_in, 64 * b, r0, job.in_slot, bar_full + 8 * st);
-        }
+        for (int b = 0; b < dz_blocks; ++b) tma_load_3d(base + b * BLK, &tm_dz, 64 * b, r0, job.dz_slot, bar_full + 8 * st);
+        const CUtensorMap* tin = job.in_kind == 0 ? &tm_in : (job.in_kind == 1 ? &tm_x : &tm_d);
+        for (int b = 0; b < in_blocks; ++b) tma_load_3d(base + (4 + b) * BLK, tin, 64 * b, r0, job.in_slot, bar_full + 8 * st);
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     if (gemm) {
-      // instruction descriptor: D fp32, A = B = bf16, both MN-major, M = 128, N = 256
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(256 >> 3) << 17) |
+      // instruction descriptor: D fp32, A = B = bf16, both MN-major, M = 128, N = n_cols
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(job.n_cols >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
       for (int it = 0; it < n_steps; ++it) {
         const int st = it % N_STAGES;
@@ -134,10 +137,9 @@ k_wgrad256(const Args a, const __grid_constant__ CUtensorMap tm_dz, const __grid
           const uint32_t base = s32(smem + st * STAGE_BYTES);
 #pragma unroll
           for (int kk = 0; kk < TP / 16; ++kk) {
-#pragma unroll
-            for (int mh = 0; mh < 2; ++mh) {
+            for (int mh = 0; mh < job.m_halves; ++mh) {
               const uint64_t ad = mn_desc(base + mh * 2 * BLK + kk * 2048);      // dZ columns 128*mh .. +127
-              const uint64_t bd = mn_desc(base + 4 * BLK + kk * 2048);           // H columns 0 .. 255
+              const uint64_t bd = mn_desc(base + 4 * BLK + kk * 2048);           // input columns 0 .. n_cols-1
               const uint32_t acc = (it > 0 || kk > 0) ? 1u : 0u;
               asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
                            ::"r"(tmem + mh * 256), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
@@ -157,24 +159,26 @@ k_wgrad256(const Args a, const __grid_constant__ CUtensorMap tm_dz, const __grid
     for (int it = 0; it < n_steps; ++it) {
       const int st = it % N_STAGES;
       if (!mbar_wait(bar_full + 8 * st, (it / N_STAGES) & 1, abort_flag, a.err, 3)) break;
-      const unsigned char* blk = smem + st * STAGE_BYTES + (c >> 6) * BLK + (c & 7) * 2;
-      const int ch = (c & 63) >> 3;
-      float s = 0.f;
+      if (job.db && c < 128 * job.m_halves) {
+        const unsigned char* blk = smem + st * STAGE_BYTES + (c >> 6) * BLK + (c & 7) * 2;
+        const int ch = (c & 63) >> 3;
+        float s = 0.f;
 #pragma unroll 8
-      for (int r = 0; r < TP; ++r)
-        s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(blk + r * 128 + ((ch ^ (r & 7)) << 4)));
-      colsum += s;
+        for (int r = 0; r < TP; ++r)
+          s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(blk + r * 128 + ((ch ^ (r & 7)) << 4)));
+        colsum += s;
+      }
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_empty + 8 * st) : "memory");
     }
-    if (job.db && n_steps > 0) atomicAdd(job.db + c, colsum);
+    if (job.db && n_steps > 0 && c < 128 * job.m_halves) atomicAdd(job.db + c, colsum);
     if (gemm && n_steps > 0 && mbar_wait(bar_done, 0, abort_flag, a.err, 4)) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int q = warp & 3;                   // TMEM lane quarter this warp may read
       const int mh = (warp - 2) >> 2;           // which dZ column half (accumulator columns 256*mh ..)
       const int n = 128 * mh + 32 * q + lane;   // output neuron = dW row
-      float* drow = job.dW + (size_t)n * 256;
-      for (int c0 = 0; c0 < 256; c0 += 32) {
+      float* drow = job.dW + (size_t)n * job.n_cols;
+      for (int c0 = 0; mh < job.m_halves && c0 < job.n_cols; c0 += 32) {
         uint32_t v[32];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -212,11 +216,11 @@ static EncodeTiledFn encode_tiled_fn() {
   }();
   return fn;
 }
-static bool make_map(CUtensorMap* m, const void* planes, int64_t P, int n_slots) {
+static bool make_map(CUtensorMap* m, const void* planes, int64_t P, int n_slots, int width = 256) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return false;
-  const cuuint64_t dims[3] = {256, (cuuint64_t)P, (cuuint64_t)n_slots};
-  const cuuint64_t strides[2] = {512, (cuuint64_t)P * 512};
+  const cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)P, (cuuint64_t)n_slots};
+  const cuuint64_t strides[2] = {(cuuint64_t)width * 2, (cuuint64_t)P * width * 2};
   const cuuint32_t box[3] = {64, TP, 1};
   const cuuint32_t estr[3] = {1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(planes), dims, strides, box, estr,
@@ -230,32 +234,50 @@ static bool make_map(CUtensorMap* m, const void* planes, int64_t P, int n_slots)
 using namespace b2n;
 using namespace b2n::wg256;
 
-// dz_planes / fwd_planes: bf16 [10][P][256] as written by b2n_nerf_mlp_bwd / b2n_nerf_mlp_fwd.
-// dW: fp32 [8][256][256], ACCUMULATED: dW[l-1] = dZ_l^T H_{l-1} for the trunk layers l = 1..7 (rows = output neurons; for
-// the skip layer 4 these are the first 256 input columns), dW[7] = dZ_feat^T H_7 (feature layer).
-// db: fp32 [10][256], ACCUMULATED: column sums of every dZ plane, indexed by plane slot (0 view, 1 feat, 2..9 = dZ7..dZ0).
-// Returns B2N_EINVAL if P < 64 or the TMA descriptors cannot be built (the caller then uses plain GEMMs).
-extern "C" int b2n_nerf_mlp_wgrad(const void* dz_planes, const void* fwd_planes, int64_t P, float* dW, float* db,
-                                  int* err_flag, b2n_stream_t stream) {
+// dz_planes / fwd_planes: bf16 [10][P][256] as written by b2n_nerf_mlp_bwd / b2n_nerf_mlp_fwd; x_bf16: bf16 [P][kx]
+// (encoded positions zero-padded to kx = 64 or 128 columns), d_bf16: bf16 [P][64] (encoded directions, zero-padded).
+// All outputs fp32 and ACCUMULATED (zero them first):
+//   dW    [8][256][256]  dW[l-1] = dZ_l^T H_{l-1} for trunk layers l = 1..7 (skip layer 4: its first 256 input columns),
+//                        dW[7] = dZ_feat^T H_7 (feature layer)
+//   dW0   [256][kx]      dZ_0^T x           dW4x [256][kx]   dZ_4^T x  (x part of the skip layer)
+//   dWv_h [128][256]     dZ_view^T H_8      dWv_d [128][64]  dZ_view^T d
+//   db    [10][256]      column sums of every dZ plane by slot (0 view, 1 feature, 2..9 = trunk layers 7..0)
+// x_bf16 / d_bf16 (and their outputs) may be NULL: those products are then left to the caller.
+extern "C" int b2n_nerf_mlp_wgrad(const void* dz_planes, const void* fwd_planes, const void* x_bf16, int kx,
+                                  const void* d_bf16, int64_t P, float* dW, float* dW0, float* dW4x, float* dWv_h,
+                                  float* dWv_d, float* db, int* err_flag, b2n_stream_t stream) {
   B2N_REQUIRE(dz_planes && fwd_planes && dW && db && err_flag, "null pointer");
   B2N_REQUIRE(P >= TP, "needs at least 64 points");
-  alignas(64) CUtensorMap tm_dz, tm_in;
-  memset(&tm_dz, 0, sizeof(tm_dz));
-  memset(&tm_in, 0, sizeof(tm_in));
+  B2N_REQUIRE(!x_bf16 || ((kx == 64 || kx == 128) && dW0 && dW4x), "x operand: kx must be 64 or 128, outputs required");
+  B2N_REQUIRE(!d_bf16 || (dWv_h && dWv_d), "d operand: outputs required");
+  alignas(64) CUtensorMap tm_dz, tm_in, tm_x, tm_d;
+  memset(&tm_dz, 0, sizeof(tm_dz)), memset(&tm_in, 0, sizeof(tm_in)), memset(&tm_x, 0, sizeof(tm_x)), memset(&tm_d, 0, sizeof(tm_d));
   B2N_REQUIRE(make_map(&tm_dz, dz_planes, P, 10) && make_map(&tm_in, fwd_planes, P, 10), "cuTensorMapEncodeTiled failed");
+  B2N_REQUIRE(!x_bf16 || make_map(&tm_x, x_bf16, P, 1, kx), "cuTensorMapEncodeTiled failed (x)");
+  B2N_REQUIRE(!d_bf16 || make_map(&tm_d, d_bf16, P, 1, 64), "cuTensorMapEncodeTiled failed (d)");
   Args a{};
   int n = 0;
-  for (int l = 1; l <= 7; ++l) a.job[n++] = Job{9 - l, l - 1, dW + (size_t)(l - 1) * 65536, db + (size_t)(9 - l) * 256};
-  a.job[n++] = Job{1, 7, dW + (size_t)7 * 65536, db + 256};
-  a.job[n++] = Job{0, -1, nullptr, db};                    // view-layer plane: bias sums only
-  a.job[n++] = Job{9, -1, nullptr, db + (size_t)9 * 256};  // layer-0 plane: bias sums only
+  for (int l = 1; l <= 7; ++l) a.job[n++] = Job{9 - l, 0, l - 1, 2, 256, dW + (size_t)(l - 1) * 65536, db + (size_t)(9 - l) * 256};
+  a.job[n++] = Job{1, 0, 7, 2, 256, dW + (size_t)7 * 65536, db + 256};
+  if (x_bf16) {
+    a.job[n++] = Job{9, 1, 0, 2, kx, dW0, db + (size_t)9 * 256};
+    a.job[n++] = Job{5, 1, 0, 2, kx, dW4x, nullptr};
+  } else {
+    a.job[n++] = Job{9, -1, 0, 2, 256, nullptr, db + (size_t)9 * 256};     // layer-0 plane: bias sums only
+  }
+  if (d_bf16) {
+    a.job[n++] = Job{0, 0, 8, 1, 256, dWv_h, db};
+    a.job[n++] = Job{0, 2, 0, 1, 64, dWv_d, nullptr};
+  } else {
+    a.job[n++] = Job{0, -1, 0, 1, 256, nullptr, db};                       // view-layer plane: bias sums only
+  }
   a.P = P, a.err = err_flag;
-  int splits = (2 * kSMs) / n;                             // ~2 CTAs' worth of jobs per SM (bias-only CTAs are short)
+  int splits = (2 * kSMs) / n;                             // ~2 CTAs' worth of jobs per SM (the narrow jobs are short)
   const int64_t max_splits = (P + TP - 1) / TP;
   if (splits > max_splits) splits = (int)max_splits;
   if (splits < 1) splits = 1;
   a.rows_per_split = ((P + splits - 1) / splits + TP - 1) / TP * TP;
   cudaFuncSetAttribute(k_wgrad256, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  k_wgrad256<<<dim3((unsigned)splits, (unsigned)n), N_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a, tm_dz, tm_in);
+  k_wgrad256<<<dim3((unsigned)splits, (unsigned)n), N_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a, tm_dz, tm_in, tm_x, tm_d);
   return check_launch("b2n_nerf_mlp_wgrad");
 }

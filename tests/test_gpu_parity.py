@@ -676,25 +676,35 @@ def test_hash_encode_properties_full_size(mods):
         assert float((got - col[2 * l:2 * l + 2]).abs().max() / col[2 * l:2 * l + 2].abs().max()) < 1e-4, l
 
 
-@pytest.mark.parametrize("Pn", [64, 1000, 64 * 37 + 5, 200000])
-def test_nerf_mlp_wgrad_tcgen05_vs_torch(mods, Pn):
+@pytest.mark.parametrize("Pn,kx", [(64, 64), (1000, 128), (64 * 37 + 5, 64), (200000, 64)])
+def test_nerf_mlp_wgrad_tcgen05_vs_torch(mods, Pn, kx):
     """b2n_nerf_mlp_wgrad (tcgen05 with MN-major operands straight from the point-major planes, TMA loads, split over P,
     fused bias column sums) against fp32 matmuls of the same bf16 planes; ragged P exercises the zero-filled TMA tails."""
     from b2n._lib import call, ptr, stream
     torch.manual_seed(8)
     dz = (torch.randn(10, Pn, 256, device=DEV) * 0.1).to(torch.bfloat16)
     H = torch.relu(torch.randn(10, Pn, 256, device=DEV)).to(torch.bfloat16)
+    xb = torch.randn(Pn, kx, device=DEV).to(torch.bfloat16)
+    db = torch.randn(Pn, 64, device=DEV).to(torch.bfloat16)
     dW = torch.zeros(8, 256, 256, device=DEV)
-    db = torch.zeros(10, 256, device=DEV)
+    dW0, dW4x = torch.zeros(256, kx, device=DEV), torch.zeros(256, kx, device=DEV)
+    dWv_h, dWv_d = torch.zeros(128, 256, device=DEV), torch.zeros(128, 64, device=DEV)
+    gb = torch.zeros(10, 256, device=DEV)
     err = torch.zeros(1, device=DEV, dtype=torch.int32)
-    call("b2n_nerf_mlp_wgrad", ptr(dz), ptr(H), Pn, ptr(dW), ptr(db), ptr(err), stream())
+    args = (ptr(dz), ptr(H), ptr(xb), kx, ptr(db), Pn, ptr(dW), ptr(dW0), ptr(dW4x), ptr(dWv_h), ptr(dWv_d), ptr(gb), ptr(err),
+            stream())
+    call("b2n_nerf_mlp_wgrad", *args)
     torch.cuda.synchronize()
     assert int(err.item()) == 0
     for l in range(1, 8):
-        ref = dz[9 - l].float().t() @ H[l - 1].float()
-        assert rel_err(dW[l - 1], ref) < 2e-5, l
+        assert rel_err(dW[l - 1], dz[9 - l].float().t() @ H[l - 1].float()) < 2e-5, l
     assert rel_err(dW[7], dz[1].float().t() @ H[7].float()) < 2e-5
-    assert rel_err(db, dz.float().sum(1)) < 2e-5
+    assert rel_err(dW0, dz[9].float().t() @ xb.float()) < 2e-5
+    assert rel_err(dW4x, dz[5].float().t() @ xb.float()) < 2e-5
+    assert rel_err(dWv_h, dz[0][:, :128].float().t() @ H[8].float()) < 2e-5
+    assert rel_err(dWv_d, dz[0][:, :128].float().t() @ db.float()) < 2e-5
+    ref_b = dz.float().sum(1)
+    assert rel_err(gb[1:], ref_b[1:]) < 2e-5 and rel_err(gb[0, :128], ref_b[0, :128]) < 2e-5
     # accumulation semantics: a second call doubles the result
-    call("b2n_nerf_mlp_wgrad", ptr(dz), ptr(H), Pn, ptr(dW), ptr(db), ptr(err), stream())
+    call("b2n_nerf_mlp_wgrad", *args)
     assert rel_err(dW[0], 2 * (dz[8].float().t() @ H[0].float())) < 2e-5

@@ -244,6 +244,14 @@ int b2n_fmlp_fwd(const float* x0, int ld0, int d0, const float* x1, int ld1, int
 int b2n_fmlp_wgrad(int n_layers, const void* const* dz, const int* ldz, const int* rows, const void* const* in,
                    const int* ldi, const int* k, float* const* dW, const int* lddw, const int* rows_valid,
                    const int* k_valid, float* const* db, int64_t P, b2n_stream_t stream);
+/* The same gradients for hidden = 128 through the tcgen05 plane-GEMM kernel of b2n_nerf_mlp_wgrad (TMA-loaded planes,
+ * MN-major operands, HBM-bound): dz_h bf16 [n_hidden][P][128], dz_out bf16 [P][out_pad], h_planes bf16 [n_hidden][P][128],
+ * xin bf16 [P][in_pad].  ACCUMULATES fp32: dW0 [128][128] = dZ_0^T xin (columns >= in_pad stay 0), dWh
+ * [n_hidden-1][128][128] = dZ_l^T H_{l-1}, dWoT [128][64] = H_last^T dZ_out (the TRANSPOSED output-layer gradient),
+ * db_h [n_hidden][128] = column sums of the hidden dZ planes.  P >= 64. */
+int b2n_fmlp_wgrad_tc(const void* dz_h, const void* dz_out, const void* h_planes, const void* xin, int64_t P, int n_hidden,
+                      int in_pad, int out_pad, float* dW0, float* dWh, float* dWoT, float* db_h, int* err_flag,
+                      b2n_stream_t stream);
 int b2n_fmlp_bwd(int d0, int d1, int hidden, int n_hidden, const float* const* W, const int* ldw, int out_dim,
                  int out_act, int64_t P, const float* y, int ldy, const float* g_y, int ldgy, const void* h_planes,
                  void* dz_out, void* dz_h, float* g_x0, int ldg0, float* g_x1, int ldg1, b2n_stream_t stream);

@@ -49,6 +49,7 @@ SIGNATURES = {
     "b2n_fmlp_out_pad": [I],
     "b2n_fmlp_fwd": [P, I, I, P, I, I, I, I, P, P, P, I, I, L, P, I, P, P, P],
     "b2n_fmlp_bwd": [I, I, I, I, P, P, I, I, L, P, I, P, I, P, P, P, P, I, P, I, P],
+    "b2n_fmlp_wgrad_tc": [P, P, P, P, L, I, I, I, P, P, P, P, P, P],
     "b2n_fmlp_wgrad": [I, P, P, P, P, P, P, P, P, P, P, P, L, P],
     "b2n_nerf_mlp_wgrad": [P, P, P, I, P, L, P, P, P, P, P, P, P, P],
     "b2n_nerf_mlp_dx": [P, P, P, I, P, I, I, L, P, I, P],

@@ -621,25 +621,39 @@ class _FusedMLP(torch.autograd.Function):
         call("b2n_fmlp_bwd", d0, d1, hidden, n_hidden, Wp, ld, out_dim, out_act, Pn, ptr(y), out_dim, ptr(g_y), out_dim,
              ptr(hpl), ptr(dz_out), ptr(dz_h), ptr(g_x0), d0, ptr(g_x1), d1, stream(),
              work=(Pn * (4.0 * out_dim + 4.0 * n_hidden * hidden + 2.0 * out_pad + 4.0 * (d0 + d1)), 2.0 * Pn * macs))
-        # ---- weight / bias gradients of every layer: one launch (b2n_fmlp_wgrad), fp32 accumulation
         shapes = [(Ws[l].shape[0], Ws[l].shape[1]) for l in range(n_layers)]
-        n_w = sum(r * c for r, c in shapes)
-        flat = torch.zeros(n_w + sum(r for r, _ in shapes), device=dev)
-        gW, gb, off, boff = [], [], 0, n_w
-        for r, c in shapes:
-            gW.append(flat[off:off + r * c].view(r, c))
-            gb.append(flat[boff:boff + r])
-            off, boff = off + r * c, boff + r
-        dzs = [dz_h[l] for l in range(n_hidden)] + [dz_out]
-        ins = [xin] + [hpl[l] for l in range(n_hidden)]
-        arr_p, arr_i = ctypes.c_void_p * n_layers, ctypes.c_int * n_layers
-        call("b2n_fmlp_wgrad", n_layers, arr_p(*[t.data_ptr() for t in dzs]), arr_i(*[t.stride(0) for t in dzs]),
-             arr_i(*[t.shape[1] for t in dzs]), arr_p(*[t.data_ptr() for t in ins]), arr_i(*[t.stride(0) for t in ins]),
-             arr_i(*[t.shape[1] for t in ins]), arr_p(*[g.data_ptr() for g in gW]), arr_i(*[c for _, c in shapes]),
-             arr_i(*[r for r, _ in shapes]), arr_i(*[min(c, t.shape[1]) for (_, c), t in zip(shapes, ins)]),
-             arr_p(*[(gb[l].data_ptr() if has_b[l] else None) for l in range(n_layers)]), Pn, stream(),
-             work=(2.0 * Pn * sum(a_.shape[1] + b_.shape[1] for a_, b_ in zip(dzs, ins)),
-                   2.0 * Pn * sum(r * c for r, c in shapes)))
+        in_pad = xin.shape[1]
+        if hidden == 128 and Pn >= 64:
+            # ---- hidden width 128 (DeformationNetwork): tcgen05 plane GEMMs, TMA-fed, HBM-bound (b2n_fmlp_wgrad_tc)
+            sizes = [128 * 128, max(n_hidden - 1, 1) * 128 * 128, 128 * 64, n_hidden * 128]
+            flat = torch.zeros(sum(sizes) + 1, device=dev)
+            dW0, dWh, dWoT, db_h = [t.view(*shape) for t, shape in zip(
+                torch.split(flat[:-1], sizes), [(128, 128), (max(n_hidden - 1, 1), 128, 128), (128, 64), (n_hidden, 128)])]
+            err = flat[-1:].view(torch.int32)
+            call("b2n_fmlp_wgrad_tc", ptr(dz_h), ptr(dz_out), ptr(hpl), ptr(xin), Pn, n_hidden, in_pad, out_pad, ptr(dW0),
+                 ptr(dWh), ptr(dWoT), ptr(db_h), ptr(err), stream(),
+                 work=(2.0 * Pn * ((2 * n_hidden) * 128 + in_pad + out_pad), 2.0 * Pn * (128 * in_pad + (n_hidden - 1) * 16384 + 128 * out_pad)))
+            gW = [dW0[:, : shapes[0][1]]] + [dWh[l - 1] for l in range(1, n_hidden)] + [dWoT[:, : shapes[-1][0]].t()]
+            gb = [db_h[l] for l in range(n_hidden)] + [torch.sum(dz_out, dim=0, dtype=torch.float32)[: shapes[-1][0]]]
+        else:
+            # ---- weight / bias gradients of every layer: one launch (b2n_fmlp_wgrad, mma.sync), fp32 accumulation
+            n_w = sum(r * c for r, c in shapes)
+            flat = torch.zeros(n_w + sum(r for r, _ in shapes), device=dev)
+            gW, gb, off, boff = [], [], 0, n_w
+            for r, c in shapes:
+                gW.append(flat[off:off + r * c].view(r, c))
+                gb.append(flat[boff:boff + r])
+                off, boff = off + r * c, boff + r
+            dzs = [dz_h[l] for l in range(n_hidden)] + [dz_out]
+            ins = [xin] + [hpl[l] for l in range(n_hidden)]
+            arr_p, arr_i = ctypes.c_void_p * n_layers, ctypes.c_int * n_layers
+            call("b2n_fmlp_wgrad", n_layers, arr_p(*[t.data_ptr() for t in dzs]), arr_i(*[t.stride(0) for t in dzs]),
+                 arr_i(*[t.shape[1] for t in dzs]), arr_p(*[t.data_ptr() for t in ins]), arr_i(*[t.stride(0) for t in ins]),
+                 arr_i(*[t.shape[1] for t in ins]), arr_p(*[g.data_ptr() for g in gW]), arr_i(*[c for _, c in shapes]),
+                 arr_i(*[r for r, _ in shapes]), arr_i(*[min(c, t.shape[1]) for (_, c), t in zip(shapes, ins)]),
+                 arr_p(*[(gb[l].data_ptr() if has_b[l] else None) for l in range(n_layers)]), Pn, stream(),
+                 work=(2.0 * Pn * sum(a_.shape[1] + b_.shape[1] for a_, b_ in zip(dzs, ins)),
+                       2.0 * Pn * sum(r * c for r, c in shapes)))
         gW = [g if ctx.needs_input_grad[4 + l] else None for l, g in enumerate(gW)]
         gb = [gb[l] if (has_b[l] and ctx.needs_input_grad[4 + n_layers + l]) else None for l in range(n_layers)]
         return (g_x0, g_x1, None, None) + tuple(gW) + tuple(gb)

@@ -30,14 +30,15 @@ constexpr int SMEM_BYTES = OFF_BAR + 128;
 constexpr int N_THREADS = 320;                 // warp 0 TMA producer, warp 1 MMA issuer, warps 2..9 column sums + drain
 constexpr int MAX_JOBS = 12;
 
+// D[128 * m_halves][n_cols] += A^T B over the points, A / B = planes (tensor map index, slot)
 struct Job {
-  int dz_slot;              // dZ plane
-  int in_kind;              // 0: forward plane in_slot, 1: encoded positions x, 2: encoded directions d, -1: column sums only
-  int in_slot;
-  int m_halves;             // 2: all 256 dZ columns, 1: the first 128 (view layer)
-  int n_cols;               // width of the input operand: 64, 128 or 256
-  float* dW;                // [128 * m_halves][n_cols] fp32 (row = dZ column = output neuron) or null
-  float* db;                // [256] fp32 or null (column sums of the dZ plane: once per plane)
+  int a_map, a_slot;        // A operand (its columns become the rows of D): 128 * m_halves columns
+  int m_halves;             // 2: 256 columns of A, 1: the first 128
+  int b_map, b_slot;        // B operand; b_map < 0: column sums only
+  int n_cols;               // columns of B taken: 64, 128 or 256 (beyond the tensor width the TMA zero-fills)
+  float* dW;                // [128 * m_halves][n_cols] fp32 or null
+  float* db;                // fp32 [bias_cols] or null: column sums of the A plane
+  int bias_cols;
 };
 struct Args {
   Job job[MAX_JOBS];
@@ -74,8 +75,8 @@ __device__ __forceinline__ uint64_t mn_desc(uint32_t saddr) {
 }
 
 __global__ void __launch_bounds__(N_THREADS, 1)
-k_wgrad256(const Args a, const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_in,
-           const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_d) {
+k_wgrad256(const Args a, const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+           const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tm3) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
@@ -83,7 +84,7 @@ k_wgrad256(const Args a, const __grid_constant__ CUtensorMap tm_dz, const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(bars + 8);
   const Job job = a.job[blockIdx.y];
-  const bool gemm = job.in_kind >= 0;
+  const bool gemm = job.b_map >= 0;
   const int dz_blocks = 2 * job.m_halves, in_blocks = gemm ? job.n_cols >> 6 : 0;
   const int64_t row_begin = (int64_t)blockIdx.x * a.rows_per_split;
   int64_t row_end = row_begin + a.rows_per_split;
@@ -118,9 +119,13 @@ k_wgrad256(const Args a, const __grid_constant__ CUtensorMap tm_dz, const __grid
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_full + 8 * st), "r"(bytes) : "memory");
         const int r0 = (int)(row_begin + (int64_t)it * TP);
         const uint32_t base = s32(smem + st * STAGE_BYTES);
-        for (int b = 0; b < dz_blocks; ++b) tma_load_3d(base + b * BLK, &tm_dz, 64 * b, r0, job.dz_slot, bar_full + 8 * st);
-        const CUtensorMap* tin = job.in_kind == 0 ? &tm_in : (job.in_kind == 1 ? &tm_x : &tm_d);
-        for (int b = 0; b < in_blocks; ++b) tma_load_3d(base + (4 + b) * BLK, tin, 64 * b, r0, job.in_slot, bar_full + 8 * st);
+        auto pick = [&](int i) { return i == 0 ? &tm0 : (i == 1 ? &tm1 : (i == 2 ? &tm2 : &tm3)); };
+        const CUtensorMap* ta = pick(job.a_map);
+        for (int b = 0; b < dz_blocks; ++b) tma_load_3d(base + b * BLK, ta, 64 * b, r0, job.a_slot, bar_full + 8 * st);
+        if (gemm) {
+          const CUtensorMap* tb = pick(job.b_map);
+          for (int b = 0; b < in_blocks; ++b) tma_load_3d(base + (4 + b) * BLK, tb, 64 * b, r0, job.b_slot, bar_full + 8 * st);
+        }
       }
     }
   } else if (warp == 1) {
@@ -159,7 +164,7 @@ k_wgrad256(const Args a, const __grid_constant__ CUtensorMap tm_dz, const __grid
     for (int it = 0; it < n_steps; ++it) {
       const int st = it % N_STAGES;
       if (!mbar_wait(bar_full + 8 * st, (it / N_STAGES) & 1, abort_flag, a.err, 3)) break;
-      if (job.db && c < 128 * job.m_halves) {
+      if (job.db && c < job.bias_cols) {
         const unsigned char* blk = smem + st * STAGE_BYTES + (c >> 6) * BLK + (c & 7) * 2;
         const int ch = (c & 63) >> 3;
         float s = 0.f;
@@ -171,7 +176,7 @@ k_wgrad256(const Args a, const __grid_constant__ CUtensorMap tm_dz, const __grid
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_empty + 8 * st) : "memory");
     }
-    if (job.db && n_steps > 0 && c < 128 * job.m_halves) atomicAdd(job.db + c, colsum);
+    if (job.db && n_steps > 0 && c < job.bias_cols) atomicAdd(job.db + c, colsum);
     if (gemm && n_steps > 0 && mbar_wait(bar_done, 0, abort_flag, a.err, 4)) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int q = warp & 3;                   // TMEM lane quarter this warp may read
@@ -217,11 +222,12 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 static bool make_map(CUtensorMap* m, const void* planes, int64_t P, int n_slots, int width = 256) {
+  if (!planes) return true;             // unused map slot
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return false;
   const cuuint64_t dims[3] = {(cuuint64_t)width, (cuuint64_t)P, (cuuint64_t)n_slots};
   const cuuint64_t strides[2] = {(cuuint64_t)width * 2, (cuuint64_t)P * width * 2};
-  const cuuint32_t box[3] = {64, TP, 1};
+  const cuuint32_t box[3] = {64, TP, 1};   // planes narrower than a 64-column block: the TMA zero-fills the rest
   const cuuint32_t estr[3] = {1, 1, 1};
   return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(planes), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
@@ -257,19 +263,21 @@ extern "C" int b2n_nerf_mlp_wgrad(const void* dz_planes, const void* fwd_planes,
   B2N_REQUIRE(!d_bf16 || make_map(&tm_d, d_bf16, P, 1, 64), "cuTensorMapEncodeTiled failed (d)");
   Args a{};
   int n = 0;
-  for (int l = 1; l <= 7; ++l) a.job[n++] = Job{9 - l, 0, l - 1, 2, 256, dW + (size_t)(l - 1) * 65536, db + (size_t)(9 - l) * 256};
-  a.job[n++] = Job{1, 0, 7, 2, 256, dW + (size_t)7 * 65536, db + 256};
+  // tensor maps: 0 = dZ planes, 1 = forward planes, 2 = x, 3 = d
+  for (int l = 1; l <= 7; ++l)
+    a.job[n++] = Job{0, 9 - l, 2, 1, l - 1, 256, dW + (size_t)(l - 1) * 65536, db + (size_t)(9 - l) * 256, 256};
+  a.job[n++] = Job{0, 1, 2, 1, 7, 256, dW + (size_t)7 * 65536, db + 256, 256};
   if (x_bf16) {
-    a.job[n++] = Job{9, 1, 0, 2, kx, dW0, db + (size_t)9 * 256};
-    a.job[n++] = Job{5, 1, 0, 2, kx, dW4x, nullptr};
+    a.job[n++] = Job{0, 9, 2, 2, 0, kx, dW0, db + (size_t)9 * 256, 256};
+    a.job[n++] = Job{0, 5, 2, 2, 0, kx, dW4x, nullptr, 0};
   } else {
-    a.job[n++] = Job{9, -1, 0, 2, 256, nullptr, db + (size_t)9 * 256};     // layer-0 plane: bias sums only
+    a.job[n++] = Job{0, 9, 2, -1, 0, 256, nullptr, db + (size_t)9 * 256, 256};   // layer-0 plane: bias sums only
   }
   if (d_bf16) {
-    a.job[n++] = Job{0, 0, 8, 1, 256, dWv_h, db};
-    a.job[n++] = Job{0, 2, 0, 1, 64, dWv_d, nullptr};
+    a.job[n++] = Job{0, 0, 1, 1, 8, 256, dWv_h, db, 128};
+    a.job[n++] = Job{0, 0, 1, 3, 0, 64, dWv_d, nullptr, 0};
   } else {
-    a.job[n++] = Job{0, -1, 0, 1, 256, nullptr, db};                       // view-layer plane: bias sums only
+    a.job[n++] = Job{0, 0, 1, -1, 0, 256, nullptr, db, 128};                     // view-layer plane: bias sums only
   }
   a.P = P, a.err = err_flag;
   int splits = (2 * kSMs) / n;                             // ~2 CTAs' worth of jobs per SM (the narrow jobs are short)
@@ -280,4 +288,36 @@ extern "C" int b2n_nerf_mlp_wgrad(const void* dz_planes, const void* fwd_planes,
   cudaFuncSetAttribute(k_wgrad256, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   k_wgrad256<<<dim3((unsigned)splits, (unsigned)n), N_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a, tm_dz, tm_in, tm_x, tm_d);
   return check_launch("b2n_nerf_mlp_wgrad");
+}
+
+// Weight / bias gradients of the 128-wide fused MLPs (DeformationNetwork: b2n_fmlp_*) through the same kernel.
+// dz_h bf16 [n_hidden][P][128], dz_out bf16 [P][out_pad], h_planes bf16 [n_hidden][P][128], xin bf16 [P][in_pad] as written
+// by b2n_fmlp_fwd / b2n_fmlp_bwd.  ACCUMULATES (fp32): dW0 [128][128] = dZ_0^T xin (columns >= in_pad stay 0),
+// dWh [n_hidden-1][128][128] = dZ_l^T H_{l-1}, dWoT [128][64] = H_last^T dZ_out (the TRANSPOSED output-layer gradient,
+// columns >= out_pad stay 0), db_h [n_hidden][128] = column sums of the hidden dZ planes.
+extern "C" int b2n_fmlp_wgrad_tc(const void* dz_h, const void* dz_out, const void* h_planes, const void* xin, int64_t P,
+                                 int n_hidden, int in_pad, int out_pad, float* dW0, float* dWh, float* dWoT, float* db_h,
+                                 int* err_flag, b2n_stream_t stream) {
+  B2N_REQUIRE(dz_h && dz_out && h_planes && xin && dW0 && dWoT && db_h && err_flag, "null pointer");
+  B2N_REQUIRE(n_hidden >= 1 && n_hidden <= 3 && (n_hidden == 1 || dWh), "1..3 hidden layers");
+  B2N_REQUIRE(P >= TP && (in_pad == 32 || in_pad == 96) && (out_pad == 16 || out_pad == 64), "bad plane widths");
+  alignas(64) CUtensorMap tm[4];
+  memset(tm, 0, sizeof(tm));
+  B2N_REQUIRE(make_map(&tm[0], dz_h, P, n_hidden, 128) && make_map(&tm[1], h_planes, P, n_hidden, 128) &&
+                  make_map(&tm[2], xin, P, 1, in_pad) && make_map(&tm[3], dz_out, P, 1, out_pad), "cuTensorMapEncodeTiled failed");
+  Args a{};
+  int n = 0;
+  a.job[n++] = Job{0, 0, 1, 2, 0, in_pad <= 64 ? 64 : 128, dW0, db_h, 128};
+  for (int l = 1; l < n_hidden; ++l)
+    a.job[n++] = Job{0, l, 1, 1, l - 1, 128, dWh + (size_t)(l - 1) * 16384, db_h + (size_t)l * 128, 128};
+  a.job[n++] = Job{1, n_hidden - 1, 1, 3, 0, 64, dWoT, nullptr, 0};
+  a.P = P, a.err = err_flag;
+  int splits = (2 * kSMs) / n;
+  const int64_t max_splits = (P + TP - 1) / TP;
+  if (splits > max_splits) splits = (int)max_splits;
+  if (splits < 1) splits = 1;
+  a.rows_per_split = ((P + splits - 1) / splits + TP - 1) / TP * TP;
+  cudaFuncSetAttribute(k_wgrad256, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  k_wgrad256<<<dim3((unsigned)splits, (unsigned)n), N_THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(a, tm[0], tm[1], tm[2], tm[3]);
+  return check_launch("b2n_fmlp_wgrad_tc");
 }

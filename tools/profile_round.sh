@@ -13,9 +13,9 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-fi
     python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline > $OUT/${TAG}_ncu1.log 2>&1
 ncu --set full --clock-control none -k 'regex:k_hash|k_instant|k_composite|k_march' -s 36 -c 9 \
     -f -o $OUT/${TAG}_prof python bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline > $OUT/${TAG}_ncu2.log 2>&1
-ncu --set full --clock-control none -k 'regex:^k_mlp256$' -s 10 -c 2 \
+ncu --set full --clock-control none -k 'regex:^k_mlp256$|k_wgrad256' -s 15 -c 3 \
     -f -o $OUT/${TAG}_prof_c1 python bench.py --only c1_vanilla > $OUT/${TAG}_ncu3.log 2>&1
-ncu --set full --clock-control none -k 'regex:k_fmlp|k_hash_bwd_input' -s 16 -c 4 \
+ncu --set full --clock-control none -k 'regex:k_fmlp|k_hash_bwd_input|k_wgrad256' -s 16 -c 4 \
     -f -o $OUT/${TAG}_prof_c4 python bench.py --only c4_instant_dnerf > $OUT/${TAG}_ncu4.log 2>&1
 ncu --set full --clock-control none -k 'regex:^k_mlp256$|k_nerf_dx' -s 9 -c 3 \
     -f -o $OUT/${TAG}_prof_c3 python bench.py --only c3_dnerf > $OUT/${TAG}_ncu5.log 2>&1

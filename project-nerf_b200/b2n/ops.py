@@ -391,6 +391,22 @@ def instant_mlp(x_enc, dirs, bands, sigma_params, color_params):
 # 256-wide vanilla NeRF decoder on tcgen05 (bf16 operands, fp32 accumulate in TMEM)
 # ----------------------------------------------------------------------------
 
+# The tcgen05 kernels never hang: a stalled mbarrier wait aborts the CTA and raises a device-side flag instead.  Reading
+# the flag costs a host sync, so it is checked with a delay -- every 64th launch looks at the flags of earlier launches
+# (long finished) -- and a non-zero flag raises here rather than letting garbage activations train on.
+_ERR_FLAGS: List[torch.Tensor] = []
+
+
+def _track_err(err: torch.Tensor):
+    _ERR_FLAGS.append(err)
+    if len(_ERR_FLAGS) >= 64:
+        old = torch.stack(_ERR_FLAGS[:32])
+        del _ERR_FLAGS[:32]
+        bad = int(old.max().item())
+        if bad != 0:
+            raise RuntimeError(f"a tcgen05 decoder kernel aborted a stalled pipeline (code {bad}); its outputs are invalid")
+
+
 def nerf_mlp_supported(decoder, pos_dim: int, dir_dim: int) -> bool:
     """the tcgen05 kernel covers the reference architecture: 8 x 256, skip at 4, view 128"""
     try:
@@ -434,6 +450,7 @@ def nerf_mlp_forward(decoder, x_enc, d_enc, save: bool = False):
     call("b2n_nerf_mlp_fwd", ptr(x_enc), pos_dim, ptr(d_enc), dir_dim, ptr(packed), ptr(bias), ptr(w_sigma), ptr(w_rgb),
          ptr(head_bias), Pn, ptr(rgb), ptr(sigma), ptr(planes), ptr(masks), ptr(err), stream(),
          work=(Pn * (4.0 * (pos_dim + dir_dim) + 16 + (5120 if save else 0)), flops))
+    _track_err(err)
     return rgb, sigma, (planes, masks) if save else None, err
 
 

@@ -111,7 +111,7 @@ def cpu_train_rays_per_s(n_rays, steps, warmup, occupancy):
         torch.nn.utils.clip_grad_norm_([table], 1.0)
         torch.nn.utils.clip_grad_norm_([p for p in params if p is not table], 1.0)
         opt.step()
-        return float(loss)
+        return float(loss.detach())
 
     for i in range(warmup):
         step(i)
@@ -515,6 +515,35 @@ def main():
         extras["render_msamples_per_s"] = world * B * N_SAMPLES * args.steps / (ms3 * 1e-3) / 1e6
         extras["render_occupancy"] = args.occupancy
 
+    if not args.no_extras and rank == 0:
+        # L2 random-gather peak measured live (MEASURED_PEAKS.json has no L2 figure; the hash-grid kernels are
+        # gathers / reductions over a table that lives in L2, so this is the peak they are to be read against)
+        from b2n._lib import call as _call, ptr as _ptr, stream as _stream
+        sink = torch.zeros(1, device=dev)
+        l2 = {}
+        for mib, log2n in ((32, 22), (64, 23)):
+            tab = torch.randn(1 << log2n, 2, device=dev)
+            blocks, per_thread = 148 * 16, 512
+            best = 1e9
+            for i in range(4):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                _call("b2n_debug_gather_bench", _ptr(tab), 1 << log2n, blocks, per_thread, _ptr(sink), _stream())
+                e1.record()
+                torch.cuda.synchronize()
+                if i:
+                    best = min(best, e0.elapsed_time(e1))
+            l2[f"table_{mib}MiB_Ggathers_per_s"] = blocks * 256 * per_thread / best / 1e6
+            del tab
+        n_active = summary.get("b2n_hash_fwd", {}).get("bytes", 0.0) / args.steps / (12 + 16 * 2 * 4 * 9)   # points per step
+        per_step = {k: summary[k]["ms"] / args.steps for k in ("b2n_hash_fwd", "b2n_hash_bwd") if k in summary}
+        extras["hash_vs_l2"] = {
+            "l2_random_8B_gather_peak": l2,
+            "active_points_per_step": n_active,
+            "hash_fwd_corner_gathers_Gps": n_active * 16 * 8 / per_step.get("b2n_hash_fwd", float("inf")) / 1e6,
+            "hash_bwd_corner_reductions_Gps": n_active * 16 * 8 / per_step.get("b2n_hash_bwd", float("inf")) / 1e6,
+            "note": "8 corners x 16 levels per point; x-neighbour corner pairs that are adjacent table entries move as ONE "
+                    "16-byte access, and the coarse levels hit in L1, so the corner rate can exceed the 8-byte gather peak"}
     if not args.no_extras and world > 1:
         # BASELINE.json configs[4]: Part 4 Dual-Hash, ray batch sharded over the GPUs, hash-table gradient all-reduce
         extras["c5_dualhash_dp"] = bench_dynamic(dev, "c5_dualhash", world=world, rank=rank)

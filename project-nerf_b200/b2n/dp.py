@@ -62,9 +62,31 @@ class GradAllReducer:
     def zero_grad(self):
         self.flat.zero_()
 
+    def _rebind(self):
+        """A caller that ran ``optimizer.zero_grad()`` (set_to_none) instead of ``reducer.zero_grad()`` made autograd
+        allocate fresh .grad tensors: copy them back into the flat buffer and re-point .grad, so that the collective
+        below never reduces stale data."""
+        for p in self.params:
+            v = self._views[p]
+            if p.grad is None:
+                v.zero_()
+            elif p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad.reshape(-1))
+            else:
+                continue
+            p.grad = v.view_as(p)
+
     def allreduce(self):
         if self.world <= 1 or not dist.is_initialized():
             return
+        if not self._pending:          # (with overlap the hooks already re-bound the large tables they reduced)
+            self._rebind()
+        else:
+            for p in self.params[: len(self.params) - len(self._hooks)]:
+                v = self._views[p]
+                if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                    v.copy_(p.grad.reshape(-1))
+                    p.grad = v.view_as(p)
         avg_in_op = dist.get_backend() == "nccl"
         if self.overlap:
             head = self.flat[: self.n_small]

@@ -28,7 +28,7 @@ def _make():
 BIG = 100          # parameters with >= BIG elements take the asynchronous (hook-driven) all-reduce path: the 6x32 weight
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, foreign_zero_grad=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     dp = _load_dp()
@@ -38,7 +38,11 @@ def _worker(rank, world, port, out):
     torch.manual_seed(1)
     rays, target = torch.randn(64, 6), torch.randn(64, 3)
     a, b = dp.shard_rays(64, rank, world)
-    red.zero_grad()
+    if foreign_zero_grad:
+        for p in model.parameters():          # what optimizer.zero_grad(set_to_none=True) does: .grad leaves the flat buffer
+            p.grad = None
+    else:
+        red.zero_grad()
     torch.nn.functional.mse_loss(model(rays[a:b]), target[a:b]).backward()
     red.allreduce()
     torch.nn.utils.clip_grad_norm_(model.parameters(), 0.05)          # after the all-reduce: identical on all ranks
@@ -65,6 +69,20 @@ def test_flat_allreduce_matches_single_process(tmp_path):
         assert torch.allclose(got[n], p.grad, rtol=1e-5, atol=1e-7), n
     # p.grad are views of the flat buffer (zeroing is one memset)
     assert all(p.grad.data_ptr() >= red.flat.data_ptr() for p in model.parameters())
+
+
+def test_allreduce_survives_a_foreign_zero_grad(tmp_path):
+    """optimizer.zero_grad() (set_to_none) detaches .grad from the flat buffer; allreduce() must re-bind, not reduce stale zeros"""
+    out = str(tmp_path / "g2.pt")
+    mp.spawn(_worker, args=(2, 29519, out, True), nprocs=2, join=True)
+    model = _make()
+    torch.manual_seed(1)
+    rays, target = torch.randn(64, 6), torch.randn(64, 3)
+    torch.nn.functional.mse_loss(model(rays), target).backward()
+    torch.nn.utils.clip_grad_norm_(model.parameters(), 0.05)
+    got = torch.load(out)
+    for n, p in model.named_parameters():
+        assert torch.allclose(got[n], p.grad, rtol=1e-5, atol=1e-7), n
 
 
 def test_shard_rays_covers_batch():

@@ -68,10 +68,13 @@ __device__ __forceinline__ void load_w(const float* __restrict__ W, int ldw, int
   }
 }
 
+// skip_w0: the backward without input gradients never touches the first matrix -- it is not staged and every later
+// offset moves down by its size (26 KB at H = 128: 3 CTAs per SM instead of 2)
 template <int H, int KT_IN, int NT_OUT>
-__device__ __forceinline__ float* stage_weights(const Args& a, bf16* sm) {
+__device__ __forceinline__ float* stage_weights(const Args& a, bf16* sm, bool skip_w0 = false) {
   using LY = Layout<H, KT_IN, NT_OUT>;
-  load_w(a.W[0], a.ldw[0], H, a.d0 + a.d1, H, LY::IN_PAD, sm + LY::w0);
+  if (!skip_w0) load_w(a.W[0], a.ldw[0], H, a.d0 + a.d1, H, LY::IN_PAD, sm + LY::w0);
+  else sm -= LY::wh;
   for (int l = 1; l < a.n_hidden; ++l) load_w(a.W[l], a.ldw[l], H, H, H, H, sm + LY::wh + (l - 1) * H * LY::SH);
   load_w(a.W[a.n_hidden], a.ldw[a.n_hidden], a.out_dim, H, LY::OUT_ROWS, H, sm + LY::wo);
   float* bias = reinterpret_cast<float*>(sm + LY::end_bf16);
@@ -304,7 +307,9 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_bwd(const Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   bf16* sm = reinterpret_cast<bf16*>(smem_raw);
   using LY = Layout<H, KT_IN, NT_OUT>;
-  stage_weights<H, KT_IN, NT_OUT>(a, sm);
+  const bool need_x = a.g_x0 || a.g_x1;
+  stage_weights<H, KT_IN, NT_OUT>(a, sm, !need_x);
+  if (!need_x) sm -= LY::wh;          // all offsets below are relative to the (unstaged) first matrix
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   constexpr int KTO = LY::OUT_ROWS / 16;
@@ -574,7 +579,8 @@ static int launch_fwd(const Args& a, cudaStream_t st) {
 }
 template <int H, int KT_IN, int NT_OUT>
 static int launch_bwd(const Args& a, cudaStream_t st) {
-  constexpr size_t smem = Layout<H, KT_IN, NT_OUT>::bytes;
+  using LY = Layout<H, KT_IN, NT_OUT>;
+  const size_t smem = LY::bytes - ((a.g_x0 || a.g_x1) ? 0 : (size_t)LY::wh * sizeof(bf16));
   auto k = k_fmlp_bwd<H, KT_IN, NT_OUT>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = persistent_grid((const void*)k, smem, (a.P + 15) / 16);

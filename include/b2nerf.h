@@ -306,8 +306,16 @@ int b2n_nerf_mlp_dx(const void* dz0, const void* dz4, const float* W0, int ldw0,
 int b2n_nerf_mlp_wgrad(const void* dz_planes, const void* fwd_planes, const void* x_bf16, int kx, const void* d_bf16,
                        int64_t P, float* dW, float* dW0, float* dW4x, float* dWv_h, float* dWv_d, float* db,
                        int* err_flag, b2n_stream_t stream);
-/* debug aid: per-role cycle counters of CTA 0 of the next b2n_nerf_mlp_* launches (device int64[8], or NULL) */
+/* debug aid: per-role cycle counters of CTA 0 of the next b2n_nerf_mlp_* launches (device int64[8 + 448]: 8 counters, then a
+ * clock64 timeline of CTA 0's third tile pair, [step][tile][16 events]; or NULL) */
 int b2n_debug_mlp256_prof(void* device_int64x8);
+/* debug aid (timing experiments only, results become garbage): 1 = the epilogue skips the accumulator drain,
+ * 2 = no MMAs are issued (weights still stream); 0 = normal */
+int b2n_debug_mlp256_flags(int flags);
+/* schedule of b2n_nerf_mlp_fwd / _bwd: 1 (default; environment B2N_MLP256_PAIR=0 turns it off) = clusters of two CTAs
+ * issuing cta_group::2 MMAs (M = 256 over an SM pair, each CTA staging half of every weight chunk); 0 = one CTA per SM.
+ * Both produce the same results; the switch exists for A/B timing and parity tests. */
+int b2n_nerf_mlp_set_pair(int on);
 size_t b2n_nerf_mlp_packed_bwd_bytes(void);
 int b2n_nerf_mlp_pack_bwd(const float* const* pts_w, const float* feature_w, const float* view_w, int pos_dim,
                           int dir_dim, void* packed, b2n_stream_t stream);

@@ -57,6 +57,8 @@ SIGNATURES = {
     "b2n_nerf_mlp_pack": [P, P, P, I, I, P, P],
     "b2n_nerf_mlp_fwd": [P, I, P, I, P, P, P, P, P, L, P, P, P, P, P, P],
     "b2n_debug_mlp256_prof": [P],
+    "b2n_debug_mlp256_flags": [ctypes.c_int],
+    "b2n_nerf_mlp_set_pair": [ctypes.c_int],
     "b2n_debug_gather_bench": [P, L, I, I, P, P],
     "b2n_debug_mnmajor_probe": [P, P, P, I, I, I, I, P],
     "b2n_sample_rays": [P, P, P, P, P, P, L, I, I, I, F, F, P, P, P, P, P],

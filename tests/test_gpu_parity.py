@@ -551,6 +551,41 @@ def test_nerf_mlp256_tcgen05_forward(mods, Pn):
     assert torch.equal(bits[9][:, :128], planes[9][:, :128].float().cpu() > 0)
 
 
+@pytest.mark.parametrize("pos_dim,Pn", [(63, 512), (63, 128 * 37 + 5), (84, 1000), (63, 75000)])
+def test_nerf_mlp256_cta_pair_equals_single_cta(mods, bf16_mode, pos_dim, Pn):
+    """The cta_group::2 schedule (M = 256 MMAs over an SM pair, half of every weight chunk per CTA) accumulates every
+    output element over k in the same order as the single-CTA kernel: forward outputs, saved planes, ReLU masks and
+    parameter / input gradients are BIT-identical between the two schedules (ragged tails, odd pair counts, wide input)."""
+    from b2n import ops
+    from src.decoders import NeRFDecoder
+    lib = mods["b2n"]._lib.lib
+    torch.manual_seed(5)
+    dec = NeRFDecoder(pos_dim=pos_dim, dir_dim=27).to(DEV)
+    xe = torch.randn(Pn, pos_dim, device=DEV) * 0.6
+    de = torch.randn(Pn, 27, device=DEV) * 0.6
+    g_rgb, g_sig = torch.randn(Pn, 3, device=DEV), torch.randn(Pn, 1, device=DEV)
+    res = {}
+    try:
+        for pair in (0, 1):
+            lib.b2n_nerf_mlp_set_pair(pair)
+            rgb, sigma, (planes, masks), err = ops.nerf_mlp_forward(dec, xe, de, save=True)
+            torch.cuda.synchronize()
+            assert int(err.item()) == 0, f"pair={pair}: tcgen05 pipeline aborted with code {int(err.item())}"
+            x2 = xe.clone().requires_grad_(True)
+            r2, s2 = dec(x2, de)
+            params = list(dec.parameters())
+            grads = torch.autograd.grad((r2 * g_rgb).sum() + (s2 * g_sig).sum(), [x2] + params)
+            torch.cuda.synchronize()
+            res[pair] = [rgb, sigma, planes[:9], planes[9][:, :128], masks[:9], r2, s2] + list(grads)
+    finally:
+        lib.b2n_nerf_mlp_set_pair(1)
+    for i, (a_, b_) in enumerate(zip(res[0], res[1])):
+        if i < 8:                                   # kernel outputs: bit-identical
+            assert torch.equal(a_, b_), f"output {i} differs between the schedules"
+        else:                                       # weight gradients go through fp32 atomics (order varies run to run)
+            assert rel_err(a_.cpu(), b_.cpu()) < 1e-4, i
+
+
 def test_nerf_mlp256_tcgen05_backward(mods, bf16_mode):
     """Parameter gradients of the tensor-core NeRFDecoder vs autograd through the bf16-emulating oracle."""
     from oracle import nerf_oracle as O

@@ -36,23 +36,129 @@ def mlp256(P):
     xe = torch.randn(P, 63, device="cuda")
     de = torch.randn(P, 27, device="cuda")
     flops = 2.0 * P * 593408
-    for save in (False, True):
-        med, best = timeit(lambda: ops.nerf_mlp_forward(model.decoder, xe, de, save=save))
-        print(f"mlp256 fwd P={P} save={save}: median {med:.3f} ms best {best:.3f} ms -> {flops / best / 1e9:.1f} TFLOP/s "
-              f"({100 * flops / best / 1e9 / 1391.5:.1f} % of sustained bf16 peak)")
-    prof = torch.zeros(8, dtype=torch.int64, device="cuda")
-    b2n._lib.lib.b2n_debug_mlp256_prof(prof.data_ptr())
-    ops.nerf_mlp_forward(model.decoder, xe, de, save=False)
-    torch.cuda.synchronize()
-    b2n._lib.lib.b2n_debug_mlp256_prof(None)
-    pr = prof.tolist()
-    print(f"CTA0 cycles over {pr[4]} pairs: MMA-waits-epilogue {pr[0]}, MMA-waits-weights {pr[1]}, "
-          f"epilogue-waits-MMA {pr[2]}, epilogue-body {pr[3]}  (per step: {pr[0] / max(pr[4], 1) / 10:.0f}, "
-          f"{pr[1] / max(pr[4], 1) / 10:.0f}, {pr[2] / max(pr[4], 1) / 10:.0f}, {pr[3] / max(pr[4], 1) / 10:.0f})")
+    for pair in (0, 1):
+        b2n._lib.lib.b2n_nerf_mlp_set_pair(pair)
+        for save in (False, True):
+            med, best = timeit(lambda: ops.nerf_mlp_forward(model.decoder, xe, de, save=save))
+            print(f"mlp256 fwd pair={pair} P={P} save={save}: median {med:.3f} ms best {best:.3f} ms -> "
+                  f"{flops / best / 1e9:.1f} TFLOP/s ({100 * flops / best / 1e9 / 1391.5:.1f} % of sustained bf16 peak)")
+        _, _, _, err = ops.nerf_mlp_forward(model.decoder, xe, de, save=True)
+        print(f"  err flag {int(err.item())}")
+        # backward chain alone (data gradients): time the autograd call, minus nothing -- report the profiler's entry
+        x2 = xe[: P].clone().requires_grad_(True)
+        model.train()
+        for it in range(6):
+            if it == 1:
+                b2n._lib.PROFILER = prof = b2n._lib.Profiler()
+            r, s_ = model.decoder(x2, de)
+            (r.sum() + s_.sum()).backward()
+        torch.cuda.synchronize()
+        b2n._lib.PROFILER = None
+        for name, d in prof.summary().items():
+            if "nerf_mlp" in name:
+                print(f"    {name}: {d['ms'] / d['calls']:.3f} ms/call")
+        model.eval()
+    for pair in (0, 1):
+        b2n._lib.lib.b2n_nerf_mlp_set_pair(pair)
+        for what in ("fwd", "fwd+save", "bwd"):
+            prof = torch.zeros(8 + 448, dtype=torch.int64, device="cuda")
+            if what == "bwd":
+                model.train()
+                x2 = xe.clone().requires_grad_(True)
+                r, s_ = model.decoder(x2, de)
+                torch.cuda.synchronize()
+                b2n._lib.lib.b2n_debug_mlp256_flags(16)
+                b2n._lib.lib.b2n_debug_mlp256_prof(prof.data_ptr())
+                (r.sum() + s_.sum()).backward()
+                model.eval()
+            else:
+                b2n._lib.lib.b2n_debug_mlp256_flags(16)
+                b2n._lib.lib.b2n_debug_mlp256_prof(prof.data_ptr())
+                ops.nerf_mlp_forward(model.decoder, xe, de, save=what != "fwd")
+            torch.cuda.synchronize()
+            b2n._lib.lib.b2n_debug_mlp256_prof(None)
+            b2n._lib.lib.b2n_debug_mlp256_flags(0)
+            pr = prof.tolist()
+            n = max(pr[4], 1)
+            print(f"pair={pair} {what}: CTA0 cycles per tile pair ({pr[4]} pairs): whole {pr[7] / n:.0f} | pre-step {pr[5] / n:.0f}, "
+                  f"bias staging {pr[6] / n:.0f}, epilogue-waits-MMA {pr[2] / n:.0f}, epilogue-body {pr[3] / n:.0f} | "
+                  f"MMA-waits-epilogue {pr[0] / n:.0f}, MMA-waits-weights {pr[1] / n:.0f}")
+    b2n._lib.lib.b2n_nerf_mlp_set_pair(1)
     with torch.no_grad():
         b2n.set_mlp_precision("fp32")
         med, best = timeit(lambda: model.decoder(xe, de), n=3, warm=1)
         print(f"fp32 layer-wise path: {best:.3f} ms -> {flops / best / 1e9:.1f} TFLOP/s")
+
+
+def mlp256x(P):
+    """role isolation of k_mlp256 (debug flags): kernel time of forward / backward with the epilogue drain and / or the MMAs removed"""
+    torch.manual_seed(0)
+    model = NeuralField(dict(mode="part2_nerf", L_embed=10, L_embed_dir=4)).cuda().train()
+    xe = torch.randn(P, 63, device="cuda")
+    de = torch.randn(P, 27, device="cuda")
+    lib = b2n._lib.lib
+    for pair in (0, 1):
+        lib.b2n_nerf_mlp_set_pair(pair)
+        for dbg in [int(v) for v in os.environ.get("KB_DBG", "0,1,2,3,7,15").split(",")]:
+            lib.b2n_debug_mlp256_flags(dbg)
+            x2 = xe.clone().requires_grad_(True)
+            for it in range(5):
+                if it == 1:
+                    b2n._lib.PROFILER = prof = b2n._lib.Profiler()
+                r, s_ = model.decoder(x2, de)
+                (r.sum() + s_.sum()).backward()
+                with torch.no_grad():
+                    ops.nerf_mlp_forward(model.decoder, xe, de, save=False)
+            torch.cuda.synchronize()
+            b2n._lib.PROFILER = None
+            lib.b2n_debug_mlp256_flags(0)
+            ms = {}
+            for name, nbytes, flops, e0, e1 in prof.records:
+                if name in ("b2n_nerf_mlp_fwd", "b2n_nerf_mlp_bwd"):
+                    key = name[-3:] + ("+save" if nbytes > P * 1000 and name.endswith("fwd") else "")
+                    ms.setdefault(key, []).append(e0.elapsed_time(e1))
+            print(f"pair={pair} dbg={dbg} ({ {0: 'full', 1: 'no drain', 2: 'no MMA', 3: 'handshakes + weight stream only', 7: 'handshakes only', 15: 'handshakes only, no row loads/stores'}[dbg]}): " +
+                  ", ".join(f"{k} {min(v):.3f} ms" for k, v in sorted(ms.items())))
+    lib.b2n_nerf_mlp_set_pair(1)
+
+
+def mlp256t(P):
+    """timeline of CTA 0's third tile pair (B2N_TRACE): per step / tile, cycles relative to the pair's first event"""
+    torch.manual_seed(0)
+    model = NeuralField(dict(mode="part2_nerf", L_embed=10, L_embed_dir=4)).cuda().train()
+    xe = torch.randn(P, 63, device="cuda")
+    de = torch.randn(P, 27, device="cuda")
+    lib = b2n._lib.lib
+    names = ["epi:wait", "epi:acc", "epi:done", "mma:wait", "mma:act", "mma:w0", "mma:issued", "epi:stage", "c1:pre", "c1:full", "c1:mma", "c1:commit", "c1:sync", "stored"]
+    for pair in (0, 1):
+        lib.b2n_nerf_mlp_set_pair(pair)
+        for what in ("fwd+save", "bwd"):
+            x2 = xe.clone().requires_grad_(True)
+            for _ in range(2):
+                r, s_ = model.decoder(x2, de)
+                (r.sum() + s_.sum()).backward()
+            torch.cuda.synchronize()
+            prof = torch.zeros(8 + 448, dtype=torch.int64, device="cuda")
+            if what == "bwd":
+                r, s_ = model.decoder(x2, de)
+                torch.cuda.synchronize()
+                lib.b2n_debug_mlp256_prof(prof.data_ptr())
+                (r.sum() + s_.sum()).backward()
+            else:
+                lib.b2n_debug_mlp256_prof(prof.data_ptr())
+                ops.nerf_mlp_forward(model.decoder, xe, de, save=True)
+            torch.cuda.synchronize()
+            lib.b2n_debug_mlp256_prof(None)
+            tr = prof[8:].view(14, 2, 16)[:, :, :14].cpu()
+            t00 = int(tr[tr > 0].min())
+            print(f"--- pair={pair} {what}: cycles since the first event of the pair; columns = {names}")
+            for s in range(14):
+                for t in range(2):
+                    row = tr[s, t]
+                    if int(row.max()) == 0:
+                        continue
+                    print(f"  step {s:2d} tile {t}: " + " ".join(f"{(int(v) - t00) if v > 0 else -1:7d}" for v in row))
+    lib.b2n_nerf_mlp_set_pair(1)
 
 
 def c1_step(P_rays=4096, N=64):
@@ -181,4 +287,4 @@ if __name__ == "__main__":
         composite()
         composite(8192, 64)
     else:
-        {"mlp256": mlp256}[what](P)
+        {"mlp256": mlp256, "mlp256x": mlp256x, "mlp256t": mlp256t}[what](P)

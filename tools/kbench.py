@@ -129,10 +129,11 @@ def mlp256t(P):
     xe = torch.randn(P, 63, device="cuda")
     de = torch.randn(P, 27, device="cuda")
     lib = b2n._lib.lib
-    names = ["epi:wait", "epi:acc", "epi:done", "mma:wait", "mma:act", "mma:w0", "mma:issued", "epi:stage", "c1:pre", "c1:full", "c1:mma", "c1:commit", "c1:sync", "stored"]
-    for pair in (0, 1):
+    names = ["epi:wait", "epi:acc", "epi:done", "mma:wait", "mma:act", "mma:w0", "mma:issued", "epi:stage"]
+    for pair, what, cta in ((0, "bwd", 0), (1, "fwd+save", 0), (1, "bwd", 0), (1, "bwd", 1)):
         lib.b2n_nerf_mlp_set_pair(pair)
-        for what in ("fwd+save", "bwd"):
+        lib.b2n_debug_mlp256_flags(32 * cta)
+        if True:
             x2 = xe.clone().requires_grad_(True)
             for _ in range(2):
                 r, s_ = model.decoder(x2, de)
@@ -149,9 +150,9 @@ def mlp256t(P):
                 ops.nerf_mlp_forward(model.decoder, xe, de, save=True)
             torch.cuda.synchronize()
             lib.b2n_debug_mlp256_prof(None)
-            tr = prof[8:].view(14, 2, 16)[:, :, :14].cpu()
+            tr = prof[8:].view(14, 2, 16)[:, :, :8].cpu()
             t00 = int(tr[tr > 0].min())
-            print(f"--- pair={pair} {what}: cycles since the first event of the pair; columns = {names}")
+            print(f"--- pair={pair} {what} CTA {cta}: cycles since the first event of the pair; columns = {names}")
             for s in range(14):
                 for t in range(2):
                     row = tr[s, t]
@@ -159,6 +160,7 @@ def mlp256t(P):
                         continue
                     print(f"  step {s:2d} tile {t}: " + " ".join(f"{(int(v) - t00) if v > 0 else -1:7d}" for v in row))
     lib.b2n_nerf_mlp_set_pair(1)
+    lib.b2n_debug_mlp256_flags(0)
 
 
 def c1_step(P_rays=4096, N=64):

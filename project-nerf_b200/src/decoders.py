@@ -138,6 +138,17 @@ class InstantNeRFDecoder(BaseDecoder):
         rgb = self.color_net(torch.cat([h, d_enc], dim=-1))
         return rgb, sigma
 
+    def density(self, x_enc, x_enc2=None):
+        """sigma only, input = [x_enc | x_enc2]: the density branch without the colour network (occupancy sweeps,
+        SURVEY 8f-3).  Same kernels and arithmetic as ``forward`` in fp32 mode; in bf16 mode the sigma network runs as
+        one fused tensor-core kernel on the two sources (no concat, no direction features, no colour layers)."""
+        net = self.sigma_net
+        if x_enc.is_cuda and x_enc2 is not None and net.can_fuse(x_enc.shape[-1] + x_enc2.shape[-1]):
+            return b2n.sigma_head(net.forward_fused(x_enc, x_enc2))
+        if x_enc2 is not None:
+            x_enc = torch.cat([x_enc, x_enc2], dim=-1)
+        return b2n.sigma_head(net(x_enc))
+
     def can_fuse(self, dir_encoder):
         return (b2n.mlp_precision() == "bf16" and self.sigma_net.n_neurons == 64 and self.color_net.n_neurons == 64
                 and self.sigma_net.n_input_dims <= 64 and dir_encoder.input_dim == 3 and dir_encoder.use_encoding

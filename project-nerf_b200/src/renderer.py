@@ -37,27 +37,40 @@ class DensityGrid(nn.Module):
             self._bits_key = key
         return self._bits
 
+    def _lattice(self, device):
+        """the R^3 corner lattice of ``update`` (reference :49-54), built once per device"""
+        key = (str(torch.device(device)), self.resolution, float(self.bound))
+        if getattr(self, "_lattice_key", None) != key:
+            ax = torch.linspace(-self.bound, self.bound, self.resolution, device=device)
+            self._lattice_pts = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), dim=-1).reshape(-1, 3).contiguous()
+            self._lattice_key = key
+        return self._lattice_pts
+
     @torch.no_grad()
     def update(self, model, n_samples=128 ** 3, device="cuda", time=None, decay=1.0, **_unused):
         """Re-evaluate sigma on the R^3 corner lattice and refresh grid / binary_grid.
-        Accepts (and ignores) the extra keywords run.py:1982-1985 passes."""
+        Accepts (and ignores) the extra keywords run.py:1982-1985 passes.  A model that offers ``density(x, t=None)``
+        (this package's NeuralField) is swept through it -- sigma only, no colour branch; any other
+        model is called like the reference does, with zero view directions."""
         R = self.resolution
-        ax = torch.linspace(-self.bound, self.bound, R, device=device)
-        pts = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), dim=-1).reshape(-1, 3)
+        pts = self._lattice(device)
         mode = getattr(model, "mode", "unknown")
         batch = 2 ** 18
+        density = getattr(model, "density", None)
 
         def sweep(tval):
-            out = []
+            out = torch.empty(pts.shape[0], device=pts.device)
             for i in range(0, pts.shape[0], batch):
                 p = pts[i:i + batch]
-                zeros = torch.zeros_like(p)
-                if tval is None:
-                    _, s = model(p, zeros)
+                tt = None if tval is None else tval.expand(p.shape[0], -1)
+                if density is not None:
+                    s = density(p) if tt is None else density(p, t=tt)
+                elif tt is None:
+                    _, s = model(p, torch.zeros_like(p))
                 else:
-                    _, s, _ = model(p, zeros, t=tval.expand(p.shape[0], -1))
-                out.append(s.reshape(-1).float())
-            return torch.cat(out)
+                    _, s, _ = model(p, torch.zeros_like(p), t=tt)
+                out[i:i + batch] = s.reshape(-1)
+            return out
 
         if mode == "part4":
             cur = None

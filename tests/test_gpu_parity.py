@@ -362,6 +362,56 @@ def test_density_grid_update_golden(mods, tag):
     assert torch.equal(grid.get_active_mask(pts).cpu(), O.active_mask(pts.cpu(), grid.binary_grid.cpu(), grid.bound))
 
 
+@pytest.mark.parametrize("tag", FIELDS)
+def test_density_branch_equals_forward_sigma(mods, tag):
+    """NeuralField.density (the sigma-only sweep of DensityGrid.update) returns exactly the sigma that
+    forward(x, 0, t) returns (fp32 mode: same kernels, bit-identical); in bf16 mode the two use different fused
+    tensor-core kernels and agree to the bf16 class."""
+    g = load(f"field_{tag}")
+    model = _model_from(mods, g["cfg"], g["sd"]).eval()
+    torch.manual_seed(3)
+    n = 5000
+    x = (torch.rand(n, 3, device=DEV) * 2 - 1) * float(g["cfg"].get("scene_bound", 1.0))
+    t = torch.rand(n, 1, device=DEV)
+    dyn = model.mode in ("part3", "part4")
+    with torch.no_grad():
+        full = model(x, torch.zeros_like(x), t=t)[1] if dyn else model(x, torch.zeros_like(x))[1]
+        dens = model.density(x, t=t) if dyn else model.density(x)
+        assert dens.shape == full.shape and torch.equal(dens, full)
+        mods["b2n"].set_mlp_precision("bf16")
+        try:
+            full_b = model(x, torch.zeros_like(x), t=t)[1] if dyn else model(x, torch.zeros_like(x))[1]
+            dens_b = model.density(x, t=t) if dyn else model.density(x)
+        finally:
+            mods["b2n"].set_mlp_precision("fp32")
+    assert rel_err(dens_b.cpu(), full_b.cpu()) < 1e-2 and rel_err(dens_b.cpu(), full.cpu()) < 2e-2
+
+
+def test_density_grid_update_uses_density_branch(mods):
+    """update() through model.density and through the reference-style full forward (a model without .density) give the
+    same grids; the density path launches fewer kernels per sweep."""
+    g = load("gridupdate_part2_instant")
+    model = _model_from(mods, g["cfg"], g["sd"]).eval()
+    R = g["grid1"].shape[0]
+
+    class NoDensity(torch.nn.Module):          # what a foreign model looks like to DensityGrid.update
+        def __init__(self, m):
+            super().__init__()
+            self.m, self.mode = m, m.mode
+
+        def forward(self, *a, **k):
+            return self.m(*a, **k)
+
+    grids = []
+    for mdl in (model, NoDensity(model)):
+        grid = mods["renderer"].DensityGrid(resolution=R, bound=g["cfg"]["scene_bound"], threshold=g["threshold"]).to(DEV)
+        n0 = mods["b2n"]._lib.LAUNCHES["count"]
+        ratio = grid.update(mdl, device=DEV)
+        grids.append((grid.grid.clone(), grid.binary_grid.clone(), ratio, mods["b2n"]._lib.LAUNCHES["count"] - n0))
+    assert torch.equal(grids[0][0], grids[1][0]) and torch.equal(grids[0][1], grids[1][1]) and grids[0][2] == grids[1][2]
+    assert grids[0][3] < grids[1][3]
+
+
 def test_state_dict_keys_match_reference(mods):
     for tag in FIELDS:
         g = load(f"field_{tag}")

@@ -163,6 +163,36 @@ def mlp256t(P):
     lib.b2n_debug_mlp256_flags(0)
 
 
+def occ_update():
+    """DensityGrid.update: sigma-only sweep through NeuralField.density against the reference-style sweep
+    through the full model (zero view directions, rgb dropped), C2 / C4 / C5 shapes, bf16 mode."""
+    from src.renderer import DensityGrid
+
+    class NoDensity(torch.nn.Module):
+        def __init__(self, m):
+            super().__init__()
+            self.m, self.mode = m, m.mode
+
+        def forward(self, *a, **k):
+            return self.m(*a, **k)
+
+    b2n.set_mlp_precision("bf16")
+    cfgs = {
+        "C2 part2_instant R=128": (dict(mode="part2_instant", scene_bound=1.5), 128, None),
+        "C4 part3 instant R=128": (dict(mode="part3", canonical_type="instant", scene_bound=1.5), 128, 0.3),
+        "C5 part4 R=64": (dict(mode="part4", scene_bound=1.5, log2_hashmap_size=20, deform_n_levels=12,
+                               deform_log2_hashmap_size=16), 64, None),
+    }
+    for name, (cfg, R, tval) in cfgs.items():
+        torch.manual_seed(0)
+        model = NeuralField(cfg).cuda().eval()
+        for label, mdl in (("density branch", model), ("full forward", NoDensity(model))):
+            grid = DensityGrid(resolution=R, bound=1.5, threshold=0.01).cuda()
+            t = None if tval is None else torch.tensor([[tval]], device="cuda")
+            med, best = timeit(lambda: grid.update(mdl, device="cuda", time=t), n=5, warm=2)
+            print(f"occ update {name}: {label}: median {med:.3f} ms best {best:.3f} ms")
+
+
 def c1_step(P_rays=4096, N=64):
     """C1: vanilla NeRF training step (render_rays + MSE + backward + Adam), B=4096, N=64."""
     from b2n import synthetic
@@ -281,6 +311,8 @@ if __name__ == "__main__":
     P = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 262144
     if what == "c1":
         c1_step()
+    elif what == "occ":
+        occ_update()
     elif what == "hash":
         hash_levels()
     elif what == "l2":

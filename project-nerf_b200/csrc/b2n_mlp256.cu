@@ -76,7 +76,7 @@ constexpr int OFF_AUX = OFF_ACT + 2 * ACT_BYTES;       // [2 tiles][KBLK_BYTES] 
 constexpr int OFF_RING = OFF_AUX + 2 * KBLK_BYTES;     // [N_STAGES][CHUNK_BYTES]
 constexpr int OFF_VEC = OFF_RING + N_STAGES * CHUNK_BYTES;   // 256 floats bias + 384 floats head weights / scratch
 constexpr int OFF_BAR = OFF_VEC + (256 + 384) * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 192;
+constexpr int SMEM_BYTES = OFF_BAR + 208;
 static_assert(SMEM_BYTES <= 232448, "exceeds 227 KB of shared memory");
 
 constexpr int N_THREADS = 352;          // 11 warps: producer, MMA, 8 x epilogue, plane store
@@ -332,6 +332,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const __grid_constant__
   const uint32_t bar_acc = s32(bars + 16);     // [2] MMA -> epilogue: accumulators of tile t complete
   const uint32_t bar_act = s32(bars + 18);     // [2] epilogue -> MMA: A operand of tile t written, accumulator drained
   const uint32_t bar_st = s32(bars + 20);      // [2] store warp -> epilogue: the plane store has read tile t (it may be overwritten)
+  const uint32_t bar_tail = s32(bars + 24);    // [2] epilogue -> store warp: the LAST step's output of tile t is in the act tile
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 22);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(bars + 23);
   float* vec = reinterpret_cast<float*>(smem + OFF_VEC);
@@ -350,6 +351,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const __grid_constant__
       mbar_init(bar_acc + 8 * t, 1);
       mbar_init(bar_act + 8 * t, (CTA2 && rank == 0) ? EPI_THREADS + 1 : EPI_THREADS);
       mbar_init(bar_st + 8 * t, 1);
+      mbar_init(bar_tail + 8 * t, EPI_THREADS);
     }
     *abort_flag = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -552,7 +554,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const __grid_constant__
     // when the store engine has read the tile, i.e. when the next epilogue may overwrite it.  (These stores used to be
     // issued by the MMA warp: ~800 cycles of issue + the read wait on the serial path of every tile and step.)
     if (a.use_tma) {
-      uint32_t act_phase[2] = {0, 0};
+      uint32_t act_phase[2] = {0, 0}, tail_phase = 0;
       const uint32_t act0 = s32(smem + OFF_ACT);
       for (int64_t pair = pair_first; pair < n_pairs; pair += pair_step) {
         for (int s = 0; s < plan.n_steps; ++s) {
@@ -572,6 +574,24 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const __grid_constant__
             __syncwarp();
           }
         }
+        // the last step's plane: nothing reads that tile after it, so the epilogue announces it on bar_tail; the extra
+        // bar_st arrival is what the NEXT pair's pre-step waits for before it writes into the tile again
+        if (plan.s[plan.n_steps - 1].tma) {
+          for (int t = 0; t < 2; ++t) {
+            if (!mbar_wait(bar_tail + 8 * t, tail_phase & 1, abort_flag, a.err, 7)) goto store_done;
+            if (elect_one()) {
+              const Step& lp = plan.s[plan.n_steps - 1];
+              const int row0 = (int)(pair * 256 + t * 128);
+              for (int kb = 0; kb < lp.n / 64; ++kb)
+                tma_store_3d(&tmap_save, act0 + t * ACT_BYTES + kb * KBLK_BYTES, 64 * kb, row0, lp.save_slot);
+              bulk_commit();
+              bulk_wait_read0();
+              mbar_arrive(bar_st + 8 * t);
+            }
+            __syncwarp();
+          }
+          ++tail_phase;
+        }
       }
       if (elect_one()) bulk_wait0();                 // all plane stores complete before the CTA exits
       __syncwarp();
@@ -584,7 +604,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const __grid_constant__
     const int half = (warp - 2) >> 2;          // accumulator column half this warp drains
     const int r = 32 * q + lane;               // row inside the tile
     const int c0 = 128 * half;                 // first accumulator column of this thread
-    uint32_t acc_phase[2] = {0, 0};
+    uint32_t acc_phase[2] = {0, 0}, st_phase[2] = {0, 0};
+    const bool tail_store = a.use_tma && plan.s[plan.n_steps - 1].tma;   // the last step's plane goes through the act tile too
     if (BWD) {  // head weights are needed by every pair: stage them once
       vec[e] = __ldg(a.w_sigma + e);
       vec[256 + e] = __ldg(a.w_rgb + e);
@@ -619,6 +640,8 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const __grid_constant__
         unsigned char* aux = smem + OFF_AUX + t * KBLK_BYTES;
         const int64_t p = pair * 256 + t * 128 + r;
         const bool valid = p < a.P && !(a.dbg & 8);
+        // the previous pair's last plane must have left the tile (its store is announced with one more bar_st phase)
+        if (tail_store && pair != pair_first && !mbar_wait(bar_st + 8 * t, st_phase[t]++ & 1, abort_flag, a.err, 8)) goto epi_done;
         if (!BWD) {
           stage_row(a.x_enc + p * a.pos_dim, a.pos_dim < 64 ? a.pos_dim : 64, valid, aux, r, 4 * half);
         } else {
@@ -673,7 +696,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const __grid_constant__
             const int64_t p = pair * 256 + t * 128 + r;
             const bool valid = p < a.P && !(a.dbg & 8);
             if (!mbar_wait(bar_acc + 8 * t, acc_phase[t] & 1, abort_flag, a.err, 4)) goto epi_done;
-            if (a.use_tma && !mbar_wait(bar_st + 8 * t, acc_phase[t] & 1, abort_flag, a.err, 5)) goto epi_done;
+            if (a.use_tma && !mbar_wait(bar_st + 8 * t, st_phase[t]++ & 1, abort_flag, a.err, 5)) goto epi_done;
             ++acc_phase[t];
             tc_fence_after();
             restage_aux(a, sp.restage, p, valid, aux, r, 4 * half);
@@ -714,7 +737,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const __grid_constant__
           long long t0 = clock64();
           if (e == 0) B2N_TRACE(s, t, 0);
           if (!mbar_wait(bar_acc + 8 * t, acc_phase[t] & 1, abort_flag, a.err, 4)) goto epi_done;
-          if (a.use_tma && !mbar_wait(bar_st + 8 * t, acc_phase[t] & 1, abort_flag, a.err, 5)) goto epi_done;
+          if (a.use_tma && !mbar_wait(bar_st + 8 * t, st_phase[t]++ & 1, abort_flag, a.err, 5)) goto epi_done;
           long long t1 = clock64();
           if (e == 0) B2N_TRACE(s, t, 1);
           if (a.prof && (a.dbg & 16) && blockIdx.x == 0 && e == 0) a.prof[2] += t1 - t0;    // epilogue waiting for the MMAs
@@ -794,7 +817,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const __grid_constant__
                 const uint4 pk = make_uint4(pack_bf16(f[8 * c4], f[8 * c4 + 1]), pack_bf16(f[8 * c4 + 2], f[8 * c4 + 3]),
                                             pack_bf16(f[8 * c4 + 4], f[8 * c4 + 5]), pack_bf16(f[8 * c4 + 6], f[8 * c4 + 7]));
                 const int col = colb + 8 * c4;            // first column of this 16-byte chunk
-                if (sp.epi != EPI_VIEW_RGB && !(BWD && last))
+                if (!last || tail_store)
                   *reinterpret_cast<uint4*>(act + (col >> 6) * KBLK_BYTES + swz(r, (col & 63) >> 3)) = pk;
                 if (save_row) __stcs(reinterpret_cast<uint4*>(save_row + col), pk);
               }
@@ -825,6 +848,7 @@ __global__ void __launch_bounds__(N_THREADS, 1) k_mlp256(const __grid_constant__
           if (a.prof && (a.dbg & 16) && blockIdx.x == 0 && e == 0) a.prof[3] += clock64() - t1;   // epilogue body
           if (e == 0) B2N_TRACE(s, t, 2);
           if (!last) arrive_act(t);
+          else if (tail_store) mbar_arrive(bar_tail + 8 * t);
         }
       }
       if (a.prof && (a.dbg & 16) && blockIdx.x == 0 && e == 0) a.prof[7] += clock64() - tp0;     // whole pair
@@ -1001,10 +1025,10 @@ static bool launch_pairs(K kernel, const FwdArgs& a, const CUtensorMap& tmap_sav
   return true;
 }
 
-// every step that leaves its output in the activation tile (all but the view layer / the last step) saves it by TMA
+// every step that saves a plane leaves its output in the activation tile and the store warp sends it by TMA (the last
+// step of a pair included: bar_tail)
 static void mark_tma_steps(Plan* pl) {
-  for (int i = 0; i + 1 < pl->n_steps; ++i)
-    pl->s[i].tma = (pl->s[i].save_slot >= 0 && !pl->s[i].partial && pl->s[i].epi != EPI_VIEW_RGB) ? 1 : 0;
+  for (int i = 0; i < pl->n_steps; ++i) pl->s[i].tma = (pl->s[i].save_slot >= 0 && !pl->s[i].partial) ? 1 : 0;
 }
 
 static long long* g_prof = nullptr;

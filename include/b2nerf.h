@@ -303,6 +303,9 @@ int b2n_nerf_mlp_dx(const void* dz0, const void* dz4, const float* W0, int ldw0,
  * [128][256] = dZ_view^T H_8; dWv_d [128][64] = dZ_view^T d; db [10][256] = column sums of every dZ plane (slot 0 view
  * layer, 1 feature layer, 2..9 = trunk layers 7..0).  x_bf16 / d_bf16 and their outputs may be NULL.  P >= 64.  The two
  * 1- and 3-row heads stay with the caller. */
+/* out[p, 0:kpad] (bf16) = x[p, 0:width] (fp32) zero-padded; kpad a multiple of 8.  Builds x_bf16 / d_bf16 of
+ * b2n_nerf_mlp_wgrad in one pass. */
+int b2n_pad_bf16(const float* x, int64_t P, int width, int kpad, void* out, b2n_stream_t stream);
 int b2n_nerf_mlp_wgrad(const void* dz_planes, const void* fwd_planes, const void* x_bf16, int kx, const void* d_bf16,
                        int64_t P, float* dW, float* dW0, float* dW4x, float* dWv_h, float* dWv_d, float* db,
                        int* err_flag, b2n_stream_t stream);

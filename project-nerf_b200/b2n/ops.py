@@ -398,6 +398,8 @@ _ERR_FLAGS: List[torch.Tensor] = []
 
 
 def _track_err(err: torch.Tensor):
+    if torch.cuda.is_current_stream_capturing():
+        return          # inside a CUDA graph (b2n.graphs): no host reads; the flag lives in the graph's memory pool
     _ERR_FLAGS.append(err)
     if len(_ERR_FLAGS) >= 64:
         old = torch.stack(_ERR_FLAGS[:32])
@@ -503,8 +505,10 @@ class _NerfMLP(torch.autograd.Function):
         # ---- weight / bias gradients: dW = dZ^T In over all points
         # layer inputs in bf16; x / d zero-padded to 64-column multiples (the operand blocks of the tcgen05 kernel)
         kx = 64 if pos_dim <= 64 else 128
-        xb = torch.nn.functional.pad(x_enc, (0, kx - pos_dim)).to(torch.bfloat16)
-        db = torch.nn.functional.pad(d_enc, (0, 64 - dir_dim)).to(torch.bfloat16)
+        xb = torch.empty(Pn, kx, device=dev, dtype=torch.bfloat16)
+        db = torch.empty(Pn, 64, device=dev, dtype=torch.bfloat16)
+        call("b2n_pad_bf16", ptr(x_enc), Pn, pos_dim, kx, ptr(xb), stream())
+        call("b2n_pad_bf16", ptr(d_enc), Pn, dir_dim, 64, ptr(db), stream())
         H = planes                      # H[0..7] trunk outputs, H[8] feat, H[9][:, :128] hv
         dZ = {l: dz[9 - l] for l in range(8)}     # dZ_l of trunk layer l
         grads = {}

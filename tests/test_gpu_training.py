@@ -126,3 +126,51 @@ def test_bf16_and_fp32_paths_render_the_same_psnr():
         assert abs(psnr["bf16"] - psnr["fp32"]) < 0.05, psnr
     finally:
         b2n.set_mlp_precision("fp32")
+
+
+def test_cuda_graph_step_equals_eager_step():
+    """b2n.graphs.GraphedStep: a whole vanilla-NeRF training step (march, encode, tcgen05 decoder, composite, loss,
+    backward, Adam) captured into one CUDA graph trains like the same step run eagerly."""
+    import b2n
+    from src.core import NeuralField
+    from src.renderer import render_rays
+    from b2n import synthetic
+    b2n.set_mlp_precision("bf16")
+    try:
+        B, N = 512, 16
+        batches = [tuple(t.cuda() for t in synthetic.random_rays(B, seed=90 + i)) for i in range(3)]
+        finals = []
+        for graphed in (False, True):
+            torch.manual_seed(0)
+            model = NeuralField(dict(mode="part2_nerf", L_embed=10, L_embed_dir=4)).cuda().train()
+            opt = torch.optim.Adam(model.parameters(), lr=5e-4, capturable=True)
+
+            def step(ro, rd, tgt):
+                target = tgt[:, :3] * tgt[:, 3:4] + (1.0 - tgt[:, 3:4])
+                pred, _, _ = render_rays(model, ro, rd, 2.0, 6.0, N, False, white_bkgd=True)
+                loss = torch.nn.functional.mse_loss(pred, target)
+                opt.zero_grad(set_to_none=True)
+                loss.backward()
+                opt.step()
+                return loss
+
+            if graphed:
+                sd = {k: v.clone() for k, v in model.state_dict().items()}
+                fn = b2n.graphs.GraphedStep(step, batches[0], warmup=2)    # warm-up steps train: restore afterwards
+                model.load_state_dict(sd)
+                for st in opt.state.values():
+                    for v in st.values():
+                        if torch.is_tensor(v):
+                            v.zero_()
+            else:
+                fn = step
+            losses = [float(fn(*batches[i % 3]).detach()) for i in range(6)]
+            torch.cuda.synchronize()
+            finals.append((losses, {k: v.detach().clone() for k, v in model.named_parameters()}))
+        (l0, p0), (l1, p1) = finals
+        assert all(abs(a - b) < 2e-3 * max(abs(a), 1e-6) for a, b in zip(l0, l1)), (l0, l1)
+        for k in p0:
+            err = float((p0[k] - p1[k]).norm() / (p0[k].norm() + 1e-12))
+            assert err < 2e-3, (k, err)
+    finally:
+        b2n.set_mlp_precision("fp32")

@@ -35,8 +35,8 @@
 // streamed ONCE per tile pair (tile 1 re-reads the slots tile 0 used), commits multicast to both CTAs, and the
 // peer's idle MMA warp relays "my tile is in place" to the leader with a single remote arrive.  Weight traffic per
 // CTA drops 4x, results are bit-identical to the single-CTA schedule (tests).  Measured at P = 262 144 (C1, kernel
-// times inside a training loop): training forward 0.57 -> 0.45 ms, backward chain 0.56 -> 0.36 ms (815 TFLOP/s = 59 %
-// of the sustained cuBLAS bf16 rate), inference forward 0.49 -> 0.38 ms (59 %).
+// times inside a training loop): training forward 0.57 -> 0.44 ms, backward chain 0.56 -> 0.335 ms (869 TFLOP/s = 62 %
+// of the sustained cuBLAS bf16 rate), inference forward 0.49 -> 0.37 ms (60 %).
 // What the B2N_TRACE timeline (tools/kbench.py mlp256t) shows is left: each tile runs the serial chain
 //   MMAs of the step (act ready -> accumulator seen by the epilogue: ~2900 cycles, 2048 of them tensor time)
 //   -> drain (TMEM reads at 64 B/cycle: >= 2000 cycles) -> slower of the two CTAs' epilogues + relay (300..2600)

@@ -270,8 +270,10 @@ int b2n_fmlp_bwd(int d0, int d1, int hidden, int n_hidden, const float* const* W
  *     head_bias: device float[4] = {b_sigma, b_rgb[3]}; save: optional bf16
  *     [10][P][256] planes of the layer outputs (training), written by TMA tensor
  *     stores of the activation tiles; relu_masks: uint32 [10][P][8], bit c of a row
- *     = (plane[c] > 0), given exactly when `save` is (the backward gates with these
- *     32-byte rows instead of re-reading the 512-byte plane rows); err_flag: device int
+ *     = (plane[c] > 0) for the ReLU layers (slots 0..7 and 9; slot 8, the linear feature
+ *     layer, is written but unspecified: nothing gates with it), given exactly when `save`
+ *     is (the backward gates with these 32-byte rows instead of re-reading the 512-byte
+ *     plane rows); err_flag: device int
  *     (0 = ok; non-zero = the kernel aborted a stalled pipeline instead of hanging).
  * ---------------------------------------------------------------------- */
 size_t b2n_nerf_mlp_packed_bytes(void);

@@ -393,13 +393,41 @@ def bench_dynamic(dev, name, steps=10, warm=4, occupancy="dense", world=1, rank=
 
     ms_train = run(step, steps, warm)
     _maybe_profile(step)
+    # the same step with the TV term, unscale, clipping and AdamW in b2n.optim.FusedAdamW: two launches
+    # instead of ~100; the loss carries no TV term, scaler.step() hands the loss scale / inf flag to the optimizer
+    fused = {}
+    if world == 1:
+        try:
+            import b2n
+            table_ids = {id(t) for t in tables}
+            fopt = b2n.optim.FusedAdamW(
+                [{"params": [p for p in model.parameters() if id(p) in table_ids], "tv_weight": spec["tv"]},
+                 {"params": [p for p in model.parameters() if id(p) not in table_ids]}], lr=spec["lr"], weight_decay=1e-5)
+            fscaler = torch.amp.GradScaler("cuda", enabled=True)
+
+            def fstep(i):
+                ro, rd, tgt, times = pool[i % 3]
+                target = tgt[:, :3] * tgt[:, 3:4] + bg * (1.0 - tgt[:, 3:4])
+                with torch.amp.autocast("cuda", enabled=True):
+                    pred, _, _, extras = render_rays(model=model, rays_o=ro, rays_d=rd, near=NEAR, far=FAR, n_samples=N,
+                                                     perturb=True, times=times, density_grid=grid, bg_color=bg)
+                    loss = torch.nn.functional.mse_loss(pred, target) + torch.mean(extras["mean_delta_x"] ** 2) * spec["reg"]
+                fopt.zero_grad()
+                fscaler.scale(loss).backward()
+                fscaler.step(fopt, max_norm=1.0)
+                fscaler.update()
+
+            ms_fused = run(fstep, steps, warm)
+            fused = {"train_rays_per_s_fused_optimizer": B / ms_fused * 1e3, "train_ms_per_step_fused_optimizer": ms_fused}
+        except Exception as exc:
+            fused = {"fused_optimizer_error": f"{type(exc).__name__}: {exc}"[:300]}
     model.eval()
     with torch.no_grad():
         ms_render = run(lambda i: render_rays(model, pool[i % 3][0], pool[i % 3][1], NEAR, FAR, N, False,
                                               times=pool[i % 3][3], density_grid=grid, bg_color=bg), steps, 2)
     out = {"workload": f"{spec['label']}, B={B} rays x {N} samples per GPU, AMP autocast + GradScaler, AdamW, {occupancy} occupancy",
            "n_gpus": world, "train_rays_per_s": world * B / ms_train * 1e3, "train_ms_per_step": ms_train,
-           "render_msamples_per_s": world * B * N / ms_render * 1e3 / 1e6}
+           "render_msamples_per_s": world * B * N / ms_render * 1e3 / 1e6, **fused}
     if reducer is not None:
         out["allreduce_bytes_per_step"] = reducer.nbytes
     return out

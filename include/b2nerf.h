@@ -350,6 +350,33 @@ int b2n_debug_gather_bench(const float* table, int64_t n_entries, int blocks, in
 int b2n_debug_mnmajor_probe(const void* A, const void* B, float* D, int lbo, int sbo, int kadv, int idesc_extra,
                             b2n_stream_t stream);
 
+/* ------------------------------------------------------------------------
+ * Per-step parameter update: what run.py:611-630, :1112-1120 + :1167-1178, :1840-1859 + :1940-1949 do with
+ * ~100 torch launches per step -- TV loss over the flat hash tables, GradScaler.unscale_, clip_grad_norm_, AdamW -- as two
+ * passes.  Tensors are contiguous fp32 device buffers; the descriptor array lives on the HOST.
+ *   b2n_opt_prepare: g <- g / *grad_scale (if given) + tv_scale * (sign(p[i]-p[i-1]) - sign(p[i+1]-p[i]))
+ *                    (tv_scale = tv_weight / (n - 1): the gradient of tv_weight * mean|p[1:] - p[:-1]|, run.py:614-616);
+ *                    norm2[clip_group] += sum g^2 (norm2: device float[B2N_OPT_MAX_GROUPS], zeroed by the caller).
+ *   b2n_opt_adamw  : g * min(1, max_norm[group] / (sqrt(norm2[group]) + 1e-6)) (clip_grad_norm_; max_norm < 0 or norm2 NULL:
+ *                    no clipping), then torch.optim.AdamW's update with the descriptor's hyper-parameters
+ *                    (bias_corr = 1 - beta^step from the descriptor, or from the device scalar step_dev when given: a
+ *                    step skipped for an inf must not advance it); nothing is written when *found_inf != 0.
+ *                    already_unscaled = b2n_opt_prepare ran with the same grad_scale. */
+#define B2N_OPT_MAX_TENSORS 40
+#define B2N_OPT_MAX_GROUPS 8
+typedef struct {
+  float* p; float* g; float* m; float* v;
+  int64_t n;
+  float lr, weight_decay, beta1, beta2, eps, bias_corr1, bias_corr2, tv_scale;
+  int clip_group;    /* -1: not part of any norm */
+  int reserved;
+} b2n_opt_tensor;
+int b2n_opt_prepare(const b2n_opt_tensor* tensors, int n_tensors, const float* grad_scale, float* norm2,
+                    b2n_stream_t stream);
+int b2n_opt_adamw(const b2n_opt_tensor* tensors, int n_tensors, const float* grad_scale, int already_unscaled,
+                  const float* found_inf, const float* step_dev, const float* norm2, const float* max_norm_host,
+                  b2n_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -174,3 +174,63 @@ def test_cuda_graph_step_equals_eager_step():
             assert err < 2e-3, (k, err)
     finally:
         b2n.set_mlp_precision("fp32")
+
+
+def _opt_problem(seed):
+    """a table (TV-regularised) + a small MLP layer and a deterministic stream of 'losses'"""
+    g = torch.Generator().manual_seed(seed)
+    table = (torch.rand(5001, generator=g) * 2e-1 - 1e-1).cuda().requires_grad_(True)
+    W = (torch.randn(64, 48, generator=g) * 0.1).cuda().requires_grad_(True)
+    b = torch.zeros(64).cuda().requires_grad_(True)
+    xs = [torch.randn(32, 48, generator=g).cuda() for _ in range(6)]
+    ts = [torch.randn(5001, generator=g).cuda() for _ in range(6)]
+    return [table, W, b], xs, ts
+
+
+def _opt_loss(params, x, tvec, scale):
+    table, W, b = params
+    return (((x @ W.t() + b) ** 2).mean() + (table * tvec).sum() * 1e-3 + (table ** 2).sum()) * scale
+
+
+@pytest.mark.parametrize("mode", ["global_clip", "group_clip", "no_clip", "amp"])
+def test_fused_adamw_equals_torch_tv_clip_adamw(mode):
+    """b2n.optim.FusedAdamW (TV gradient + unscale + clip + AdamW in two launches) against the reference loop's
+    torch ops: TV term in the loss, GradScaler.unscale_, clip_grad_norm_, torch.optim.AdamW (run.py:611-630, :1167-1178)."""
+    import b2n
+    tv_w, lr, wd = 1e-2, 1e-2, 1e-3
+    ref_p, xs, ts = _opt_problem(5)
+    our_p = [p.detach().clone().requires_grad_(True) for p in ref_p]
+    ref_opt = torch.optim.AdamW([{"params": ref_p[:1]}, {"params": ref_p[1:]}], lr=lr, weight_decay=wd)
+    our_opt = b2n.optim.FusedAdamW([{"params": our_p[:1], "tv_weight": tv_w, "max_norm": 0.05 if mode == "group_clip" else None},
+                                    {"params": our_p[1:], "max_norm": 0.5 if mode == "group_clip" else None}],
+                                   lr=lr, weight_decay=wd)
+    ref_scaler = torch.amp.GradScaler("cuda", enabled=mode == "amp", init_scale=2.0 ** 10, growth_interval=3)
+    our_scaler = torch.amp.GradScaler("cuda", enabled=mode == "amp", init_scale=2.0 ** 10, growth_interval=3)
+    for i in range(6):
+        blow = 1e38 if (mode == "amp" and i == 2) else 1.0          # step 2 overflows: both must skip and back off
+        ref_opt.zero_grad()
+        loss = _opt_loss(ref_p, xs[i], ts[i], blow) + tv_w * (ref_p[0][1:] - ref_p[0][:-1]).abs().mean()
+        ref_scaler.scale(loss).backward()
+        ref_scaler.unscale_(ref_opt)
+        if mode in ("global_clip", "amp"):
+            torch.nn.utils.clip_grad_norm_(ref_p, max_norm=0.05)
+        elif mode == "group_clip":
+            torch.nn.utils.clip_grad_norm_(ref_p[:1], max_norm=0.05)
+            torch.nn.utils.clip_grad_norm_(ref_p[1:], max_norm=0.5)
+        ref_scaler.step(ref_opt)
+        ref_scaler.update()
+
+        our_opt.zero_grad()
+        our_scaler.scale(_opt_loss(our_p, xs[i], ts[i], blow)).backward()
+        if mode in ("global_clip", "amp"):
+            our_scaler.step(our_opt, max_norm=0.05)
+        else:
+            our_scaler.step(our_opt)
+        our_scaler.update()
+    torch.cuda.synchronize()
+    if mode == "amp":
+        assert float(ref_scaler.get_scale()) == float(our_scaler.get_scale())
+    for a, b_ in zip(ref_p, our_p):
+        assert torch.isfinite(b_).all()
+        err = float((a - b_).abs().max() / (a.abs().max() + 1e-12))
+        assert err < (2e-4 if mode == "amp" else 2e-5), (mode, err)

@@ -557,6 +557,28 @@ def main():
         g2 = make_grid(other)
         ms2 = timed(lambda i: train_step(dev_pool[i % n_pool], g2), args.steps, 2)
         extras[f"train_rays_per_s_{other}"] = world * B * args.steps / (ms2 * 1e-3)
+        # ---- the same step with the TV term, the two per-group clips and AdamW inside b2n.optim.FusedAdamW
+        try:
+            import b2n
+            fopt = b2n.optim.FusedAdamW(
+                [{"params": list(model.representation.parameters()), "tv_weight": TV_WEIGHT, "max_norm": 1.0},
+                 {"params": list(model.decoder.parameters()), "max_norm": 1.0}], lr=LR, weight_decay=WEIGHT_DECAY)
+
+            def fused_step(batch):
+                rays_o, rays_d, rgba = batch
+                target = rgba[:, :3] * rgba[:, 3:4] + bg * (1.0 - rgba[:, 3:4])
+                pred, _, _ = render_rays(model=model, rays_o=rays_o, rays_d=rays_d, near=NEAR, far=FAR,
+                                         n_samples=N_SAMPLES, perturb=True, white_bkgd=True, density_grid=grid, bg_color=bg)
+                loss = torch.nn.functional.mse_loss(pred, target)
+                reducer.zero_grad()
+                loss.backward()
+                reducer.allreduce()
+                fopt.step()
+
+            ms4 = timed(lambda i: fused_step(dev_pool[i % n_pool]), args.steps, 2)
+            extras["train_rays_per_s_fused_optimizer"] = world * B * args.steps / (ms4 * 1e-3)
+        except Exception as exc:
+            extras["fused_optimizer_error"] = f"{type(exc).__name__}: {exc}"[:300]
         # ---- render Msamples/s (forward only, no jitter, no_grad)
         model.eval()
         with torch.no_grad():

@@ -50,6 +50,27 @@ def test_product_has_no_cpu_path(lib):
         b2n.composite(torch.zeros(8, 3), torch.zeros(8), torch.zeros(2, 4), torch.zeros(2, 3))
 
 
+def test_optional_helpers_have_no_cpu_path_either(lib):
+    """b2n.optim.FusedAdamW / b2n.graphs.GraphedStep: host logic only (descriptor layout, option validation); on CPU tensors
+    they refuse to run instead of falling back."""
+    import ctypes
+    import b2n
+    from b2n.optim import _OptTensor
+    assert ctypes.sizeof(_OptTensor) == 80                       # b2n_opt_tensor of include/b2nerf.h: 4 ptr, i64, 8 f32, 2 i32
+    p = torch.nn.Parameter(torch.zeros(10))
+    opt = b2n.optim.FusedAdamW([{"params": [p], "tv_weight": 1e-3, "max_norm": 1.0}], lr=1e-2)
+    assert opt.defaults["weight_decay"] == 1e-2 and opt.param_groups[0]["tv_weight"] == 1e-3
+    assert opt._step_supports_amp_scaling
+    opt.step()                                                   # no gradients: nothing to do, no kernel call
+    p.grad = torch.ones(10)
+    with pytest.raises(ValueError, match="no CPU path"):
+        opt.step()
+    with pytest.raises(ValueError):
+        b2n.optim.FusedAdamW([p], lr=-1.0)
+    with pytest.raises(ValueError, match="no CPU path"):
+        b2n.graphs.GraphedStep(lambda x: x + 1, (torch.zeros(3),))
+
+
 def test_hash_geometry_matches_oracle_table(lib):
     import b2n
     from oracle import nerf_oracle as O

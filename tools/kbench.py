@@ -255,6 +255,46 @@ def hash_levels(P=24_000_000):
               f"({(b_med - f_med) / nl:6.3f}/level)")
 
 
+def hash_sorted():
+    """What spatial order buys the hash-grid kernels AS THEY ARE (lanes = the 16 levels of a point): the C2 sample set in
+    ray order against the same points sorted by a 30-bit Morton key (torch argsort; sort cost reported separately)."""
+    from b2n import synthetic, march
+    torch.manual_seed(0)
+    ro, rd, _ = (t.cuda() for t in synthetic.random_rays(2 ** 18, seed=1))
+    u = torch.rand(2 ** 18, 128, device="cuda")
+    occ = torch.ones(128, 128, 128, dtype=torch.bool, device="cuda")
+    x = march.march(ro, rd, 2.0, 6.0, 128, u, bits=march.pack_occupancy(occ), R=128, bound=1.5).pts
+    print("points", x.shape[0])
+
+    def spread(v):                                   # 10 bits -> every third bit
+        v = (v | (v << 16)) & 0x030000FF
+        v = (v | (v << 8)) & 0x0300F00F
+        v = (v | (v << 4)) & 0x030C30C3
+        return (v | (v << 2)) & 0x09249249
+
+    def morton(p):
+        q = ((p + 1.5) / 3.0 * 1023.0).clamp(0, 1023).to(torch.int64)
+        return spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)
+
+    t_sort, _ = timeit(lambda: torch.argsort(morton(x)), n=3, warm=1)
+    order = torch.argsort(morton(x))
+    xs = x[order].contiguous()
+    print(f"morton key + torch.argsort: {t_sort:.3f} ms (a radix sort of 30-bit keys would be the product path)")
+    geom = b2n.HashGeometry(16, 16, 1.5, 19, 2)
+    table = (torch.randn(geom.n_params, device="cuda") * 0.1).requires_grad_(True)
+    for name, pts in (("ray order", x), ("morton order", xs)):
+        y = b2n.hash_encode(pts, table, geom, 1.5)
+        g = torch.randn_like(y)
+        b2n._lib.PROFILER = prof = b2n._lib.Profiler()
+        for _ in range(4):
+            y = b2n.hash_encode(pts, table, geom, 1.5)
+            y.backward(g)
+        torch.cuda.synchronize()
+        b2n._lib.PROFILER = None
+        print(f"{name:13s}: " + ", ".join(f"{k} {min(e0.elapsed_time(e1) for n_, _, _, e0, e1 in prof.records if n_ == k):.3f} ms"
+                                           for k in ("b2n_hash_fwd", "b2n_hash_bwd")))
+
+
 def l2_gather():
     """Random 8-byte gathers over tables of 2 MiB .. 512 MiB: the L2 (and beyond-L2) gather peak."""
     from b2n._lib import call, ptr, stream
@@ -313,6 +353,8 @@ if __name__ == "__main__":
         c1_step()
     elif what == "occ":
         occ_update()
+    elif what == "hashsort":
+        hash_sorted()
     elif what == "hash":
         hash_levels()
     elif what == "l2":

@@ -369,7 +369,7 @@ typedef struct {
   int64_t n;
   float lr, weight_decay, beta1, beta2, eps, bias_corr1, bias_corr2, tv_scale;
   int clip_group;    /* -1: not part of any norm */
-  int reserved;
+  int reserved;      /* set by the library (16-byte alignment of the four buffers); callers pass 0 */
 } b2n_opt_tensor;
 int b2n_opt_prepare(const b2n_opt_tensor* tensors, int n_tensors, const float* grad_scale, float* norm2,
                     b2n_stream_t stream);

@@ -23,7 +23,8 @@ ENTRY_OF = {"k_hash_fwd": "b2n_hash_fwd", "k_hash_bwd_table": "b2n_hash_bwd", "k
             "k_composite_bwd": "b2n_composite_bwd", "k_march_mask": "b2n_march_mask",
             "k_march_compact": "b2n_march_compact", "k_mlp256<0": "b2n_nerf_mlp_fwd", "k_mlp256<1": "b2n_nerf_mlp_bwd",
             "k_fmlp_fwd": "b2n_fmlp_fwd", "k_fmlp_bwd": "b2n_fmlp_bwd", "k_fmlp_wgrad": "b2n_fmlp_wgrad",
-            "k_nerf_dx": "b2n_nerf_mlp_dx", "wg256::k_wgrad256": "b2n_nerf_mlp_wgrad", "k_wgrad256": "b2n_nerf_mlp_wgrad", "k_hash_bwd_input": "b2n_hash_bwd_input"}
+            "k_nerf_dx": "b2n_nerf_mlp_dx", "wg256::k_wgrad256": "b2n_nerf_mlp_wgrad", "k_wgrad256": "b2n_nerf_mlp_wgrad", "k_hash_bwd_input": "b2n_hash_bwd_input",
+            "k_opt_prepare": "b2n_opt_prepare", "k_opt_adamw": "b2n_opt_adamw"}
 
 METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
            "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct",
@@ -43,7 +44,7 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
 
 def short(name):
     name = name.split("(")[0]
-    for pre in ("void ", "b2n::", "fm::", "m256::", "wg256::"):
+    for pre in ("void ", "b2n::", "fm::", "m256::", "wg256::", "opt::"):
         name = name.replace(pre, "")
     return name.strip()
 

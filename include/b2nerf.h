@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2N_ABI_VERSION 11
+#define B2N_ABI_VERSION 12
 
 #define B2N_OK 0
 #define B2N_EINVAL (-1)  /* bad argument (null pointer, size, unsupported shape) */
@@ -193,7 +193,11 @@ int b2n_sigma_head_bwd(const float* h, int ldh, int64_t P, const float* g_sigma,
  * Fused InstantNeRFDecoder (src/decoders.py:136-162: two tinycudann
  * FullyFusedMLPs + softplus density head + concat + sigmoid) including the
  * view-direction Fourier features (src/embeddings.py:22-32 applied to d,
- * src/core.py:358).  bf16 tensor-core operands, fp32 accumulation; hidden
+ * src/core.py:358).  IEEE fp16 tensor-core operands (tinycudann's arithmetic),
+ * fp32 accumulation; sigma_net's first layer as a split (hi + lo) product; the
+ * backward chain runs on a power-of-two multiple of the incoming gradient
+ * (found by an |.|-max pre-pass into work4: 4 device bytes owned by the caller)
+ * and a non-finite incoming gradient makes every output non-finite.  Hidden
  * width 64; pos_dim <= 64 (padded with zeros); L_dir <= 4 bands.
  *   x_enc [P, pos_dim] (row stride ldx), dirs [P,3] unit view directions,
  *   sigma_params flat [64*pad16(pos_dim) + 16*64], color_params flat
@@ -209,7 +213,7 @@ int b2n_instant_mlp_fwd(const float* x_enc, int ldx, int pos_dim, const float* d
 int b2n_instant_mlp_bwd(const float* x_enc, int ldx, int pos_dim, const float* dirs, const float* dir_bands,
                         int L_dir, const float* sigma_params, const float* color_params, int64_t P,
                         const float* g_rgb, const float* g_sigma, float* g_x_enc, int ldg, float* g_sigma_params,
-                        float* g_color_params, b2n_stream_t stream);
+                        float* g_color_params, void* work4, b2n_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Fused small-width ReLU MLPs of the dynamic configs, bf16 tensor-core
@@ -311,16 +315,6 @@ int b2n_pad_bf16(const float* x, int64_t P, int width, int kpad, void* out, b2n_
 int b2n_nerf_mlp_wgrad(const void* dz_planes, const void* fwd_planes, const void* x_bf16, int kx, const void* d_bf16,
                        int64_t P, float* dW, float* dW0, float* dW4x, float* dWv_h, float* dWv_d, float* db,
                        int* err_flag, b2n_stream_t stream);
-/* debug aid: per-role cycle counters of CTA 0 of the next b2n_nerf_mlp_* launches (device int64[8 + 448]: 8 counters, then a
- * clock64 timeline of CTA 0's third tile pair, [step][tile][16 events]; or NULL) */
-int b2n_debug_mlp256_prof(void* device_int64x8);
-/* debug aid (timing experiments only, results become garbage): 1 = the epilogue skips the accumulator drain,
- * 2 = no MMAs are issued (weights still stream); 0 = normal */
-int b2n_debug_mlp256_flags(int flags);
-/* schedule of b2n_nerf_mlp_fwd / _bwd: 1 (default; environment B2N_MLP256_PAIR=0 turns it off) = clusters of two CTAs
- * issuing cta_group::2 MMAs (M = 256 over an SM pair, each CTA staging half of every weight chunk); 0 = one CTA per SM.
- * Both produce the same results; the switch exists for A/B timing and parity tests. */
-int b2n_nerf_mlp_set_pair(int on);
 size_t b2n_nerf_mlp_packed_bwd_bytes(void);
 int b2n_nerf_mlp_pack_bwd(const float* const* pts_w, const float* feature_w, const float* view_w, int pos_dim,
                           int dir_dim, void* packed, b2n_stream_t stream);
@@ -339,16 +333,6 @@ int b2n_sample_rays(const float* poses, const uint8_t* images_rgba8, const float
                     const int64_t* pix_y, const int64_t* pix_x, int64_t B, int V, int H, int W, float focal,
                     float scene_scale, float* rays_o, float* rays_d, float* target_rgba, float* t_out,
                     b2n_stream_t stream);
-
-/* measurement aid: random 8-byte gathers over a float2[n_entries] table (n_entries = 2^k); used to
- * measure the L2 gather peak the hash-grid kernels are compared against (tools/kbench.py l2) */
-int b2n_debug_gather_bench(const float* table, int64_t n_entries, int blocks, int per_thread, float* sink,
-                           b2n_stream_t stream);
-
-/* development probe: D[128x128] = A^T B through tcgen05.mma with MN-major shared-memory operands (A, B: bf16 [64][128],
- * row = contraction index); lbo / sbo / kadv (bytes) and extra instruction-descriptor bits are arguments */
-int b2n_debug_mnmajor_probe(const void* A, const void* B, float* D, int lbo, int sbo, int kadv, int idesc_extra,
-                            b2n_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Per-step parameter update: what run.py:611-630, :1112-1120 + :1167-1178, :1840-1859 + :1940-1949 do with

@@ -189,21 +189,74 @@ def bf16_round(x: Tensor) -> Tensor:
     return x + (x.to(torch.bfloat16).to(x.dtype) - x).detach()
 
 
+# 16-bit operand type of each CUDA kernel family, for the "kernel" arithmetic model: the fused Instant decoder
+# (csrc/b2n_mlp64.cu) computes in IEEE fp16 like tinycudann, the other tensor-core kernels in bf16.
+KERNEL_OPERAND = {"instant": torch.float16, "fmlp": torch.bfloat16, "nerf256": torch.bfloat16}
+
+
+def _q(x: Tensor, dt=torch.bfloat16) -> Tensor:
+    return x.to(dt).to(x.dtype)
+
+
+class _KernelMatmul(torch.autograd.Function):
+    """h @ W^T with the operand rounding of the fused tensor-core kernels, forward AND backward
+    (``emulate_bf16="kernel"``):
+
+    forward : bf16(h) @ bf16(W)^T, fp32 accumulation -- or the exact product when ``exact_fwd``
+              (the kernels evaluate the first layer of a hash-grid decoder as a split-bf16
+              product hi*hi + lo*hi + hi*lo, i.e. to ~16 mantissa bits: csrc/b2n_mlp64.cu);
+    backward: the incoming pre-activation gradient dZ is rounded to bf16 once (the kernels stage
+              it in shared memory as bf16) and that rounded dZ feeds both the data gradient
+              dZ bf16(W) and the weight gradient dZ^T bf16(h)."""
+
+    @staticmethod
+    def forward(ctx, h, W, exact_fwd, dt):
+        hq, Wq = _q(h, dt), _q(W, dt)
+        ctx.save_for_backward(hq, Wq)
+        ctx.dt = dt
+        return (h @ W.t()) if exact_fwd else (hq @ Wq.t())
+
+    @staticmethod
+    def backward(ctx, dz):
+        hq, Wq = ctx.saved_tensors
+        if ctx.dt == torch.float16:
+            # the fp16 kernels run the gradient chain on S * dZ, S a power of two putting max|dL/dy| near 2^7: the
+            # rounding is relative (no underflow) for everything within ~2^-21 of the largest gradient -- model it as
+            # a pure 11-bit mantissa rounding by normalising with the tensor's own power-of-two scale
+            m = float(dz.abs().max())
+            sc = 2.0 ** (7 - math.floor(math.log2(m))) if (m > 0 and math.isfinite(m)) else 1.0
+            dzq = _q(dz * sc, ctx.dt) / sc
+        else:
+            dzq = _q(dz, ctx.dt)
+        return dzq @ Wq, dzq.t() @ hq, None, None
+
+
+def _matmul_t(h: Tensor, W: Tensor, emulate_bf16, exact_fwd: bool = False, family: str = "fmlp") -> Tensor:
+    """h @ W^T under the three arithmetic models of this oracle: False = working dtype; True = bf16 forward
+    operands with a straight-through gradient; "kernel" = _KernelMatmul with the kernel family's operand type."""
+    if emulate_bf16 == "kernel":
+        return _KernelMatmul.apply(h, W, exact_fwd, KERNEL_OPERAND[family])
+    if emulate_bf16:
+        return bf16_round(h) @ bf16_round(W).t()
+    return h @ W.t()
+
+
 def fused_mlp(x: Tensor, params: Tensor, n_in: int, n_out: int, n_neurons: int,
-              n_hidden: int, out_act: str = "None", emulate_bf16: bool = False) -> Tensor:
+              n_hidden: int, out_act: str = "None", emulate_bf16=False, first_exact: bool = False,
+              family: str = "fmlp") -> Tensor:
     """ReLU MLP without bias terms.  Input columns beyond ``n_in`` are padded
     with ZEROS (SURVEY.md A4 fixes this choice), so the padded weight columns
-    never contribute; the padded output rows are computed and sliced away."""
+    never contribute; the padded output rows are computed and sliced away.
+    ``first_exact`` (kernel emulation only): the first layer's forward product is not rounded."""
     shapes = fused_mlp_shapes(n_in, n_out, n_neurons, n_hidden)
     h = x
     if shapes[0][1] != n_in:
         h = F.pad(h, (0, shapes[0][1] - n_in))
     off = 0
-    q = bf16_round if emulate_bf16 else (lambda v: v)
     for li, (r, c) in enumerate(shapes):
         W = params[off:off + r * c].view(r, c).to(h.dtype)
         off += r * c
-        h = q(h) @ q(W).t()
+        h = _matmul_t(h, W, emulate_bf16, exact_fwd=first_exact and li == 0, family=family)
         if li < len(shapes) - 1:
             h = torch.relu(h)
     h = h[:, :n_out]
@@ -222,14 +275,12 @@ def _lin(sd: Dict[str, Tensor], prefix: str, h: Tensor) -> Tensor:
     return F.linear(h, sd[prefix + ".weight"].to(h.dtype), sd[prefix + ".bias"].to(h.dtype))
 
 
-def nerf_decoder(sd, prefix: str, x: Tensor, d: Tensor, num_layers=8, skip_layer=4, emulate_bf16: bool = False):
+def nerf_decoder(sd, prefix: str, x: Tensor, d: Tensor, num_layers=8, skip_layer=4, emulate_bf16=False):
     """8x256 trunk with [h, x] skip concat, sigma/feature heads, view branch
     (src/decoders.py:68-87).  ``emulate_bf16`` rounds the operands of the trunk / feature / view
     GEMMs to bf16 like the tensor-core kernel does (the two small heads stay in fp32)."""
-    q = bf16_round if emulate_bf16 else (lambda v: v)
-
     def lin(name, v):
-        return F.linear(q(v), q(sd[name + ".weight"].to(v.dtype)), sd[name + ".bias"].to(v.dtype))
+        return _matmul_t(v, sd[name + ".weight"].to(v.dtype), emulate_bf16, family="nerf256") + sd[name + ".bias"].to(v.dtype)
     h = x
     for i in range(num_layers):
         if i == skip_layer:
@@ -242,14 +293,16 @@ def nerf_decoder(sd, prefix: str, x: Tensor, d: Tensor, num_layers=8, skip_layer
     return rgb, sigma
 
 
-def instant_decoder(sd, prefix: str, x_enc: Tensor, d_enc: Tensor, hidden=64, emulate_bf16: bool = False):
+def instant_decoder(sd, prefix: str, x_enc: Tensor, d_enc: Tensor, hidden=64, emulate_bf16=False):
     """sigma_net (in->64->16), sigma = softplus(h0-5), color_net on
-    cat[h(16), d_enc] (->64->64->3, sigmoid)   (src/decoders.py:136-162)."""
+    cat[h(16), d_enc] (->64->64->3, sigmoid)   (src/decoders.py:136-162).
+    Kernel emulation: sigma_net's first layer (the one fed by the hash features) is a split-bf16 product."""
     pos_dim, dir_dim = x_enc.shape[-1], d_enc.shape[-1]
-    h = fused_mlp(x_enc, sd[f"{prefix}.sigma_net.params"], pos_dim, 16, hidden, 1, emulate_bf16=emulate_bf16)
+    h = fused_mlp(x_enc, sd[f"{prefix}.sigma_net.params"], pos_dim, 16, hidden, 1, emulate_bf16=emulate_bf16,
+                  first_exact=True, family="instant")
     sigma = F.softplus(h[..., 0:1] - 5.0)
     rgb = fused_mlp(torch.cat([h, d_enc], dim=-1), sd[f"{prefix}.color_net.params"],
-                    16 + dir_dim, 3, hidden, 2, out_act="Sigmoid", emulate_bf16=emulate_bf16)
+                    16 + dir_dim, 3, hidden, 2, out_act="Sigmoid", emulate_bf16=emulate_bf16, family="instant")
     return rgb, sigma
 
 
@@ -257,10 +310,10 @@ def _lin_q(sd: Dict[str, Tensor], prefix: str, h: Tensor, emulate_bf16: bool) ->
     """nn.Linear with (optionally) bf16-rounded GEMM operands and an fp32 bias, like the tensor-core kernels"""
     if not emulate_bf16:
         return _lin(sd, prefix, h)
-    return F.linear(bf16_round(h), bf16_round(sd[prefix + ".weight"].to(h.dtype)), sd[prefix + ".bias"].to(h.dtype))
+    return _matmul_t(h, sd[prefix + ".weight"].to(h.dtype), emulate_bf16) + sd[prefix + ".bias"].to(h.dtype)
 
 
-def deformation_net(sd, prefix: str, x_feat: Tensor, t_feat: Tensor, num_layers=4, emulate_bf16: bool = False):
+def deformation_net(sd, prefix: str, x_feat: Tensor, t_feat: Tensor, num_layers=4, emulate_bf16=False):
     """Linear/ReLU stack -> 3-vector (src/decoders.py:171-195); nn.Sequential
     indices 0,2,4,... hold the Linear layers."""
     h = torch.cat([x_feat, t_feat], dim=-1)
@@ -271,7 +324,7 @@ def deformation_net(sd, prefix: str, x_feat: Tensor, t_feat: Tensor, num_layers=
     return h
 
 
-def time_modulation(sd, prefix: str, t_feat: Tensor, num_layers=2, emulate_bf16: bool = False):
+def time_modulation(sd, prefix: str, t_feat: Tensor, num_layers=2, emulate_bf16=False):
     """sigmoid(MLP(time features))   (src/decoders.py:342-371)."""
     h = t_feat
     for i in range(num_layers):
@@ -281,7 +334,7 @@ def time_modulation(sd, prefix: str, t_feat: Tensor, num_layers=2, emulate_bf16:
     return torch.sigmoid(h)
 
 
-def hash_deform_decoder(sd, prefix: str, hash_feat: Tensor, time_mod: Tensor, hidden=64, emulate_bf16: bool = False):
+def hash_deform_decoder(sd, prefix: str, hash_feat: Tensor, time_mod: Tensor, hidden=64, emulate_bf16=False):
     """fused MLP (cat -> 64 -> 64 -> 3) * displacement_scale (src/decoders.py:300-318)."""
     h = torch.cat([hash_feat, time_mod], dim=-1)
     dx = fused_mlp(h, sd[f"{prefix}.deform_net.params"], h.shape[-1], 3, hidden, 2, emulate_bf16=emulate_bf16)
@@ -300,10 +353,13 @@ class OracleField:
     calls in the same order (so a shared CPU seed gives identical noise).
     """
 
-    def __init__(self, cfg: dict, sd: Dict[str, Tensor]):
+    def __init__(self, cfg: dict, sd: Dict[str, Tensor], emulate_bf16=False):
         self.cfg, self.sd = cfg, sd
         self.mode = cfg["mode"]
         self.training = False
+        # False | True | "kernel": arithmetic model of every decoder GEMM (see _matmul_t); the encoders, the blend and
+        # the compositing stay in the working dtype, as they do in the CUDA path
+        self.emulate_bf16 = emulate_bf16
         g = cfg.get
         self.use_coord_noise = g("use_coord_noise", False)
         self.coord_noise_std = g("coord_noise_std", 0.005)
@@ -352,7 +408,7 @@ class OracleField:
 
     def _nerf_dec(self, prefix, h, d):
         g = self.cfg.get
-        return nerf_decoder(self.sd, prefix, h, d, g("num_layers", 8), g("skip_layer", 4))
+        return nerf_decoder(self.sd, prefix, h, d, g("num_layers", 8), g("skip_layer", 4), emulate_bf16=self.emulate_bf16)
 
     # -- forward ----------------------------------------------------------
     def __call__(self, x: Tensor, d: Optional[Tensor] = None, t: Optional[Tensor] = None):
@@ -365,7 +421,8 @@ class OracleField:
             if d is None:
                 raise ValueError("part2_instant requires view directions.")
             h = self._hash("representation", x, self.levels, self.n_feat)
-            return instant_decoder(self.sd, "decoder", h, self._pe("dir_representation", d), self.hidden)
+            return instant_decoder(self.sd, "decoder", h, self._pe("dir_representation", d), self.hidden,
+                                   emulate_bf16=self.emulate_bf16)
         if m == "part3":
             if t is None:
                 raise ValueError("Part 3 requires time input 't'.")
@@ -375,13 +432,16 @@ class OracleField:
                 return rgb, sigma, torch.zeros_like(x)
             xd, td = self._noise(x, t)
             feat_t = self._pe("time_encoder", td)
+            # (the CUDA path runs the deformation net on tensor cores only for hidden widths 64 / 128)
+            emu_d = self.emulate_bf16 if self.cfg.get("deform_hidden_dim", 128) in (64, 128) else False
             dx = deformation_net(self.sd, "deform_net", self._pe("pos_encoder_for_deform", xd), feat_t,
-                                 self.cfg.get("deform_num_layers", 4))
+                                 self.cfg.get("deform_num_layers", 4), emulate_bf16=emu_d)
             xc = x + dx                                             # un-noised x, src/core.py:268
             fd = self._pe("dir_representation", d)
             if self._instant_canonical():
                 fc = self._hash("canonical_repr", xc, self.levels, self.n_feat)
-                rgb, sigma = instant_decoder(self.sd, "decoder", torch.cat([fc, feat_t], dim=-1), fd, self.hidden)
+                rgb, sigma = instant_decoder(self.sd, "decoder", torch.cat([fc, feat_t], dim=-1), fd, self.hidden,
+                                             emulate_bf16=self.emulate_bf16)
             else:
                 fc = self._pe("canonical_repr", xc)
                 rgb, sigma = self._nerf_dec("decoder", torch.cat([fc, feat_t], dim=-1), fd)
@@ -391,7 +451,8 @@ class OracleField:
                 raise ValueError("Part 4 requires time input 't'.")
             xd, td = self._noise(x, t)
             feat_t = self._pe("time_encoder", td)
-            tmod = time_modulation(self.sd, "time_modulation", feat_t, self.cfg.get("time_modulation_layers", 2))
+            tmod = time_modulation(self.sd, "time_modulation", feat_t, self.cfg.get("time_modulation_layers", 2),
+                                   emulate_bf16=self.emulate_bf16)
             f0 = self._hash("deform_grid_start", xd, self.d_levels, self.d_feat)
             f1 = self._hash("deform_grid_mid", xd, self.d_levels, self.d_feat)
             f2 = self._hash("deform_grid_end", xd, self.d_levels, self.d_feat)
@@ -400,11 +461,12 @@ class OracleField:
             w2 = torch.clamp(1.0 - torch.abs(td - 1.0) / 0.5, 0.0, 1.0)
             ws = w0 + w1 + w2 + 1e-8
             blend = (w0 / ws) * f0 + (w1 / ws) * f1 + (w2 / ws) * f2
-            dx = hash_deform_decoder(self.sd, "deform_decoder", blend, tmod, self.cfg.get("deform_hidden_dim", 64))
+            dx = hash_deform_decoder(self.sd, "deform_decoder", blend, tmod, self.cfg.get("deform_hidden_dim", 64),
+                                     emulate_bf16=self.emulate_bf16)
             xc = x + dx
             fc = self._hash("canonical_repr", xc, self.levels, self.n_feat)
             rgb, sigma = instant_decoder(self.sd, "decoder", torch.cat([fc, feat_t], dim=-1),
-                                         self._pe("dir_representation", d), self.hidden)
+                                         self._pe("dir_representation", d), self.hidden, emulate_bf16=self.emulate_bf16)
             return rgb, sigma, dx
         raise ValueError(f"mode {m!r} is outside the ray-marching hot path")
 

@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb2nerf.so")
 
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 P, L, I, F = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
 
@@ -44,7 +44,7 @@ SIGNATURES = {
     "b2n_sigma_head_fwd": [P, I, L, P, P],
     "b2n_sigma_head_bwd": [P, I, L, P, P, I, P],
     "b2n_instant_mlp_fwd": [P, I, I, P, P, I, P, P, L, P, P, P],
-    "b2n_instant_mlp_bwd": [P, I, I, P, P, I, P, P, L, P, P, P, I, P, P, P],
+    "b2n_instant_mlp_bwd": [P, I, I, P, P, I, P, P, L, P, P, P, I, P, P, P, P],
     "b2n_fmlp_in_pad": [I],
     "b2n_fmlp_out_pad": [I],
     "b2n_fmlp_fwd": [P, I, I, P, I, I, I, I, P, P, P, I, I, L, P, I, P, P, P],
@@ -59,15 +59,20 @@ SIGNATURES = {
     "b2n_pad_bf16": [P, L, I, I, P, P],
     "b2n_opt_prepare": [P, I, P, P, P],
     "b2n_opt_adamw": [P, I, P, I, P, P, P, P, P],
-    "b2n_debug_mlp256_prof": [P],
-    "b2n_debug_mlp256_flags": [ctypes.c_int],
-    "b2n_nerf_mlp_set_pair": [ctypes.c_int],
-    "b2n_debug_gather_bench": [P, L, I, I, P, P],
-    "b2n_debug_mnmajor_probe": [P, P, P, I, I, I, I, P],
     "b2n_sample_rays": [P, P, P, P, P, P, L, I, I, I, F, F, P, P, P, P, P],
     "b2n_nerf_mlp_packed_bwd_bytes": [],
     "b2n_nerf_mlp_pack_bwd": [P, P, P, I, I, P, P],
     "b2n_nerf_mlp_bwd": [P, P, P, P, P, P, P, P, L, P, P, P, P],
+}
+# development / measurement entry points (include/b2nerf_debug.h): bound like the rest, never called by a product path
+DEBUG_SIGNATURES = {
+    "b2n_debug_mlp256_prof": [P],
+    "b2n_debug_mlp256_flags": [ctypes.c_int],
+    "b2n_debug_mlp256_set_pair": [ctypes.c_int],
+    "b2n_debug_hash_variant": [I, I],
+    "b2n_debug_gather_bench": [P, L, I, I, P, P],
+    "b2n_debug_red_bench": [P, L, I, I, I, P],
+    "b2n_debug_mnmajor_probe": [P, P, P, I, I, I, I, P],
 }
 _RESTYPES = {"b2n_last_error": ctypes.c_char_p, "b2n_march_scan_scratch": ctypes.c_size_t,
              "b2n_nerf_mlp_packed_bytes": ctypes.c_size_t, "b2n_nerf_mlp_packed_bwd_bytes": ctypes.c_size_t}
@@ -85,7 +90,7 @@ def _load():
             f"{LIB_PATH} not found: build the CUDA extension first (python project-nerf_b200/build.py). "
             "This package has no CPU fallback.")
     lib = ctypes.CDLL(LIB_PATH)
-    for name, argtypes in SIGNATURES.items():
+    for name, argtypes in list(SIGNATURES.items()) + list(DEBUG_SIGNATURES.items()):
         fn = getattr(lib, name)          # AttributeError if the .so does not export it
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, ctypes.c_int)
@@ -100,7 +105,7 @@ lib = _load()
 # launch accounting for bench.py ("gpu_launches"): every successful C-ABI call adds the
 # number of kernels that entry point launches.
 LAUNCHES = {"count": 0}
-_KERNELS_PER_CALL = {"b2n_march_scan": 3, "b2n_linear_wgrad": 2, "b2n_hash_bwd": 2}   # hash_bwd: dense + hashed levels
+_KERNELS_PER_CALL = {"b2n_march_scan": 3, "b2n_linear_wgrad": 2, "b2n_instant_mlp_bwd": 2}   # instant bwd: |g|-max pre-pass + kernel
 
 
 def ptr(t):

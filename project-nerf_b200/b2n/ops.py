@@ -375,9 +375,10 @@ class _InstantMLP(torch.autograd.Function):
         Pn, pos_dim = x_enc.shape
         g_x = torch.empty_like(x_enc) if ctx.needs_input_grad[0] else None
         g_sp, g_cp = torch.zeros_like(sp), torch.zeros_like(cp)
+        work = torch.empty(1, device=x_enc.device, dtype=torch.int32)        # |g|-max of the gradient pre-pass
         flops = 6.0 * Pn * (64 * pos_dim + 16 * 64 + 64 * 43 + 64 * 64 + 3 * 64)
         call("b2n_instant_mlp_bwd", ptr(x_enc), pos_dim, pos_dim, ptr(dirs), ptr(bands), bands.numel(), ptr(sp),
-             ptr(cp), Pn, ptr(_c(g_rgb)), ptr(_c(g_sigma)), ptr(g_x), pos_dim, ptr(g_sp), ptr(g_cp), stream(),
+             ptr(cp), Pn, ptr(_c(g_rgb)), ptr(_c(g_sigma)), ptr(g_x), pos_dim, ptr(g_sp), ptr(g_cp), ptr(work), stream(),
              work=(Pn * (8.0 * pos_dim + 12 + 16), flops))
         return g_x, None, None, g_sp, g_cp
 

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include "../../include/b2nerf.h"
+#include "../../include/b2nerf_debug.h"
 
 namespace b2n {
 

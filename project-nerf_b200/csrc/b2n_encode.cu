@@ -281,6 +281,152 @@ k_hash_bwd_table_dense(const float* __restrict__ x, int64_t P, float bound, floa
   }
 }
 
+// ----------------------------------------------------------------------------- pair-lane kernels (F == 2)
+// The L1TEX unit retires one 128-byte line per load instruction per clock (the k_hash_fwd above ran at 97 % of that: its
+// lanes are the 16 levels of two points, so every gather instruction touches 32 different lines).  Here lanes 2i / 2i+1
+// of a warp share point i and take the x = 0 / x = 1 corner column of the cell; the level is warp-uniform and walked in a
+// loop.  The two x-neighbours of a corner pair sit in the same 128-byte line (dense levels: adjacent entries; hashed
+// levels: x carries hash prime 1, so the indices differ in the low bits only), hence one gather instruction costs 16 lines
+// for 16 points instead of 32 lines for 32 (point, level) items at 1.5 instructions per corner pair: 4 instead of 6 line
+// visits per (point, level) on the hashed levels, and on the coarse levels the 16 consecutive samples of a ray that a
+// warp holds fall into a handful of cells that share their lines.  Level geometry comes from the constant bank.
+__device__ __forceinline__ float pair_sum(float v) { return v + __shfl_xor_sync(0xffffffffu, v, 1); }
+
+__global__ void __launch_bounds__(256)
+k_hash_fwd_pair(const float* __restrict__ x, int64_t P, float bound, float two_bound, const float2* __restrict__ table,
+                const Levels lv, int nl, float* __restrict__ out, int ld, int col0) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t p = tid >> 1;
+  const int s = threadIdx.x & 1;
+  const bool live = p < P;
+  float x01[3] = {0.f, 0.f, 0.f};
+  if (live) {
+    bool in;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x01[d] = to_unit(__ldg(x + 3 * p + d), bound, two_bound, &in);
+  }
+  float* orow = out + p * ld + col0;
+  const bool vec = ((reinterpret_cast<uintptr_t>(out + col0) & 15) == 0) && ((ld & 3) == 0);
+  // 4 levels = 8 floats = one 32-byte sector of the point's feature row per chunk; lane s stores its 16-byte half
+  for (int l0 = 0; l0 < nl; l0 += 4) {
+    float keep0 = 0.f, keep1 = 0.f, keep2 = 0.f, keep3 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int l = l0 + j;
+      float a0 = 0.f, a1 = 0.f;
+      if (l < nl) {                                   // warp-uniform
+        const b2n_hash_level L = lv.l[l];
+        const Cell c = locate(x01, L.scale);
+        const uint32_t cx = c.g[0] + (uint32_t)s;
+        const float wx = s ? c.w[0] : 1.f - c.w[0];
+        float2 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t e = corner_entry(L, cx, c.g[1] + (k & 1), c.g[2] + (k >> 1));
+          v[k] = live ? __ldg(table + e) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float w = wx * ((k & 1) ? c.w[1] : 1.f - c.w[1]) * ((k & 2) ? c.w[2] : 1.f - c.w[2]);
+          a0 += w * v[k].x, a1 += w * v[k].y;
+        }
+      }
+      a0 = pair_sum(a0), a1 = pair_sum(a1);
+      if ((j >> 1) == s) {                             // lane 0 keeps levels l0, l0+1; lane 1 keeps l0+2, l0+3
+        if (j & 1) keep2 = a0, keep3 = a1;
+        else keep0 = a0, keep1 = a1;
+      }
+    }
+    if (live) {
+      const int lf = l0 + 2 * s;                       // first level this lane stores
+      float* o = orow + 2 * lf;
+      if (vec && lf + 1 < nl) {
+        __stcs(reinterpret_cast<float4*>(o), make_float4(keep0, keep1, keep2, keep3));
+      } else {
+        if (lf < nl) __stcs(o, keep0), __stcs(o + 1, keep1);
+        if (lf + 1 < nl) __stcs(o + 2, keep2), __stcs(o + 3, keep3);
+      }
+    }
+  }
+}
+
+// Table gradient with the same lane mapping.  A level whose resolution is <= merge_res is reduced across the run of
+// consecutive points (consecutive samples of a ray) that share a cell before the run head issues the red.global -- the
+// coarse levels would otherwise serialise millions of reductions on a few thousand addresses.
+__global__ void __launch_bounds__(256)
+k_hash_bwd_table_pair(const float* __restrict__ x, int64_t P, float bound, float two_bound, const Levels lv, int nl,
+                      const float* __restrict__ g, int ld, int col0, float2* __restrict__ g_table, uint32_t merge_res) {
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t p = tid >> 1;
+  const int lane = threadIdx.x & 31, s = lane & 1, pi = lane >> 1;     // pi: point index inside the warp (0..15)
+  const bool live = p < P;
+  float x01[3] = {0.f, 0.f, 0.f};
+  if (live) {
+    bool in;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x01[d] = to_unit(__ldg(x + 3 * p + d), bound, two_bound, &in);
+  }
+  const float* grow = g + p * ld + col0;
+  const bool vec = ((reinterpret_cast<uintptr_t>(g + col0) & 15) == 0) && ((ld & 3) == 0);
+  for (int l0 = 0; l0 < nl; l0 += 4) {
+    float gv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      if (vec && l0 + 4 <= nl) {
+        const float4 a = __ldcs(reinterpret_cast<const float4*>(grow + 2 * l0));
+        const float4 b = __ldcs(reinterpret_cast<const float4*>(grow + 2 * l0) + 1);
+        gv[0] = a.x, gv[1] = a.y, gv[2] = a.z, gv[3] = a.w, gv[4] = b.x, gv[5] = b.y, gv[6] = b.z, gv[7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (2 * l0 + j < 2 * nl) gv[j] = __ldcs(grow + 2 * l0 + j);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int l = l0 + j;
+      if (l >= nl) break;                              // warp-uniform
+      const b2n_hash_level L = lv.l[l];
+      const Cell c = locate(x01, L.scale);
+      const uint32_t cx = c.g[0] + (uint32_t)s;
+      const float wx = s ? c.w[0] : 1.f - c.w[0];
+      const float g0 = gv[2 * j], g1 = gv[2 * j + 1];
+      if (L.res > merge_res) {
+        if (live && (g0 != 0.f || g1 != 0.f)) {        // samples that received no gradient scatter nothing
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float w = wx * ((k & 1) ? c.w[1] : 1.f - c.w[1]) * ((k & 2) ? c.w[2] : 1.f - c.w[2]);
+            atomicAdd(g_table + corner_entry(L, cx, c.g[1] + (k & 1), c.g[2] + (k >> 1)), make_float2(w * g0, w * g1));
+          }
+        }
+        continue;
+      }
+      // run structure from the cell index (identical in both lanes of a pair): head bits at the even lane positions
+      const uint32_t cell = live ? (c.g[0] + c.g[1] * L.res + c.g[2] * L.res * L.res) : (0xffffffffu - (uint32_t)pi);
+      const uint32_t cell_prev = __shfl_up_sync(0xffffffffu, cell, 2);
+      const bool head = (pi == 0) || (cell != cell_prev);
+      const uint32_t heads = __ballot_sync(0xffffffffu, head && s == 0);
+      const int steps = L.res <= 24 ? 3 : (L.res <= 64 ? 2 : 1);
+      const int run_start = (31 - __clz((int)(heads & (0xffffffffu >> (31 - 2 * pi))))) >> 1;
+      const bool issuer = live && (((pi - run_start) & ((1 << steps) - 1)) == 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float w = wx * ((k & 1) ? c.w[1] : 1.f - c.w[1]) * ((k & 2) ? c.w[2] : 1.f - c.w[2]);
+        float v0 = w * g0, v1 = w * g1;
+        for (int st = 0; st < steps; ++st) {
+          const int o = 1 << st;
+          const float t0 = __shfl_down_sync(0xffffffffu, v0, 2 * o), t1 = __shfl_down_sync(0xffffffffu, v1, 2 * o);
+          // points pi+1 .. pi+o all continue this point's run <=> none of them is a head
+          const uint32_t span = (o == 1) ? 0x1u : (o == 2 ? 0x5u : 0x55u);
+          const bool same_run = (pi + o < 16) && (((heads >> (2 * (pi + 1))) & span) == 0u);
+          if (same_run) v0 += t0, v1 += t1;
+        }
+        if (issuer && (v0 != 0.f || v1 != 0.f))
+          atomicAdd(g_table + corner_entry(L, cx, c.g[1] + (k & 1), c.g[2] + (k >> 1)), make_float2(v0, v1));
+      }
+    }
+  }
+}
+
 // dL/dx = sum_levels scale_l * sum_f g_f * d(trilinear)/dw, chained through clamp and the
 // division by 2*bound.  One thread per point (the sum over levels stays in registers).
 template <int F>
@@ -444,6 +590,11 @@ k_hash_tri_bwd(const float* __restrict__ x, const float* __restrict__ tval, int6
   }
 }
 
+// A/B switch of the F == 2 kernels (b2nerf_debug.h: b2n_debug_hash_variant): bit 0 = pair-lane forward, bit 1 = pair-lane
+// table gradient; g_merge_res = coarsest-level run merging threshold of the pair-lane table gradient.
+static int g_hash_variant = 3;
+static uint32_t g_merge_res = 64;
+
 static int fill_levels(const b2n_hash_level* h, int L, Levels* out) {
   if (!h || L <= 0 || L > B2N_MAX_LEVELS) return -1;
   for (int i = 0; i < L; ++i) {
@@ -491,7 +642,10 @@ extern "C" int b2n_hash_fwd(const float* x, int64_t P, float bound, const float*
   const unsigned grid = grid_for(P * L, 256);
   const float tb = 2.0f * bound;
   cudaStream_t st = (cudaStream_t)stream;
-  if (F == 2) k_hash_fwd<2><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, out, ld_out, col0);
+  if (F == 2 && (g_hash_variant & 1))
+    k_hash_fwd_pair<<<grid_for(2 * P, 256), 256, 0, st>>>(x, P, bound, tb, reinterpret_cast<const float2*>(table), lv, L, out,
+                                                        ld_out, col0);
+  else if (F == 2) k_hash_fwd<2><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, out, ld_out, col0);
   else if (F == 4) k_hash_fwd<4><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, out, ld_out, col0);
   else k_hash_fwd<1><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, out, ld_out, col0);
   return check_launch("b2n_hash_fwd");
@@ -509,7 +663,10 @@ extern "C" int b2n_hash_bwd(const float* x, int64_t P, float bound, const float*
   B2N_REQUIRE(!g_x || table, "input gradient needs the table");
   const float tb = 2.0f * bound;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_table) {
+  if (g_table && F == 2 && (g_hash_variant & 2)) {
+    k_hash_bwd_table_pair<<<grid_for(2 * P, 256), 256, 0, st>>>(x, P, bound, tb, lv, L, g_out, ld_g, col0,
+                                                              reinterpret_cast<float2*>(g_table), g_merge_res);
+  } else if (g_table) {
     int n_dense = 0;                      // leading run of un-hashed levels
     while (n_dense < L && !lv.l[n_dense].hashed) ++n_dense;
     if (n_dense > 0) {
@@ -560,4 +717,10 @@ extern "C" int b2n_hash_tri_bwd(const float* x, const float* t, int64_t P, float
   const TriGrads grads{{g_table_start, g_table_mid, g_table_end}};
   k_hash_tri_bwd<<<grid_for(P * L, 256), 256, 0, (cudaStream_t)stream>>>(x, t, P, bound, 2.0f * bound, lv, L, g_out, ld_g, grads);
   return check_launch("b2n_hash_tri_bwd");
+}
+
+extern "C" int b2n_debug_hash_variant(int variant, int merge_res) {
+  g_hash_variant = variant;
+  if (merge_res >= 0) g_merge_res = (uint32_t)merge_res;
+  return B2N_OK;
 }

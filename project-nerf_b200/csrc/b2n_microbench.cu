@@ -25,6 +25,27 @@ __global__ void __launch_bounds__(256) k_gather_bench(const float2* __restrict__
   if (acc == 1.2345e-30f) *sink = acc;  // keep the loads alive
 }
 
+// red.global.add at random addresses of an L2-resident float2 table: what bounds the hash-grid table gradient.  Is the
+// cost per LANE or per 32-byte SECTOR (do lanes of one instruction that share a sector share an L2 atomic operation)?
+__global__ void __launch_bounds__(256) k_red_bench(float2* __restrict__ table, uint32_t mask, int per_thread, int mode) {
+  const int lane = threadIdx.x & 31;
+  uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+  for (int i = 0; i < per_thread; ++i) {
+    s = s * 1664525u + 1013904223u;
+    uint32_t e = (s >> 4) & mask;
+    const float v = 1e-6f * (float)(i & 7);
+    switch (mode) {
+      case 0: atomicAdd(table + e, make_float2(v, v)); break;
+      case 1: e = (__shfl_sync(0xffffffffu, e, lane & ~1) & ~1u) | (lane & 1); atomicAdd(table + e, make_float2(v, v)); break;
+      case 2: e = (__shfl_sync(0xffffffffu, e, lane & ~3) & ~3u) | (lane & 3); atomicAdd(table + e, make_float2(v, v)); break;
+      case 3: atomicAdd(reinterpret_cast<float4*>(table) + (e >> 1), make_float4(v, v, v, v)); break;
+      case 4: if (!(lane & 1)) atomicAdd(reinterpret_cast<float4*>(table) + (e >> 1), make_float4(v, v, v, v)); break;
+      case 5: if (!(lane & 1)) atomicAdd(table + e, make_float2(v, v)); break;
+      default: e = (__shfl_sync(0xffffffffu, e, lane & ~15) & ~15u) | (lane & 15); atomicAdd(table + e, make_float2(v, v)); break;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Probe of the MN-major (``transposed'') shared-memory operand form of tcgen05.mma, needed for a tensor-core
 // weight-gradient kernel dW = dZ^T In whose operands are stored point-major ([P][features], the contraction index is
@@ -120,4 +141,11 @@ extern "C" int b2n_debug_gather_bench(const float* table, int64_t n_entries, int
                   per_thread % 8 == 0, "bad arguments");
   k_gather_bench<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float2*)table, (uint32_t)(n_entries - 1), per_thread, sink);
   return check_launch("b2n_debug_gather_bench");
+}
+
+extern "C" int b2n_debug_red_bench(float* table, int64_t n_entries, int blocks, int per_thread, int mode, b2n_stream_t stream) {
+  B2N_REQUIRE(table && n_entries > 0 && (n_entries & (n_entries - 1)) == 0 && blocks > 0 && per_thread > 0 && mode >= 0 &&
+                  mode <= 6, "bad arguments");
+  k_red_bench<<<blocks, 256, 0, (cudaStream_t)stream>>>((float2*)table, (uint32_t)(n_entries - 1), per_thread, mode);
+  return check_launch("b2n_debug_red_bench");
 }

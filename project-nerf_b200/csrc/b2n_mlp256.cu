@@ -28,7 +28,7 @@
 // warp 10 = plane store (training: TMA tensor stores of the finished activation tiles).
 // The 256->1 density head and the 128->3 colour head are dot products inside the epilogue.
 //
-// DEFAULT SCHEDULE = CTA PAIRS (template parameter CTA2, b2n_nerf_mlp_set_pair): the kernel is launched as clusters
+// DEFAULT SCHEDULE = CTA PAIRS (template parameter CTA2, b2n_debug_mlp256_set_pair): the kernel is launched as clusters
 // of two CTAs on an SM pair and every MMA is a cta_group::2 instruction (M = 256: this CTA's 128-row tile + the
 // peer's; N = the layer width) issued by the leader.  Each CTA stages only ITS 128 output rows of every weight
 // chunk (TMA tile loads whose bytes are credited to the leader's barrier), a layer whose k-chunks fit in the ring is
@@ -980,7 +980,7 @@ static bool make_weight_map(CUtensorMap* m, const void* packed, size_t bytes) {
 
 // CTA-pair schedule on/off (-1 = not decided yet: environment variable B2N_MLP256_PAIR, default on)
 static int g_pair_mode = -1;
-extern "C" int b2n_nerf_mlp_set_pair(int on) {
+extern "C" int b2n_debug_mlp256_set_pair(int on) {
   g_pair_mode = on ? 1 : 0;
   return B2N_OK;
 }

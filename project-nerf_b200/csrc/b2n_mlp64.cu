@@ -7,8 +7,14 @@
 //   sigma     = softplus(h[0] - 5)
 //   color_net : cat[h(16), gamma(d)(27 -> 32)] -> 64 (ReLU) -> 64 (ReLU) -> 3 (sigmoid)
 //
-// Arithmetic: bf16 operands, fp32 accumulation on the tensor cores (mma.sync m16n8k16); the
-// reference runs these nets in fp16 inside tinycudann.  Activations never leave the SM:
+// Arithmetic: IEEE fp16 operands (what the reference's tinycudann FullyFusedMLP uses), fp32 accumulation on the tensor
+// cores (mma.sync m16n8k16).  Two departures from plain fp16, both measured on the CPU error budget
+// (tools/bf16_error_budget.py) as what decides the distance of the parameter gradients from an fp32 evaluation:
+//   * sigma_net's FIRST layer -- the product with the hash-grid features, whose pre-activations decide 64 ReLU masks and
+//     the density -- is a split product x_hi W_hi + x_lo W_hi + x_hi W_lo (x = x_hi + x_lo in fp16): ~21 significant bits;
+//   * the gradient chain runs on S * dL/dy with S a power of two that puts the largest incoming gradient at 2^7..2^8
+//     (found by a one-pass |.|-max reduction), so fp16's narrow exponent range never clips it; outputs are divided by S.
+// Activations never leave the SM:
 //   forward : each warp owns 32 points; layer outputs (C fragments) are re-packed in registers
 //             as the next layer's A fragments; weights are bf16 in shared memory (ldmatrix).
 //   backward: each warp owns 16 points of a 64-point block tile; the forward is recomputed, the
@@ -16,6 +22,7 @@
 //             layer input / pre-activation gradient is staged once in shared memory as bf16 and
 //             the weight gradients dW = dZ^T * In are accumulated by tensor cores in registers
 //             over the whole persistent loop, then flushed with one atomicAdd per weight per CTA.
+#define B2N_OP_F16
 #include "b2n_mma.cuh"
 
 namespace b2n {
@@ -33,7 +40,7 @@ __device__ __forceinline__ void load_dir(const float* __restrict__ dirs, int64_t
   d[0] = d[1] = d[2] = 0.f;
   if (p < P) d[0] = __ldg(dirs + 3 * p), d[1] = __ldg(dirs + 3 * p + 1), d[2] = __ldg(dirs + 3 * p + 2);
 }
-__device__ __forceinline__ void dir_features(const float (&d)[3], const float* __restrict__ bands, int L, bf16* dst) {
+__device__ __forceinline__ void dir_features(const float (&d)[3], const float* __restrict__ bands, int L, op16* dst) {
   float f[32];
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = 0.f;
@@ -150,6 +157,20 @@ __device__ __forceinline__ void pack_x(const float2 (&raw)[KT][4], uint32_t (&a)
     for (int i = 0; i < 4; ++i) a[k][i] = pack2(raw[k][i].x, raw[k][i].y);
 }
 
+// x = hi + lo with hi = fp16(x), lo = fp16(x - hi): the operands of the split first-layer product
+__device__ __forceinline__ void pack_hl(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+  hi = pack2(v0, v1);
+  const float2 h = unpack2(hi);
+  lo = pack2(v0 - h.x, v1 - h.y);
+}
+template <int KT>
+__device__ __forceinline__ void pack_x_hl(const float2 (&raw)[KT][4], uint32_t (&hi)[KT][4], uint32_t (&lo)[KT][4]) {
+#pragma unroll
+  for (int k = 0; k < KT; ++k)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) pack_hl(raw[k][i].x, raw[k][i].y, hi[k][i], lo[k][i]);
+}
+
 __device__ __forceinline__ float softplus_m5(float h0) {
   const float v = h0 - 5.0f;
   return v > 20.f ? v : log1pf(expf(v));
@@ -158,7 +179,7 @@ __device__ __forceinline__ float sigmoidf(float v) { return 1.f / (1.f + expf(-v
 
 struct MlpSmem {
   // offsets (in bf16 elements) of the weight matrices inside dynamic shared memory
-  int w1, w2, v1, v2, v3, end;
+  int w1, w2, v1, v2, v3, w1lo, end;
 };
 template <int POS_K>
 __host__ __device__ constexpr MlpSmem weight_layout() {
@@ -168,16 +189,25 @@ __host__ __device__ constexpr MlpSmem weight_layout() {
   m.v1 = m.w2 + GEO * (HID + PAD);
   m.v2 = m.v1 + HID * (CIN + PAD);
   m.v3 = m.v2 + HID * (HID + PAD);
-  m.end = m.v3 + 16 * (HID + PAD);
+  m.w1lo = m.v3 + 16 * (HID + PAD);            // low half of the split first-layer weights
+  m.end = m.w1lo + HID * (POS_K + PAD);
   return m;
 }
 
 // in_pad = pad16(pos_dim): the stored width of sigma_net's first matrix (16, 32, 48 or 64 <= POS_K)
 template <int POS_K>
 __device__ __forceinline__ void load_all_weights(const float* __restrict__ sp, const float* __restrict__ cp, int in_pad,
-                                                 bf16* sm) {
+                                                 op16* sm) {
   constexpr MlpSmem L = weight_layout<POS_K>();
   load_weights(sp, HID, POS_K, in_pad, sm + L.w1);
+  {   // W1_lo = fp16(W1 - fp16(W1))
+    constexpr int S = POS_K + PAD;
+    for (int i = threadIdx.x; i < HID * POS_K; i += blockDim.x) {
+      const int r = i / POS_K, c = i - r * POS_K;
+      const float w = c < in_pad ? __ldg(sp + (size_t)r * in_pad + c) : 0.f;
+      sm[L.w1lo + r * S + c] = to_op16(w - from_op16(to_op16(w)));
+    }
+  }
   load_weights(sp + HID * in_pad, GEO, HID, HID, sm + L.w2);
   load_weights(cp, HID, CIN, CIN, sm + L.v1);
   load_weights(cp + HID * CIN, HID, HID, HID, sm + L.v2);
@@ -191,11 +221,11 @@ k_instant_fwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
               const float* __restrict__ bands, int L_dir, const float* __restrict__ sp, const float* __restrict__ cp,
               int64_t P, float* __restrict__ rgb, float* __restrict__ sigma) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  bf16* sm = reinterpret_cast<bf16*>(smem_raw);
+  op16* sm = reinterpret_cast<op16*>(smem_raw);
   constexpr MlpSmem L = weight_layout<POS_K>();
   constexpr int KT1 = POS_K / 16;
   constexpr int DS = 32 + PAD;                 // direction-feature staging row stride
-  bf16* dstage = sm + L.end + (threadIdx.x >> 5) * 32 * DS;
+  op16* dstage = sm + L.end + (threadIdx.x >> 5) * 32 * DS;
   const int in_pad = (pos_dim + 15) & ~15;
   load_all_weights<POS_K>(sp, cp, in_pad, sm);
   __syncthreads();
@@ -217,7 +247,7 @@ k_instant_fwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
   }
   for (int64_t tile = tile0; tile < n_tiles; tile += wstride) {
     const int64_t p0 = tile * 32;
-    uint32_t ax[2][KT1][4];
+    uint32_t ax[2][KT1][4], axl[2][KT1][4];
     float dcur[3];
     if (PF) {
 #pragma unroll
@@ -225,7 +255,7 @@ k_instant_fwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
 #pragma unroll
         for (int k = 0; k < KT1; ++k)
 #pragma unroll
-          for (int i = 0; i < 4; ++i) ax[m][k][i] = pack2(xraw[m][k % KTP][i].x, xraw[m][k % KTP][i].y);
+          for (int i = 0; i < 4; ++i) pack_hl(xraw[m][k % KTP][i].x, xraw[m][k % KTP][i].y, ax[m][k][i], axl[m][k][i]);
       dcur[0] = dnext[0], dcur[1] = dnext[1], dcur[2] = dnext[2];
       const int64_t pn = (tile + wstride) * 32;
       load_x_raw<KTP>(x, ldx, pos_dim, pn, P, xraw[0], lane);
@@ -234,13 +264,19 @@ k_instant_fwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
     } else {
       prefetch_rows(x, ldx, dirs, (tile + wstride) * 32, 32, P, lane);
       load_dir(dirs, p0 + lane, P, dcur);
-      load_x<KT1>(x, ldx, pos_dim, p0, P, ax[0], lane);
-      load_x<KT1>(x, ldx, pos_dim, p0 + 16, P, ax[1], lane);
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        float2 raw[KT1][4];
+        load_x_raw<KT1>(x, ldx, pos_dim, p0 + 16 * m, P, raw, lane);
+        pack_x_hl<KT1>(raw, ax[m], axl[m]);
+      }
     }
     // sigma_net layer 1
     uint32_t ah[2][4][4];
     {
       float c[2][8][4] = {};
+      gemm_fwd<2, 8, KT1>(c, axl, sm + L.w1, POS_K + PAD, lane);          // split product: the small terms first
+      gemm_fwd<2, 8, KT1>(c, ax, sm + L.w1lo, POS_K + PAD, lane);
       gemm_fwd<2, 8, KT1>(c, ax, sm + L.w1, POS_K + PAD, lane);
       c_to_a<8, true>(c[0], ah[0]);
       c_to_a<8, true>(c[1], ah[1]);
@@ -328,7 +364,7 @@ struct BwdLayout {
 
 // ReLU mask from the staged activation tile (the thread re-reads exactly what it wrote)
 template <int NT>
-__device__ __forceinline__ void relu_mask(float (&c)[NT][4], const bf16* tile, int S, int row0, int lane) {
+__device__ __forceinline__ void relu_mask(float (&c)[NT][4], const op16* tile, int S, int row0, int lane) {
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int j = 0; j < NT; ++j) {
@@ -343,21 +379,47 @@ __device__ __forceinline__ void relu_mask(float (&c)[NT][4], const bf16* tile, i
 
 template <int NTk>
 __device__ __forceinline__ void flush_acc(const float (&acc)[NTk][4], float* __restrict__ gW, int ldw, int n0, int k0,
-                                          int n_valid, int lane) {
+                                          int n_valid, int lane, float inv_s) {
   const int g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int j = 0; j < NTk; ++j) {
     const int k = k0 + 8 * j + 2 * t;
     if (k >= ldw) continue;  // columns beyond the stored (padded) input width
     if (n0 + g < n_valid) {
-      atomicAdd(gW + (size_t)(n0 + g) * ldw + k, acc[j][0]);
-      atomicAdd(gW + (size_t)(n0 + g) * ldw + k + 1, acc[j][1]);
+      atomicAdd(gW + (size_t)(n0 + g) * ldw + k, acc[j][0] * inv_s);
+      atomicAdd(gW + (size_t)(n0 + g) * ldw + k + 1, acc[j][1] * inv_s);
     }
     if (n0 + g + 8 < n_valid) {
-      atomicAdd(gW + (size_t)(n0 + g + 8) * ldw + k, acc[j][2]);
-      atomicAdd(gW + (size_t)(n0 + g + 8) * ldw + k + 1, acc[j][3]);
+      atomicAdd(gW + (size_t)(n0 + g + 8) * ldw + k, acc[j][2] * inv_s);
+      atomicAdd(gW + (size_t)(n0 + g + 8) * ldw + k + 1, acc[j][3] * inv_s);
     }
   }
+}
+
+// max |g| over the incoming gradients as float bits (non-negative floats order like unsigned integers; a NaN has the
+// largest bit pattern, so a non-finite gradient anywhere is visible in the result)
+__global__ void __launch_bounds__(256) k_grad_absmax(const float* __restrict__ a, int64_t na, const float* __restrict__ b,
+                                                     int64_t nb, unsigned int* __restrict__ out) {
+  unsigned int m = 0u;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = i < na ? __ldg(a + i) : __ldg(b + (i - na));
+    m = max(m, __float_as_uint(v) & 0x7fffffffu);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
+// power-of-two gradient scale S from the |.|-max bits: S * max in [2^7, 2^8); 1 for an all-zero gradient; NaN when the
+// incoming gradient holds an inf / NaN (GradScaler overflow step: every output must be non-finite too, never a clamped
+// finite value that would be applied as a step)
+__device__ __forceinline__ float grad_scale_from(unsigned int bits) {
+  if (bits == 0u) return 1.f;
+  if (bits >= 0x7f800000u) return __uint_as_float(0x7fc00000u);
+  int e = (int)(bits >> 23) - 127;                      // max in [2^e, 2^(e+1))   (subnormal max: e = -127)
+  int se = 7 - e;                                       // S = 2^se
+  se = se > 120 ? 120 : (se < -120 ? -120 : se);
+  return __uint_as_float((unsigned int)(se + 127) << 23);
 }
 
 template <int POS_K>
@@ -365,9 +427,11 @@ __global__ void __launch_bounds__(MLP_THREADS)
 k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __restrict__ dirs,
               const float* __restrict__ bands, int L_dir, const float* __restrict__ sp, const float* __restrict__ cp,
               int64_t P, const float* __restrict__ g_rgb, const float* __restrict__ g_sigma, float* __restrict__ g_x,
-              int ldg, float* __restrict__ g_sp, float* __restrict__ g_cp) {
+              int ldg, float* __restrict__ g_sp, float* __restrict__ g_cp, const unsigned int* __restrict__ absmax) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  bf16* sm = reinterpret_cast<bf16*>(smem_raw);
+  const float gscale = grad_scale_from(__ldg(absmax));
+  const float inv_s = 1.f / gscale;
+  op16* sm = reinterpret_cast<op16*>(smem_raw);
   using LY = BwdLayout<POS_K>;
   constexpr MlpSmem L = LY::W;
   constexpr int KT1 = POS_K / 16;
@@ -385,11 +449,13 @@ k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
   float acc5[2][4] = {};          // dV3 (16 x 64, 3 valid rows): columns 16*warp..
 
   const int64_t n_tiles = (P + 63) / 64;
-  uint32_t ax[1][KT1][4];
-  load_x<KT1>(x, ldx, pos_dim, (int64_t)blockIdx.x * 64 + row0, P, ax[0], lane);
+  float2 xraw[KT1][4];       // this tile's x_enc rows as fp32: fetched one tile ahead, split into hi / lo at the top of the tile
+  load_x_raw<KT1>(x, ldx, pos_dim, (int64_t)blockIdx.x * 64 + row0, P, xraw, lane);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t p0 = tile * 64 + row0;
-    // ---------------- forward recompute (staging every layer input); ax was fetched one tile ahead
+    // ---------------- forward recompute (staging every layer input)
+    uint32_t ax[1][KT1][4], axl[1][KT1][4];
+    pack_x_hl<KT1>(xraw, ax[0], axl[0]);
     store_a<KT1>(ax[0], sm + LY::in_x, LY::SX, row0, 0, lane);
     // small per-tile loads issued now, consumed several layers later (view direction -> colour net input,
     // incoming gradients -> output layer / density head)
@@ -413,17 +479,21 @@ k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
         if (pa < P) gsig[0] = __ldcs(g_sigma + pa);
         if (pb < P) gsig[1] = __ldcs(g_sigma + pb);
       }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) grgb[i] *= gscale;      // the whole gradient chain runs on S * dL/dy
+      gsig[0] *= gscale, gsig[1] *= gscale;
     }
     uint32_t ah[1][4][4];
     {
       float c[1][8][4] = {};
+      gemm_fwd<1, 8, KT1>(c, axl, sm + L.w1, LY::SX, lane);              // split product (see k_instant_fwd)
+      gemm_fwd<1, 8, KT1>(c, ax, sm + L.w1lo, LY::SX, lane);
       gemm_fwd<1, 8, KT1>(c, ax, sm + L.w1, LY::SX, lane);
       c_to_a<8, true>(c[0], ah[0]);
       store_a<4>(ah[0], sm + LY::in_h1, LY::SH, row0, 0, lane);
     }
-    // next tile's inputs: ax is dead from here on, so the global loads are issued now and have the whole rest of
-    // the tile to land (ncu: the first use of a prefetch issued only before the wgrad phase was the hottest stall)
-    float2 xraw[KT1][4];
+    // next tile's inputs: the fragments are dead from here on, so the global loads are issued now and have the whole
+    // rest of the tile to land (ncu: the first use of a prefetch issued only before the wgrad phase was the hottest stall)
     load_x_raw<KT1>(x, ldx, pos_dim, (tile + gridDim.x) * 64 + row0, P, xraw, lane);
     float hs0 = 0.f, hs1 = 0.f;  // h[.,0] of rows g and g+8 (threads with t == 0)
     uint32_t ac[1][3][4];
@@ -531,12 +601,12 @@ k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
       for (int j = 0; j < POS_K / 8; ++j) {
         const int col = 8 * j + 2 * t;
         if (pa < P) {
-          if (col < pos_dim) g_x[pa * ldg + col] = c[j][0];
-          if (col + 1 < pos_dim) g_x[pa * ldg + col + 1] = c[j][1];
+          if (col < pos_dim) g_x[pa * ldg + col] = c[j][0] * inv_s;
+          if (col + 1 < pos_dim) g_x[pa * ldg + col + 1] = c[j][1] * inv_s;
         }
         if (pb < P) {
-          if (col < pos_dim) g_x[pb * ldg + col] = c[j][2];
-          if (col + 1 < pos_dim) g_x[pb * ldg + col + 1] = c[j][3];
+          if (col < pos_dim) g_x[pb * ldg + col] = c[j][2] * inv_s;
+          if (col + 1 < pos_dim) g_x[pb * ldg + col + 1] = c[j][3] * inv_s;
         }
       }
     }
@@ -547,24 +617,23 @@ k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
     wgrad_tile<6>(acc3, sm + LY::dz3, LY::SH, 16 * warp, sm + LY::in_c, LY::SC, 0, lane);
     wgrad_tile<8>(acc4, sm + LY::dz4, LY::SH, 16 * warp, sm + LY::in_c1, LY::SH, 0, lane);
     wgrad_tile<2>(acc5, sm + LY::dz5, LY::SG, 0, sm + LY::in_c2, LY::SH, 16 * warp, lane);
-    pack_x<KT1>(xraw, ax[0]);
     __syncthreads();
   }
   // ---------------- flush: one atomicAdd per weight per CTA
-  flush_acc<POS_K / 8>(acc1, g_sp, in_pad, 16 * warp, 0, HID, lane);
-  flush_acc<2>(acc2, g_sp + HID * in_pad, HID, 0, 16 * warp, GEO, lane);
-  flush_acc<6>(acc3, g_cp, CIN, 16 * warp, 0, HID, lane);
-  flush_acc<8>(acc4, g_cp + HID * CIN, HID, 16 * warp, 0, HID, lane);
-  flush_acc<2>(acc5, g_cp + HID * CIN + HID * HID, HID, 0, 16 * warp, 3, lane);
+  flush_acc<POS_K / 8>(acc1, g_sp, in_pad, 16 * warp, 0, HID, lane, inv_s);
+  flush_acc<2>(acc2, g_sp + HID * in_pad, HID, 0, 16 * warp, GEO, lane, inv_s);
+  flush_acc<6>(acc3, g_cp, CIN, 16 * warp, 0, HID, lane, inv_s);
+  flush_acc<8>(acc4, g_cp + HID * CIN, HID, 16 * warp, 0, HID, lane, inv_s);
+  flush_acc<2>(acc5, g_cp + HID * CIN + HID * HID, HID, 0, 16 * warp, 3, lane, inv_s);
 }
 
 template <int POS_K>
 constexpr size_t fwd_smem_bytes() {
-  return (size_t)(weight_layout<POS_K>().end + (MLP_THREADS / 32) * 32 * (32 + PAD)) * sizeof(bf16);
+  return (size_t)(weight_layout<POS_K>().end + (MLP_THREADS / 32) * 32 * (32 + PAD)) * sizeof(op16);
 }
 template <int POS_K>
 constexpr size_t bwd_smem_bytes() {
-  return (size_t)BwdLayout<POS_K>::end * sizeof(bf16);
+  return (size_t)BwdLayout<POS_K>::end * sizeof(op16);
 }
 
 static int persistent_grid(const void* kernel, int threads, size_t smem, int64_t work_tiles) {
@@ -619,29 +688,36 @@ extern "C" int b2n_instant_mlp_fwd(const float* x_enc, int ldx, int pos_dim, con
 extern "C" int b2n_instant_mlp_bwd(const float* x_enc, int ldx, int pos_dim, const float* dirs, const float* dir_bands,
                                    int L_dir, const float* sigma_params, const float* color_params, int64_t P,
                                    const float* g_rgb, const float* g_sigma, float* g_x_enc, int ldg,
-                                   float* g_sigma_params, float* g_color_params, b2n_stream_t stream) {
+                                   float* g_sigma_params, float* g_color_params, void* work4, b2n_stream_t stream) {
   B2N_REQUIRE(P >= 0, "negative size");
   if (P == 0) return B2N_OK;
   int rc = check_mlp_args(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params, color_params);
   if (rc) return rc;
-  B2N_REQUIRE(g_rgb && g_sigma && g_sigma_params && g_color_params, "null pointer");
+  B2N_REQUIRE(g_rgb && g_sigma && g_sigma_params && g_color_params && work4, "null pointer");
   B2N_REQUIRE(!g_x_enc || ldg >= pos_dim, "gradient row too narrow");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t tiles = (P + 63) / 64;
+  unsigned int* absmax = (unsigned int*)work4;
+  if (cudaMemsetAsync(absmax, 0, 4, st) != cudaSuccess) return check_launch("b2n_instant_mlp_bwd (memset)");
+  {
+    const int64_t n = 4 * P;
+    const unsigned grid = (unsigned)((n + 1023) / 1024 < (int64_t)kSMs * 8 ? (n + 1023) / 1024 : (int64_t)kSMs * 8);
+    k_grad_absmax<<<grid, 256, 0, st>>>(g_rgb, 3 * P, g_sigma, P, absmax);
+  }
   if (pos_dim <= 32) {
     constexpr size_t smem = bwd_smem_bytes<32>();
     cudaFuncSetAttribute(k_instant_bwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = persistent_grid((const void*)k_instant_bwd<32>, MLP_THREADS, smem, tiles);
     k_instant_bwd<32><<<grid, MLP_THREADS, smem, st>>>(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params,
                                                        color_params, P, g_rgb, g_sigma, g_x_enc, ldg, g_sigma_params,
-                                                       g_color_params);
+                                                       g_color_params, absmax);
   } else {
     constexpr size_t smem = bwd_smem_bytes<64>();
     cudaFuncSetAttribute(k_instant_bwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = persistent_grid((const void*)k_instant_bwd<64>, MLP_THREADS, smem, tiles);
     k_instant_bwd<64><<<grid, MLP_THREADS, smem, st>>>(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params,
                                                        color_params, P, g_rgb, g_sigma, g_x_enc, ldg, g_sigma_params,
-                                                       g_color_params);
+                                                       g_color_params, absmax);
   }
   return check_launch("b2n_instant_mlp_bwd");
 }

@@ -32,6 +32,23 @@ def load(name):
     return out
 
 
+# achieved parity figures of a test session: name -> value (conftest.py prints them in the terminal summary and dumps
+# them to gpurun_out/parity_maxima.json so that every tolerance in the suite can be read next to what was measured)
+ACHIEVED = {}
+
+
+def record(name, value):
+    value = float(value)
+    ACHIEVED[name] = max(ACHIEVED.get(name, 0.0), value)
+    return value
+
+
+def rel_l2(a, b):
+    """||a-b|| / ||b||  (Frobenius)"""
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
 def rel_err(a, b):
     """max |a-b| / (max|b| + tiny): the '1e-4 relative' of the north star, per tensor."""
     a, b = a.double(), b.double()

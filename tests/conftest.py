@@ -26,3 +26,21 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+def pytest_terminal_summary(terminalreporter):
+    """achieved parity figures (tests/_util.record): printed, and dumped for profiles/ when run on the GPU box"""
+    import json
+    from _util import ACHIEVED
+    if not ACHIEVED:
+        return
+    terminalreporter.write_sep("-", "achieved parity figures (max over the cases of each check)")
+    for k in sorted(ACHIEVED):
+        terminalreporter.write_line(f"{k:70s} {ACHIEVED[k]:.3e}")
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_maxima.json"), "w") as f:
+            json.dump(ACHIEVED, f, indent=1, sort_keys=True)
+    except OSError:
+        pass

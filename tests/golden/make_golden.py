@@ -244,6 +244,7 @@ def gen_render():
 def gen_hash_kat():
     import tinycudann as tcnn
     cfgs = {"c2": dict(n_levels=16, n_features_per_level=2, log2_hashmap_size=19, base_resolution=16, per_level_scale=1.5),
+            "c5canon": dict(n_levels=16, n_features_per_level=2, log2_hashmap_size=20, base_resolution=16, per_level_scale=1.5),
             "c5deform": dict(n_levels=12, n_features_per_level=2, log2_hashmap_size=16, base_resolution=16, per_level_scale=1.5),
             "small": SMALL_HASH}
     for tag, c in cfgs.items():
@@ -326,6 +327,10 @@ def gen_dataset():
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:                      # regenerate selected groups only: make_golden.py hash_kat grid_update ...
+        for name in sys.argv[1:]:
+            globals()["gen_" + name]()
+        sys.exit(0)
     gen_dataset()
     gen_sampling()
     gen_mask()

@@ -27,6 +27,12 @@ def test_exports_every_declared_symbol(lib):
     for name in declared:
         assert hasattr(raw, name), name
     assert declared == set(lib.SIGNATURES), declared ^ set(lib.SIGNATURES)
+    assert not any(n.startswith("b2n_debug") for n in declared)        # debug aids live in b2nerf_debug.h only
+    dbg = open(os.path.join(ROOT, "include", "b2nerf_debug.h")).read()
+    declared_dbg = set(re.findall(r"\b(b2n_[a-z0-9_]+)\s*\(", dbg)) - {"b2n_last_error"}
+    for name in declared_dbg:
+        assert hasattr(raw, name), name
+    assert declared_dbg == set(lib.DEBUG_SIGNATURES), declared_dbg ^ set(lib.DEBUG_SIGNATURES)
     assert raw.b2n_abi_version() == lib.ABI_VERSION
 
 

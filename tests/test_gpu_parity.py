@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from _util import GOLDEN, full_nerf_state_dict, load, rel_err
+from _util import GOLDEN, full_nerf_state_dict, load, record, rel_err, rel_l2
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-4
@@ -192,7 +192,7 @@ def test_fourier_golden(mods, D, L):
         assert rel_err(gx.cpu(), g["g_x"]) < TOL
 
 
-@pytest.mark.parametrize("tag", ["c2", "c5deform", "small"])
+@pytest.mark.parametrize("tag", ["c2", "c5canon", "c5deform", "small"])
 def test_hash_encode_vs_oracle(mods, tag):
     from oracle import nerf_oracle as O
     g = load(f"hash_kat_{tag}")
@@ -212,10 +212,10 @@ def test_hash_encode_vs_oracle(mods, tag):
     gt_ref, gx_ref = torch.autograd.grad((y_ref * gy).sum(), [t_ref, x_ref])
     t_cu, x_cu = cu(table).requires_grad_(True), cu(xw).requires_grad_(True)
     y = mods["b2n"].hash_encode(x_cu, t_cu, geom, bound)
-    assert rel_err(y.cpu(), y_ref) < 1e-5
+    assert record(f"hash_{tag}:features", rel_err(y.cpu(), y_ref)) < 1e-5
     gt, gx = torch.autograd.grad((y * cu(gy)).sum(), [t_cu, x_cu])
-    assert rel_err(gt.cpu(), gt_ref) < TOL
-    assert rel_err(gx.cpu(), gx_ref) < TOL
+    assert record(f"hash_{tag}:g_table", rel_err(gt.cpu(), gt_ref)) < TOL
+    assert record(f"hash_{tag}:g_x", rel_err(gx.cpu(), gx_ref)) < TOL
     # which table entries receive gradient is an INDEX decision: must match exactly
     assert torch.equal(gt.cpu() != 0, gt_ref != 0)
 
@@ -243,6 +243,41 @@ def test_hash_index_kat_exact(mods):
                 wt = wt * (wd if (k >> d) & 1 else 1 - wd)
             acc += wt * ent[li, :, k].double()
         assert ((y[:, li].double() - acc).abs() / (acc.abs() + 1)).max() < 1e-5, li
+
+
+@pytest.mark.parametrize("variant,merge_res", [(3, 64), (3, 0), (3, 200), (0, 64), (1, 64), (2, 24)])
+@pytest.mark.parametrize("log2T", [19, 20])
+def test_hash_table_grad_on_ray_ordered_samples(mods, variant, merge_res, log2T):
+    """Consecutive samples of a ray share coarse cells: the table-gradient kernels merge such runs inside a warp before
+    they issue red.global.  Points marched along rays (runs of 1..10 lanes, ragged total, rays ending mid-warp), every
+    kernel variant / merge threshold, both canonical geometries (T = 2^20 makes level 4 a dense 81^3 level)."""
+    from oracle import nerf_oracle as O
+    b2n = mods["b2n"]
+    lib = b2n._lib.lib
+    geom = b2n.HashGeometry(16, 16, 1.5, log2T, 2)
+    lv = O.hash_level_table(16, 16, 1.5, log2T)
+    gen = torch.Generator().manual_seed(9)
+    o = (torch.rand(37, 1, 3, generator=gen) * 2 - 1) * 1.2
+    dirs = torch.nn.functional.normalize(torch.randn(37, 1, 3, generator=gen), dim=-1)
+    tt = torch.arange(97).view(1, -1, 1) * 0.013
+    xw = (o + dirs * tt).reshape(-1, 3)[: 37 * 97 - 5].contiguous()
+    table = torch.randn(geom.n_params, generator=gen) * 0.5
+    t_ref, x_ref = table.clone().requires_grad_(True), xw.clone().requires_grad_(True)
+    y_ref = O.hash_representation(x_ref, t_ref, lv, 2, 1.5)
+    gy = torch.randn(y_ref.shape, generator=gen)
+    gy[::11] = 0.0                                  # samples that receive no gradient
+    gt_ref, gx_ref = torch.autograd.grad((y_ref * gy).sum(), [t_ref, x_ref])
+    try:
+        lib.b2n_debug_hash_variant(variant, merge_res)
+        t_cu, x_cu = cu(table).requires_grad_(True), cu(xw).requires_grad_(True)
+        y = b2n.hash_encode(x_cu, t_cu, geom, 1.5)
+        gt, gx = torch.autograd.grad((y * cu(gy)).sum(), [t_cu, x_cu])
+    finally:
+        lib.b2n_debug_hash_variant(3, 64)
+    assert rel_err(y.cpu(), y_ref) < 1e-5
+    assert record(f"hash_rays[v{variant},m{merge_res},T{log2T}]:g_table", rel_err(gt.cpu(), gt_ref)) < TOL
+    assert rel_err(gx.cpu(), gx_ref) < TOL
+    assert torch.equal(gt.cpu() != 0, gt_ref != 0)
 
 
 def test_linear_vs_torch(mods):
@@ -275,27 +310,85 @@ def _model_from(mods, cfg, sd):
     return model.to(DEV)
 
 
-def _check_grads(model, loss, g, tol, l2=False):
-    """l2=True: relative Frobenius error instead of max-norm -- the metric for the bf16 decoder, whose
-    per-point gradients differ from fp32 by isolated ReLU-mask flips (unbiased, not small in max-norm)."""
+def _fp64_truth(g, pert):
+    """parameter gradients of a golden render case evaluated by the CPU oracle in fp64 (the exact result, to ~1e-12)"""
+    from oracle import nerf_oracle as O
+    dt = torch.float64
+    sd0 = g["sd"] if g["sd"] else full_nerf_state_dict(int(g["seed"]))
+    sd = {k: (v.to(dt) if v.is_floating_point() else v).clone().requires_grad_(v.is_floating_point() and "freq" not in k)
+          for k, v in sd0.items()}
+    if "deformation_grid.encoding.params" in sd:
+        sd["deformation_grid.encoding.params"] = sd["deform_grid_start.encoding.params"]
+    field = O.OracleField(g["cfg"], sd).train(False)
+    out = O.render_rays(field, g["rays_o"].to(dt), g["rays_d"].to(dt), g["near"], g["far"], int(g["n_samples"]),
+                        g["u"].to(dt) if pert else None, binary_grid=g.get("binary_grid"),
+                        grid_bound=g.get("grid_bound", 1.0), bg_color=g["bg"].to(dt),
+                        times=g["times"].to(dt) if "times" in g else None)
+    loss = (out[0] * g["g_color"].to(dt)).sum()
+    if "mean_delta_x" in g:
+        loss = loss + (out[3]["mean_delta_x"] * g["g_mdx"].to(dt)).sum()
+    names = [n for n in sd if sd[n].requires_grad and n != "deformation_grid.encoding.params"]
+    grads = torch.autograd.grad(loss, [sd[n] for n in names], allow_unused=True)
+    return {n: gr for n, gr in zip(names, grads) if gr is not None}
+
+
+def _sums(t):
+    t = t.double()
+    return torch.stack([t.sum(), t.abs().sum(), (t ** 2).sum()])
+
+
+def _sum_err(s, ref):
+    # sum(g) cancels; it is judged against sum|g| (the scale of its terms), the two norms relatively
+    return max(float((s[0] - ref[0]).abs() / (ref[1] + 1e-30)), float((s[1] - ref[1]).abs() / (ref[1] + 1e-30)),
+               float((s[2] - ref[2]).abs() / (ref[2] + 1e-30)))
+
+
+def _check_grads(model, loss, g, tol, l2=False, tag="", truth=None):
+    """Max-norm relative error per parameter tensor against the reference's autograd gradients (fp32 bar: 1e-4).
+    l2=True: relative Frobenius error -- the metric for the 16-bit tensor-core decoders, whose per-point gradients
+    differ from fp32 by isolated ReLU-mask flips (unbiased, not small in max-norm).
+
+    ``truth`` (fp32 path only): a callable returning the fp64 gradients of the same case.  The reference's own fp32
+    gradients sit 0.4 - 2.2e-4 from the exact ones on the sigma-head weights of the 256-wide decoder (long sums with
+    cancellation: measured on the fixtures), so two fp32 evaluations with different summation
+    orders cannot be asked to agree to 1e-4 there.  A tensor that misses ``tol`` against the fixture passes only if it
+    is within ``tol`` of the EXACT gradient, or at least as close to it as the reference's fp32 result is."""
     names = list(g["grads"]) + list(g["gradsum"])
     params = dict(model.named_parameters())
     grads = torch.autograd.grad(loss, [params[n] for n in names], allow_unused=True)
+    worst = 0.0
     for n, gr in zip(names, grads):
         gr = torch.zeros_like(params[n]) if gr is None else gr
         gr = gr.cpu()
         if l2:
             if n in g["grads"]:
-                ref = g["grads"][n].double()
-                assert float((gr.double() - ref).norm() / (ref.norm() + 1e-30)) < tol, n
+                e = record(f"{tag}:grad_l2:{n}", rel_l2(gr, g["grads"][n]))
+                worst = max(worst, e)
+                assert e < tol, (n, e)
             continue
         if n in g["grads"]:
-            assert rel_err(gr, g["grads"][n]) < tol, n
+            e = record(f"{tag}:grad_max:{n}", rel_err(gr, g["grads"][n]))
+            if e >= tol and truth is not None:
+                exact = truth()[n]
+                e_ours = record(f"{tag}:grad_max_vs_fp64:{n}", rel_err(gr, exact))
+                e_ref = record(f"{tag}:reference_fp32_vs_fp64:{n}", rel_err(g["grads"][n], exact))
+                assert e_ours < tol or e_ours <= e_ref, (n, e, e_ours, e_ref)
+            else:
+                assert e < tol, (n, e)
         else:
-            s = torch.stack([gr.double().sum(), gr.double().abs().sum(), (gr.double() ** 2).sum()])
-            assert torch.allclose(s, g["gradsum"][n], rtol=5e-4, atol=1e-8), n
+            ref = g["gradsum"][n].double()
+            e = record(f"{tag}:gradsum:{n}", _sum_err(_sums(gr), ref))
+            if e >= tol and truth is not None:
+                exact = _sums(truth()[n])
+                e_ours = record(f"{tag}:gradsum_vs_fp64:{n}", _sum_err(_sums(gr), exact))
+                e_ref = record(f"{tag}:reference_fp32_vs_fp64:{n}", _sum_err(ref, exact))
+                assert e_ours < tol or e_ours <= e_ref, (n, e, e_ours, e_ref)
+            else:
+                assert e < tol, (n, e)
             if n in g["gradhead"]:
-                assert rel_err(gr.reshape(-1)[:4096], g["gradhead"][n]) < tol, n
+                e = record(f"{tag}:gradhead:{n}", rel_err(gr.reshape(-1)[:4096], g["gradhead"][n]))
+                assert e < tol, (n, e)
+    return worst
 
 
 @pytest.mark.parametrize("tag", FIELDS)
@@ -304,12 +397,13 @@ def test_field_golden(mods, tag):
     model = _model_from(mods, g["cfg"], g["sd"]).eval()
     dyn = g["cfg"]["mode"] in ("part3", "part4")
     out = model(cu(g["x"]), cu(g["d"]), t=cu(g["t"])) if dyn else model(cu(g["x"]), cu(g["d"]))
-    assert rel_err(out[0].cpu(), g["rgb"]) < TOL and rel_err(out[1].cpu(), g["sigma"]) < TOL
+    assert record(f"field_{tag}:rgb", rel_err(out[0].cpu(), g["rgb"])) < TOL
+    assert record(f"field_{tag}:sigma", rel_err(out[1].cpu(), g["sigma"])) < TOL
     loss = (out[0] * cu(g["g_rgb"])).sum() + (out[1] * cu(g["g_sigma"])).sum()
     if dyn:
         assert rel_err(out[2].cpu(), g["dx"]) < TOL
         loss = loss + (out[2] * cu(g["g_dx"])).sum()
-    _check_grads(model, loss, g, 2e-4)
+    _check_grads(model, loss, g, TOL, tag=f"field_{tag}")
 
 
 @pytest.mark.parametrize("tag", FIELDS + ["part2_nerf_full"])
@@ -327,14 +421,20 @@ def test_render_rays_golden(mods, tag, pert):
                                        int(g["n_samples"]), pert == "pert", density_grid=grid, times=times,
                                        bg_color=cu(g["bg"]), _jitter=cu(g["u"]) if pert == "pert" else None)
     assert len(out) == (4 if times is not None else 3)
-    assert rel_err(out[0].cpu(), g["color"]) < TOL
-    assert rel_err(out[1].cpu(), g["depth"]) < TOL
-    assert rel_err(out[2].cpu(), g["acc"]) < TOL
+    assert record(f"render_{tag}_{pert}:color", rel_err(out[0].cpu(), g["color"])) < TOL
+    assert record(f"render_{tag}_{pert}:depth", rel_err(out[1].cpu(), g["depth"])) < TOL
+    assert record(f"render_{tag}_{pert}:acc", rel_err(out[2].cpu(), g["acc"])) < TOL
     loss = (out[0] * cu(g["g_color"])).sum()
     if "mean_delta_x" in g:
         assert rel_err(out[3]["mean_delta_x"].cpu(), g["mean_delta_x"]) < TOL
         loss = loss + (out[3]["mean_delta_x"] * cu(g["g_mdx"])).sum()
-    _check_grads(model, loss, g, 3e-4)
+    cache = {}
+
+    def truth():
+        if not cache:
+            cache.update(_fp64_truth(g, pert == "pert"))
+        return cache
+    _check_grads(model, loss, g, TOL, tag=f"render_{tag}_{pert}", truth=truth)
 
 
 @pytest.mark.parametrize("tag", ["part2_instant", "part3_instant", "part4"])
@@ -437,8 +537,13 @@ def test_amp_autocast_compatible(mods):
 BF16_TOL = 1e-2
 
 
-@pytest.mark.parametrize("pos_dim,Pn", [(32, 1000), (32, 64 * 37), (53, 777), (32, 5), (64, 130)])
-def test_instant_mlp_bf16_vs_oracle(mods, pos_dim, Pn):
+@pytest.mark.parametrize("pos_dim,Pn", [(32, 1000), (32, 64 * 37), (53, 777), (32, 5), (64, 130), (32, 40000)])
+@pytest.mark.parametrize("gscale", [1.0, 65536.0, 2.0 ** -22])
+def test_instant_mlp_fp16_vs_oracle(mods, pos_dim, Pn, gscale):
+    """Fused Instant decoder (fp16 operands, split first layer, power-of-two scaled gradient chain) against
+    (a) the oracle evaluated in the kernel's arithmetic model -- tight, forward and backward -- and
+    (b) the plain fp32 oracle -- the north star's 1e-2 bar for the 16-bit MLP, outputs and gradients.
+    gscale multiplies the incoming gradient (GradScaler-sized and underflow-sized): the result must scale with it."""
     from oracle import nerf_oracle as O
     torch.manual_seed(7)
     gen = torch.Generator().manual_seed(7)
@@ -448,30 +553,57 @@ def test_instant_mlp_bf16_vs_oracle(mods, pos_dim, Pn):
     d = torch.randn(Pn, 3)
     d = d / d.norm(dim=-1, keepdim=True)
     bands = O.fourier_bands(4)
-    # (a) true fp32 oracle: the 1e-2 bar on the outputs; (b) oracle with the kernel's bf16 operand
-    # rounding emulated: ReLU masks then coincide, so per-point gradients can be compared tightly
+    wrt = [x, sd["d.sigma_net.params"], sd["d.color_net.params"]]
     rgb, sigma = O.instant_decoder(sd, "d", x, O.fourier_encode(d, bands), 64)
-    rgb_q, sigma_q = O.instant_decoder(sd, "d", x, O.fourier_encode(d, bands), 64, emulate_bf16=True)
-    g_rgb, g_sigma = torch.randn_like(rgb), torch.randn_like(sigma)
-    ref = torch.autograd.grad((rgb_q * g_rgb).sum() + (sigma_q * g_sigma).sum(),
-                              [x, sd["d.sigma_net.params"], sd["d.color_net.params"]])
+    rgb_q, sigma_q = O.instant_decoder(sd, "d", x, O.fourier_encode(d, bands), 64, emulate_bf16="kernel")
+    g_rgb, g_sigma = torch.randn_like(rgb) * gscale, torch.randn_like(sigma) * gscale
+    ref32 = torch.autograd.grad((rgb * g_rgb).sum() + (sigma * g_sigma).sum(), wrt)
+    ref_q = torch.autograd.grad((rgb_q * g_rgb).sum() + (sigma_q * g_sigma).sum(), wrt)
     x2 = cu(x.detach()).requires_grad_(True)
     sp, cp = (cu(sd[k].detach()).requires_grad_(True) for k in ("d.sigma_net.params", "d.color_net.params"))
     rgb2, sigma2 = mods["b2n"].instant_mlp(x2, cu(d), cu(bands), sp, cp)
     assert rgb2.shape == (Pn, 3) and sigma2.shape == (Pn, 1)
-    assert rel_err(rgb2.cpu(), rgb) < BF16_TOL
-    assert rel_err(sigma2.cpu(), sigma) < BF16_TOL
-    assert rel_err(rgb2.cpu(), rgb_q) < 2e-3 and rel_err(sigma2.cpu(), sigma_q) < 2e-3
+    tag = f"instant_mlp[{pos_dim},{Pn}]"
+    assert record(f"{tag}:rgb_vs_fp32", rel_err(rgb2.cpu(), rgb)) < BF16_TOL
+    assert record(f"{tag}:sigma_vs_fp32", rel_err(sigma2.cpu(), sigma)) < BF16_TOL
+    assert record(f"{tag}:rgb_vs_kernel_model", rel_err(rgb2.cpu(), rgb_q)) < 1e-3
+    assert record(f"{tag}:sigma_vs_kernel_model", rel_err(sigma2.cpu(), sigma_q)) < 1e-3
     got = torch.autograd.grad((rgb2 * cu(g_rgb)).sum() + (sigma2 * cu(g_sigma)).sum(), [x2, sp, cp])
-    for a_, b_, name in zip(got, ref, ("g_x", "g_sigma_params", "g_color_params")):
+    for a_, bq, b32, name in zip(got, ref_q, ref32, ("g_x", "g_sigma_params", "g_color_params")):
         a_ = a_.cpu()
-        l2 = float((a_ - b_).norm() / (b_.norm() + 1e-30))
-        assert l2 < 2e-2, (name, l2)                     # gradient operands are rounded to bf16 as well
-        bad_rows = ((a_ - b_).abs().reshape(len(b_), -1).max(dim=-1)[0] > 0.05 * b_.abs().max()).float().mean()
-        assert float(bad_rows) < 0.02, (name, float(bad_rows))   # rare ReLU-mask ties only
+        assert torch.isfinite(a_).all()
+        # kernel vs the oracle in the kernel's arithmetic: what is left is accumulation order and rounding ties
+        assert record(f"{tag}:{name}_l2_vs_kernel_model", rel_l2(a_, bq)) < 5e-3, name
+        # kernel vs fp32: the 1e-2 class for the parameter gradients (sums over points).  The PER-POINT input gradient
+        # of this adversarial case (i.i.d. N(0, 0.5) features, N(0, 1) output gradients, Xavier weights) is dominated
+        # by ReLU-mask flips of individual points in ANY 11-bit arithmetic (2-3e-2; the arithmetic model gives the
+        # same figure); in the pipeline it only enters summed over the points of a table entry, and the golden render
+        # tests bound that sum by 1e-2
+        assert record(f"{tag}:{name}_l2_vs_fp32", rel_l2(a_, b32)) < (5e-2 if name == "g_x" else BF16_TOL), name
     # padded rows/columns of the flat parameter vectors never receive gradient
     V3 = got[2][64 * 48 + 64 * 64:].view(16, 64)
     assert float(V3[3:].abs().max()) == 0.0
+
+
+def test_instant_mlp_nonfinite_gradient_propagates(mods):
+    """GradScaler's overflow detection needs an inf / NaN incoming gradient to stay visible: the saturating fp16
+    conversions of the kernel must not turn it into a large finite step."""
+    from oracle import nerf_oracle as O
+    gen = torch.Generator().manual_seed(3)
+    sp = cu(O._fused_init(32, 16, 64, 1, gen)).requires_grad_(True)
+    cp = cu(O._fused_init(43, 3, 64, 2, gen)).requires_grad_(True)
+    x = (torch.randn(300, 32, device=DEV) * 0.5).requires_grad_(True)
+    d = torch.nn.functional.normalize(torch.randn(300, 3, device=DEV), dim=-1)
+    for bad in (float("inf"), float("nan")):
+        rgb, sigma = mods["b2n"].instant_mlp(x, d, cu(O.fourier_bands(4)), sp, cp)
+        g = torch.ones_like(rgb)
+        g[17, 1] = bad
+        grads = torch.autograd.grad((rgb * g).sum() + sigma.sum(), [x, sp, cp])
+        assert all(not torch.isfinite(t).all() for t in grads[1:])
+        assert not torch.isfinite(grads[0]).all()
+    rgb, sigma = mods["b2n"].instant_mlp(x, d, cu(O.fourier_bands(4)), sp, cp)       # all-zero gradient: exact zeros out
+    grads = torch.autograd.grad((rgb * 0).sum() + (sigma * 0).sum(), [x, sp, cp])
+    assert all(float(t.abs().max()) == 0.0 for t in grads)
 
 
 
@@ -546,6 +678,15 @@ def test_fused_mlp_rejects_bad_shapes(mods):
         b2n.fused_mlp(x[:, :8], None, [torch.zeros(32, 8, device=DEV), torch.zeros(3, 32, device=DEV)], [None, None])
 
 
+# relative-L2 bars of the 16-bit path's PARAMETER GRADIENTS against the reference's fp32 autograd on the golden
+# fixtures.  Part 2 Instant runs entirely on the fp16 decoder kernel and meets the north star's 1e-2.  The dynamic
+# configs also go through the bf16 deformation / time-modulation kernels (b2n_fmlp_*): an 8-bit-mantissa forward
+# moves ReLU masks and the softplus density enough for 3-5e-2 on those nets' own gradients (the CPU error budget,
+# tools/bf16_error_budget.py, reproduces these figures without a GPU); the bars below are what that arithmetic model
+# predicts, with 1.5x head-room, not a tolerance fitted to the kernel.
+GRAD_L2_BAR_16BIT = {"part2_instant": 1e-2, "part3_instant": 8e-2, "part4": 8e-2}
+
+
 @pytest.mark.parametrize("tag", ["part2_instant", "part3_instant", "part4"])
 @pytest.mark.parametrize("pert", ["flat", "pert"])
 def test_render_rays_golden_bf16(mods, bf16_mode, tag, pert):
@@ -558,13 +699,54 @@ def test_render_rays_golden_bf16(mods, bf16_mode, tag, pert):
     out = mods["renderer"].render_rays(model, cu(g["rays_o"]), cu(g["rays_d"]), g["near"], g["far"],
                                        int(g["n_samples"]), pert == "pert", density_grid=grid, times=times,
                                        bg_color=cu(g["bg"]), _jitter=cu(g["u"]) if pert == "pert" else None)
-    assert rel_err(out[0].cpu(), g["color"]) < BF16_TOL
-    assert rel_err(out[1].cpu(), g["depth"]) < BF16_TOL
-    assert rel_err(out[2].cpu(), g["acc"]) < BF16_TOL
+    name = f"render16_{tag}_{pert}"
+    assert record(f"{name}:color", rel_err(out[0].cpu(), g["color"])) < BF16_TOL
+    assert record(f"{name}:depth", rel_err(out[1].cpu(), g["depth"])) < BF16_TOL
+    assert record(f"{name}:acc", rel_err(out[2].cpu(), g["acc"])) < BF16_TOL
     loss = (out[0] * cu(g["g_color"])).sum()
     if "mean_delta_x" in g:
         loss = loss + (out[3]["mean_delta_x"] * cu(g["g_mdx"])).sum()
-    _check_grads(model, loss, g, 0.1, l2=True)
+    _check_grads(model, loss, g, GRAD_L2_BAR_16BIT[tag], l2=True, tag=name)
+
+
+@pytest.mark.parametrize("tag", ["part2_instant", "part3_instant", "part4"])
+@pytest.mark.parametrize("pert", ["flat", "pert"])
+def test_render_rays_16bit_vs_kernel_arithmetic_model(mods, bf16_mode, tag, pert):
+    """The same golden inputs through the CPU oracle evaluated in the kernels' own arithmetic model (operand types,
+    split first layer, rounded dZ: oracle.OracleField(emulate_bf16="kernel")): gradients agree to 1e-2 relative-L2 per
+    tensor -- what separates the CUDA path from its own arithmetic model is accumulation order and rounding ties."""
+    from oracle import nerf_oracle as O
+    g = load(f"render_{tag}_{pert}")
+    model = _model_from(mods, g["cfg"], g["sd"]).train(pert == "pert")
+    grid = mods["renderer"].DensityGrid(resolution=g["binary_grid"].shape[0], bound=g["grid_bound"]).to(DEV)
+    grid.binary_grid = cu(g["binary_grid"])
+    times = cu(g["times"]) if "times" in g else None
+    torch.manual_seed(0)
+    out = mods["renderer"].render_rays(model, cu(g["rays_o"]), cu(g["rays_d"]), g["near"], g["far"],
+                                       int(g["n_samples"]), pert == "pert", density_grid=grid, times=times,
+                                       bg_color=cu(g["bg"]), _jitter=cu(g["u"]) if pert == "pert" else None)
+    sd = {k: v.clone().requires_grad_(v.is_floating_point() and "freq" not in k) for k, v in g["sd"].items()}
+    if "deformation_grid.encoding.params" in sd:
+        sd["deformation_grid.encoding.params"] = sd["deform_grid_start.encoding.params"]
+    field = O.OracleField(g["cfg"], sd, emulate_bf16="kernel").train(False)      # the fixtures were made without input noise
+    ref = O.render_rays(field, g["rays_o"], g["rays_d"], g["near"], g["far"], int(g["n_samples"]),
+                        g["u"] if pert == "pert" else None, binary_grid=g["binary_grid"], grid_bound=g["grid_bound"],
+                        bg_color=g["bg"], times=g.get("times"))
+    name = f"render16_vs_model_{tag}_{pert}"
+    assert record(f"{name}:color", rel_err(out[0].cpu(), ref[0])) < 2e-3
+    loss = (out[0] * cu(g["g_color"])).sum()
+    loss_ref = (ref[0] * g["g_color"]).sum()
+    if "mean_delta_x" in g:
+        loss = loss + (out[3]["mean_delta_x"] * cu(g["g_mdx"])).sum()
+        loss_ref = loss_ref + (ref[3]["mean_delta_x"] * g["g_mdx"]).sum()
+    names = [n for n in g["grads"] if n in sd and sd[n].requires_grad]
+    params = dict(model.named_parameters())
+    got = torch.autograd.grad(loss, [params[n] for n in names], allow_unused=True)
+    want = torch.autograd.grad(loss_ref, [sd[n] for n in names], allow_unused=True)
+    for n, a_, b_ in zip(names, got, want):
+        if a_ is None or b_ is None:
+            continue
+        assert record(f"{name}:grad_l2:{n}", rel_l2(a_.cpu(), b_)) < 1e-2, n
 
 
 # ------------------------------------------------------------------ tcgen05 256-wide decoder
@@ -617,7 +799,7 @@ def test_nerf_mlp256_cta_pair_equals_single_cta(mods, bf16_mode, pos_dim, Pn):
     res = {}
     try:
         for pair in (0, 1):
-            lib.b2n_nerf_mlp_set_pair(pair)
+            lib.b2n_debug_mlp256_set_pair(pair)
             rgb, sigma, (planes, masks), err = ops.nerf_mlp_forward(dec, xe, de, save=True)
             torch.cuda.synchronize()
             assert int(err.item()) == 0, f"pair={pair}: tcgen05 pipeline aborted with code {int(err.item())}"
@@ -628,7 +810,7 @@ def test_nerf_mlp256_cta_pair_equals_single_cta(mods, bf16_mode, pos_dim, Pn):
             torch.cuda.synchronize()
             res[pair] = [rgb, sigma, planes[:9], planes[9][:, :128], masks[:9], r2, s2] + list(grads)
     finally:
-        lib.b2n_nerf_mlp_set_pair(1)
+        lib.b2n_debug_mlp256_set_pair(1)
     for i, (a_, b_) in enumerate(zip(res[0], res[1])):
         if i < 8:                                   # kernel outputs: bit-identical
             assert torch.equal(a_, b_), f"output {i} differs between the schedules"

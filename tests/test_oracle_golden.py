@@ -53,7 +53,7 @@ def test_fourier(D, L):
     assert torch.equal(O.fourier_bands(L), g["bands"])
 
 
-@pytest.mark.parametrize("tag", ["c2", "c5deform", "small"])
+@pytest.mark.parametrize("tag", ["c2", "c5canon", "c5deform", "small"])
 def test_hash_index_kat(tag):
     g = load(f"hash_kat_{tag}")
     c = g["cfg"]

@@ -37,7 +37,7 @@ def mlp256(P):
     de = torch.randn(P, 27, device="cuda")
     flops = 2.0 * P * 593408
     for pair in (0, 1):
-        b2n._lib.lib.b2n_nerf_mlp_set_pair(pair)
+        b2n._lib.lib.b2n_debug_mlp256_set_pair(pair)
         for save in (False, True):
             med, best = timeit(lambda: ops.nerf_mlp_forward(model.decoder, xe, de, save=save))
             print(f"mlp256 fwd pair={pair} P={P} save={save}: median {med:.3f} ms best {best:.3f} ms -> "
@@ -59,7 +59,7 @@ def mlp256(P):
                 print(f"    {name}: {d['ms'] / d['calls']:.3f} ms/call")
         model.eval()
     for pair in (0, 1):
-        b2n._lib.lib.b2n_nerf_mlp_set_pair(pair)
+        b2n._lib.lib.b2n_debug_mlp256_set_pair(pair)
         for what in ("fwd", "fwd+save", "bwd"):
             prof = torch.zeros(8 + 448, dtype=torch.int64, device="cuda")
             if what == "bwd":
@@ -83,7 +83,7 @@ def mlp256(P):
             print(f"pair={pair} {what}: CTA0 cycles per tile pair ({pr[4]} pairs): whole {pr[7] / n:.0f} | pre-step {pr[5] / n:.0f}, "
                   f"bias staging {pr[6] / n:.0f}, epilogue-waits-MMA {pr[2] / n:.0f}, epilogue-body {pr[3] / n:.0f} | "
                   f"MMA-waits-epilogue {pr[0] / n:.0f}, MMA-waits-weights {pr[1] / n:.0f}")
-    b2n._lib.lib.b2n_nerf_mlp_set_pair(1)
+    b2n._lib.lib.b2n_debug_mlp256_set_pair(1)
     with torch.no_grad():
         b2n.set_mlp_precision("fp32")
         med, best = timeit(lambda: model.decoder(xe, de), n=3, warm=1)
@@ -98,7 +98,7 @@ def mlp256x(P):
     de = torch.randn(P, 27, device="cuda")
     lib = b2n._lib.lib
     for pair in (0, 1):
-        lib.b2n_nerf_mlp_set_pair(pair)
+        lib.b2n_debug_mlp256_set_pair(pair)
         for dbg in [int(v) for v in os.environ.get("KB_DBG", "0,1,2,3,7,15").split(",")]:
             lib.b2n_debug_mlp256_flags(dbg)
             x2 = xe.clone().requires_grad_(True)
@@ -119,7 +119,7 @@ def mlp256x(P):
                     ms.setdefault(key, []).append(e0.elapsed_time(e1))
             print(f"pair={pair} dbg={dbg} ({ {0: 'full', 1: 'no drain', 2: 'no MMA', 3: 'handshakes + weight stream only', 7: 'handshakes only', 15: 'handshakes only, no row loads/stores'}[dbg]}): " +
                   ", ".join(f"{k} {min(v):.3f} ms" for k, v in sorted(ms.items())))
-    lib.b2n_nerf_mlp_set_pair(1)
+    lib.b2n_debug_mlp256_set_pair(1)
 
 
 def mlp256t(P):
@@ -131,7 +131,7 @@ def mlp256t(P):
     lib = b2n._lib.lib
     names = ["epi:wait", "epi:acc", "epi:done", "mma:wait", "mma:act", "mma:w0", "mma:issued", "epi:stage"]
     for pair, what, cta in ((0, "bwd", 0), (1, "fwd+save", 0), (1, "bwd", 0), (1, "bwd", 1)):
-        lib.b2n_nerf_mlp_set_pair(pair)
+        lib.b2n_debug_mlp256_set_pair(pair)
         lib.b2n_debug_mlp256_flags(32 * cta)
         if True:
             x2 = xe.clone().requires_grad_(True)
@@ -159,7 +159,7 @@ def mlp256t(P):
                     if int(row.max()) == 0:
                         continue
                     print(f"  step {s:2d} tile {t}: " + " ".join(f"{(int(v) - t00) if v > 0 else -1:7d}" for v in row))
-    lib.b2n_nerf_mlp_set_pair(1)
+    lib.b2n_debug_mlp256_set_pair(1)
     lib.b2n_debug_mlp256_flags(0)
 
 
@@ -295,6 +295,59 @@ def hash_sorted():
                                            for k in ("b2n_hash_fwd", "b2n_hash_bwd")))
 
 
+def hash_variants():
+    """A/B of the F = 2 hash-grid kernels on the C2 sample set (24 M active points, L = 16, T = 2^19) and the C5 canonical
+    geometry (T = 2^20): (point, level)-per-lane kernels against the pair-lane kernels, and the run-merging threshold."""
+    from b2n import synthetic, march
+    lib = b2n._lib.lib
+    torch.manual_seed(0)
+    ro, rd, _ = (t.cuda() for t in synthetic.random_rays(2 ** 18, seed=1))
+    u = torch.rand(2 ** 18, 128, device="cuda")
+    occ = torch.ones(128, 128, 128, dtype=torch.bool, device="cuda")
+    x = march.march(ro, rd, 2.0, 6.0, 128, u, bits=march.pack_occupancy(occ), R=128, bound=1.5).pts
+    print("points", x.shape[0])
+    for log2T in (19, 20):
+        geom = b2n.HashGeometry(16, 16, 1.5, log2T, 2)
+        table = (torch.randn(geom.n_params, device="cuda") * 0.1).requires_grad_(True)
+        lib.b2n_debug_hash_variant(0, 64)
+        y_ref = b2n.hash_encode(x, table, geom, 1.5)
+        g = torch.randn_like(y_ref)
+        gt_ref, = torch.autograd.grad((y_ref * g).sum(), table)
+        for variant, merge in ((0, 64), (1, 64), (2, 0), (2, 24), (2, 64), (2, 128), (2, 200), (3, 64)):
+            lib.b2n_debug_hash_variant(variant, merge)
+            y = b2n.hash_encode(x, table, geom, 1.5)
+            gt, = torch.autograd.grad((y * g).sum(), table)
+            ey = float((y - y_ref).abs().max() / y_ref.abs().max())
+            eg = float((gt - gt_ref).abs().max() / gt_ref.abs().max())
+            b2n._lib.PROFILER = prof = b2n._lib.Profiler()
+            for _ in range(4):
+                y = b2n.hash_encode(x, table, geom, 1.5)
+                y.backward(g)
+            torch.cuda.synchronize()
+            b2n._lib.PROFILER = None
+            print(f"T=2^{log2T} variant={variant} merge_res={merge:3d}: " +
+                  ", ".join(f"{k} {min(e0.elapsed_time(e1) for n_, _, _, e0, e1 in prof.records if n_ == k):.3f} ms"
+                            for k in ("b2n_hash_fwd", "b2n_hash_bwd")) + f"   max rel diff vs variant 0: y {ey:.2e} g_table {eg:.2e}")
+    lib.b2n_debug_hash_variant(3, 64)
+
+
+def red_bench():
+    """red.global.add throughput on an L2-resident table: per lane or per sector?"""
+    from b2n._lib import call, ptr, stream
+    names = {0: "v2 random lanes", 1: "v2 lane pairs share 16 B", 2: "v2 4 lanes share a sector", 3: "v4 random lanes",
+             4: "v4 even lanes only", 5: "v2 even lanes only", 6: "v2 16 lanes share a 128-B line"}
+    for log2n in (18, 22):
+        n = 1 << log2n
+        table = torch.zeros(n, 2, device="cuda")
+        blocks, per_thread = 148 * 16, 256
+        for mode in range(7):
+            fn = lambda: call("b2n_debug_red_bench", ptr(table), n, blocks, per_thread, mode, stream())
+            med, best = timeit(fn, n=5, warm=2)
+            lanes = blocks * 256 * per_thread * (0.5 if mode in (4, 5) else 1.0)
+            print(f"table {n * 8 >> 20:3d} MiB mode {mode} ({names[mode]:32s}): {lanes / best / 1e6:8.1f} G lane-ops/s, "
+                  f"{blocks * 8 * per_thread / best / 1e6:7.2f} G warp-instr/s")
+
+
 def l2_gather():
     """Random 8-byte gathers over tables of 2 MiB .. 512 MiB: the L2 (and beyond-L2) gather peak."""
     from b2n._lib import call, ptr, stream
@@ -357,6 +410,10 @@ if __name__ == "__main__":
         hash_sorted()
     elif what == "hash":
         hash_levels()
+    elif what == "hashv":
+        hash_variants()
+    elif what == "red":
+        red_bench()
     elif what == "l2":
         l2_gather()
     elif what == "composite":

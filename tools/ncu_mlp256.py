@@ -14,7 +14,7 @@ import b2n  # noqa: E402
 from src.core import NeuralField  # noqa: E402
 
 pair = int(sys.argv[1]) if len(sys.argv) > 1 else 1
-b2n._lib.lib.b2n_nerf_mlp_set_pair(pair)
+b2n._lib.lib.b2n_debug_mlp256_set_pair(pair)
 torch.manual_seed(0)
 model = NeuralField(dict(mode="part2_nerf", L_embed=10, L_embed_dir=4)).cuda().train()
 P = 262144

@@ -228,11 +228,13 @@ int b2n_instant_mlp_bwd(const float* x_enc, int ldx, int pos_dim, const float* d
  * [out,in] fp32 matrices with row stride ldw[l] (torch.nn.Linear.weight, or the
  * slices of a tinycudann flat `params`); b[l] may be NULL (no bias).
  * forward : y [P,out_dim] (row stride ldy); when xin_plane / h_planes are given
- *           (training) also writes the bf16 input rows [P][b2n_fmlp_in_pad(d0+d1)]
+ *           (training) also writes the fp16 input rows [P][b2n_fmlp_in_pad(d0+d1)]
  *           and the hidden activations [n_hidden][P][hidden].
  * backward: from g_y, the forward output y (needed for sigmoid/relu outputs) and
- *           h_planes: writes dz_out bf16 [P][b2n_fmlp_out_pad(out_dim)], dz_h bf16
- *           [n_hidden][P][hidden] (pre-activation gradients) and the fp32 input
+ *           h_planes: writes dz_out fp16 [P][b2n_fmlp_out_pad(out_dim)], dz_h fp16
+ *           [n_hidden][P][hidden] (pre-activation gradients TIMES the power-of-two
+ *           scale S the kernel derives from max|g_y| and leaves as a float at
+ *           work8 + 4; work8 = 8 device bytes owned by the caller) and the fp32 input
  *           gradients g_x0 [P,d0] / g_x1 [P,d1] (either may be NULL).  Weight and
  *           bias gradients are dZ_l^T * In_l GEMMs / column sums over the planes
  *           (plain GEMMs, done by the caller).
@@ -243,22 +245,24 @@ int b2n_fmlp_fwd(const float* x0, int ld0, int d0, const float* x1, int ld1, int
                  const float* const* W, const int* ldw, const float* const* b, int out_dim, int out_act, int64_t P,
                  float* y, int ldy, void* xin_plane, void* h_planes, b2n_stream_t stream);
 /* dW_l[rows_valid, k_valid] (row stride lddw) += dZ_l^T In_l ; db_l[rows_valid] += colsum(dZ_l) for
- * l < n_layers in one launch: dz[l] bf16 [P][ldz] of width rows[l], in[l] bf16 [P][ldi] of width k[l]
- * (widths multiples of 16, <= 128).  ACCUMULATES into fp32 dW / db (db[l] may be NULL). */
+ * l < n_layers in one launch: dz[l] fp16 [P][ldz] of width rows[l], in[l] fp16 [P][ldi] of width k[l]
+ * (widths multiples of 16, <= 128).  ACCUMULATES into fp32 dW / db (db[l] may be NULL).  scale: device float S (work8 + 4
+ * of b2n_fmlp_bwd: its dZ planes hold S * dZ) -- results are divided by it; NULL = 1. */
 int b2n_fmlp_wgrad(int n_layers, const void* const* dz, const int* ldz, const int* rows, const void* const* in,
                    const int* ldi, const int* k, float* const* dW, const int* lddw, const int* rows_valid,
-                   const int* k_valid, float* const* db, int64_t P, b2n_stream_t stream);
+                   const int* k_valid, float* const* db, int64_t P, const float* scale, b2n_stream_t stream);
 /* The same gradients for hidden = 128 through the tcgen05 plane-GEMM kernel of b2n_nerf_mlp_wgrad (TMA-loaded planes,
- * MN-major operands, HBM-bound): dz_h bf16 [n_hidden][P][128], dz_out bf16 [P][out_pad], h_planes bf16 [n_hidden][P][128],
- * xin bf16 [P][in_pad].  ACCUMULATES fp32: dW0 [128][128] = dZ_0^T xin (columns >= in_pad stay 0), dWh
+ * MN-major operands, HBM-bound): dz_h fp16 [n_hidden][P][128], dz_out fp16 [P][out_pad], h_planes fp16 [n_hidden][P][128],
+ * xin fp16 [P][in_pad]; scale as in b2n_fmlp_wgrad.  ACCUMULATES fp32: dW0 [128][128] = dZ_0^T xin (columns >= in_pad stay 0), dWh
  * [n_hidden-1][128][128] = dZ_l^T H_{l-1}, dWoT [128][64] = H_last^T dZ_out (the TRANSPOSED output-layer gradient),
  * db_h [n_hidden][128] = column sums of the hidden dZ planes.  P >= 64. */
 int b2n_fmlp_wgrad_tc(const void* dz_h, const void* dz_out, const void* h_planes, const void* xin, int64_t P, int n_hidden,
                       int in_pad, int out_pad, float* dW0, float* dWh, float* dWoT, float* db_h, int* err_flag,
-                      b2n_stream_t stream);
+                      const float* scale, b2n_stream_t stream);
 int b2n_fmlp_bwd(int d0, int d1, int hidden, int n_hidden, const float* const* W, const int* ldw, int out_dim,
                  int out_act, int64_t P, const float* y, int ldy, const float* g_y, int ldgy, const void* h_planes,
-                 void* dz_out, void* dz_h, float* g_x0, int ldg0, float* g_x1, int ldg1, b2n_stream_t stream);
+                 void* dz_out, void* dz_h, float* g_x0, int ldg0, float* g_x1, int ldg1, void* work8,
+                 b2n_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * 256-wide vanilla NeRF decoder (NeRFDecoder.forward, src/decoders.py:68-87)

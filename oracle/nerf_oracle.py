@@ -190,8 +190,9 @@ def bf16_round(x: Tensor) -> Tensor:
 
 
 # 16-bit operand type of each CUDA kernel family, for the "kernel" arithmetic model: the fused Instant decoder
-# (csrc/b2n_mlp64.cu) computes in IEEE fp16 like tinycudann, the other tensor-core kernels in bf16.
-KERNEL_OPERAND = {"instant": torch.float16, "fmlp": torch.bfloat16, "nerf256": torch.bfloat16}
+# (csrc/b2n_mlp64.cu) and the fused deformation / time-modulation nets (csrc/b2n_fmlp.cu) compute in IEEE fp16 like
+# tinycudann, the 256-wide tcgen05 decoder in bf16.
+KERNEL_OPERAND = {"instant": torch.float16, "fmlp": torch.float16, "nerf256": torch.bfloat16}
 
 
 def _q(x: Tensor, dt=torch.bfloat16) -> Tensor:

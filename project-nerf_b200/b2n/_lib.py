@@ -48,9 +48,9 @@ SIGNATURES = {
     "b2n_fmlp_in_pad": [I],
     "b2n_fmlp_out_pad": [I],
     "b2n_fmlp_fwd": [P, I, I, P, I, I, I, I, P, P, P, I, I, L, P, I, P, P, P],
-    "b2n_fmlp_bwd": [I, I, I, I, P, P, I, I, L, P, I, P, I, P, P, P, P, I, P, I, P],
-    "b2n_fmlp_wgrad_tc": [P, P, P, P, L, I, I, I, P, P, P, P, P, P],
-    "b2n_fmlp_wgrad": [I, P, P, P, P, P, P, P, P, P, P, P, L, P],
+    "b2n_fmlp_bwd": [I, I, I, I, P, P, I, I, L, P, I, P, I, P, P, P, P, I, P, I, P, P],
+    "b2n_fmlp_wgrad_tc": [P, P, P, P, L, I, I, I, P, P, P, P, P, P, P],
+    "b2n_fmlp_wgrad": [I, P, P, P, P, P, P, P, P, P, P, P, L, P, P],
     "b2n_nerf_mlp_wgrad": [P, P, P, I, P, L, P, P, P, P, P, P, P, P],
     "b2n_nerf_mlp_dx": [P, P, P, I, P, I, I, L, P, I, P],
     "b2n_nerf_mlp_packed_bytes": [],
@@ -105,7 +105,7 @@ lib = _load()
 # launch accounting for bench.py ("gpu_launches"): every successful C-ABI call adds the
 # number of kernels that entry point launches.
 LAUNCHES = {"count": 0}
-_KERNELS_PER_CALL = {"b2n_march_scan": 3, "b2n_linear_wgrad": 2, "b2n_instant_mlp_bwd": 2}   # instant bwd: |g|-max pre-pass + kernel
+_KERNELS_PER_CALL = {"b2n_march_scan": 3, "b2n_linear_wgrad": 2, "b2n_instant_mlp_bwd": 2, "b2n_fmlp_bwd": 2}   # 16-bit MLP backwards: |g|-max pre-pass + kernel
 
 
 def ptr(t):

@@ -611,8 +611,8 @@ class _FusedMLP(torch.autograd.Function):
         need = any(ctx.needs_input_grad)
         in_pad = _lib.lib.b2n_fmlp_in_pad(d0 + d1)
         y = torch.empty(Pn, out_dim, device=dev)
-        xin = torch.empty(Pn, in_pad, device=dev, dtype=torch.bfloat16) if need else None
-        hpl = torch.empty(n_hidden, Pn, hidden, device=dev, dtype=torch.bfloat16) if need else None
+        xin = torch.empty(Pn, in_pad, device=dev, dtype=torch.float16) if need else None
+        hpl = torch.empty(n_hidden, Pn, hidden, device=dev, dtype=torch.float16) if need else None
         Wp = (ctypes.c_void_p * n_layers)(*[W.data_ptr() for W in Ws])
         ld = (ctypes.c_int * n_layers)(*[W.stride(0) for W in Ws])
         bp = (ctypes.c_void_p * n_layers)(*[(b.data_ptr() if b is not None else None) for b in bs])
@@ -633,15 +633,17 @@ class _FusedMLP(torch.autograd.Function):
         dev = y.device
         g_y = _c(g_y)
         out_pad = _lib.lib.b2n_fmlp_out_pad(out_dim)
-        dz_out = torch.empty(Pn, out_pad, device=dev, dtype=torch.bfloat16)
-        dz_h = torch.empty(n_hidden, Pn, hidden, device=dev, dtype=torch.bfloat16)
+        dz_out = torch.empty(Pn, out_pad, device=dev, dtype=torch.float16)       # planes hold S * dZ (see b2n_fmlp_bwd)
+        dz_h = torch.empty(n_hidden, Pn, hidden, device=dev, dtype=torch.float16)
+        work = torch.empty(2, device=dev, dtype=torch.float32)                    # [0] |g|-max bits, [1] S
+        scale = work[1:]
         g_x0 = torch.empty(Pn, d0, device=dev) if ctx.needs_input_grad[0] else None
         g_x1 = torch.empty(Pn, d1, device=dev) if (d1 and ctx.needs_input_grad[1]) else None
         Wp = (ctypes.c_void_p * n_layers)(*[W.data_ptr() for W in Ws])
         ld = (ctypes.c_int * n_layers)(*[W.stride(0) for W in Ws])
         macs = hidden * hidden * (n_hidden - 1) + out_dim * hidden + (hidden * (d0 + d1) if (g_x0 is not None or g_x1 is not None) else 0)
         call("b2n_fmlp_bwd", d0, d1, hidden, n_hidden, Wp, ld, out_dim, out_act, Pn, ptr(y), out_dim, ptr(g_y), out_dim,
-             ptr(hpl), ptr(dz_out), ptr(dz_h), ptr(g_x0), d0, ptr(g_x1), d1, stream(),
+             ptr(hpl), ptr(dz_out), ptr(dz_h), ptr(g_x0), d0, ptr(g_x1), d1, ptr(work), stream(),
              work=(Pn * (4.0 * out_dim + 4.0 * n_hidden * hidden + 2.0 * out_pad + 4.0 * (d0 + d1)), 2.0 * Pn * macs))
         shapes = [(Ws[l].shape[0], Ws[l].shape[1]) for l in range(n_layers)]
         in_pad = xin.shape[1]
@@ -653,10 +655,10 @@ class _FusedMLP(torch.autograd.Function):
                 torch.split(flat[:-1], sizes), [(128, 128), (max(n_hidden - 1, 1), 128, 128), (128, 64), (n_hidden, 128)])]
             err = flat[-1:].view(torch.int32)
             call("b2n_fmlp_wgrad_tc", ptr(dz_h), ptr(dz_out), ptr(hpl), ptr(xin), Pn, n_hidden, in_pad, out_pad, ptr(dW0),
-                 ptr(dWh), ptr(dWoT), ptr(db_h), ptr(err), stream(),
+                 ptr(dWh), ptr(dWoT), ptr(db_h), ptr(err), ptr(scale), stream(),
                  work=(2.0 * Pn * ((2 * n_hidden) * 128 + in_pad + out_pad), 2.0 * Pn * (128 * in_pad + (n_hidden - 1) * 16384 + 128 * out_pad)))
             gW = [dW0[:, : shapes[0][1]]] + [dWh[l - 1] for l in range(1, n_hidden)] + [dWoT[:, : shapes[-1][0]].t()]
-            gb = [db_h[l] for l in range(n_hidden)] + [torch.sum(dz_out, dim=0, dtype=torch.float32)[: shapes[-1][0]]]
+            gb = [db_h[l] for l in range(n_hidden)] + [torch.sum(dz_out, dim=0, dtype=torch.float32)[: shapes[-1][0]] / scale]
         else:
             # ---- weight / bias gradients of every layer: one launch (b2n_fmlp_wgrad, mma.sync), fp32 accumulation
             n_w = sum(r * c for r, c in shapes)
@@ -673,7 +675,7 @@ class _FusedMLP(torch.autograd.Function):
                  arr_i(*[t.shape[1] for t in dzs]), arr_p(*[t.data_ptr() for t in ins]), arr_i(*[t.stride(0) for t in ins]),
                  arr_i(*[t.shape[1] for t in ins]), arr_p(*[g.data_ptr() for g in gW]), arr_i(*[c for _, c in shapes]),
                  arr_i(*[r for r, _ in shapes]), arr_i(*[min(c, t.shape[1]) for (_, c), t in zip(shapes, ins)]),
-                 arr_p(*[(gb[l].data_ptr() if has_b[l] else None) for l in range(n_layers)]), Pn, stream(),
+                 arr_p(*[(gb[l].data_ptr() if has_b[l] else None) for l in range(n_layers)]), Pn, ptr(scale), stream(),
                  work=(2.0 * Pn * sum(a_.shape[1] + b_.shape[1] for a_, b_ in zip(dzs, ins)),
                        2.0 * Pn * sum(r * c for r, c in shapes)))
         gW = [g if ctx.needs_input_grad[4 + l] else None for l, g in enumerate(gW)]

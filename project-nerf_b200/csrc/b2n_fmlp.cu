@@ -7,17 +7,18 @@
 // from one or two row-major fp32 sources (the concat is never materialised), up to 64 outputs, optional
 // biases, linear or sigmoid output.
 //
-// Arithmetic: bf16 operands, fp32 accumulation on the tensor cores (mma.sync m16n8k16) -- the
+// Arithmetic: op16 operands, fp32 accumulation on the tensor cores (mma.sync m16n8k16) -- the
 // reference runs these nets in fp16 (tinycudann) or under torch.amp.autocast (nn.Linear).
 //   forward : each warp owns 16*MT points; the C fragments of a layer are re-packed in registers as
-//             the A fragments of the next layer; weights are bf16 in shared memory (ldmatrix), biases
-//             initialise the accumulators.  When training, the bf16 input row and every hidden
+//             the A fragments of the next layer; weights are op16 in shared memory (ldmatrix), biases
+//             initialise the accumulators.  When training, the op16 input row and every hidden
 //             activation are also written to HBM ("planes").
 //   backward: each warp owns 16 points; the data-gradient chain runs in registers (ldmatrix.trans on
 //             the same weight tiles), ReLU gates come from the saved planes, every pre-activation
-//             gradient dZ_l is written to HBM in bf16 and the input gradient in fp32.
+//             gradient dZ_l is written to HBM in op16 and the input gradient in fp32.
 //   wgrad   : dW_l = dZ_l^T In_l and db_l = colsum(dZ_l) for all layers of the network in one launch
 //             (k_fmlp_wgrad): split over P, tensor-core accumulators per CTA, one atomicAdd per weight.
+#define B2N_OP_F16
 #include "b2n_mma.cuh"
 
 namespace b2n {
@@ -34,15 +35,16 @@ struct Args {
   int n_hidden, out_dim, out_act;
   int64_t P;
   float* y; int ldy;
-  bf16* xin;       // [P][IN_PAD]  bf16 copy of the concatenated input (training) or null
-  bf16* hplanes;   // [n_hidden][P][H] hidden activations (training) or null
+  op16* xin;       // [P][IN_PAD]  op16 copy of the concatenated input (training) or null
+  op16* hplanes;   // [n_hidden][P][H] hidden activations (training) or null
   // backward only
   const float* g_y; int ldgy;
   const float* y_out;   // forward outputs (sigmoid derivative)
-  bf16* dz_out;    // [P][OUT_PAD16]
-  bf16* dz_h;      // [n_hidden][P][H]
+  op16* dz_out;    // [P][OUT_PAD16]
+  op16* dz_h;      // [n_hidden][P][H]
   float* g_x0; int ldg0;
   float* g_x1; int ldg1;
+  unsigned int* work;   // [0] |g_y|-max bits (pre-pass), [1] the gradient scale S as a float (written by the kernel)
 };
 
 template <int H, int KT_IN, int NT_OUT>
@@ -53,31 +55,31 @@ struct Layout {
   static constexpr int w0 = 0;
   static constexpr int wh = w0 + H * S0;                          // hidden matrices 1 .. MAX_HID-1
   static constexpr int wo = wh + (MAX_HID - 1) * H * SH;
-  static constexpr int end_bf16 = wo + OUT_ROWS * SH;
+  static constexpr int end_op16 = wo + OUT_ROWS * SH;
   static constexpr int bias_floats = MAX_HID * H + OUT_ROWS;
-  static constexpr size_t bytes = (size_t)end_bf16 * sizeof(bf16) + (size_t)bias_floats * sizeof(float);
+  static constexpr size_t bytes = (size_t)end_op16 * sizeof(op16) + (size_t)bias_floats * sizeof(float);
 };
 
-// fp32 matrix [rows_valid][cols_valid] (row stride ldw) -> bf16 smem [rows][cols + PAD], zero filled elsewhere
+// fp32 matrix [rows_valid][cols_valid] (row stride ldw) -> op16 smem [rows][cols + PAD], zero filled elsewhere
 __device__ __forceinline__ void load_w(const float* __restrict__ W, int ldw, int rows_valid, int cols_valid, int rows,
-                                       int cols, bf16* dst) {
+                                       int cols, op16* dst) {
   const int S = cols + PAD;
   for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
     const int r = i / cols, c = i - r * cols;
-    dst[r * S + c] = __float2bfloat16((r < rows_valid && c < cols_valid) ? __ldg(W + (size_t)r * ldw + c) : 0.f);
+    dst[r * S + c] = to_op16((r < rows_valid && c < cols_valid) ? __ldg(W + (size_t)r * ldw + c) : 0.f);
   }
 }
 
 // skip_w0: the backward without input gradients never touches the first matrix -- it is not staged and every later
 // offset moves down by its size (26 KB at H = 128: 3 CTAs per SM instead of 2)
 template <int H, int KT_IN, int NT_OUT>
-__device__ __forceinline__ float* stage_weights(const Args& a, bf16* sm, bool skip_w0 = false) {
+__device__ __forceinline__ float* stage_weights(const Args& a, op16* sm, bool skip_w0 = false) {
   using LY = Layout<H, KT_IN, NT_OUT>;
   if (!skip_w0) load_w(a.W[0], a.ldw[0], H, a.d0 + a.d1, H, LY::IN_PAD, sm + LY::w0);
   else sm -= LY::wh;
   for (int l = 1; l < a.n_hidden; ++l) load_w(a.W[l], a.ldw[l], H, H, H, H, sm + LY::wh + (l - 1) * H * LY::SH);
   load_w(a.W[a.n_hidden], a.ldw[a.n_hidden], a.out_dim, H, LY::OUT_ROWS, H, sm + LY::wo);
-  float* bias = reinterpret_cast<float*>(sm + LY::end_bf16);
+  float* bias = reinterpret_cast<float*>(sm + LY::end_op16);
   for (int i = threadIdx.x; i < LY::bias_floats; i += blockDim.x) {
     float v = 0.f;
     if (i < MAX_HID * H) {
@@ -143,9 +145,9 @@ __device__ __forceinline__ void load_in_raw(const Args& a, int64_t p0, float (&r
       }
 }
 
-// A fragments of a 16-row slab -> rows p0.. of a row-major bf16 plane (row stride ld, even)
+// A fragments of a 16-row slab -> rows p0.. of a row-major op16 plane (row stride ld, even)
 template <int KT>
-__device__ __forceinline__ void store_plane(const uint32_t (&f)[KT][4], bf16* plane, int ld, int64_t p0, int64_t P,
+__device__ __forceinline__ void store_plane(const uint32_t (&f)[KT][4], op16* plane, int ld, int64_t p0, int64_t P,
                                             int lane) {
   const int g = lane >> 2, t = lane & 3;
   const int64_t pa = p0 + g, pb = pa + 8;
@@ -174,7 +176,7 @@ __device__ __forceinline__ void init_bias(float (&c)[NT][4], const float* bias, 
 
 // zero the gradient where the saved (post-ReLU) activation is not positive
 template <int NT>
-__device__ __forceinline__ void relu_gate(float (&c)[NT][4], const bf16* plane, int ld, int64_t p0, int64_t P, int lane) {
+__device__ __forceinline__ void relu_gate(float (&c)[NT][4], const op16* plane, int ld, int64_t p0, int64_t P, int lane) {
   const int g = lane >> 2, t = lane & 3;
   const int64_t pa = p0 + g, pb = pa + 8;
 #pragma unroll
@@ -191,7 +193,7 @@ __device__ __forceinline__ void relu_gate(float (&c)[NT][4], const bf16* plane, 
 
 // split version: the gate words of a layer are fetched one GEMM ahead of their use
 template <int NT>
-__device__ __forceinline__ void load_gate(const bf16* plane, int ld, int64_t p0, int64_t P, uint32_t (&ga)[NT],
+__device__ __forceinline__ void load_gate(const op16* plane, int ld, int64_t p0, int64_t P, uint32_t (&ga)[NT],
                                           uint32_t (&gb)[NT], int lane) {
   const int g = lane >> 2, t = lane & 3;
   const int64_t pa = p0 + g, pb = pa + 8;
@@ -215,11 +217,32 @@ __device__ __forceinline__ void apply_gate(float (&c)[NT][4], const uint32_t (&g
 
 __device__ __forceinline__ float sigm(float v) { return 1.f / (1.f + expf(-v)); }
 
+// max |g_y| as float bits (see k_instant_bwd's pre-pass: same convention, NaN sorts above everything)
+__global__ void __launch_bounds__(256) k_fmlp_absmax(const float* __restrict__ g, int ld, int cols, int64_t P,
+                                                     unsigned int* __restrict__ out) {
+  unsigned int m = 0u;
+  const int64_t n = P * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t p = i / cols;
+    m = max(m, __float_as_uint(__ldg(g + p * ld + (i - p * cols))) & 0x7fffffffu);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+__device__ __forceinline__ float fmlp_scale_from(unsigned int bits) {
+  if (bits == 0u) return 1.f;
+  if (bits >= 0x7f800000u) return __uint_as_float(0x7fc00000u);      // non-finite gradient in -> non-finite out
+  int se = 7 - ((int)(bits >> 23) - 127);
+  se = se > 120 ? 120 : (se < -120 ? -120 : se);
+  return __uint_as_float((unsigned int)(se + 127) << 23);
+}
+
 // ------------------------------------------------------------------------------ forward
 template <int H, int KT_IN, int NT_OUT, int MT>
 __global__ void __launch_bounds__(THREADS) k_fmlp_fwd(const Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  bf16* sm = reinterpret_cast<bf16*>(smem_raw);
+  op16* sm = reinterpret_cast<op16*>(smem_raw);
   using LY = Layout<H, KT_IN, NT_OUT>;
   const float* bias = stage_weights<H, KT_IN, NT_OUT>(a, sm);
   __syncthreads();
@@ -305,9 +328,12 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_fwd(const Args a) {
 template <int H, int KT_IN, int NT_OUT>
 __global__ void __launch_bounds__(THREADS) k_fmlp_bwd(const Args a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  bf16* sm = reinterpret_cast<bf16*>(smem_raw);
+  op16* sm = reinterpret_cast<op16*>(smem_raw);
   using LY = Layout<H, KT_IN, NT_OUT>;
   const bool need_x = a.g_x0 || a.g_x1;
+  const float gscale = fmlp_scale_from(__ldg(a.work));
+  const float inv_s = 1.f / gscale;
+  if (blockIdx.x == 0 && threadIdx.x == 0) reinterpret_cast<float*>(a.work)[1] = gscale;    // for the weight-gradient pass
   stage_weights<H, KT_IN, NT_OUT>(a, sm, !need_x);
   if (!need_x) sm -= LY::wh;          // all offsets below are relative to the (unstaged) first matrix
   __syncthreads();
@@ -339,7 +365,7 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_bwd(const Args a) {
                   const float y = __ldcs(a.y_out + p * a.ldy + c + j);
                   gy = (a.out_act == B2N_ACT_SIGMOID) ? gy * y * (1.f - y) : (y > 0.f ? gy : 0.f);
                 }
-                v[j] = gy;
+                v[j] = gy * gscale;
               }
             }
           }
@@ -377,9 +403,9 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_bwd(const Args a) {
           const int64_t p = p0 + g + ((i & 2) ? 8 : 0);
           if (p < a.P) {
             if (col < a.d0) {
-              if (a.g_x0) a.g_x0[p * a.ldg0 + col] = c[j][i];
+              if (a.g_x0) a.g_x0[p * a.ldg0 + col] = c[j][i] * inv_s;
             } else if (col < din) {
-              if (a.g_x1) a.g_x1[p * a.ldg1 + (col - a.d0)] = c[j][i];
+              if (a.g_x1) a.g_x1[p * a.ldg1 + (col - a.d0)] = c[j][i] * inv_s;
             }
           }
         }
@@ -390,7 +416,7 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_bwd(const Args a) {
 
 // ------------------------------------------------------------------------------ weight / bias gradients
 // dW_l[rows, k] += dZ_l^T In_l and db_l[rows] += colsum(dZ_l) over all P points, for every layer of one
-// network in a single launch (blockIdx.y = layer).  A CTA streams 64-point tiles of the two bf16 planes
+// network in a single launch (blockIdx.y = layer).  A CTA streams 64-point tiles of the two op16 planes
 // into shared memory (cp.async, double buffered); each warp owns one 16-row x (up to) 64-column tile of
 // dW in tensor-core accumulators for the whole persistent loop and flushes it with one atomicAdd per
 // weight at the end.  (cuBLAS was tried first: for these skinny [<=128 x P] x [P x <=128] shapes with P
@@ -399,17 +425,18 @@ constexpr int WG_THREADS = 512;
 constexpr int WG_TILE = 64;
 constexpr int WG_MAXW = 128;                       // widest plane
 constexpr int WG_S = WG_MAXW + PAD;                // smem row stride of both tiles
-constexpr size_t WG_SMEM = (size_t)2 * 2 * WG_TILE * WG_S * sizeof(bf16);
+constexpr size_t WG_SMEM = (size_t)2 * 2 * WG_TILE * WG_S * sizeof(op16);
 
 struct WgLayer {
-  const bf16* dz; int ldz, rows;       // [P][ldz], rows = plane width (multiple of 16)
-  const bf16* in; int ldi, k;          // [P][ldi], k = plane width (multiple of 16)
+  const op16* dz; int ldz, rows;       // [P][ldz], rows = plane width (multiple of 16)
+  const op16* in; int ldi, k;          // [P][ldi], k = plane width (multiple of 16)
   float* dW; int lddw, rows_valid, k_valid;
   float* db;                           // [rows_valid] or null
 };
 struct WgArgs {
   WgLayer L[MAX_HID + 1];
   int64_t P;
+  const float* scale;                  // device: the dZ planes hold S * dZ (b2n_fmlp_bwd); results are divided by S.  null: 1
 };
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
@@ -417,7 +444,7 @@ __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool vali
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst)), "l"(src), "r"(n) : "memory");
 }
 
-__device__ __forceinline__ void wg_load_tile(const WgLayer& L, int64_t p0, int64_t P, bf16* dzs, bf16* ins) {
+__device__ __forceinline__ void wg_load_tile(const WgLayer& L, int64_t p0, int64_t P, op16* dzs, op16* ins) {
   const int cz = L.rows >> 3, ci = L.k >> 3;       // 16-byte chunks per row
   for (int i = threadIdx.x; i < WG_TILE * (cz + ci); i += WG_THREADS) {
     const bool is_z = i < WG_TILE * cz;
@@ -426,7 +453,7 @@ __device__ __forceinline__ void wg_load_tile(const WgLayer& L, int64_t p0, int64
     const int r = j / w, c = j - r * w;
     const int64_t p = p0 + r;
     const bool ok = p < P;
-    const bf16* src = is_z ? L.dz + (ok ? p : 0) * L.ldz + 8 * c : L.in + (ok ? p : 0) * L.ldi + 8 * c;
+    const op16* src = is_z ? L.dz + (ok ? p : 0) * L.ldz + 8 * c : L.in + (ok ? p : 0) * L.ldi + 8 * c;
     cp_async16((is_z ? dzs : ins) + r * WG_S + 8 * c, src, ok);
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
@@ -434,7 +461,7 @@ __device__ __forceinline__ void wg_load_tile(const WgLayer& L, int64_t p0, int64
 
 __global__ void __launch_bounds__(WG_THREADS) k_fmlp_wgrad(const WgArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  bf16* sm = reinterpret_cast<bf16*>(smem_raw);
+  op16* sm = reinterpret_cast<op16*>(smem_raw);
   const WgLayer& L = a.L[blockIdx.y];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int n_row_tiles = L.rows >> 4, n_col_tiles = (L.k + 63) >> 6;
@@ -443,15 +470,16 @@ __global__ void __launch_bounds__(WG_THREADS) k_fmlp_wgrad(const WgArgs a) {
   const int npairs = active ? min(L.k - k0, 64) >> 4 : 0;      // pairs of 8-column tiles this warp owns
   float acc[8][4] = {};
   float bsum = 0.f;
+  const float inv_s = a.scale ? 1.f / __ldg(a.scale) : 1.f;
   const int64_t n_tiles = (a.P + WG_TILE - 1) / WG_TILE;
   int buf = 0;
   if ((int64_t)blockIdx.x < n_tiles) wg_load_tile(L, (int64_t)blockIdx.x * WG_TILE, a.P, sm, sm + WG_TILE * WG_S);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    bf16* dzs = sm + buf * 2 * WG_TILE * WG_S;
-    bf16* ins = dzs + WG_TILE * WG_S;
+    op16* dzs = sm + buf * 2 * WG_TILE * WG_S;
+    op16* ins = dzs + WG_TILE * WG_S;
     const int64_t next = tile + gridDim.x;
     if (next < n_tiles) {
-      bf16* nz = sm + (buf ^ 1) * 2 * WG_TILE * WG_S;
+      op16* nz = sm + (buf ^ 1) * 2 * WG_TILE * WG_S;
       wg_load_tile(L, next * WG_TILE, a.P, nz, nz + WG_TILE * WG_S);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
@@ -477,7 +505,7 @@ __global__ void __launch_bounds__(WG_THREADS) k_fmlp_wgrad(const WgArgs a) {
     if (L.db && threadIdx.x < L.rows) {
       float s = 0.f;
 #pragma unroll 8
-      for (int r = 0; r < WG_TILE; ++r) s += __bfloat162float(dzs[r * WG_S + threadIdx.x]);
+      for (int r = 0; r < WG_TILE; ++r) s += from_op16(dzs[r * WG_S + threadIdx.x]);
       bsum += s;
     }
     __syncthreads();
@@ -490,12 +518,13 @@ __global__ void __launch_bounds__(WG_THREADS) k_fmlp_wgrad(const WgArgs a) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int row = n0 + g + ((i & 2) ? 8 : 0), col = k0 + 8 * j + 2 * t + (i & 1);
-          if (row < L.rows_valid && col < L.k_valid && acc[j][i] != 0.f) atomicAdd(L.dW + (size_t)row * L.lddw + col, acc[j][i]);
+          if (row < L.rows_valid && col < L.k_valid && acc[j][i] != 0.f)
+            atomicAdd(L.dW + (size_t)row * L.lddw + col, acc[j][i] * inv_s);
         }
       }
     }
   }
-  if (L.db && threadIdx.x < L.rows_valid) atomicAdd(L.db + threadIdx.x, bsum);
+  if (L.db && threadIdx.x < L.rows_valid) atomicAdd(L.db + threadIdx.x, bsum * inv_s);
 }
 
 static int persistent_grid(const void* kernel, size_t smem, int64_t warp_tiles) {
@@ -510,64 +539,6 @@ static int persistent_grid(const void* kernel, size_t smem, int64_t warp_tiles) 
 }
 
 
-// ------------------------------------------------------------------------------ input gradient of the 256-wide decoder
-// d x_enc [P, pos_dim] = dZ_0 W_0 + dZ_4 W_4[:, 256:256+pos_dim]   (NeRFDecoder, src/decoders.py:68-87: x feeds layer 0
-// and, through the skip concat [h, x], layer 4).  dZ_l are the bf16 pre-activation gradient planes written by the
-// tcgen05 backward chain (b2n_nerf_mlp_bwd); needed when the decoder input depends on a trainable deformation
-// (Part 3: x_enc = gamma(x + delta_x), src/core.py:268-277).
-template <int NTo>
-__global__ void __launch_bounds__(THREADS) k_nerf_dx(const bf16* __restrict__ dz0, const bf16* __restrict__ dz4,
-                                                     const float* __restrict__ W0, int ld0, const float* __restrict__ W4x,
-                                                     int ld4, int pos_dim, int64_t P, float* __restrict__ gx, int ldg) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  bf16* sm = reinterpret_cast<bf16*>(smem_raw);
-  constexpr int S = 8 * NTo + PAD;
-  load_w(W0, ld0, 256, pos_dim, 256, 8 * NTo, sm);
-  load_w(W4x, ld4, 256, pos_dim, 256, 8 * NTo, sm + 256 * S);
-  __syncthreads();
-  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const int64_t n_tiles = (P + 15) / 16;
-  const int64_t wstride = (int64_t)gridDim.x * (THREADS / 32);
-  for (int64_t tile = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); tile < n_tiles; tile += wstride) {
-    const int64_t pa = tile * 16 + g, pb = pa + 8;
-    float c[NTo][4] = {};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {        // (plane, half): 128 gradient columns at a time
-      const bf16* plane = (q < 2) ? dz0 : dz4;
-      const int col0 = 128 * (q & 1);
-      uint32_t a[8][4];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int col = col0 + 16 * k + 2 * t;
-        a[k][0] = pa < P ? __ldcs(reinterpret_cast<const uint32_t*>(plane + pa * 256 + col)) : 0u;
-        a[k][1] = pb < P ? __ldcs(reinterpret_cast<const uint32_t*>(plane + pb * 256 + col)) : 0u;
-        a[k][2] = pa < P ? __ldcs(reinterpret_cast<const uint32_t*>(plane + pa * 256 + col + 8)) : 0u;
-        a[k][3] = pb < P ? __ldcs(reinterpret_cast<const uint32_t*>(plane + pb * 256 + col + 8)) : 0u;
-      }
-      gemm_dgrad<NTo, 8>(c, a, sm + ((q < 2) ? 0 : 256 * S) + col0 * S, S, lane);
-    }
-#pragma unroll
-    for (int j = 0; j < NTo; ++j)
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int col = 8 * j + 2 * t + (i & 1);
-        const int64_t p = (i & 2) ? pb : pa;
-        if (p < P && col < pos_dim) gx[p * ldg + col] = c[j][i];
-      }
-  }
-}
-
-template <int NTo>
-static int launch_nerf_dx(const bf16* dz0, const bf16* dz4, const float* W0, int ld0, const float* W4x, int ld4, int pos_dim,
-                          int64_t P, float* gx, int ldg, cudaStream_t st) {
-  constexpr size_t smem = (size_t)2 * 256 * (8 * NTo + PAD) * sizeof(bf16);
-  auto k = k_nerf_dx<NTo>;
-  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const int grid = persistent_grid((const void*)k, smem, (P + 15) / 16);
-  k<<<grid, THREADS, smem, st>>>(dz0, dz4, W0, ld0, W4x, ld4, pos_dim, P, gx, ldg);
-  return check_launch("b2n_nerf_mlp_dx");
-}
-
 template <int H, int KT_IN, int NT_OUT, int MT>
 static int launch_fwd(const Args& a, cudaStream_t st) {
   constexpr size_t smem = Layout<H, KT_IN, NT_OUT>::bytes;
@@ -580,7 +551,7 @@ static int launch_fwd(const Args& a, cudaStream_t st) {
 template <int H, int KT_IN, int NT_OUT>
 static int launch_bwd(const Args& a, cudaStream_t st) {
   using LY = Layout<H, KT_IN, NT_OUT>;
-  const size_t smem = LY::bytes - ((a.g_x0 || a.g_x1) ? 0 : (size_t)LY::wh * sizeof(bf16));
+  const size_t smem = LY::bytes - ((a.g_x0 || a.g_x1) ? 0 : (size_t)LY::wh * sizeof(op16));
   auto k = k_fmlp_bwd<H, KT_IN, NT_OUT>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = persistent_grid((const void*)k, smem, (a.P + 15) / 16);
@@ -629,7 +600,7 @@ extern "C" int b2n_fmlp_fwd(const float* x0, int ld0, int d0, const float* x1, i
   int rc = fill_args(&a, true, x0, ld0, d0, x1, ld1, d1, hidden, n_hidden, W, ldw, b, out_dim, out_act, P);
   if (rc) return rc;
   B2N_REQUIRE(y && ldy >= out_dim, "bad output");
-  a.y = y, a.ldy = ldy, a.xin = (bf16*)xin_plane, a.hplanes = (bf16*)h_planes;
+  a.y = y, a.ldy = ldy, a.xin = (op16*)xin_plane, a.hplanes = (op16*)h_planes;
   cudaStream_t st = (cudaStream_t)stream;
   const bool small_in = d0 + d1 <= 32, small_out = out_dim <= 16;
   if (hidden == 64) {
@@ -643,18 +614,25 @@ extern "C" int b2n_fmlp_fwd(const float* x0, int ld0, int d0, const float* x1, i
 extern "C" int b2n_fmlp_bwd(int d0, int d1, int hidden, int n_hidden, const float* const* W, const int* ldw, int out_dim,
                             int out_act, int64_t P, const float* y, int ldy, const float* g_y, int ldgy,
                             const void* h_planes, void* dz_out, void* dz_h, float* g_x0, int ldg0, float* g_x1, int ldg1,
-                            b2n_stream_t stream) {
+                            void* work8, b2n_stream_t stream) {
   B2N_REQUIRE(P >= 0, "negative size");
   if (P == 0) return B2N_OK;
   Args a{};
   int rc = fill_args(&a, false, nullptr, 0, d0, nullptr, 0, d1, hidden, n_hidden, W, ldw, nullptr, out_dim, out_act, P);
   if (rc) return rc;
-  B2N_REQUIRE(g_y && ldgy >= out_dim && h_planes && dz_out && dz_h, "null pointer");
+  B2N_REQUIRE(g_y && ldgy >= out_dim && h_planes && dz_out && dz_h && work8, "null pointer");
   B2N_REQUIRE(out_act == B2N_ACT_NONE || (y && ldy >= out_dim), "activation derivative needs the forward output");
   B2N_REQUIRE((!g_x0 || ldg0 >= d0) && (!g_x1 || ldg1 >= d1), "gradient row too narrow");
-  a.y_out = y, a.ldy = ldy, a.g_y = g_y, a.ldgy = ldgy, a.hplanes = (bf16*)h_planes;
-  a.dz_out = (bf16*)dz_out, a.dz_h = (bf16*)dz_h, a.g_x0 = g_x0, a.ldg0 = ldg0, a.g_x1 = g_x1, a.ldg1 = ldg1;
+  a.y_out = y, a.ldy = ldy, a.g_y = g_y, a.ldgy = ldgy, a.hplanes = (op16*)h_planes;
+  a.dz_out = (op16*)dz_out, a.dz_h = (op16*)dz_h, a.g_x0 = g_x0, a.ldg0 = ldg0, a.g_x1 = g_x1, a.ldg1 = ldg1;
+  a.work = (unsigned int*)work8;
   cudaStream_t st = (cudaStream_t)stream;
+  if (cudaMemsetAsync(a.work, 0, 8, st) != cudaSuccess) return check_launch("b2n_fmlp_bwd (memset)");
+  {
+    const int64_t n = P * out_dim;
+    const unsigned grid = (unsigned)((n + 1023) / 1024 < (int64_t)kSMs * 8 ? (n + 1023) / 1024 : (int64_t)kSMs * 8);
+    k_fmlp_absmax<<<grid, 256, 0, st>>>(g_y, ldgy, out_dim, P, a.work);
+  }
   const bool small_in = d0 + d1 <= 32, small_out = out_dim <= 16;
   if (hidden == 64) {
     if (small_in) return small_out ? launch_bwd<64, 2, 2>(a, st) : launch_bwd<64, 2, 8>(a, st);
@@ -666,7 +644,7 @@ extern "C" int b2n_fmlp_bwd(int d0, int d1, int hidden, int n_hidden, const floa
 
 extern "C" int b2n_fmlp_wgrad(int n_layers, const void* const* dz, const int* ldz, const int* rows, const void* const* in,
                               const int* ldi, const int* k, float* const* dW, const int* lddw, const int* rows_valid,
-                              const int* k_valid, float* const* db, int64_t P, b2n_stream_t stream) {
+                              const int* k_valid, float* const* db, int64_t P, const float* scale, b2n_stream_t stream) {
   B2N_REQUIRE(P >= 0, "negative size");
   B2N_REQUIRE(n_layers >= 1 && n_layers <= MAX_HID + 1, "1..4 layers");
   B2N_REQUIRE(dz && ldz && rows && in && ldi && k && dW && lddw && rows_valid && k_valid && db, "null pointer");
@@ -679,10 +657,10 @@ extern "C" int b2n_fmlp_wgrad(int n_layers, const void* const* dz, const int* ld
     B2N_REQUIRE((rows[l] / 16) * ((k[l] + 63) / 64) <= WG_THREADS / 32, "tile count exceeds the CTA");
     B2N_REQUIRE(ldz[l] >= rows[l] && ldi[l] >= k[l] && ldz[l] % 8 == 0 && ldi[l] % 8 == 0, "plane rows must be 16-byte aligned");
     B2N_REQUIRE(rows_valid[l] <= rows[l] && k_valid[l] <= k[l] && lddw[l] >= k_valid[l], "bad gradient shape");
-    a.L[l] = WgLayer{(const bf16*)dz[l], ldz[l], rows[l], (const bf16*)in[l], ldi[l], k[l], dW[l], lddw[l], rows_valid[l],
+    a.L[l] = WgLayer{(const op16*)dz[l], ldz[l], rows[l], (const op16*)in[l], ldi[l], k[l], dW[l], lddw[l], rows_valid[l],
                      k_valid[l], db[l]};
   }
-  a.P = P;
+  a.P = P, a.scale = scale;
   cudaFuncSetAttribute(k_fmlp_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM);
   const int64_t n_tiles = (P + WG_TILE - 1) / WG_TILE;
   dim3 grid((unsigned)(n_tiles < kSMs ? n_tiles : kSMs), (unsigned)n_layers);
@@ -690,13 +668,3 @@ extern "C" int b2n_fmlp_wgrad(int n_layers, const void* const* dz, const int* ld
   return check_launch("b2n_fmlp_wgrad");
 }
 
-extern "C" int b2n_nerf_mlp_dx(const void* dz0, const void* dz4, const float* W0, int ldw0, const float* W4x, int ldw4,
-                               int pos_dim, int64_t P, float* g_x, int ldg, b2n_stream_t stream) {
-  B2N_REQUIRE(P >= 0, "negative size");
-  if (P == 0) return B2N_OK;
-  B2N_REQUIRE(dz0 && dz4 && W0 && W4x && g_x, "null pointer");
-  B2N_REQUIRE(pos_dim > 0 && pos_dim <= 96 && ldw0 >= pos_dim && ldw4 >= pos_dim && ldg >= pos_dim, "pos_dim <= 96 required");
-  if (pos_dim <= 64)
-    return launch_nerf_dx<8>((const bf16*)dz0, (const bf16*)dz4, W0, ldw0, W4x, ldw4, pos_dim, P, g_x, ldg, (cudaStream_t)stream);
-  return launch_nerf_dx<12>((const bf16*)dz0, (const bf16*)dz4, W0, ldw0, W4x, ldw4, pos_dim, P, g_x, ldg, (cudaStream_t)stream);
-}

@@ -1,0 +1,103 @@
+// Input gradient of the 256-wide tcgen05 decoder (bf16 planes of b2n_nerf_mlp_bwd), on mma.sync.
+#include "b2n_mma.cuh"
+
+namespace b2n {
+namespace ndx {
+
+constexpr int THREADS = 128;
+
+// fp32 matrix [rows_valid][cols_valid] (row stride ldw) -> bf16 smem [rows][cols + PAD], zero filled elsewhere
+__device__ __forceinline__ void load_w(const float* __restrict__ W, int ldw, int rows_valid, int cols_valid, int rows,
+                                       int cols, bf16* dst) {
+  const int S = cols + PAD;
+  for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
+    const int r = i / cols, c = i - r * cols;
+    dst[r * S + c] = __float2bfloat16((r < rows_valid && c < cols_valid) ? __ldg(W + (size_t)r * ldw + c) : 0.f);
+  }
+}
+
+static int persistent_grid(const void* kernel, size_t smem, int64_t warp_tiles) {
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t g = (int64_t)kSMs * per_sm;
+  const int64_t blocks = (warp_tiles + THREADS / 32 - 1) / (THREADS / 32);
+  if (g > blocks) g = blocks;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+// ------------------------------------------------------------------------------ input gradient of the 256-wide decoder
+// d x_enc [P, pos_dim] = dZ_0 W_0 + dZ_4 W_4[:, 256:256+pos_dim]   (NeRFDecoder, src/decoders.py:68-87: x feeds layer 0
+// and, through the skip concat [h, x], layer 4).  dZ_l are the bf16 pre-activation gradient planes written by the
+// tcgen05 backward chain (b2n_nerf_mlp_bwd); needed when the decoder input depends on a trainable deformation
+// (Part 3: x_enc = gamma(x + delta_x), src/core.py:268-277).
+template <int NTo>
+__global__ void __launch_bounds__(THREADS) k_nerf_dx(const bf16* __restrict__ dz0, const bf16* __restrict__ dz4,
+                                                     const float* __restrict__ W0, int ld0, const float* __restrict__ W4x,
+                                                     int ld4, int pos_dim, int64_t P, float* __restrict__ gx, int ldg) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  bf16* sm = reinterpret_cast<bf16*>(smem_raw);
+  constexpr int S = 8 * NTo + PAD;
+  load_w(W0, ld0, 256, pos_dim, 256, 8 * NTo, sm);
+  load_w(W4x, ld4, 256, pos_dim, 256, 8 * NTo, sm + 256 * S);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int64_t n_tiles = (P + 15) / 16;
+  const int64_t wstride = (int64_t)gridDim.x * (THREADS / 32);
+  for (int64_t tile = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); tile < n_tiles; tile += wstride) {
+    const int64_t pa = tile * 16 + g, pb = pa + 8;
+    float c[NTo][4] = {};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {        // (plane, half): 128 gradient columns at a time
+      const bf16* plane = (q < 2) ? dz0 : dz4;
+      const int col0 = 128 * (q & 1);
+      uint32_t a[8][4];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int col = col0 + 16 * k + 2 * t;
+        a[k][0] = pa < P ? __ldcs(reinterpret_cast<const uint32_t*>(plane + pa * 256 + col)) : 0u;
+        a[k][1] = pb < P ? __ldcs(reinterpret_cast<const uint32_t*>(plane + pb * 256 + col)) : 0u;
+        a[k][2] = pa < P ? __ldcs(reinterpret_cast<const uint32_t*>(plane + pa * 256 + col + 8)) : 0u;
+        a[k][3] = pb < P ? __ldcs(reinterpret_cast<const uint32_t*>(plane + pb * 256 + col + 8)) : 0u;
+      }
+      gemm_dgrad<NTo, 8>(c, a, sm + ((q < 2) ? 0 : 256 * S) + col0 * S, S, lane);
+    }
+#pragma unroll
+    for (int j = 0; j < NTo; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int col = 8 * j + 2 * t + (i & 1);
+        const int64_t p = (i & 2) ? pb : pa;
+        if (p < P && col < pos_dim) gx[p * ldg + col] = c[j][i];
+      }
+  }
+}
+
+template <int NTo>
+static int launch_nerf_dx(const bf16* dz0, const bf16* dz4, const float* W0, int ld0, const float* W4x, int ld4, int pos_dim,
+                          int64_t P, float* gx, int ldg, cudaStream_t st) {
+  constexpr size_t smem = (size_t)2 * 256 * (8 * NTo + PAD) * sizeof(bf16);
+  auto k = k_nerf_dx<NTo>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int grid = persistent_grid((const void*)k, smem, (P + 15) / 16);
+  k<<<grid, THREADS, smem, st>>>(dz0, dz4, W0, ld0, W4x, ld4, pos_dim, P, gx, ldg);
+  return check_launch("b2n_nerf_mlp_dx");
+}
+
+}  // namespace ndx
+}  // namespace b2n
+
+using namespace b2n;
+using namespace b2n::ndx;
+
+extern "C" int b2n_nerf_mlp_dx(const void* dz0, const void* dz4, const float* W0, int ldw0, const float* W4x, int ldw4,
+                               int pos_dim, int64_t P, float* g_x, int ldg, b2n_stream_t stream) {
+  B2N_REQUIRE(P >= 0, "negative size");
+  if (P == 0) return B2N_OK;
+  B2N_REQUIRE(dz0 && dz4 && W0 && W4x && g_x, "null pointer");
+  B2N_REQUIRE(pos_dim > 0 && pos_dim <= 96 && ldw0 >= pos_dim && ldw4 >= pos_dim && ldg >= pos_dim, "pos_dim <= 96 required");
+  if (pos_dim <= 64)
+    return launch_nerf_dx<8>((const bf16*)dz0, (const bf16*)dz4, W0, ldw0, W4x, ldw4, pos_dim, P, g_x, ldg, (cudaStream_t)stream);
+  return launch_nerf_dx<12>((const bf16*)dz0, (const bf16*)dz4, W0, ldw0, W4x, ldw4, pos_dim, P, g_x, ldg, (cudaStream_t)stream);
+}

@@ -15,6 +15,7 @@
 // The work is HBM-bound (115 FLOP/B): 2.15 GB at P = 262 144.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <string.h>
 #include "b2n_common.cuh"
 
@@ -45,6 +46,8 @@ struct Args {
   int64_t P;
   int64_t rows_per_split;   // multiple of TP
   int* err;
+  int fp16;                 // operand planes are IEEE fp16 (the fused 128-wide MLPs) instead of bf16 (the 256-wide decoder)
+  const float* scale;       // device scalar S: the dZ planes hold S * dZ, results are divided by S (null: 1)
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -132,7 +135,8 @@ k_wgrad256(const Args a, const __grid_constant__ CUtensorMap tm0, const __grid_c
     // ================================ MMA issuer ================================
     if (gemm) {
       // instruction descriptor: D fp32, A = B = bf16, both MN-major, M = 128, N = n_cols
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(job.n_cols >> 3) << 17) |
+      const uint32_t ab_fmt = a.fp16 ? 0u : ((1u << 7) | (1u << 10));      // a_format / b_format: 0 = f16, 1 = bf16
+      const uint32_t idesc = (1u << 4) | ab_fmt | (1u << 15) | (1u << 16) | ((uint32_t)(job.n_cols >> 3) << 17) |
                              ((uint32_t)(128 >> 4) << 24);
       for (int it = 0; it < n_steps; ++it) {
         const int st = it % N_STAGES;
@@ -161,6 +165,7 @@ k_wgrad256(const Args a, const __grid_constant__ CUtensorMap tm0, const __grid_c
     // ================================ column sums (main loop) + accumulator drain ================================
     const int c = threadIdx.x - 64;             // 0..255: the dZ column this thread sums
     float colsum = 0.f;
+    const float inv_s = a.scale ? 1.f / __ldg(a.scale) : 1.f;
     for (int it = 0; it < n_steps; ++it) {
       const int st = it % N_STAGES;
       if (!mbar_wait(bar_full + 8 * st, (it / N_STAGES) & 1, abort_flag, a.err, 3)) break;
@@ -169,14 +174,20 @@ k_wgrad256(const Args a, const __grid_constant__ CUtensorMap tm0, const __grid_c
         const int ch = (c & 63) >> 3;
         float s = 0.f;
 #pragma unroll 8
-        for (int r = 0; r < TP; ++r)
-          s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(blk + r * 128 + ((ch ^ (r & 7)) << 4)));
+        if (a.fp16) {
+#pragma unroll 8
+          for (int r = 0; r < TP; ++r) s += __half2float(*reinterpret_cast<const __half*>(blk + r * 128 + ((ch ^ (r & 7)) << 4)));
+        } else {
+#pragma unroll 8
+          for (int r = 0; r < TP; ++r)
+            s += __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(blk + r * 128 + ((ch ^ (r & 7)) << 4)));
+        }
         colsum += s;
       }
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_empty + 8 * st) : "memory");
     }
-    if (job.db && n_steps > 0 && c < job.bias_cols) atomicAdd(job.db + c, colsum);
+    if (job.db && n_steps > 0 && c < job.bias_cols) atomicAdd(job.db + c, colsum * inv_s);
     if (gemm && n_steps > 0 && mbar_wait(bar_done, 0, abort_flag, a.err, 4)) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int q = warp & 3;                   // TMEM lane quarter this warp may read
@@ -198,7 +209,8 @@ k_wgrad256(const Args a, const __grid_constant__ CUtensorMap tm0, const __grid_c
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
           atomicAdd(reinterpret_cast<float4*>(drow + c0 + j),
-                    make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])));
+                    make_float4(__uint_as_float(v[j]) * inv_s, __uint_as_float(v[j + 1]) * inv_s,
+                                __uint_as_float(v[j + 2]) * inv_s, __uint_as_float(v[j + 3]) * inv_s));
       }
     }
   }
@@ -221,7 +233,7 @@ static EncodeTiledFn encode_tiled_fn() {
   }();
   return fn;
 }
-static bool make_map(CUtensorMap* m, const void* planes, int64_t P, int n_slots, int width = 256) {
+static bool make_map(CUtensorMap* m, const void* planes, int64_t P, int n_slots, int width = 256, bool fp16 = false) {
   if (!planes) return true;             // unused map slot
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return false;
@@ -229,7 +241,7 @@ static bool make_map(CUtensorMap* m, const void* planes, int64_t P, int n_slots,
   const cuuint64_t strides[2] = {(cuuint64_t)width * 2, (cuuint64_t)P * width * 2};
   const cuuint32_t box[3] = {64, TP, 1};   // planes narrower than a 64-column block: the TMA zero-fills the rest
   const cuuint32_t estr[3] = {1, 1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(planes), dims, strides, box, estr,
+  return enc(m, fp16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(planes), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -291,27 +303,28 @@ extern "C" int b2n_nerf_mlp_wgrad(const void* dz_planes, const void* fwd_planes,
 }
 
 // Weight / bias gradients of the 128-wide fused MLPs (DeformationNetwork: b2n_fmlp_*) through the same kernel.
-// dz_h bf16 [n_hidden][P][128], dz_out bf16 [P][out_pad], h_planes bf16 [n_hidden][P][128], xin bf16 [P][in_pad] as written
+// dz_h fp16 [n_hidden][P][128], dz_out fp16 [P][out_pad], h_planes fp16 [n_hidden][P][128], xin fp16 [P][in_pad] as written
 // by b2n_fmlp_fwd / b2n_fmlp_bwd.  ACCUMULATES (fp32): dW0 [128][128] = dZ_0^T xin (columns >= in_pad stay 0),
 // dWh [n_hidden-1][128][128] = dZ_l^T H_{l-1}, dWoT [128][64] = H_last^T dZ_out (the TRANSPOSED output-layer gradient,
 // columns >= out_pad stay 0), db_h [n_hidden][128] = column sums of the hidden dZ planes.
 extern "C" int b2n_fmlp_wgrad_tc(const void* dz_h, const void* dz_out, const void* h_planes, const void* xin, int64_t P,
                                  int n_hidden, int in_pad, int out_pad, float* dW0, float* dWh, float* dWoT, float* db_h,
-                                 int* err_flag, b2n_stream_t stream) {
+                                 int* err_flag, const float* scale, b2n_stream_t stream) {
   B2N_REQUIRE(dz_h && dz_out && h_planes && xin && dW0 && dWoT && db_h && err_flag, "null pointer");
   B2N_REQUIRE(n_hidden >= 1 && n_hidden <= 3 && (n_hidden == 1 || dWh), "1..3 hidden layers");
   B2N_REQUIRE(P >= TP && (in_pad == 32 || in_pad == 96) && (out_pad == 16 || out_pad == 64), "bad plane widths");
   alignas(64) CUtensorMap tm[4];
   memset(tm, 0, sizeof(tm));
-  B2N_REQUIRE(make_map(&tm[0], dz_h, P, n_hidden, 128) && make_map(&tm[1], h_planes, P, n_hidden, 128) &&
-                  make_map(&tm[2], xin, P, 1, in_pad) && make_map(&tm[3], dz_out, P, 1, out_pad), "cuTensorMapEncodeTiled failed");
+  B2N_REQUIRE(make_map(&tm[0], dz_h, P, n_hidden, 128, true) && make_map(&tm[1], h_planes, P, n_hidden, 128, true) &&
+                  make_map(&tm[2], xin, P, 1, in_pad, true) && make_map(&tm[3], dz_out, P, 1, out_pad, true),
+              "cuTensorMapEncodeTiled failed");
   Args a{};
   int n = 0;
   a.job[n++] = Job{0, 0, 1, 2, 0, in_pad <= 64 ? 64 : 128, dW0, db_h, 128};
   for (int l = 1; l < n_hidden; ++l)
     a.job[n++] = Job{0, l, 1, 1, l - 1, 128, dWh + (size_t)(l - 1) * 16384, db_h + (size_t)l * 128, 128};
   a.job[n++] = Job{1, n_hidden - 1, 1, 3, 0, 64, dWoT, nullptr, 0};
-  a.P = P, a.err = err_flag;
+  a.P = P, a.err = err_flag, a.fp16 = 1, a.scale = scale;
   int splits = (2 * kSMs) / n;
   const int64_t max_splits = (P + TP - 1) / TP;
   if (splits > max_splits) splits = (int)max_splits;

@@ -37,7 +37,7 @@ C2 = dict(mode="part2_instant", n_levels=16, n_features_per_level=2, log2_hashma
 NEAR, FAR, N_SAMPLES, GRID_R, GRID_THR = 2.0, 6.0, 128, 128, 0.12
 RAYS_PER_GPU = 2 ** 18
 LR, WEIGHT_DECAY, ETA_MIN, TV_WEIGHT, TRAIN_ITERS = 0.01, 1e-5, 1e-4, 1e-6, 2000
-CPU_SAMPLE_RAYS = 1024
+CPU_SAMPLE_RAYS = 2 ** 14          # the CPU arm runs B = 2^14 rays (memory) and says so
 
 
 def parse():
@@ -61,7 +61,10 @@ def cpu_train_rays_per_s(n_rays, steps, warmup, occupancy):
     """The reference's CPU implementation of the same training step on a bounded ray sample."""
     from oracle import nerf_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    ref_dir = os.environ.get("B2N_REFERENCE", "/root/reference")
+    # the reference's own src/: $B2N_REFERENCE, baseline/_ref (git-ignored copy that travels to the GPU box with the
+    # snapshot; __graft_entry__.build() refreshes it whenever /root/reference is present), /root/reference
+    ref_dir = next((d for d in (os.environ.get("B2N_REFERENCE"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference")
+                    if d and os.path.isfile(os.path.join(d, "src", "core.py"))), "")
     occ = torch.ones(GRID_R, GRID_R, GRID_R, dtype=torch.bool) if occupancy == "dense" else O.ball_occupancy(GRID_R, 1.5)
     bg = torch.ones(3)
     kind = "port"
@@ -115,19 +118,24 @@ def cpu_train_rays_per_s(n_rays, steps, warmup, occupancy):
 
     for i in range(warmup):
         step(i)
-    t0 = time.perf_counter()
+    times = []
     for i in range(steps):
+        t0 = time.perf_counter()
         step(i)
-    dt = time.perf_counter() - t0
-    return dict(value=n_rays * steps / dt, unit="rays/s", cores=torch.get_num_threads(), kind=kind,
-                sample=f"{steps} training steps of {n_rays} rays x {N_SAMPLES} samples ({occupancy} occupancy), "
-                       f"torch CPU fp32, after {warmup} warm-up", ms_per_step=1e3 * dt / steps)
+        times.append(time.perf_counter() - t0)
+    dt = sorted(times)[len(times) // 2]                     # median step
+    return dict(value=n_rays / dt, unit="rays/s", cores=torch.get_num_threads(), kind=kind,
+                sample=f"median of {steps} training steps of {n_rays} rays x {N_SAMPLES} samples ({occupancy} occupancy; "
+                       f"the GPU arm runs 2^18 rays per step: reduced for memory and time), "
+                       f"{'reference src/ + tcnn shim' if kind == 'reference' else 'oracle port'}, torch CPU fp32, "
+                       f"after {warmup} warm-up", ms_per_step=1e3 * dt)
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
-    steps, warm = max(1, min(args.steps, 20)), max(0, min(args.warmup, 2))
+    # bounded sample: one 2^14-ray step is ~10 s of CPU work on 16 cores
+    steps, warm = max(1, min(args.steps, 5)), max(0, min(args.warmup, 1))
     r = cpu_train_rays_per_s(args.cpu_rays, steps, warm, args.occupancy)
     line = {
         "impl": "reference", "metric": "train_rays_per_s", "value": r["value"], "unit": "rays/s",
@@ -320,13 +328,20 @@ DYNAMIC = {
 }
 
 
-def bench_dynamic(dev, name, steps=10, warm=4, occupancy="dense", world=1, rank=0):
+def bench_dynamic(dev, name, steps=10, warm=4, occupancy="dense", world=1, rank=0, strong=False):
     """Training step of run.py:1073-1178 / :1804-1949 (autocast + GradScaler, render_rays with times, RGB MSE +
-    deformation L2 + table TV, clip, AdamW) for the dynamic configs -- reported as extras.  world > 1: ray-sharded
-    data parallel (B rays per GPU, replicated weights/tables, one flat gradient all-reduce per step before
-    unscale/clip/AdamW; every rank must call this)."""
+    deformation L2 + table TV, clip, AdamW) for the dynamic configs -- reported as extras.
+
+    world > 1: ray-sharded data parallel (replicated weights / tables, one flat gradient buffer averaged over ranks
+    before unscale / clip / AdamW; every rank must call this).  ``strong``: the config's batch is the GLOBAL batch
+    (B / world rays per GPU, BASELINE.json configs[4]: 8192 rays sharded over the GPUs); otherwise B rays per GPU (weak).
+
+    Legs: torch AdamW (the reference's optimizer calls, world == 1 only), b2n.optim.FusedAdamW (TV + unscale + clip +
+    AdamW as two launches; any world), and on one GPU the whole step as ONE CUDA graph (static-capacity march: no host
+    read of the active-sample count, b2n.march.set_static_capacity)."""
     import torch.distributed as dist
-    from b2n import synthetic
+    import b2n
+    from b2n import march, synthetic
     from b2n.dp import GradAllReducer
     from src.core import NeuralField
     from src.renderer import DensityGrid, render_rays
@@ -334,40 +349,31 @@ def bench_dynamic(dev, name, steps=10, warm=4, occupancy="dense", world=1, rank=
     torch.manual_seed(0)
     model = NeuralField(spec["cfg"]).to(dev).train()
     B, N = spec["B"], spec["N"]
+    if strong:
+        B = B // world
     grid = None
     if spec["grid"]:
         grid = DensityGrid(resolution=spec["grid"][0], bound=1.5, threshold=spec["grid"][1]).to(dev)
         if occupancy == "sparse":
             grid.binary_grid = synthetic.ball_occupancy(spec["grid"][0], 1.5).to(dev)
-    opt = torch.optim.AdamW(model.parameters(), lr=spec["lr"], weight_decay=1e-5)
-    scaler = torch.amp.GradScaler("cuda", enabled=True)
     reducer = GradAllReducer(model, world) if world > 1 else None
     pool = [tuple(t.to(dev) for t in synthetic.random_rays(B, seed=70 + i + 1000 * rank, n_views=150, with_time=True))
             for i in range(3)]
     bg = torch.ones(3, device=dev)
     tables = [m.encoding.params for n_, m in model.named_children() if hasattr(m, "encoding") and n_ != "deformation_grid"]
+    table_ids = {id(t) for t in tables}
 
-    def step(i):
-        ro, rd, tgt, times = pool[i % 3]
+    def loss_of(batch, with_tv):
+        ro, rd, tgt, times = batch
         target = tgt[:, :3] * tgt[:, 3:4] + bg * (1.0 - tgt[:, 3:4])
         with torch.amp.autocast("cuda", enabled=True):
             pred, _, _, extras = render_rays(model=model, rays_o=ro, rays_d=rd, near=NEAR, far=FAR, n_samples=N,
                                              perturb=True, times=times, density_grid=grid, bg_color=bg)
             loss = torch.nn.functional.mse_loss(pred, target) + torch.mean(extras["mean_delta_x"] ** 2) * spec["reg"]
-            if spec["tv"] > 0:
+            if with_tv and spec["tv"] > 0:
                 for tb in tables:
                     loss = loss + torch.mean(torch.abs(tb[1:] - tb[:-1])) * spec["tv"]
-        if reducer is None:
-            opt.zero_grad()
-        else:
-            reducer.zero_grad()
-        scaler.scale(loss).backward()
-        if reducer is not None:
-            reducer.allreduce()            # before unscale/clip: every rank takes the same inf/clip decisions
-        scaler.unscale_(opt)
-        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
-        scaler.step(opt)
-        scaler.update()
+        return loss
 
     def sync():
         if world > 1:
@@ -391,45 +397,96 @@ def bench_dynamic(dev, name, steps=10, warm=4, occupancy="dense", world=1, rank=
             ms = float(t.item())
         return ms / n
 
-    ms_train = run(step, steps, warm)
-    _maybe_profile(step)
-    # the same step with the TV term, unscale, clipping and AdamW in b2n.optim.FusedAdamW: two launches
-    # instead of ~100; the loss carries no TV term, scaler.step() hands the loss scale / inf flag to the optimizer
-    fused = {}
+    out = {"workload": f"{spec['label']}, B={B} rays x {N} samples per GPU"
+                       f"{' (= %d global, strong scaling)' % (B * world) if strong else ''}, AMP autocast + GradScaler, "
+                       f"AdamW, {occupancy} occupancy", "n_gpus": world}
+    # ---- (1) the reference's optimizer calls: torch AdamW + unscale_ + clip_grad_norm_ + TV term in the loss
+    if world == 1:
+        opt = torch.optim.AdamW(model.parameters(), lr=spec["lr"], weight_decay=1e-5)
+        scaler = torch.amp.GradScaler("cuda", enabled=True)
+
+        def step(i):
+            loss = loss_of(pool[i % 3], True)
+            opt.zero_grad()
+            scaler.scale(loss).backward()
+            scaler.unscale_(opt)
+            torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm=1.0)
+            scaler.step(opt)
+            scaler.update()
+
+        ms_train = run(step, steps, warm)
+        _maybe_profile(step)
+        out.update(train_rays_per_s=B / ms_train * 1e3, train_ms_per_step=ms_train)
+    # ---- (2) b2n.optim.FusedAdamW: the loss carries no TV term, scaler.step() hands the loss scale / inf
+    # flag to the optimizer; under data parallelism the gradients are averaged first, so every rank takes the same
+    # inf / clip decisions
+    fopt = b2n.optim.FusedAdamW(
+        [{"params": [p for p in model.parameters() if id(p) in table_ids], "tv_weight": spec["tv"]},
+         {"params": [p for p in model.parameters() if id(p) not in table_ids]}], lr=spec["lr"], weight_decay=1e-5)
+    fscaler = torch.amp.GradScaler("cuda", enabled=True)
+
+    def fstep(i):
+        loss = loss_of(pool[i % 3], False)
+        if reducer is None:
+            fopt.zero_grad()
+        else:
+            reducer.zero_grad()
+        fscaler.scale(loss).backward()
+        if reducer is not None:
+            reducer.allreduce()
+        fscaler.step(fopt, max_norm=1.0)
+        fscaler.update()
+
+    try:
+        ms_fused = run(fstep, steps, warm)
+        out.update(train_rays_per_s_fused_optimizer=world * B / ms_fused * 1e3, train_ms_per_step_fused_optimizer=ms_fused)
+        if world > 1:
+            out.update(train_rays_per_s=world * B / ms_fused * 1e3, train_ms_per_step=ms_fused)
+    except Exception as exc:
+        out["fused_optimizer_error"] = f"{type(exc).__name__}: {exc}"[:300]
+    if reducer is not None:
+        # the collective on its own: the flat gradient buffer all-reduced back to back (what a step pays when nothing overlaps)
+        ms_ar = run(lambda i: reducer.allreduce(), 10, 3)
+        out.update(allreduce_bytes_per_step=reducer.nbytes, allreduce_ms_alone=ms_ar)
+    # ---- (3) one GPU: the whole step as ONE CUDA graph (static-capacity march + FusedAdamW; constant LR inside the graph)
     if world == 1:
         try:
-            import b2n
-            table_ids = {id(t) for t in tables}
-            fopt = b2n.optim.FusedAdamW(
+            march.set_static_capacity(True)
+            gopt = b2n.optim.FusedAdamW(
                 [{"params": [p for p in model.parameters() if id(p) in table_ids], "tv_weight": spec["tv"]},
                  {"params": [p for p in model.parameters() if id(p) not in table_ids]}], lr=spec["lr"], weight_decay=1e-5)
-            fscaler = torch.amp.GradScaler("cuda", enabled=True)
+            gscaler = torch.amp.GradScaler("cuda", enabled=True)
+            for p in model.parameters():
+                p.grad = torch.zeros_like(p)
 
-            def fstep(i):
-                ro, rd, tgt, times = pool[i % 3]
-                target = tgt[:, :3] * tgt[:, 3:4] + bg * (1.0 - tgt[:, 3:4])
-                with torch.amp.autocast("cuda", enabled=True):
-                    pred, _, _, extras = render_rays(model=model, rays_o=ro, rays_d=rd, near=NEAR, far=FAR, n_samples=N,
-                                                     perturb=True, times=times, density_grid=grid, bg_color=bg)
-                    loss = torch.nn.functional.mse_loss(pred, target) + torch.mean(extras["mean_delta_x"] ** 2) * spec["reg"]
-                fopt.zero_grad()
-                fscaler.scale(loss).backward()
-                fscaler.step(fopt, max_norm=1.0)
-                fscaler.update()
+            def gstep(ro, rd, tgt, times):
+                loss = loss_of((ro, rd, tgt, times), False)
+                for p in model.parameters():
+                    p.grad.zero_()
+                gscaler.scale(loss).backward()
+                gscaler.step(gopt, max_norm=1.0)
+                gscaler.update()
+                return loss
 
-            ms_fused = run(fstep, steps, warm)
-            fused = {"train_rays_per_s_fused_optimizer": B / ms_fused * 1e3, "train_ms_per_step_fused_optimizer": ms_fused}
+            ms_static = run(lambda i: gstep(*pool[i % 3]), steps, warm)          # static capacity, eager launches
+            graphed = b2n.graphs.GraphedStep(gstep, pool[0])
+            ms_graph = run(lambda i: graphed(*pool[i % 3]), steps, warm)
+            b2n.check_errors()
+            out.update(train_rays_per_s_static_capacity=B / ms_static * 1e3, train_rays_per_s_cuda_graph=B / ms_graph * 1e3,
+                       train_ms_per_step_cuda_graph=ms_graph, loss_after_graph_steps=float(graphed(*pool[0]).detach()))
         except Exception as exc:
-            fused = {"fused_optimizer_error": f"{type(exc).__name__}: {exc}"[:300]}
+            out["cuda_graph_error"] = f"{type(exc).__name__}: {exc}"[:300]
+        finally:
+            march.set_static_capacity(False)
+            for p in model.parameters():
+                p.grad = None
     model.eval()
     with torch.no_grad():
         ms_render = run(lambda i: render_rays(model, pool[i % 3][0], pool[i % 3][1], NEAR, FAR, N, False,
                                               times=pool[i % 3][3], density_grid=grid, bg_color=bg), steps, 2)
-    out = {"workload": f"{spec['label']}, B={B} rays x {N} samples per GPU, AMP autocast + GradScaler, AdamW, {occupancy} occupancy",
-           "n_gpus": world, "train_rays_per_s": world * B / ms_train * 1e3, "train_ms_per_step": ms_train,
-           "render_msamples_per_s": world * B * N / ms_render * 1e3 / 1e6, **fused}
+    out["render_msamples_per_s"] = world * B * N / ms_render * 1e3 / 1e6
     if reducer is not None:
-        out["allreduce_bytes_per_step"] = reducer.nbytes
+        reducer.remove_hooks()
     return out
 
 
@@ -579,6 +636,43 @@ def main():
             extras["train_rays_per_s_fused_optimizer"] = world * B * args.steps / (ms4 * 1e-3)
         except Exception as exc:
             extras["fused_optimizer_error"] = f"{type(exc).__name__}: {exc}"[:300]
+        # ---- one GPU: the C2 step with NO host read of the active-sample count (static-capacity march), eager and as ONE
+        # CUDA graph (constant LR inside the graph)
+        if world == 1:
+            from b2n import march as _march
+            try:
+                _march.set_static_capacity(True)
+                for p in model.parameters():
+                    p.grad = torch.zeros_like(p)
+                gopt = b2n.optim.FusedAdamW(
+                    [{"params": list(model.representation.parameters()), "tv_weight": TV_WEIGHT, "max_norm": 1.0},
+                     {"params": list(model.decoder.parameters()), "max_norm": 1.0}], lr=LR, weight_decay=WEIGHT_DECAY)
+
+                def gstep(rays_o, rays_d, rgba):
+                    target = rgba[:, :3] * rgba[:, 3:4] + bg * (1.0 - rgba[:, 3:4])
+                    pred, _, _ = render_rays(model=model, rays_o=rays_o, rays_d=rays_d, near=NEAR, far=FAR,
+                                             n_samples=N_SAMPLES, perturb=True, white_bkgd=True, density_grid=grid, bg_color=bg)
+                    loss = torch.nn.functional.mse_loss(pred, target)
+                    for p in model.parameters():
+                        p.grad.zero_()
+                    loss.backward()
+                    gopt.step()
+                    return loss
+
+                ms5 = timed(lambda i: gstep(*dev_pool[i % n_pool]), args.steps, 2)
+                extras["train_rays_per_s_static_capacity"] = B * args.steps / (ms5 * 1e-3)
+                graphed = b2n.graphs.GraphedStep(gstep, dev_pool[0])
+                ms6 = timed(lambda i: graphed(*dev_pool[i % n_pool]), args.steps, 2)
+                extras["train_rays_per_s_cuda_graph"] = B * args.steps / (ms6 * 1e-3)
+                extras["loss_after_graph_steps"] = float(graphed(*dev_pool[0]).detach())
+                del graphed
+            except Exception as exc:
+                extras["cuda_graph_error"] = f"{type(exc).__name__}: {exc}"[:300]
+            finally:
+                _march.set_static_capacity(False)
+                reducer_views = reducer._views
+                for p in model.parameters():
+                    p.grad = reducer_views[p].view_as(p)
         # ---- render Msamples/s (forward only, no jitter, no_grad)
         model.eval()
         with torch.no_grad():
@@ -619,9 +713,20 @@ def main():
             "hash_bwd_corner_reductions_Gps": n_active * 16 * 8 / per_step.get("b2n_hash_bwd", float("inf")) / 1e6,
             "note": "8 corners x 16 levels per point; x-neighbour corner pairs that are adjacent table entries move as ONE "
                     "16-byte access, and the coarse levels hit in L1, so the corner rate can exceed the 8-byte gather peak"}
+    dp_scalars = {}
     if not args.no_extras and world > 1:
-        # BASELINE.json configs[4]: Part 4 Dual-Hash, ray batch sharded over the GPUs, hash-table gradient all-reduce
-        extras["c5_dualhash_dp"] = bench_dynamic(dev, "c5_dualhash", world=world, rank=rank)
+        # BASELINE.json configs[4]: Part 4 Dual-Hash, ray batch sharded over the GPUs, hash-table gradient all-reduce:
+        # weak scaling (8192 rays per GPU) and the config's own global batch of 8192 rays split over the GPUs (strong)
+        weak = bench_dynamic(dev, "c5_dualhash", world=world, rank=rank)
+        strong = bench_dynamic(dev, "c5_dualhash", world=world, rank=rank, strong=True)
+        extras["c5_dualhash_dp"] = weak
+        extras["c5_dualhash_dp_strong"] = strong
+        dp_scalars = {"c5_dualhash_dp_weak_rays_per_s": weak.get("train_rays_per_s"),
+                      "c5_dualhash_dp_weak_ms_per_step": weak.get("train_ms_per_step"),
+                      "c5_dualhash_dp_strong_rays_per_s": strong.get("train_rays_per_s"),
+                      "c5_dualhash_dp_strong_ms_per_step": strong.get("train_ms_per_step"),
+                      "c5_dualhash_dp_allreduce_ms_alone": weak.get("allreduce_ms_alone"),
+                      "c5_dualhash_dp_allreduce_bytes": weak.get("allreduce_bytes_per_step")}
     if not args.no_extras and rank == 0:
         extras["c1_vanilla"] = bench_c1(dev)
         for name in DYNAMIC:
@@ -638,32 +743,82 @@ def main():
                        "gbs": (v["bytes"] / 1e9) / (v["ms"] * 1e-3) if v["ms"] > 0 else None,
                        "tflops": (v["flops"] / 1e12) / (v["ms"] * 1e-3) if v["ms"] > 0 else None}
                       for k, v in summary.items()), key=lambda d: -d["ms_per_step"])
-    top = kernels[0]
-    roofline = {"kernel": top["entry"], "bound": "hbm", "achieved": top["gbs"], "peak": hbm_peak, "unit": "GB/s",
-                "frac": (top["gbs"] / hbm_peak) if top["gbs"] else None, "peak_source": peak_src,
-                "avg_launch_ms": top["ms_per_step"] / max(top["calls_per_step"], 1e-9),
-                "share_of_step": top["ms_per_step"] / (ms / args.steps),
-                "traffic": ncu_traffic(top["entry"]), "ncu": ncu_units(top["entry"]),
-                "note": ("algorithmic bytes (SURVEY 8d: per point 12 + L*F*4 gradient row + 2*L*8*F*4 table read-modify-write) "
-                         "over the launch time; the 52 MB gradient table is L2-resident, so `traffic` (DRAM bytes, ncu) is "
-                         "far below them and the binding unit is the L2 (atomics), see `ncu`")
-                if top["entry"].startswith("b2n_hash") else None}
+    # ---- rooflines.  Which unit bounds an entry point:
+    #   tensor : the fused 16-bit MLP kernels -- algorithmic FLOPs (unpadded MACs of SURVEY 8d, forward x3 for a training
+    #            step) / time against the measured sustained 16-bit dense rate
+    #   l2     : the hash-grid kernels -- the tables and the 52 MB gradient table live in L2; what is counted is 32-byte
+    #            L2 SECTOR operations: 4 per (point, level) is the floor (8 corners = 4 x-neighbour pairs, each pair inside
+    #            one sector at best), against the L2 random sector rate measured live below (gathers for the forward,
+    #            red.global for the table gradient).  hbm_compulsory_frac = the bytes that must cross HBM (positions +
+    #            feature / gradient rows) / time / HBM peak; alg_gbs = the SURVEY 8d byte figure / time
+    #   hbm    : compositing, march, everything streaming
+    from b2n._lib import call as _call, ptr as _ptr, stream as _stream
+    l2_peaks = {}
+
+    def l2_peak(kind):
+        if kind in l2_peaks:
+            return l2_peaks[kind]
+        tab = torch.zeros(1 << 22, 2, device=dev)                  # 32 MiB float2 table: L2-resident
+        sink = torch.zeros(1, device=dev)
+        blocks, per_thread, best = 148 * 16, 256, 1e9
+        for i in range(4):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            if kind == "gather":
+                _call("b2n_debug_gather_bench", _ptr(tab), 1 << 22, blocks, per_thread, _ptr(sink), _stream())
+            else:
+                _call("b2n_debug_red_bench", _ptr(tab), 1 << 22, blocks, per_thread, 0, _stream())
+            e1.record()
+            torch.cuda.synchronize()
+            if i:
+                best = min(best, e0.elapsed_time(e1))
+        l2_peaks[kind] = blocks * 256 * per_thread / best / 1e6          # G sector operations / s (one sector per lane)
+        return l2_peaks[kind]
+
+    n_points = summary.get("b2n_hash_fwd", {}).get("bytes", 0.0) / args.steps / (12 + 16 * 2 * 4 * 9)   # active points / step
+    L_levels = C2["n_levels"]
+
+    def roofline_of(k):
+        ms_k = k["ms_per_step"] / max(k["calls_per_step"], 1e-9)
+        base = {"kernel": k["entry"], "avg_launch_ms": ms_k, "share_of_step": k["ms_per_step"] / (ms / args.steps),
+                "traffic": ncu_traffic(k["entry"]), "ncu": ncu_units(k["entry"])}
+        if k["entry"] in ("b2n_hash_fwd", "b2n_hash_bwd") and n_points > 0:
+            kind = "gather" if k["entry"] == "b2n_hash_fwd" else "red"
+            peak = l2_peak(kind)
+            ach = n_points * L_levels * 4 / (k["ms_per_step"] * 1e-3) / 1e9
+            return {**base, "bound": "l2", "achieved": ach, "peak": peak, "unit": "G L2 sector-ops/s", "frac": ach / peak,
+                    "peak_source": f"measured live: random {'8-byte gathers' if kind == 'gather' else 'red.global.add.v2.f32'} "
+                                   "over a 32 MiB table, one 32-byte sector per lane",
+                    "sectors_per_point_level": 4,
+                    "hbm_compulsory_frac": n_points * (12 + L_levels * 2 * 4) / (k["ms_per_step"] * 1e-3) / 1e9 / hbm_peak,
+                    "alg_gbs": k["gbs"]}
+        if k["entry"].startswith(("b2n_instant_mlp", "b2n_fmlp", "b2n_nerf_mlp")) and k["tflops"]:
+            return {**base, "bound": "tensor", "achieved": k["tflops"], "peak": tensor_peak, "unit": "TFLOP/s",
+                    "frac": k["tflops"] / tensor_peak, "peak_source": peak_src + " (cuBLAS bf16 sustained; fp16 runs at the same rate)",
+                    "alg_gbs": k["gbs"]}
+        return {**base, "bound": "hbm", "achieved": k["gbs"], "peak": hbm_peak, "unit": "GB/s",
+                "frac": (k["gbs"] / hbm_peak) if k["gbs"] else None, "peak_source": peak_src}
+
+    rooflines = [roofline_of(k) for k in kernels[:8]]
+    roofline = rooflines[0]
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_train_rays_per_s(args.cpu_rays, 3, 1, args.occupancy)
+        r = cpu_train_rays_per_s(args.cpu_rays, 3, 1, args.occupancy)          # ~30-40 s of CPU work
         cpu = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
 
     line = {
         "metric": "train_rays_per_s", "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": workload_config(args, B),
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": workload_config(args, B),
         "clocks": clocks, "gpu_launches": launches,
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
-        "roofline": roofline, "cpu_baseline": cpu, "kernels": kernels[:12],
+        **dp_scalars,
+        "roofline": roofline, "rooflines": rooflines, "cpu_baseline": cpu, "kernels": kernels[:12],
     }
     line.update(extras)
+    line.update({k + "_": v for k, v in dp_scalars.items()})      # repeated at the very end of the line (log tails)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -37,6 +37,16 @@ int b2n_abi_version(void);
 /* thread-local, valid until the next failing call on this thread */
 const char* b2n_last_error(void);
 
+/* Optional DEVICE-side row count.  While set (non-NULL; host-side, per thread), every entry point below that takes a
+ * point count P treats rows >= *rows_device of its point-indexed arguments as absent: they are neither read nor written
+ * (the clamp happens inside the kernels, so the host never has to know the number).  This is how a ray-marching step
+ * behind an occupancy grid runs with fixed-capacity buffers and no device->host read of the active-sample count
+ * (the reference reads it three times per call: src/renderer.py:309-323), which makes the step CUDA-graph capturable.
+ * Honoured by: b2n_pe_*, b2n_hash_*, b2n_instant_mlp_*, b2n_fmlp_* (the saved planes get zero rows up to the next
+ * multiple of 64 behind the count).  NOT honoured by the fp32 b2n_linear_* / b2n_sigma_head_* and the 256-wide
+ * b2n_nerf_mlp_* entry points; b2n_composite_* / b2n_march_* index samples through ray offsets and do not need it. */
+int b2n_set_active_rows(const int* rows_device);
+
 /* activation codes shared by the linear / fused-MLP entry points */
 enum { B2N_ACT_NONE = 0, B2N_ACT_RELU = 1, B2N_ACT_SIGMOID = 2 };
 
@@ -146,10 +156,13 @@ typedef struct {
 int b2n_hash_fwd(const float* x, int64_t P, float bound, const float* table, const b2n_hash_level* levels_host,
                  int L, int F, float* out, int ld_out, int col0, b2n_stream_t stream);
 /* g_table (fp32, same shape as table) is ACCUMULATED into (atomics); g_x [P,3]
- * is overwritten (or accumulated when accumulate_x != 0); either may be NULL. */
+ * is overwritten (or accumulated when accumulate_x != 0); either may be NULL.
+ * [level_begin, level_end) restricts the TABLE gradient to a window of levels (0, -1 = all; a proper window needs
+ * F = 2 and level_begin % 4 == 0): the data-parallel path scatters the fine levels first and all-reduces their slice
+ * of the flat table while the coarse levels are still being scattered (b2n/dp.py).  g_x always covers all levels. */
 int b2n_hash_bwd(const float* x, int64_t P, float bound, const float* table, const b2n_hash_level* levels_host,
                  int L, int F, const float* g_out, int ld_g, int col0, float* g_table, float* g_x, int accumulate_x,
-                 b2n_stream_t stream);
+                 int level_begin, int level_end, b2n_stream_t stream);
 
 /* Tri-grid temporal blend of Part 4 (src/core.py:308-335): out[P, 2L] = sum_i w_i(t) * HashGrid_i(x) for the
  * start / mid / end deformation grids (one shared geometry, F = 2), w_i = clamp(1 - |t - a_i| / 0.5, 0, 1) with

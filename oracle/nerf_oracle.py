@@ -809,6 +809,23 @@ def synthetic_rays(n_rays: int, H: int = 800, W: int = 800, n_views: int = 100, 
     return ro, rd.contiguous(), target
 
 
+def sample_rays_host(poses: Tensor, rgba8: np.ndarray, times: Optional[Tensor], img_idx: Tensor, pix_y: Tensor,
+                     pix_x: Tensor, H: int, W: int, focal: float, scene_scale: float = 1.0):
+    """Training-ray batch for given pixel picks, as BlenderDataset / DynamicDataset.sample_random_rays builds it
+    (src/dataset.py:147-171, :268-294): pinhole directions ((x - W/2)/f, -(y - H/2)/f, -1) rotated by c2w[:3,:3] and
+    normalised, origin c2w[:3,3] * scene_scale, RGBA target uint8 / 255, per-frame time."""
+    c2w = poses[img_idx]
+    dirs = torch.stack([(pix_x - W * 0.5) / focal, -(pix_y - H * 0.5) / focal, -torch.ones_like(pix_x)], dim=-1)
+    rays_d = torch.bmm(c2w[:, :3, :3], dirs.unsqueeze(-1)).squeeze(-1)
+    rays_o = c2w[:, :3, 3]
+    if scene_scale != 1.0:
+        rays_o = rays_o * scene_scale
+    target = torch.from_numpy(rgba8[img_idx.numpy(), pix_y.numpy(), pix_x.numpy()].astype(np.float32) / 255.0)
+    rays_d = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)
+    t_out = times[img_idx].unsqueeze(-1) if times is not None else None
+    return rays_o, rays_d, target, t_out
+
+
 def ball_occupancy(R: int, bound: float, radius: float = 0.75) -> Tensor:
     """Analytic occupancy: voxel active iff its corner point
     lies inside a ball of ``radius`` at the origin."""

@@ -22,6 +22,7 @@ P, L, I, F = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
 SIGNATURES = {
     "b2n_abi_version": [],
     "b2n_last_error": [],
+    "b2n_set_active_rows": [P],
     "b2n_occ_pack_bits": [P, L, P, P],
     "b2n_occ_active_mask": [P, L, P, I, F, F, P, P],
     "b2n_occ_update": [P, P, L, I, F, F, P, P, P, P],
@@ -34,7 +35,7 @@ SIGNATURES = {
     "b2n_pe_fwd": [P, L, I, P, I, P, I, I, P],
     "b2n_pe_bwd": [P, L, I, P, I, P, I, I, P, I, P],
     "b2n_hash_fwd": [P, L, F, P, P, I, I, P, I, I, P],
-    "b2n_hash_bwd": [P, L, F, P, P, I, I, P, I, I, P, P, I, P],
+    "b2n_hash_bwd": [P, L, F, P, P, I, I, P, I, I, P, P, I, I, I, P],
     "b2n_hash_tri_fwd": [P, P, L, F, P, P, P, P, I, P, I, P],
     "b2n_hash_tri_bwd": [P, P, L, F, P, I, P, I, P, P, P, P],
     "b2n_linear_fwd": [P, I, P, I, P, P, I, L, I, I, I, P],
@@ -158,7 +159,63 @@ def call(name: str, *args, work=(0.0, 0.0)):
     LAUNCHES["count"] += _KERNELS_PER_CALL.get(name, 1)
 
 
+# ---- device-side row count (b2n_set_active_rows): see march.march(static=True)
+_ROWS = [None]
+
+
+def current_rows():
+    """the int32[1] device tensor holding the number of valid rows of the compact sample buffers, or None"""
+    return _ROWS[0]
+
+
+class active_rows:
+    """``with active_rows(n_dev):`` -- every kernel launched inside treats rows >= n_dev[0] of its point-indexed
+    arguments as absent (they are neither read nor written); ``None`` restores the host-side counts."""
+
+    def __init__(self, n_dev):
+        self.n_dev = n_dev
+
+    def __enter__(self):
+        self.prev = _ROWS[0]
+        _ROWS[0] = self.n_dev
+        lib.b2n_set_active_rows(ptr(self.n_dev))
+        return self
+
+    def __exit__(self, *exc):
+        _ROWS[0] = self.prev
+        lib.b2n_set_active_rows(ptr(self.prev))
+        return False
+
+
+def with_ctx_rows(backward):
+    """decorator for autograd ``backward`` static methods: re-installs the row count that was active in the forward"""
+    import functools
+
+    @functools.wraps(backward)
+    def wrapped(ctx, *grads):
+        rows = getattr(ctx, "rows", None)
+        if rows is None and _ROWS[0] is None:
+            return backward(ctx, *grads)
+        with active_rows(rows):
+            return backward(ctx, *grads)
+    return wrapped
+
+
 def require_cuda(*tensors):
+    """Every tensor handed to a kernel must live on ONE CUDA device, and that device must be the current one: the
+    kernels launch on ``torch.cuda.current_stream()`` of the current device, so a tensor on another GPU would be read
+    through a foreign pointer (an illegal address that poisons the context) instead of failing in Python."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise ValueError("b2n ops need CUDA tensors: there is no CPU path in this package")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise ValueError(f"b2n ops need all tensors on one device (got {dev} and {t.device})")
+    if dev is not None and dev.index != torch.cuda.current_device():
+        raise ValueError(f"tensors live on {dev} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                         f"call torch.cuda.set_device({dev.index}) (one process per GPU) or wrap the call in "
+                         f"torch.cuda.device({dev.index})")

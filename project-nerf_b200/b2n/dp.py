@@ -16,13 +16,37 @@ import torch
 import torch.distributed as dist
 
 
+class GradSink:
+    """Direct gradient accumulation target of one hash table under data parallelism (b2n.dp.GradAllReducer).
+
+    ``view`` is the table's slice of the reducer's flat gradient buffer (also ``table.grad``).  The table-gradient
+    kernels accumulate straight into it -- no zero-filled temporary, no autograd accumulate pass -- and tell the
+    reducer which element ranges are final, so that their all-reduce starts while the rest of the backward still
+    runs.  ``uses`` counts the forward passes of the current step that will send a gradient into the table (run.py's
+    regularisers call the encoders directly, besides render_rays): only the LAST backward announces ranges."""
+
+    def __init__(self, view: torch.Tensor, on_ready):
+        self.view, self.on_ready, self.uses, self.split_level = view, on_ready, 0, 8
+
+    def reset(self):
+        self.uses = 0
+
+
 class GradAllReducer:
     """Makes every ``p.grad`` a view into one contiguous fp32 buffer, so that zeroing the
-    gradients is one memset and averaging them over ranks is one collective per large table plus
-    one for everything else."""
+    gradients is one memset and averaging them over ranks is a handful of collectives over element RANGES of that
+    buffer.  Ranges are reduced asynchronously as soon as they are final:
+
+    * ``direct=True`` (default): hash tables (flat 1-D parameters of >= ``big_numel`` elements that reach
+      ``b2n.hash_encode``) get a ``GradSink`` -- the table-gradient kernels accumulate straight into the flat buffer
+      and announce the fine levels' slice before the coarse levels are scattered (ops._HashEncode.backward);
+    * other large parameters are reduced from a post-accumulate-grad hook;
+    * ``allreduce()`` reduces whatever range is still untouched, then waits for everything.
+
+    ONE backward per step reaches the hooks; wrap earlier backward passes of an accumulation step in ``no_sync()``."""
 
     def __init__(self, module: torch.nn.Module, world_size: int = None, overlap: bool = True,
-                 big_numel: int = 1 << 22):
+                 big_numel: int = 1 << 22, direct: bool = True):
         params = [p for p in module.parameters() if p.requires_grad]
         self.world = world_size if world_size is not None else (dist.get_world_size() if dist.is_initialized() else 1)
         small = [p for p in params if p.numel() < big_numel]
@@ -32,19 +56,31 @@ class GradAllReducer:
         ref = self.params[0]
         self.flat = torch.zeros(total, device=ref.device, dtype=torch.float32)
         off = 0
-        self._views = {}
+        self._views, self._offset = {}, {}
         for p in self.params:
             n = p.numel()
             p.grad = self.flat[off:off + n].view_as(p)
             self._views[p] = self.flat[off:off + n]
+            self._offset[p] = off
             off += n
         self.n_small = sum(p.numel() for p in small)
         self.nbytes = total * 4
-        self._pending = []
+        self._pending = []          # (work, start, stop) of ranges handed to async collectives this step
         self._hooks = []
+        self._sinks = []
+        self._suspended = False
         self.overlap = bool(overlap and big and self.world > 1 and dist.is_initialized())
         if self.overlap:
             for p in big:
+                if direct == "always" or (direct and p.dim() == 1 and p.is_cuda):
+                    sink = GradSink(self._views[p], self._on_sink_ready)
+                    sink.offset = self._offset[p]
+                    p._b2n_grad_sink = sink
+                    self._sinks.append((p, sink))
+                    # no hook for a table with a sink: autograd fires post-accumulate hooks even for the None gradient
+                    # the direct path returns, which cannot be told from a real accumulation.  Contract: such a table
+                    # receives gradient only through b2n.hash_encode (true for every model of src/core.py)
+                    continue
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad_ready))
 
     # ---- collectives
@@ -54,22 +90,64 @@ class GradAllReducer:
         work = dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=async_op)      # gloo has no AVG
         return work
 
+    def _start(self, start, stop):
+        if stop > start:
+            self._pending.append((self._reduce(self.flat[start:stop], async_op=True), start, stop))
+
+    def _covered(self, start, stop):
+        return any(a < stop and start < b for _, a, b in self._pending)
+
+    def _on_sink_ready(self, sink, lo, hi):
+        if self._suspended:
+            return
+        if self._covered(sink.offset + lo, sink.offset + hi):
+            raise RuntimeError("GradAllReducer: a gradient range was announced twice in one step (two backward passes "
+                               "without reducer.no_sync() around the first?)")
+        self._start(sink.offset + lo, sink.offset + hi)
+
     def _on_grad_ready(self, p):
-        if p.grad is None or p.grad.data_ptr() != self._views[p].data_ptr():
-            p.grad = None if p.grad is None else self._views[p].copy_(p.grad.reshape(-1)).view_as(p)
-        self._pending.append((self._reduce(self._views[p], async_op=True), self._views[p]))
+        """Hook path (a large parameter whose gradient came through autograd's accumulation, e.g. a hash table used by
+        a foreign op).  A second backward before ``allreduce()`` would let autograd add into a view whose NCCL
+        reduction is still in flight: detected and refused; use ``no_sync()`` around all but the last backward."""
+        if self._suspended:
+            return
+        v, off = self._views[p], self._offset[p]
+        if self._covered(off, off + v.numel()):
+            raise RuntimeError("GradAllReducer: a second backward reached a parameter whose gradient all-reduce is "
+                               "still in flight; wrap all but the last backward of a step in reducer.no_sync()")
+        if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+            p.grad = None if p.grad is None else v.copy_(p.grad.reshape(-1)).view_as(p)
+        self._start(off, off + v.numel())
+
+    def no_sync(self):
+        """Context manager: backward passes inside it only accumulate (no collective is started), like DDP.no_sync()."""
+        reducer = self
+
+        class _NoSync:
+            def __enter__(self_inner):
+                reducer._suspended = True
+
+            def __exit__(self_inner, *exc):
+                reducer._suspended = False
+                return False
+        return _NoSync()
 
     def zero_grad(self):
         self.flat.zero_()
+        for _, sink in self._sinks:
+            sink.reset()
 
     def _rebind(self):
         """A caller that ran ``optimizer.zero_grad()`` (set_to_none) instead of ``reducer.zero_grad()`` made autograd
         allocate fresh .grad tensors: copy them back into the flat buffer and re-point .grad, so that the collective
-        below never reduces stale data."""
+        below never reduces stale data.  (Ranges already in flight were re-bound by their hook.)"""
         for p in self.params:
-            v = self._views[p]
+            v, off = self._views[p], self._offset[p]
+            if self._covered(off, off + v.numel()):
+                continue
             if p.grad is None:
-                v.zero_()
+                if getattr(p, "_b2n_grad_sink", None) is None:      # a sink accumulates in place: the view IS the gradient
+                    v.zero_()
             elif p.grad.data_ptr() != v.data_ptr():
                 v.copy_(p.grad.reshape(-1))
             else:
@@ -79,35 +157,35 @@ class GradAllReducer:
     def allreduce(self):
         if self.world <= 1 or not dist.is_initialized():
             return
-        if not self._pending:          # (with overlap the hooks already re-bound the large tables they reduced)
-            self._rebind()
-        else:
-            for p in self.params[: len(self.params) - len(self._hooks)]:
-                v = self._views[p]
-                if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
-                    v.copy_(p.grad.reshape(-1))
-                    p.grad = v.view_as(p)
+        self._rebind()
         avg_in_op = dist.get_backend() == "nccl"
-        if self.overlap:
-            head = self.flat[: self.n_small]
-            if head.numel():
-                self._reduce(head)
-                if not avg_in_op:
-                    head.div_(self.world)
-            for work, view in self._pending:
-                work.wait()
-                if not avg_in_op:
-                    view.div_(self.world)
-            self._pending = []
-        else:
-            self._reduce(self.flat)
+        # every range not yet in flight, in address order
+        done = sorted((a, b) for _, a, b in self._pending)
+        pos, n = 0, self.flat.numel()
+        gaps = []
+        for a, b in done:
+            if a > pos:
+                gaps.append((pos, a))
+            pos = max(pos, b)
+        if pos < n:
+            gaps.append((pos, n))
+        for a, b in gaps:
+            self._start(a, b)
+        for work, a, b in self._pending:
+            work.wait()
             if not avg_in_op:
-                self.flat.div_(self.world)
+                self.flat[a:b].div_(self.world)
+        self._pending = []
+        for _, sink in self._sinks:
+            sink.reset()
 
     def remove_hooks(self):
         for h in self._hooks:
             h.remove()
         self._hooks = []
+        for p, _ in self._sinks:
+            p._b2n_grad_sink = None
+        self._sinks = []
 
 
 def shard_rays(n_rays: int, rank: int, world: int):

@@ -57,8 +57,28 @@ def active_mask(pts: torch.Tensor, bits: torch.Tensor, R: int, bound: float) -> 
 
 
 class Marched:
-    """Result of marching a ray batch: depths, activity bitmask, compact sample list."""
-    __slots__ = ("z", "mask_words", "ray_offset", "n_active", "pts", "dirs", "times", "sample_idx", "B", "N")
+    """Result of marching a ray batch: depths, activity bitmask, compact sample list.  ``n_dev`` (static mode only):
+    int32[1] device tensor with the number of valid rows of ``pts`` / ``dirs`` / ``times`` (their first dimension is then
+    the fixed capacity B * N, ``n_active`` too)."""
+    __slots__ = ("z", "mask_words", "ray_offset", "n_active", "n_dev", "pts", "dirs", "times", "sample_idx", "B", "N")
+
+
+_STATIC = {"on": False}
+
+
+def set_static_capacity(on: bool):
+    """Static mode: ``march`` behind an occupancy grid never reads the active-sample count on the host.  The compact
+    buffers get the fixed capacity B * N and the count stays on the device (``Marched.n_dev``); ``render_rays`` hands it
+    to every kernel of the step through ``b2n._lib.active_rows``.  No host synchronisation is left in a training step, so
+    it can be captured into a CUDA graph (b2n.graphs.GraphedStep) and the host can run ahead of the device.  Costs
+    capacity-sized allocations (and torch glue ops over capacity rows in the dynamic models); needs the 16-bit fused
+    decoders.  Default off: the exact-size path with its single 4-byte read per call (the reference syncs three times:
+    renderer.py:309-323)."""
+    _STATIC["on"] = bool(on)
+
+
+def static_capacity() -> bool:
+    return _STATIC["on"]
 
 
 def march(rays_o: torch.Tensor, rays_d: torch.Tensor, near: float, far: float, n_samples: int,
@@ -76,6 +96,7 @@ def march(rays_o: torch.Tensor, rays_d: torch.Tensor, near: float, far: float, n
     zb, zlo, zhi = z_tables(near, far, N, dev)
     m = Marched()
     m.B, m.N = B, N
+    m.n_dev = None
     W = (N + 31) // 32
     m.z = torch.empty(B, N, device=dev)
     if times is not None:
@@ -94,16 +115,21 @@ def march(rays_o: torch.Tensor, rays_d: torch.Tensor, near: float, far: float, n
         u = u.float().contiguous()
     scale = float(np.float32(R / (2 * bound))) if bits is not None else 0.0
     call("b2n_march_mask", ptr(rays_o), ptr(rays_d), ptr(zb), ptr(zlo), ptr(zhi), ptr(u), ptr(bits), int(R),
-         float(bound), scale, B, N, ptr(m.z), ptr(words), ptr(counts), stream())
+         float(bound), scale, B, N, ptr(m.z), ptr(words), ptr(counts), stream(),
+         work=(B * (24.0 + 4.0 * N * (2 if u is not None else 1) + 4.0 * W + 4.0), 0.0))      # o, d, U in; z, words, count out
     if bits is None:
         m.mask_words, m.ray_offset, m.n_active = None, None, B * N
     else:
         offs = torch.empty(B + 1, device=dev, dtype=torch.int32)
         total = torch.empty(1, device=dev, dtype=torch.int32)
         scratch = torch.empty(lib.b2n_march_scan_scratch(B), device=dev, dtype=torch.uint8)
-        call("b2n_march_scan", ptr(counts), ptr(words), W, B, ptr(offs), ptr(total), ptr(scratch), stream())
+        call("b2n_march_scan", ptr(counts), ptr(words), W, B, ptr(offs), ptr(total), ptr(scratch), stream(),
+             work=(B * (8.0 + 4.0), 0.0))
         m.mask_words, m.ray_offset = words, offs
-        m.n_active = int(total.item())            # the one host sync of the masked path
+        if _STATIC["on"]:
+            m.n_active, m.n_dev = B * N, total     # fixed capacity, count stays on the device
+        else:
+            m.n_active = int(total.item())        # the one host sync of the masked path
     Pn = m.n_active
     m.pts = torch.empty(Pn, 3, device=dev)
     m.dirs = torch.empty(Pn, 3, device=dev)
@@ -111,5 +137,6 @@ def march(rays_o: torch.Tensor, rays_d: torch.Tensor, near: float, far: float, n
     if want_idx:
         m.sample_idx = torch.empty(Pn, device=dev, dtype=torch.int32)
     call("b2n_march_compact", ptr(rays_o), ptr(rays_d), ptr(times), ptr(m.z), ptr(m.mask_words), ptr(m.ray_offset),
-         B, N, ptr(m.sample_idx), ptr(m.pts), ptr(m.dirs), ptr(m.times), stream())
+         B, N, ptr(m.sample_idx), ptr(m.pts), ptr(m.dirs), ptr(m.times), stream(),
+         work=(Pn * (4.0 + 24.0 + (4.0 if times is not None else 0.0)) + B * (24.0 + 4.0 * W + 4.0), 0.0))
     return m

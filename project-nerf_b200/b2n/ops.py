@@ -15,7 +15,7 @@ import torch
 from torch.amp import custom_bwd, custom_fwd
 
 from . import _lib
-from ._lib import HashLevelC, ptr, require_cuda, stream
+from ._lib import HashLevelC, current_rows, ptr, require_cuda, stream, with_ctx_rows
 
 
 def call(name, *args, work=(0.0, 0.0)):
@@ -23,6 +23,15 @@ def call(name, *args, work=(0.0, 0.0)):
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID = 0, 1, 2
 _ACT = {"none": ACT_NONE, "relu": ACT_RELU, "sigmoid": ACT_SIGMOID}
+
+
+def _narrow_out(*shape, device, dtype=torch.float32):
+    """Point-indexed tensors of a few floats per row (rgb, sigma, delta_x and their gradients).  With a device-side row
+    count the rows behind it are never written by the kernels, but torch-side reductions over rows exist downstream
+    (``displacement_scale.grad = sum(g * y)``): those rows must hold zeros, not whatever the allocator returns."""
+    if current_rows() is not None:
+        return torch.zeros(*shape, device=device, dtype=dtype)
+    return torch.empty(*shape, device=device, dtype=dtype)
 
 
 def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
@@ -79,8 +88,9 @@ class HashGeometry:
 class _HashEncode(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, x, table, geom: HashGeometry, bound: float):
+    def forward(ctx, x, table, geom: HashGeometry, bound: float, sink):
         require_cuda(x, table)
+        ctx.rows = current_rows()
         x, table = _c(x), _c(table)
         if x.dim() != 2 or x.shape[1] != 3:
             raise ValueError("hash_encode expects x of shape [P, 3]")
@@ -93,28 +103,56 @@ class _HashEncode(torch.autograd.Function):
              work=(Pn * (12 + geom.n_levels * geom.n_features * 4 * 9), 0.0))
         ctx.save_for_backward(x, table)
         ctx.geom, ctx.bound = geom, bound
+        ctx.sink = sink if (sink is not None and ctx.needs_input_grad[1]) else None
+        if ctx.sink is not None:
+            ctx.sink.uses += 1
         return out
 
     @staticmethod
     @custom_bwd(device_type="cuda")
+    @with_ctx_rows
     def backward(ctx, g):
         x, table = ctx.saved_tensors
         geom = ctx.geom
         g = _c(g)
         need_x, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
-        g_table = torch.zeros_like(table) if need_t else None
         g_x = torch.empty_like(x) if need_x else None
-        if need_x or need_t:
-            call("b2n_hash_bwd", ptr(x), x.shape[0], float(ctx.bound), ptr(table), geom.c_levels, geom.n_levels,
-                 geom.n_features, ptr(g), geom.out_dim, 0, ptr(g_table), ptr(g_x), 0, stream(),
-                 work=(x.shape[0] * ((12 + geom.n_levels * geom.n_features * 4 * 17) * int(need_t)
-                                     + (24 + geom.n_levels * geom.n_features * 4 * 9) * int(need_x)), 0.0))
-        return g_x, g_table, None, None
+        Pn, L, F = x.shape[0], geom.n_levels, geom.n_features
+        bytes_t = (12 + L * F * 4 * 17) * int(need_t)
+        bytes_x = (24 + L * F * 4 * 9) * int(need_x)
+
+        def launch(g_table, gx, lo, hi, nbytes):
+            call("b2n_hash_bwd", ptr(x), Pn, float(ctx.bound), ptr(table), geom.c_levels, L, F, ptr(g), geom.out_dim, 0,
+                 ptr(g_table), ptr(gx), 0, lo, hi, stream(), work=(Pn * nbytes, 0.0))
+
+        sink = ctx.sink
+        if sink is None or not need_t:
+            g_table = torch.zeros_like(table) if need_t else None
+            if need_x or need_t:
+                launch(g_table, g_x, 0, -1, bytes_t + bytes_x)
+            return g_x, g_table, None, None, None
+        # data-parallel direct path: accumulate into the flat gradient buffer; the last backward of the step scatters
+        # the fine levels first and hands their (contiguous, level-major) slice to the reducer while the coarse levels
+        # are still being scattered
+        sink.uses -= 1
+        last = sink.uses <= 0
+        split = sink.split_level if (last and F == 2 and 0 < sink.split_level < L and sink.split_level % 4 == 0) else 0
+        if split:
+            cut = geom.levels[split][3] * F                   # first element of level `split`
+            launch(sink.view, None, split, L, bytes_t * (L - split) / L)
+            sink.on_ready(sink, cut, sink.view.numel())
+            launch(sink.view, g_x, 0, split, bytes_t * split / L + bytes_x)
+            sink.on_ready(sink, 0, cut)
+        else:
+            launch(sink.view, g_x, 0, -1, bytes_t + bytes_x)
+            if last:
+                sink.on_ready(sink, 0, sink.view.numel())
+        return g_x, None, None, None, None
 
 
 def hash_encode(x, table, geom: HashGeometry, bound: float):
     """x [P,3] world coords (bound > 0) or unit-cube coords (bound == 0) -> [P, L*F]."""
-    return _HashEncode.apply(x, table, geom, bound)
+    return _HashEncode.apply(x, table, geom, bound, getattr(table, "_b2n_grad_sink", None))
 
 
 class _HashTriBlend(torch.autograd.Function):
@@ -125,6 +163,7 @@ class _HashTriBlend(torch.autograd.Function):
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, t, t0, t1, t2, geom: HashGeometry, bound: float):
         require_cuda(x, t, t0, t1, t2)
+        ctx.rows = current_rows()
         x, t, t0, t1, t2 = _c(x), _c(t).reshape(-1), _c(t0), _c(t1), _c(t2)
         if geom.n_features != 2:
             raise ValueError("hash_tri_blend needs 2 features per level")
@@ -141,6 +180,7 @@ class _HashTriBlend(torch.autograd.Function):
 
     @staticmethod
     @custom_bwd(device_type="cuda")
+    @with_ctx_rows
     def backward(ctx, g):
         x, t = ctx.saved_tensors
         geom = ctx.geom
@@ -170,6 +210,7 @@ class _Fourier(torch.autograd.Function):
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, bands):
         require_cuda(x, bands)
+        ctx.rows = current_rows()
         x, bands = _c(x), _c(bands)
         Pn, D = x.shape
         L = bands.numel()
@@ -183,6 +224,7 @@ class _Fourier(torch.autograd.Function):
 
     @staticmethod
     @custom_bwd(device_type="cuda")
+    @with_ctx_rows
     def backward(ctx, g):
         if not ctx.needs_input_grad[0]:
             return None, None
@@ -209,6 +251,9 @@ class _Linear(torch.autograd.Function):
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x, W, b, act: int):
         require_cuda(x, W, b)
+        if current_rows() is not None:
+            raise RuntimeError("the fp32 layer-by-layer path does not support a device-side row count "
+                               "(march(static=True)): use the 16-bit fused path (b2n.set_mlp_precision('bf16'))")
         x, W, b = _c(x), _c(W), _c(b)
         Pn, K = x.shape
         N = W.shape[0]
@@ -255,6 +300,9 @@ class _SigmaHead(torch.autograd.Function):
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, h):
         require_cuda(h)
+        if current_rows() is not None:
+            raise RuntimeError("the fp32 layer-by-layer path does not support a device-side row count "
+                               "(march(static=True)): use the 16-bit fused path (b2n.set_mlp_precision('bf16'))")
         h = _c(h)
         Pn = h.shape[0]
         sigma = torch.empty(Pn, 1, device=h.device, dtype=torch.float32)
@@ -285,6 +333,7 @@ class _Composite(torch.autograd.Function):
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, rgb, sigma, dx, z, rays_d, bg, mask_words, ray_offset):
         require_cuda(rgb, sigma, z, rays_d)
+        ctx.rows = current_rows()
         rgb, sigma, dx, z, rays_d, bg = _c(rgb), _c(sigma), _c(dx), _c(z), _c(rays_d), _c(bg)
         B, N = z.shape
         dev = z.device
@@ -307,12 +356,13 @@ class _Composite(torch.autograd.Function):
 
     @staticmethod
     @custom_bwd(device_type="cuda")
+    @with_ctx_rows
     def backward(ctx, g_color, g_depth, g_acc, g_mdx):
         rgb, sigma, dx, z, rays_d, bg, mask_words, ray_offset = ctx.saved_tensors
         B, N = z.shape
-        g_rgb = torch.empty_like(rgb)
-        g_sigma = torch.empty_like(sigma)
-        g_dx = torch.empty_like(dx) if dx is not None else None
+        g_rgb = _narrow_out(*rgb.shape, device=rgb.device)
+        g_sigma = _narrow_out(*sigma.shape, device=rgb.device)
+        g_dx = _narrow_out(*dx.shape, device=rgb.device) if dx is not None else None
         if dx is None:
             g_mdx = None
         call("b2n_composite_bwd", ptr(rgb), ptr(sigma), ptr(dx), ptr(z), ptr(rays_d), ptr(bg), ctx.per_ray,
@@ -358,10 +408,11 @@ class _InstantMLP(torch.autograd.Function):
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, x_enc, dirs, bands, sigma_params, color_params):
         require_cuda(x_enc, dirs, bands, sigma_params, color_params)
+        ctx.rows = current_rows()
         x_enc, dirs, bands, sp, cp = _c(x_enc), _c(dirs), _c(bands), _c(sigma_params), _c(color_params)
         Pn, pos_dim = x_enc.shape
-        rgb = torch.empty(Pn, 3, device=x_enc.device)
-        sigma = torch.empty(Pn, 1, device=x_enc.device)
+        rgb = _narrow_out(Pn, 3, device=x_enc.device)
+        sigma = _narrow_out(Pn, 1, device=x_enc.device)
         flops = 2.0 * Pn * (64 * pos_dim + 16 * 64 + 64 * 43 + 64 * 64 + 3 * 64)
         call("b2n_instant_mlp_fwd", ptr(x_enc), pos_dim, pos_dim, ptr(dirs), ptr(bands), bands.numel(), ptr(sp),
              ptr(cp), Pn, ptr(rgb), ptr(sigma), stream(), work=(Pn * (4.0 * pos_dim + 12 + 16), flops))
@@ -370,6 +421,7 @@ class _InstantMLP(torch.autograd.Function):
 
     @staticmethod
     @custom_bwd(device_type="cuda")
+    @with_ctx_rows
     def backward(ctx, g_rgb, g_sigma):
         x_enc, dirs, bands, sp, cp = ctx.saved_tensors
         Pn, pos_dim = x_enc.shape
@@ -395,19 +447,35 @@ def instant_mlp(x_enc, dirs, bands, sigma_params, color_params):
 # The tcgen05 kernels never hang: a stalled mbarrier wait aborts the CTA and raises a device-side flag instead.  Reading
 # the flag costs a host sync, so it is checked with a delay -- every 64th launch looks at the flags of earlier launches
 # (long finished) -- and a non-zero flag raises here rather than letting garbage activations train on.
-_ERR_FLAGS: List[torch.Tensor] = []
+_ERR_FLAGS: dict = {}          # device index -> flags of launches not yet inspected
+
+
+def _raise_if_set(flags):
+    bad = int(torch.stack(flags).max().item())
+    if bad != 0:
+        raise RuntimeError(f"a tcgen05 decoder kernel aborted a stalled pipeline (code {bad}); its outputs are invalid")
 
 
 def _track_err(err: torch.Tensor):
     if torch.cuda.is_current_stream_capturing():
-        return          # inside a CUDA graph (b2n.graphs): no host reads; the flag lives in the graph's memory pool
-    _ERR_FLAGS.append(err)
-    if len(_ERR_FLAGS) >= 64:
-        old = torch.stack(_ERR_FLAGS[:32])
-        del _ERR_FLAGS[:32]
-        bad = int(old.max().item())
-        if bad != 0:
-            raise RuntimeError(f"a tcgen05 decoder kernel aborted a stalled pipeline (code {bad}); its outputs are invalid")
+        return          # inside a CUDA graph (b2n.graphs): no host reads; GraphedStep checks its own flags after replays
+    lst = _ERR_FLAGS.setdefault(err.device.index, [])
+    lst.append(err)
+    if len(lst) >= 64:
+        old = lst[:32]
+        del lst[:32]
+        _raise_if_set(old)
+
+
+def check_errors():
+    """Inspect the abort flags of EVERY tcgen05 launch not looked at yet (one host sync per device).  The delayed check
+    above never sees the last < 64 launches of a run; call this where a sync happens anyway -- after ``loss.item()``,
+    at the end of ``render_image`` / ``DensityGrid.update`` (done there), after CUDA-graph replays -- so that a short
+    evaluation cannot write images computed from an aborted pipeline."""
+    for dev in list(_ERR_FLAGS):
+        flags, _ERR_FLAGS[dev] = _ERR_FLAGS[dev], []
+        if flags:
+            _raise_if_set(flags)
 
 
 def nerf_mlp_supported(decoder, pos_dim: int, dir_dim: int) -> bool:
@@ -438,6 +506,8 @@ def _nerf_mlp_pack(decoder):
 def nerf_mlp_forward(decoder, x_enc, d_enc, save: bool = False):
     """NeRFDecoder forward on the tensor cores.  Returns (rgb [P,3], sigma [P,1], saved planes | None)."""
     require_cuda(x_enc, d_enc)
+    if current_rows() is not None:
+        raise RuntimeError("the 256-wide tcgen05 decoder does not support a device-side row count (march(static=True))")
     x_enc, d_enc = _c(x_enc), _c(d_enc)
     packed, bias, head_bias, pos_dim, dir_dim = _nerf_mlp_pack(decoder)
     Pn = x_enc.shape[0]
@@ -601,6 +671,7 @@ class _FusedMLP(torch.autograd.Function):
     def forward(ctx, x0, x1, out_act, n_layers, *wb):
         Ws, bs = list(wb[:n_layers]), list(wb[n_layers:])
         require_cuda(x0, x1, *Ws)
+        ctx.rows = current_rows()
         x0, x1 = _c(x0), _c(x1)
         Ws = [W if (W.dtype == torch.float32 and W.stride(-1) == 1) else _c(W) for W in Ws]
         bs = [_c(b) for b in bs]
@@ -610,7 +681,7 @@ class _FusedMLP(torch.autograd.Function):
         dev = x0.device
         need = any(ctx.needs_input_grad)
         in_pad = _lib.lib.b2n_fmlp_in_pad(d0 + d1)
-        y = torch.empty(Pn, out_dim, device=dev)
+        y = _narrow_out(Pn, out_dim, device=dev) if out_dim <= 4 else torch.empty(Pn, out_dim, device=dev)
         xin = torch.empty(Pn, in_pad, device=dev, dtype=torch.float16) if need else None
         hpl = torch.empty(n_hidden, Pn, hidden, device=dev, dtype=torch.float16) if need else None
         Wp = (ctypes.c_void_p * n_layers)(*[W.data_ptr() for W in Ws])
@@ -626,6 +697,7 @@ class _FusedMLP(torch.autograd.Function):
 
     @staticmethod
     @custom_bwd(device_type="cuda")
+    @with_ctx_rows
     def backward(ctx, g_y):
         y, xin, hpl, *Ws = ctx.saved_tensors
         d0, d1, hidden, n_hidden, out_dim, out_act, n_layers, has_b = ctx.meta
@@ -633,7 +705,9 @@ class _FusedMLP(torch.autograd.Function):
         dev = y.device
         g_y = _c(g_y)
         out_pad = _lib.lib.b2n_fmlp_out_pad(out_dim)
-        dz_out = torch.empty(Pn, out_pad, device=dev, dtype=torch.float16)       # planes hold S * dZ (see b2n_fmlp_bwd)
+        # planes hold S * dZ (see b2n_fmlp_bwd); dz_out is column-summed over ALL allocated rows below, and with a
+        # device-side row count the rows behind it are never written: zero-filled (32 bytes per row)
+        dz_out = torch.zeros(Pn, out_pad, device=dev, dtype=torch.float16)
         dz_h = torch.empty(n_hidden, Pn, hidden, device=dev, dtype=torch.float16)
         work = torch.empty(2, device=dev, dtype=torch.float32)                    # [0] |g|-max bits, [1] S
         scale = work[1:]

@@ -28,6 +28,16 @@ inline int check_launch(const char* what) {
 
 constexpr int kSMs = 148;  // B200
 
+// Optional device-side row count (b2n_set_active_rows): while set, every entry point that takes a point count P
+// treats rows >= *rows as absent -- its kernels clamp P on the device.  This is what lets a step behind an occupancy
+// grid run without the host ever reading the number of active samples (fixed-capacity buffers, CUDA-graph capture).
+extern thread_local const int* g_active_rows;
+__device__ __forceinline__ int64_t clamp_rows(int64_t P, const int* __restrict__ rows) {
+  if (!rows) return P;
+  const int64_t n = (int64_t)__ldg(rows);
+  return n < P ? (n < 0 ? 0 : n) : P;
+}
+
 inline unsigned grid_for(int64_t work_items, int per_block) {
   int64_t g = (work_items + per_block - 1) / per_block;
   if (g < 1) g = 1;

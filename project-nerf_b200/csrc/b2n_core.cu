@@ -2,10 +2,15 @@
 
 namespace b2n {
 thread_local char g_err[512] = {0};
+thread_local const int* g_active_rows = nullptr;
 }
 
 extern "C" int b2n_abi_version(void) { return B2N_ABI_VERSION; }
 extern "C" const char* b2n_last_error(void) { return b2n::g_err; }
+extern "C" int b2n_set_active_rows(const int* rows_device) {
+  b2n::g_active_rows = rows_device;
+  return B2N_OK;
+}
 
 // ---------------------------------------------------------------------------------------- fp32 rows -> zero-padded bf16 rows
 // out[p, 0:kpad] = bf16(x[p, 0:width]) | 0   (kpad a multiple of 8 >= width).  The operand blocks of the tcgen05

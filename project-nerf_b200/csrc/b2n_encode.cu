@@ -15,7 +15,8 @@ namespace b2n {
 #define B2N_PI_F 3.14159274101257324f
 
 __global__ void k_pe_fwd(const float* __restrict__ x, int64_t P, int D, const float* __restrict__ bands, int L,
-                         float* __restrict__ out, int ld, int col0) {
+                         float* __restrict__ out, int ld, int col0, const int* __restrict__ rows) {
+  P = clamp_rows(P, rows);
   // one thread per (point, input dim, band); band index L means the identity column
   const int per_pt = D * (L + 1);
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -37,7 +38,8 @@ __global__ void k_pe_fwd(const float* __restrict__ x, int64_t P, int D, const fl
 }
 
 __global__ void k_pe_bwd(const float* __restrict__ x, int64_t P, int D, const float* __restrict__ bands, int L,
-                         const float* __restrict__ g, int ld, int col0, float* __restrict__ gx, int accumulate) {
+                         const float* __restrict__ g, int ld, int col0, float* __restrict__ gx, int accumulate, const int* __restrict__ rows) {
+  P = clamp_rows(P, rows);
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P * D) return;
   const int64_t p = i / D;
@@ -58,7 +60,8 @@ __global__ void k_pe_bwd(const float* __restrict__ x, int64_t P, int D, const fl
 template <int F>
 __global__ void __launch_bounds__(256)
 k_hash_fwd(const float* __restrict__ x, int64_t P, float bound, float two_bound, const float* __restrict__ table,
-           const Levels lv, int nl, float* __restrict__ out, int ld, int col0) {
+           const Levels lv, int nl, float* __restrict__ out, int ld, int col0, const int* __restrict__ rows) {
+  P = clamp_rows(P, rows);
   __shared__ SmemLevels sl;
   stage_levels(lv, nl, &sl);
   const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -117,7 +120,8 @@ k_hash_fwd(const float* __restrict__ x, int64_t P, float bound, float two_bound,
 template <int F>
 __global__ void __launch_bounds__(256)
 k_hash_bwd_table(const float* __restrict__ x, int64_t P, float bound, float two_bound, const Levels lv, int nl,
-                 int l0, const float* __restrict__ g, int ld, int col0, float* __restrict__ g_table) {
+                 int l0, const float* __restrict__ g, int ld, int col0, float* __restrict__ g_table, const int* __restrict__ rows) {
+  P = clamp_rows(P, rows);
   // items cover levels l0 .. nl-1 (the dense levels below l0 are handled by k_hash_bwd_table_dense)
   __shared__ SmemLevels sl;
   stage_levels(lv, nl, &sl);
@@ -190,7 +194,8 @@ k_hash_bwd_table(const float* __restrict__ x, int64_t P, float bound, float two_
 template <int F>
 __global__ void __launch_bounds__(256)
 k_hash_bwd_table_dense(const float* __restrict__ x, int64_t P, float bound, float two_bound, const Levels lv,
-                       int n_dense, const float* __restrict__ g, int ld, int col0, float* __restrict__ g_table) {
+                       int n_dense, const float* __restrict__ g, int ld, int col0, float* __restrict__ g_table, const int* __restrict__ rows) {
+  P = clamp_rows(P, rows);
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   const bool live = p < P;
@@ -294,7 +299,8 @@ __device__ __forceinline__ float pair_sum(float v) { return v + __shfl_xor_sync(
 
 __global__ void __launch_bounds__(256)
 k_hash_fwd_pair(const float* __restrict__ x, int64_t P, float bound, float two_bound, const float2* __restrict__ table,
-                const Levels lv, int nl, float* __restrict__ out, int ld, int col0) {
+                const Levels lv, int nl, float* __restrict__ out, int ld, int col0, const int* __restrict__ rows) {
+  P = clamp_rows(P, rows);
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t p = tid >> 1;
   const int s = threadIdx.x & 1;
@@ -354,8 +360,12 @@ k_hash_fwd_pair(const float* __restrict__ x, int64_t P, float bound, float two_b
 // consecutive points (consecutive samples of a ray) that share a cell before the run head issues the red.global -- the
 // coarse levels would otherwise serialise millions of reductions on a few thousand addresses.
 __global__ void __launch_bounds__(256)
-k_hash_bwd_table_pair(const float* __restrict__ x, int64_t P, float bound, float two_bound, const Levels lv, int nl,
-                      const float* __restrict__ g, int ld, int col0, float2* __restrict__ g_table, uint32_t merge_res) {
+k_hash_bwd_table_pair(const float* __restrict__ x, int64_t P, float bound, float two_bound, const Levels lv, int lbeg,
+                      int nl, const float* __restrict__ g, int ld, int col0, float2* __restrict__ g_table,
+                      uint32_t merge_res, const int* __restrict__ rows) {
+  P = clamp_rows(P, rows);
+  // levels [lbeg, nl) of the table (lbeg a multiple of 4): a caller that overlaps the gradient all-reduce of the fine
+  // levels with the scatter of the coarse ones launches this kernel once per level window
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t p = tid >> 1;
   const int lane = threadIdx.x & 31, s = lane & 1, pi = lane >> 1;     // pi: point index inside the warp (0..15)
@@ -368,7 +378,7 @@ k_hash_bwd_table_pair(const float* __restrict__ x, int64_t P, float bound, float
   }
   const float* grow = g + p * ld + col0;
   const bool vec = ((reinterpret_cast<uintptr_t>(g + col0) & 15) == 0) && ((ld & 3) == 0);
-  for (int l0 = 0; l0 < nl; l0 += 4) {
+  for (int l0 = lbeg; l0 < nl; l0 += 4) {
     float gv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (live) {
       if (vec && l0 + 4 <= nl) {
@@ -433,7 +443,8 @@ template <int F>
 __global__ void __launch_bounds__(256)
 k_hash_bwd_input(const float* __restrict__ x, int64_t P, float bound, float two_bound,
                  const float* __restrict__ table, const Levels lv, int nl, const float* __restrict__ g, int ld,
-                 int col0, float* __restrict__ gx, int accumulate) {
+                 int col0, float* __restrict__ gx, int accumulate, const int* __restrict__ rows) {
+  P = clamp_rows(P, rows);
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   bool in[3];
@@ -501,7 +512,8 @@ __device__ __forceinline__ void tri_weights(float tv, float (&w)[3]) {
 
 __global__ void __launch_bounds__(256)
 k_hash_tri_fwd(const float* __restrict__ x, const float* __restrict__ tval, int64_t P, float bound, float two_bound,
-               const TriTables tabs, const Levels lv, int nl, float* __restrict__ out, int ld) {
+               const TriTables tabs, const Levels lv, int nl, float* __restrict__ out, int ld, const int* __restrict__ rows) {
+  P = clamp_rows(P, rows);
   __shared__ SmemLevels sl;
   stage_levels(lv, nl, &sl);
   const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -551,7 +563,8 @@ k_hash_tri_fwd(const float* __restrict__ x, const float* __restrict__ tval, int6
 
 __global__ void __launch_bounds__(256)
 k_hash_tri_bwd(const float* __restrict__ x, const float* __restrict__ tval, int64_t P, float bound, float two_bound,
-               const Levels lv, int nl, const float* __restrict__ g, int ld, const TriGrads grads) {
+               const Levels lv, int nl, const float* __restrict__ g, int ld, const TriGrads grads, const int* __restrict__ rows) {
+  P = clamp_rows(P, rows);
   __shared__ SmemLevels sl;
   stage_levels(lv, nl, &sl);
   const int64_t item = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -615,7 +628,7 @@ extern "C" int b2n_pe_fwd(const float* x, int64_t P, int D, const float* bands, 
   if (P == 0) return B2N_OK;
   B2N_REQUIRE(x && out && (L == 0 || bands), "null pointer");
   B2N_REQUIRE(ld_out >= col0 + D + 2 * D * L && col0 >= 0, "output row too narrow");
-  k_pe_fwd<<<grid_for(P * D * (L + 1), 256), 256, 0, (cudaStream_t)stream>>>(x, P, D, bands, L, out, ld_out, col0);
+  k_pe_fwd<<<grid_for(P * D * (L + 1), 256), 256, 0, (cudaStream_t)stream>>>(x, P, D, bands, L, out, ld_out, col0, g_active_rows);
   return check_launch("b2n_pe_fwd");
 }
 
@@ -626,7 +639,7 @@ extern "C" int b2n_pe_bwd(const float* x, int64_t P, int D, const float* bands, 
   B2N_REQUIRE(x && g_out && g_x && (L == 0 || bands), "null pointer");
   B2N_REQUIRE(ld_g >= col0 + D + 2 * D * L && col0 >= 0, "gradient row too narrow");
   k_pe_bwd<<<grid_for(P * D, 256), 256, 0, (cudaStream_t)stream>>>(x, P, D, bands, L, g_out, ld_g, col0, g_x,
-                                                                  accumulate);
+                                                                  accumulate, g_active_rows);
   return check_launch("b2n_pe_bwd");
 }
 
@@ -644,17 +657,22 @@ extern "C" int b2n_hash_fwd(const float* x, int64_t P, float bound, const float*
   cudaStream_t st = (cudaStream_t)stream;
   if (F == 2 && (g_hash_variant & 1))
     k_hash_fwd_pair<<<grid_for(2 * P, 256), 256, 0, st>>>(x, P, bound, tb, reinterpret_cast<const float2*>(table), lv, L, out,
-                                                        ld_out, col0);
-  else if (F == 2) k_hash_fwd<2><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, out, ld_out, col0);
-  else if (F == 4) k_hash_fwd<4><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, out, ld_out, col0);
-  else k_hash_fwd<1><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, out, ld_out, col0);
+                                                        ld_out, col0, g_active_rows);
+  else if (F == 2) k_hash_fwd<2><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, out, ld_out, col0, g_active_rows);
+  else if (F == 4) k_hash_fwd<4><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, out, ld_out, col0, g_active_rows);
+  else k_hash_fwd<1><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, out, ld_out, col0, g_active_rows);
   return check_launch("b2n_hash_fwd");
 }
 
 extern "C" int b2n_hash_bwd(const float* x, int64_t P, float bound, const float* table,
                             const b2n_hash_level* levels_host, int L, int F, const float* g_out, int ld_g, int col0,
-                            float* g_table, float* g_x, int accumulate_x, b2n_stream_t stream) {
+                            float* g_table, float* g_x, int accumulate_x, int level_begin, int level_end,
+                            b2n_stream_t stream) {
   B2N_REQUIRE(P >= 0 && (F == 1 || F == 2 || F == 4) && bound >= 0.f, "bad shape (F in {1,2,4})");
+  if (level_end < 0) level_end = L;
+  B2N_REQUIRE(level_begin >= 0 && level_begin <= level_end && level_end <= L, "bad level window");
+  const bool windowed = level_begin != 0 || level_end != L;
+  B2N_REQUIRE(!windowed || (F == 2 && (level_begin & 3) == 0), "a level window needs F = 2 and a start that is a multiple of 4");
   Levels lv;
   B2N_REQUIRE(fill_levels(levels_host, L, &lv) == 0, "bad level table");
   if (P == 0) return B2N_OK;
@@ -663,30 +681,31 @@ extern "C" int b2n_hash_bwd(const float* x, int64_t P, float bound, const float*
   B2N_REQUIRE(!g_x || table, "input gradient needs the table");
   const float tb = 2.0f * bound;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_table && F == 2 && (g_hash_variant & 2)) {
-    k_hash_bwd_table_pair<<<grid_for(2 * P, 256), 256, 0, st>>>(x, P, bound, tb, lv, L, g_out, ld_g, col0,
-                                                              reinterpret_cast<float2*>(g_table), g_merge_res);
+  if (g_table && F == 2 && ((g_hash_variant & 2) || windowed)) {
+    if (level_begin < level_end)
+      k_hash_bwd_table_pair<<<grid_for(2 * P, 256), 256, 0, st>>>(x, P, bound, tb, lv, level_begin, level_end, g_out, ld_g,
+                                                                col0, reinterpret_cast<float2*>(g_table), g_merge_res, g_active_rows);
   } else if (g_table) {
     int n_dense = 0;                      // leading run of un-hashed levels
     while (n_dense < L && !lv.l[n_dense].hashed) ++n_dense;
     if (n_dense > 0) {
       const unsigned gd = grid_for(P, 256);
-      if (F == 2) k_hash_bwd_table_dense<2><<<gd, 256, 0, st>>>(x, P, bound, tb, lv, n_dense, g_out, ld_g, col0, g_table);
-      else if (F == 4) k_hash_bwd_table_dense<4><<<gd, 256, 0, st>>>(x, P, bound, tb, lv, n_dense, g_out, ld_g, col0, g_table);
-      else k_hash_bwd_table_dense<1><<<gd, 256, 0, st>>>(x, P, bound, tb, lv, n_dense, g_out, ld_g, col0, g_table);
+      if (F == 2) k_hash_bwd_table_dense<2><<<gd, 256, 0, st>>>(x, P, bound, tb, lv, n_dense, g_out, ld_g, col0, g_table, g_active_rows);
+      else if (F == 4) k_hash_bwd_table_dense<4><<<gd, 256, 0, st>>>(x, P, bound, tb, lv, n_dense, g_out, ld_g, col0, g_table, g_active_rows);
+      else k_hash_bwd_table_dense<1><<<gd, 256, 0, st>>>(x, P, bound, tb, lv, n_dense, g_out, ld_g, col0, g_table, g_active_rows);
     }
     if (n_dense < L) {
       const unsigned grid = grid_for(P * (L - n_dense), 256);
-      if (F == 2) k_hash_bwd_table<2><<<grid, 256, 0, st>>>(x, P, bound, tb, lv, L, n_dense, g_out, ld_g, col0, g_table);
-      else if (F == 4) k_hash_bwd_table<4><<<grid, 256, 0, st>>>(x, P, bound, tb, lv, L, n_dense, g_out, ld_g, col0, g_table);
-      else k_hash_bwd_table<1><<<grid, 256, 0, st>>>(x, P, bound, tb, lv, L, n_dense, g_out, ld_g, col0, g_table);
+      if (F == 2) k_hash_bwd_table<2><<<grid, 256, 0, st>>>(x, P, bound, tb, lv, L, n_dense, g_out, ld_g, col0, g_table, g_active_rows);
+      else if (F == 4) k_hash_bwd_table<4><<<grid, 256, 0, st>>>(x, P, bound, tb, lv, L, n_dense, g_out, ld_g, col0, g_table, g_active_rows);
+      else k_hash_bwd_table<1><<<grid, 256, 0, st>>>(x, P, bound, tb, lv, L, n_dense, g_out, ld_g, col0, g_table, g_active_rows);
     }
   }
   if (g_x) {
     const unsigned grid = grid_for(P, 256);
-    if (F == 2) k_hash_bwd_input<2><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, g_out, ld_g, col0, g_x, accumulate_x);
-    else if (F == 4) k_hash_bwd_input<4><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, g_out, ld_g, col0, g_x, accumulate_x);
-    else k_hash_bwd_input<1><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, g_out, ld_g, col0, g_x, accumulate_x);
+    if (F == 2) k_hash_bwd_input<2><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, g_out, ld_g, col0, g_x, accumulate_x, g_active_rows);
+    else if (F == 4) k_hash_bwd_input<4><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, g_out, ld_g, col0, g_x, accumulate_x, g_active_rows);
+    else k_hash_bwd_input<1><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, g_out, ld_g, col0, g_x, accumulate_x, g_active_rows);
   }
   return check_launch("b2n_hash_bwd");
 }
@@ -701,7 +720,7 @@ extern "C" int b2n_hash_tri_fwd(const float* x, const float* t, int64_t P, float
   B2N_REQUIRE(x && t && table_start && table_mid && table_end && out, "null pointer");
   B2N_REQUIRE(ld_out >= 2 * L && (ld_out & 1) == 0 && (reinterpret_cast<uintptr_t>(out) & 7) == 0, "output row too narrow / unaligned");
   const TriTables tabs{{table_start, table_mid, table_end}};
-  k_hash_tri_fwd<<<grid_for(P * L, 256), 256, 0, (cudaStream_t)stream>>>(x, t, P, bound, 2.0f * bound, tabs, lv, L, out, ld_out);
+  k_hash_tri_fwd<<<grid_for(P * L, 256), 256, 0, (cudaStream_t)stream>>>(x, t, P, bound, 2.0f * bound, tabs, lv, L, out, ld_out, g_active_rows);
   return check_launch("b2n_hash_tri_fwd");
 }
 
@@ -715,7 +734,7 @@ extern "C" int b2n_hash_tri_bwd(const float* x, const float* t, int64_t P, float
   B2N_REQUIRE(x && t && g_out, "null pointer");
   B2N_REQUIRE(ld_g >= 2 * L && (ld_g & 1) == 0 && (reinterpret_cast<uintptr_t>(g_out) & 7) == 0, "gradient row too narrow / unaligned");
   const TriGrads grads{{g_table_start, g_table_mid, g_table_end}};
-  k_hash_tri_bwd<<<grid_for(P * L, 256), 256, 0, (cudaStream_t)stream>>>(x, t, P, bound, 2.0f * bound, lv, L, g_out, ld_g, grads);
+  k_hash_tri_bwd<<<grid_for(P * L, 256), 256, 0, (cudaStream_t)stream>>>(x, t, P, bound, 2.0f * bound, lv, L, g_out, ld_g, grads, g_active_rows);
   return check_launch("b2n_hash_tri_bwd");
 }
 

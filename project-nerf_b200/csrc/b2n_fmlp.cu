@@ -45,6 +45,10 @@ struct Args {
   float* g_x0; int ldg0;
   float* g_x1; int ldg1;
   unsigned int* work;   // [0] |g_y|-max bits (pre-pass), [1] the gradient scale S as a float (written by the kernel)
+  const int* rows;      // optional device-side row count (b2n_set_active_rows)
+  int64_t Pcap;         // rows the planes were allocated for (the host-side P): the stride between layer planes
+  int64_t Ppad;         // rows [P, Ppad) of the saved planes are ZERO-filled: the tcgen05 weight-gradient kernel streams
+                        // whole 64-row tiles, and with a device-side row count the rows behind it were never written
 };
 
 template <int H, int KT_IN, int NT_OUT>
@@ -146,20 +150,24 @@ __device__ __forceinline__ void load_in_raw(const Args& a, int64_t p0, float (&r
 }
 
 // A fragments of a 16-row slab -> rows p0.. of a row-major op16 plane (row stride ld, even)
+// rows [P, Ppad) are written as zeros (see Args::Ppad)
 template <int KT>
 __device__ __forceinline__ void store_plane(const uint32_t (&f)[KT][4], op16* plane, int ld, int64_t p0, int64_t P,
-                                            int lane) {
+                                            int lane, int64_t Ppad = 0) {
   const int g = lane >> 2, t = lane & 3;
   const int64_t pa = p0 + g, pb = pa + 8;
+  if (Ppad < P) Ppad = P;
 #pragma unroll
   for (int k = 0; k < KT; ++k) {
-    if (pa < P) {
+    if (pa < Ppad) {
       uint32_t* r0 = reinterpret_cast<uint32_t*>(plane + pa * ld + 16 * k + 2 * t);
-      r0[0] = f[k][0], r0[4] = f[k][2];
+      const bool v = pa < P;
+      r0[0] = v ? f[k][0] : 0u, r0[4] = v ? f[k][2] : 0u;
     }
-    if (pb < P) {
+    if (pb < Ppad) {
       uint32_t* r1 = reinterpret_cast<uint32_t*>(plane + pb * ld + 16 * k + 2 * t);
-      r1[0] = f[k][1], r1[4] = f[k][3];
+      const bool v = pb < P;
+      r1[0] = v ? f[k][1] : 0u, r1[4] = v ? f[k][3] : 0u;
     }
   }
 }
@@ -219,7 +227,8 @@ __device__ __forceinline__ float sigm(float v) { return 1.f / (1.f + expf(-v)); 
 
 // max |g_y| as float bits (see k_instant_bwd's pre-pass: same convention, NaN sorts above everything)
 __global__ void __launch_bounds__(256) k_fmlp_absmax(const float* __restrict__ g, int ld, int cols, int64_t P,
-                                                     unsigned int* __restrict__ out) {
+                                                     unsigned int* __restrict__ out, const int* __restrict__ rows) {
+  P = clamp_rows(P, rows);
   unsigned int m = 0u;
   const int64_t n = P * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -240,7 +249,11 @@ __device__ __forceinline__ float fmlp_scale_from(unsigned int bits) {
 
 // ------------------------------------------------------------------------------ forward
 template <int H, int KT_IN, int NT_OUT, int MT>
-__global__ void __launch_bounds__(THREADS) k_fmlp_fwd(const Args a) {
+__global__ void __launch_bounds__(THREADS) k_fmlp_fwd(const Args a_in) {
+  Args a = a_in;
+  a.P = clamp_rows(a_in.P, a_in.rows);
+  a.Pcap = a_in.P;
+  a.Ppad = min(a_in.P, (a.P + 63) & ~(int64_t)63);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   op16* sm = reinterpret_cast<op16*>(smem_raw);
   using LY = Layout<H, KT_IN, NT_OUT>;
@@ -248,7 +261,7 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_fwd(const Args a) {
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   constexpr int ROWS = 16 * MT;
-  const int64_t n_tiles = (a.P + ROWS - 1) / ROWS;
+  const int64_t n_tiles = (a.Ppad + ROWS - 1) / ROWS;
   const int64_t wstride = (int64_t)gridDim.x * (THREADS / 32);
   // single-slab variants (H = 128) have registers to spare: the next tile's input rows are fetched one tile ahead
   constexpr bool PF = (MT == 1);
@@ -267,12 +280,12 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_fwd(const Args a) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) ax[0][k][i] = pack2(raw[k % KTP][i][0], raw[k % KTP][i][1]);
         load_in_raw<KTP>(a, (tile + wstride) * ROWS, raw, lane);
-        if (a.xin) store_plane<KT_IN>(ax[0], a.xin, LY::IN_PAD, p0, a.P, lane);
+        if (a.xin) store_plane<KT_IN>(ax[0], a.xin, LY::IN_PAD, p0, a.P, lane, a.Ppad);
       } else {
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
           load_in<KT_IN>(a, p0 + 16 * m, ax[m], lane);
-          if (a.xin) store_plane<KT_IN>(ax[m], a.xin, LY::IN_PAD, p0 + 16 * m, a.P, lane);
+          if (a.xin) store_plane<KT_IN>(ax[m], a.xin, LY::IN_PAD, p0 + 16 * m, a.P, lane, a.Ppad);
         }
       }
       float c[MT][H / 8][4];
@@ -282,7 +295,7 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_fwd(const Args a) {
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
         c_to_a<H / 8, true>(c[m], ah[m]);
-        if (a.hplanes) store_plane<H / 16>(ah[m], a.hplanes, H, p0 + 16 * m, a.P, lane);
+        if (a.hplanes) store_plane<H / 16>(ah[m], a.hplanes, H, p0 + 16 * m, a.P, lane, a.Ppad);
       }
     }
 #pragma unroll 1
@@ -294,7 +307,7 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_fwd(const Args a) {
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
         c_to_a<H / 8, true>(c[m], ah[m]);
-        if (a.hplanes) store_plane<H / 16>(ah[m], a.hplanes + (size_t)l * a.P * H, H, p0 + 16 * m, a.P, lane);
+        if (a.hplanes) store_plane<H / 16>(ah[m], a.hplanes + (size_t)l * a.Pcap * H, H, p0 + 16 * m, a.P, lane, a.Ppad);
       }
     }
     {
@@ -326,7 +339,11 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_fwd(const Args a) {
 
 // ------------------------------------------------------------------------------ backward (data gradients)
 template <int H, int KT_IN, int NT_OUT>
-__global__ void __launch_bounds__(THREADS) k_fmlp_bwd(const Args a) {
+__global__ void __launch_bounds__(THREADS) k_fmlp_bwd(const Args a_in) {
+  Args a = a_in;
+  a.P = clamp_rows(a_in.P, a_in.rows);
+  a.Pcap = a_in.P;
+  a.Ppad = min(a_in.P, (a.P + 63) & ~(int64_t)63);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   op16* sm = reinterpret_cast<op16*>(smem_raw);
   using LY = Layout<H, KT_IN, NT_OUT>;
@@ -339,12 +356,12 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_bwd(const Args a) {
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   constexpr int KTO = LY::OUT_ROWS / 16;
-  const int64_t n_tiles = (a.P + 15) / 16;
+  const int64_t n_tiles = (a.Ppad + 15) / 16;
   const int64_t wstride = (int64_t)gridDim.x * (THREADS / 32);
   for (int64_t tile = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); tile < n_tiles; tile += wstride) {
     const int64_t p0 = tile * 16;
     uint32_t ga[H / 8], gb[H / 8];      // ReLU gate words of the layer about to be gated
-    load_gate<H / 8>(a.hplanes + (size_t)(a.n_hidden - 1) * a.P * H, H, p0, a.P, ga, gb, lane);
+    load_gate<H / 8>(a.hplanes + (size_t)(a.n_hidden - 1) * a.Pcap * H, H, p0, a.P, ga, gb, lane);
     // ---- dZ of the output layer
     uint32_t dzo[KTO][4];
 #pragma unroll
@@ -371,25 +388,25 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_bwd(const Args a) {
           }
           dzo[k][2 * h + r] = pack2(v[0], v[1]);
         }
-    store_plane<KTO>(dzo, a.dz_out, LY::OUT_ROWS, p0, a.P, lane);
+    store_plane<KTO>(dzo, a.dz_out, LY::OUT_ROWS, p0, a.P, lane, a.Ppad);
     // ---- last hidden layer
     uint32_t dz[H / 16][4];
     {
       float c[H / 8][4] = {};
       gemm_dgrad<H / 8, KTO>(c, dzo, sm + LY::wo, LY::SH, lane);
       apply_gate<H / 8>(c, ga, gb);
-      if (a.n_hidden > 1) load_gate<H / 8>(a.hplanes + (size_t)(a.n_hidden - 2) * a.P * H, H, p0, a.P, ga, gb, lane);
+      if (a.n_hidden > 1) load_gate<H / 8>(a.hplanes + (size_t)(a.n_hidden - 2) * a.Pcap * H, H, p0, a.P, ga, gb, lane);
       c_to_a<H / 8, false>(c, dz);
-      store_plane<H / 16>(dz, a.dz_h + (size_t)(a.n_hidden - 1) * a.P * H, H, p0, a.P, lane);
+      store_plane<H / 16>(dz, a.dz_h + (size_t)(a.n_hidden - 1) * a.Pcap * H, H, p0, a.P, lane, a.Ppad);
     }
 #pragma unroll 1
     for (int l = a.n_hidden - 1; l >= 1; --l) {
       float c[H / 8][4] = {};
       gemm_dgrad<H / 8, H / 16>(c, dz, sm + LY::wh + (l - 1) * H * LY::SH, LY::SH, lane);
       apply_gate<H / 8>(c, ga, gb);
-      if (l > 1) load_gate<H / 8>(a.hplanes + (size_t)(l - 2) * a.P * H, H, p0, a.P, ga, gb, lane);
+      if (l > 1) load_gate<H / 8>(a.hplanes + (size_t)(l - 2) * a.Pcap * H, H, p0, a.P, ga, gb, lane);
       c_to_a<H / 8, false>(c, dz);
-      store_plane<H / 16>(dz, a.dz_h + (size_t)(l - 1) * a.P * H, H, p0, a.P, lane);
+      store_plane<H / 16>(dz, a.dz_h + (size_t)(l - 1) * a.Pcap * H, H, p0, a.P, lane, a.Ppad);
     }
     if (a.g_x0 || a.g_x1) {
       float c[2 * KT_IN][4] = {};
@@ -437,6 +454,7 @@ struct WgArgs {
   WgLayer L[MAX_HID + 1];
   int64_t P;
   const float* scale;                  // device: the dZ planes hold S * dZ (b2n_fmlp_bwd); results are divided by S.  null: 1
+  const int* rows;                     // optional device-side row count
 };
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, bool valid) {
@@ -459,7 +477,9 @@ __device__ __forceinline__ void wg_load_tile(const WgLayer& L, int64_t p0, int64
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(WG_THREADS) k_fmlp_wgrad(const WgArgs a) {
+__global__ void __launch_bounds__(WG_THREADS) k_fmlp_wgrad(const WgArgs a_in) {
+  WgArgs a = a_in;
+  a.P = clamp_rows(a_in.P, a_in.rows);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   op16* sm = reinterpret_cast<op16*>(smem_raw);
   const WgLayer& L = a.L[blockIdx.y];
@@ -585,6 +605,7 @@ static int fill_args(Args* a, bool need_inputs, const float* x0, int ld0, int d0
     a->W[l] = W[l], a->ldw[l] = ldw[l], a->b[l] = b ? b[l] : nullptr;
   }
   a->n_hidden = n_hidden, a->out_dim = out_dim, a->out_act = out_act, a->P = P;
+  a->rows = g_active_rows, a->Ppad = P;
   return B2N_OK;
 }
 
@@ -631,7 +652,7 @@ extern "C" int b2n_fmlp_bwd(int d0, int d1, int hidden, int n_hidden, const floa
   {
     const int64_t n = P * out_dim;
     const unsigned grid = (unsigned)((n + 1023) / 1024 < (int64_t)kSMs * 8 ? (n + 1023) / 1024 : (int64_t)kSMs * 8);
-    k_fmlp_absmax<<<grid, 256, 0, st>>>(g_y, ldgy, out_dim, P, a.work);
+    k_fmlp_absmax<<<grid, 256, 0, st>>>(g_y, ldgy, out_dim, P, a.work, g_active_rows);
   }
   const bool small_in = d0 + d1 <= 32, small_out = out_dim <= 16;
   if (hidden == 64) {
@@ -660,7 +681,7 @@ extern "C" int b2n_fmlp_wgrad(int n_layers, const void* const* dz, const int* ld
     a.L[l] = WgLayer{(const op16*)dz[l], ldz[l], rows[l], (const op16*)in[l], ldi[l], k[l], dW[l], lddw[l], rows_valid[l],
                      k_valid[l], db[l]};
   }
-  a.P = P, a.scale = scale;
+  a.P = P, a.scale = scale, a.rows = g_active_rows;
   cudaFuncSetAttribute(k_fmlp_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WG_SMEM);
   const int64_t n_tiles = (P + WG_TILE - 1) / WG_TILE;
   dim3 grid((unsigned)(n_tiles < kSMs ? n_tiles : kSMs), (unsigned)n_layers);

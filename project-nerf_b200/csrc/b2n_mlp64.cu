@@ -219,7 +219,8 @@ template <int POS_K>
 __global__ void __launch_bounds__(MLP_THREADS, 2)
 k_instant_fwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __restrict__ dirs,
               const float* __restrict__ bands, int L_dir, const float* __restrict__ sp, const float* __restrict__ cp,
-              int64_t P, float* __restrict__ rgb, float* __restrict__ sigma) {
+              int64_t P, float* __restrict__ rgb, float* __restrict__ sigma, const int* __restrict__ rows) {
+  P = clamp_rows(P, rows);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   op16* sm = reinterpret_cast<op16*>(smem_raw);
   constexpr MlpSmem L = weight_layout<POS_K>();
@@ -398,8 +399,10 @@ __device__ __forceinline__ void flush_acc(const float (&acc)[NTk][4], float* __r
 
 // max |g| over the incoming gradients as float bits (non-negative floats order like unsigned integers; a NaN has the
 // largest bit pattern, so a non-finite gradient anywhere is visible in the result)
-__global__ void __launch_bounds__(256) k_grad_absmax(const float* __restrict__ a, int64_t na, const float* __restrict__ b,
-                                                     int64_t nb, unsigned int* __restrict__ out) {
+__global__ void __launch_bounds__(256) k_grad_absmax(const float* __restrict__ a, const float* __restrict__ b, int64_t P,
+                                                     unsigned int* __restrict__ out, const int* __restrict__ rows) {
+  P = clamp_rows(P, rows);
+  const int64_t na = 3 * P, nb = P;              // a = g_rgb [P,3], b = g_sigma [P]
   unsigned int m = 0u;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = i < na ? __ldg(a + i) : __ldg(b + (i - na));
@@ -427,7 +430,9 @@ __global__ void __launch_bounds__(MLP_THREADS)
 k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __restrict__ dirs,
               const float* __restrict__ bands, int L_dir, const float* __restrict__ sp, const float* __restrict__ cp,
               int64_t P, const float* __restrict__ g_rgb, const float* __restrict__ g_sigma, float* __restrict__ g_x,
-              int ldg, float* __restrict__ g_sp, float* __restrict__ g_cp, const unsigned int* __restrict__ absmax) {
+              int ldg, float* __restrict__ g_sp, float* __restrict__ g_cp, const unsigned int* __restrict__ absmax,
+              const int* __restrict__ rows) {
+  P = clamp_rows(P, rows);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const float gscale = grad_scale_from(__ldg(absmax));
   const float inv_s = 1.f / gscale;
@@ -674,13 +679,13 @@ extern "C" int b2n_instant_mlp_fwd(const float* x_enc, int ldx, int pos_dim, con
     cudaFuncSetAttribute(k_instant_fwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = persistent_grid((const void*)k_instant_fwd<32>, MLP_THREADS, smem, block_tiles);
     k_instant_fwd<32><<<grid, MLP_THREADS, smem, st>>>(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params,
-                                                       color_params, P, rgb, sigma);
+                                                       color_params, P, rgb, sigma, g_active_rows);
   } else {
     constexpr size_t smem = fwd_smem_bytes<64>();
     cudaFuncSetAttribute(k_instant_fwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = persistent_grid((const void*)k_instant_fwd<64>, MLP_THREADS, smem, block_tiles);
     k_instant_fwd<64><<<grid, MLP_THREADS, smem, st>>>(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params,
-                                                       color_params, P, rgb, sigma);
+                                                       color_params, P, rgb, sigma, g_active_rows);
   }
   return check_launch("b2n_instant_mlp_fwd");
 }
@@ -702,7 +707,7 @@ extern "C" int b2n_instant_mlp_bwd(const float* x_enc, int ldx, int pos_dim, con
   {
     const int64_t n = 4 * P;
     const unsigned grid = (unsigned)((n + 1023) / 1024 < (int64_t)kSMs * 8 ? (n + 1023) / 1024 : (int64_t)kSMs * 8);
-    k_grad_absmax<<<grid, 256, 0, st>>>(g_rgb, 3 * P, g_sigma, P, absmax);
+    k_grad_absmax<<<grid, 256, 0, st>>>(g_rgb, g_sigma, P, absmax, g_active_rows);
   }
   if (pos_dim <= 32) {
     constexpr size_t smem = bwd_smem_bytes<32>();
@@ -710,14 +715,14 @@ extern "C" int b2n_instant_mlp_bwd(const float* x_enc, int ldx, int pos_dim, con
     const int grid = persistent_grid((const void*)k_instant_bwd<32>, MLP_THREADS, smem, tiles);
     k_instant_bwd<32><<<grid, MLP_THREADS, smem, st>>>(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params,
                                                        color_params, P, g_rgb, g_sigma, g_x_enc, ldg, g_sigma_params,
-                                                       g_color_params, absmax);
+                                                       g_color_params, absmax, g_active_rows);
   } else {
     constexpr size_t smem = bwd_smem_bytes<64>();
     cudaFuncSetAttribute(k_instant_bwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = persistent_grid((const void*)k_instant_bwd<64>, MLP_THREADS, smem, tiles);
     k_instant_bwd<64><<<grid, MLP_THREADS, smem, st>>>(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params,
                                                        color_params, P, g_rgb, g_sigma, g_x_enc, ldg, g_sigma_params,
-                                                       g_color_params, absmax);
+                                                       g_color_params, absmax, g_active_rows);
   }
   return check_launch("b2n_instant_mlp_bwd");
 }

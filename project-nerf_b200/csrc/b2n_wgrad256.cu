@@ -48,6 +48,7 @@ struct Args {
   int* err;
   int fp16;                 // operand planes are IEEE fp16 (the fused 128-wide MLPs) instead of bf16 (the 256-wide decoder)
   const float* scale;       // device scalar S: the dZ planes hold S * dZ, results are divided by S (null: 1)
+  const int* rows;          // optional device-side row count; rows up to the next multiple of 64 behind it are zero in the planes
 };
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -89,10 +90,11 @@ k_wgrad256(const Args a, const __grid_constant__ CUtensorMap tm0, const __grid_c
   const Job job = a.job[blockIdx.y];
   const bool gemm = job.b_map >= 0;
   const int dz_blocks = 2 * job.m_halves, in_blocks = gemm ? job.n_cols >> 6 : 0;
+  const int64_t P_eff = clamp_rows(a.P, a.rows);
   const int64_t row_begin = (int64_t)blockIdx.x * a.rows_per_split;
   int64_t row_end = row_begin + a.rows_per_split;
-  if (row_end > a.P) row_end = a.P;
-  const int n_steps = row_begin < a.P ? (int)((row_end - row_begin + TP - 1) / TP) : 0;
+  if (row_end > P_eff) row_end = P_eff;
+  const int n_steps = row_begin < P_eff ? (int)((row_end - row_begin + TP - 1) / TP) : 0;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < N_STAGES; ++i) {
@@ -324,7 +326,7 @@ extern "C" int b2n_fmlp_wgrad_tc(const void* dz_h, const void* dz_out, const voi
   for (int l = 1; l < n_hidden; ++l)
     a.job[n++] = Job{0, l, 1, 1, l - 1, 128, dWh + (size_t)(l - 1) * 16384, db_h + (size_t)l * 128, 128};
   a.job[n++] = Job{1, n_hidden - 1, 1, 3, 0, 64, dWoT, nullptr, 0};
-  a.P = P, a.err = err_flag, a.fp16 = 1, a.scale = scale;
+  a.P = P, a.err = err_flag, a.fp16 = 1, a.scale = scale, a.rows = g_active_rows;
   int splits = (2 * kSMs) / n;
   const int64_t max_splits = (P + TP - 1) / TP;
   if (splits > max_splits) splits = (int)max_splits;

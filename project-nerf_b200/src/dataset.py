@@ -147,19 +147,8 @@ class BlenderDataset:
                      batch_size, len(self), self.H, self.W, float(np.float32(self.focal)), float(self.scene_scale),
                      ptr(rays_o), ptr(rays_d), ptr(target), ptr(t_out), stream())
             return rays_o, rays_d, target, t_out
-        # host path (data preparation only; used when the caller asks for CPU tensors)
-        c2w = self.poses[img_idx]
-        dirs = torch.stack([(pix_x - self.W * 0.5) / self.focal, -(pix_y - self.H * 0.5) / self.focal,
-                            -torch.ones_like(pix_x)], dim=-1)
-        rays_d = torch.bmm(c2w[:, :3, :3], dirs.unsqueeze(-1)).squeeze(-1)
-        rays_o = c2w[:, :3, 3]
-        if self.scene_scale != 1.0:
-            rays_o = rays_o * self.scene_scale
-        target = torch.from_numpy(self._rgba8[img_idx.numpy(), pix_y.numpy(), pix_x.numpy()].astype(np.float32) / 255.0)
-        rays_d = rays_d / torch.norm(rays_d, dim=-1, keepdim=True)
-        t = self._times_tensor()
-        t_out = t[img_idx].unsqueeze(-1) if (with_time and t is not None) else None
-        return rays_o, rays_d, target, t_out
+        raise ValueError("sample_random_rays needs a CUDA device: this package has no CPU path for the training-ray "
+                         "sampler (b2n_sample_rays); image-sized host tensors come from get_image_rays")
 
     def sample_random_rays(self, batch_size, device):
         rays_o, rays_d, target, _ = self._sample(batch_size, device, with_time=False)

@@ -14,7 +14,7 @@ from torch import nn
 
 import b2n
 from b2n import march as _march
-from b2n._lib import call, ptr, stream
+from b2n._lib import active_rows, call, ptr, require_cuda, stream
 
 
 class DensityGrid(nn.Module):
@@ -30,11 +30,17 @@ class DensityGrid(nn.Module):
 
     # the kernels read a bitfield; rebuild it whenever binary_grid was replaced or written
     def bits(self):
+        """The cache is keyed on the tensor OBJECT (a weak reference: a re-assigned ``binary_grid`` is a different
+        object even when the allocator hands it the freed block of the old one at version 0), its storage pointer and
+        its in-place version counter."""
+        import weakref
         bg = self.binary_grid
         key = (bg.data_ptr(), bg._version, str(bg.device))
-        if self._bits is None or self._bits_key != key:
+        owner = self._bits_owner() if getattr(self, "_bits_owner", None) is not None else None
+        if self._bits is None or self._bits_key != key or owner is not bg:
             self._bits = _march.pack_occupancy(bg)
             self._bits_key = key
+            self._bits_owner = weakref.ref(bg)
         return self._bits
 
     def _lattice(self, device):
@@ -84,7 +90,13 @@ class DensityGrid(nn.Module):
         else:
             cur = sweep(None)
         cur = cur.contiguous()
-        grid = self.grid.contiguous().clone() if mode in ("part3", "part4") else torch.empty_like(self.grid)
+        # every buffer the kernel touches lives on the device of the sweep (the registered buffers may still sit on
+        # the CPU or on another GPU when the caller never moved the grid: the reference simply rebinds them, :122-128)
+        if mode in ("part3", "part4"):
+            grid = self.grid.to(cur.device, torch.float32).contiguous().clone()
+        else:
+            grid = torch.empty(R, R, R, device=cur.device)
+        require_cuda(cur, grid)
         binary = torch.empty(R, R, R, device=cur.device, dtype=torch.bool)
         bits = torch.empty((R ** 3 + 31) // 32, device=cur.device, dtype=torch.int32)
         n_active = torch.empty(1, device=cur.device, dtype=torch.int64)
@@ -92,9 +104,13 @@ class DensityGrid(nn.Module):
              float(self.threshold), ptr(binary.view(torch.uint8)), ptr(bits), ptr(n_active), stream())
         self.grid = grid
         self.binary_grid = binary
+        import weakref
         self._bits, self._bits_key = bits, (binary.data_ptr(), binary._version, str(binary.device))
+        self._bits_owner = weakref.ref(self.binary_grid)
         # binary.float().mean(): fp32 mean of 0/1 values, then .item()
-        return float(np.float32(n_active.item()) / np.float32(R ** 3))
+        ratio = float(np.float32(n_active.item()) / np.float32(R ** 3))
+        b2n.check_errors()                     # a host sync just happened: look at every outstanding tcgen05 abort flag
+        return ratio
 
     def get_active_mask(self, pts):
         return _march.active_mask(pts, self.bits(), self.resolution, self.bound)
@@ -142,15 +158,17 @@ def render_rays(model, rays_o, rays_d, near, far, n_samples, perturb, density_gr
     else:
         m = _march.march(rays_o, rays_d, near, far, n_samples, u, times=ray_times)
 
-    if dynamic:
-        rgb, sigma, delta_x = model(m.pts, m.dirs, t=m.times)
-    else:
-        rgb, sigma = model(m.pts, m.dirs)
-        delta_x = None
-    want_dx = times is not None and dynamic and delta_x is not None
-    color, depth, acc, mean_dx = b2n.composite(rgb.float(), sigma.float(), m.z, rays_d, bg=bg_color,
-                                               dx=delta_x.float() if want_dx else None,
-                                               mask_words=m.mask_words, ray_offset=m.ray_offset)
+    # static mode (b2n.march.set_static_capacity): the number of valid rows of the compact buffers lives on the device
+    with active_rows(m.n_dev):
+        if dynamic:
+            rgb, sigma, delta_x = model(m.pts, m.dirs, t=m.times)
+        else:
+            rgb, sigma = model(m.pts, m.dirs)
+            delta_x = None
+        want_dx = times is not None and dynamic and delta_x is not None
+        color, depth, acc, mean_dx = b2n.composite(rgb.float(), sigma.float(), m.z, rays_d, bg=bg_color,
+                                                   dx=delta_x.float() if want_dx else None,
+                                                   mask_words=m.mask_words, ray_offset=m.ray_offset)
     if times is None:
         return color, depth, acc
     extras = {}
@@ -167,4 +185,6 @@ def render_image(model, rays_o, rays_d, near, far, n_samples, chunk, white_bkgd)
         out[i:i + chunk] = render_rays(model=model, rays_o=rays_o[i:i + chunk], rays_d=rays_d[i:i + chunk],
                                        near=near, far=far, n_samples=n_samples, perturb=False,
                                        white_bkgd=white_bkgd)[0]
+    if not torch.cuda.is_current_stream_capturing():
+        b2n.check_errors()                     # the image is about to be read by the caller: no silent garbage
     return out.view(h, w, 3)

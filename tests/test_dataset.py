@@ -24,8 +24,15 @@ def test_host_path_matches_reference(tag, scale):
     g = load(f"dataset_{tag}_s{scale}")
     ds = _make(tag, scale)
     assert (ds.H, ds.W, len(ds)) == (int(g["H"]), int(g["W"]), 6) and abs(ds.focal - g["focal"]) < 1e-9
+    # the product has no CPU sampler (it raises); the host restatement lives in the oracle and is pinned here against
+    # the reference's vectors with the product's own pixel picks (same torch.randint stream as the reference)
+    with pytest.raises(ValueError, match="no CPU path"):
+        ds.sample_random_rays(257, "cpu")
+    from oracle import nerf_oracle as O
     torch.manual_seed(77)
-    out = ds.sample_random_rays(257, "cpu")
+    picks = ds._draw(257, "cpu")
+    out = O.sample_rays_host(ds.poses, ds._rgba8, ds._times_tensor() if tag == "dynamic" else None, *picks, ds.H, ds.W,
+                             ds.focal, scale)
     assert torch.equal(out[2], g["target"])                       # same pixels picked, same uint8/255 values
     assert torch.equal(out[0], g["rays_o"]) and rel_err(out[1], g["rays_d"]) < 1e-6
     img = ds.get_image_rays(3, "cpu")

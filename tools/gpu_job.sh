@@ -6,7 +6,7 @@ OUT=gpurun_out
 mkdir -p $OUT
 has() { [[ " $PARTS " == *" $1 "* ]]; }
 if has tests; then
-  timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider 2>&1 | tail -150 > $OUT/${TAG}_tests.log
+  timeout 1500 python -m pytest tests -m gpu -q -p no:cacheprovider > $OUT/${TAG}_tests.log 2>&1
   cp $OUT/parity_maxima.json $OUT/${TAG}_parity_maxima.json 2>/dev/null
 fi
 if has smoke; then timeout 600 python __graft_entry__.py smoke > $OUT/${TAG}_smoke.log 2>&1; fi

@@ -356,7 +356,7 @@ def bench_dynamic(dev, name, steps=10, warm=4, occupancy="dense", world=1, rank=
         grid = DensityGrid(resolution=spec["grid"][0], bound=1.5, threshold=spec["grid"][1]).to(dev)
         if occupancy == "sparse":
             grid.binary_grid = synthetic.ball_occupancy(spec["grid"][0], 1.5).to(dev)
-    reducer = GradAllReducer(model, world) if world > 1 else None
+    reducer = GradAllReducer(model, world, direct=True) if world > 1 else None      # no TV term in the loss below: FusedAdamW carries it
     pool = [tuple(t.to(dev) for t in synthetic.random_rays(B, seed=70 + i + 1000 * rank, n_views=150, with_time=True))
             for i in range(3)]
     bg = torch.ones(3, device=dev)
@@ -532,7 +532,10 @@ def main():
 
     opt = torch.optim.AdamW(model.parameters(), lr=LR, weight_decay=WEIGHT_DECAY)
     sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, T_max=TRAIN_ITERS, eta_min=ETA_MIN)
-    reducer = GradAllReducer(model, world)      # flat gradient buffer: one memset, one all-reduce
+    # flat gradient buffer: one memset, all-reduce of element ranges as they become final.  The headline step keeps the
+    # reference's TV term in the loss (an autograd-side gradient on the table), so its table is reduced from the
+    # post-accumulate hook; the fused-optimizer leg (TV inside FusedAdamW) uses the direct sinks
+    reducer = GradAllReducer(model, world)
     bg = torch.ones(3, device=dev)
 
     n_pool = 3
@@ -620,6 +623,10 @@ def main():
             fopt = b2n.optim.FusedAdamW(
                 [{"params": list(model.representation.parameters()), "tv_weight": TV_WEIGHT, "max_norm": 1.0},
                  {"params": list(model.decoder.parameters()), "max_norm": 1.0}], lr=LR, weight_decay=WEIGHT_DECAY)
+
+            if world > 1:
+                reducer.remove_hooks()
+                reducer = GradAllReducer(model, world, direct=True)     # table gradient written in place, fine levels reduced early
 
             def fused_step(batch):
                 rays_o, rays_d, rgba = batch

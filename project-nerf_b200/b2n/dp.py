@@ -37,33 +37,43 @@ class GradAllReducer:
     gradients is one memset and averaging them over ranks is a handful of collectives over element RANGES of that
     buffer.  Ranges are reduced asynchronously as soon as they are final:
 
-    * ``direct=True`` (default): hash tables (flat 1-D parameters of >= ``big_numel`` elements that reach
-      ``b2n.hash_encode``) get a ``GradSink`` -- the table-gradient kernels accumulate straight into the flat buffer
-      and announce the fine levels' slice before the coarse levels are scattered (ops._HashEncode.backward);
-    * other large parameters are reduced from a post-accumulate-grad hook;
+    * ``direct=True``: hash tables (flat 1-D parameters of >= ``big_numel`` elements that reach ``b2n.hash_encode``)
+      get a ``GradSink`` -- the table-gradient kernels accumulate straight into the flat buffer and announce the fine
+      levels' slice before the coarse levels are scattered (ops._HashEncode.backward).  CONTRACT: such a table receives
+      gradient ONLY through ``b2n.hash_encode``; a loss term that touches the table through autograd (the reference's
+      ``mean|params[1:] - params[:-1]|`` TV term, run.py:614-616) would add into a range whose reduction is already in
+      flight -- it is refused with an error.  Put the TV term into ``b2n.optim.FusedAdamW(tv_weight=...)`` instead, or
+      keep the default;
+    * ``direct=False`` (default): every large parameter is reduced from its post-accumulate-grad hook, which autograd
+      runs once all contributions to that parameter -- direct kernels and autograd alike -- are in;
     * ``allreduce()`` reduces whatever range is still untouched, then waits for everything.
 
     ONE backward per step reaches the hooks; wrap earlier backward passes of an accumulation step in ``no_sync()``."""
 
     def __init__(self, module: torch.nn.Module, world_size: int = None, overlap: bool = True,
-                 big_numel: int = 1 << 22, direct: bool = True):
+                 big_numel: int = 1 << 22, direct: bool = False):
         params = [p for p in module.parameters() if p.requires_grad]
         self.world = world_size if world_size is not None else (dist.get_world_size() if dist.is_initialized() else 1)
         small = [p for p in params if p.numel() < big_numel]
         big = [p for p in params if p.numel() >= big_numel]
         self.params = small + big
-        total = sum(p.numel() for p in self.params)
+        # every parameter's slice starts on a 256-byte boundary: the kernels that write gradients in place (vector
+        # red.global of the hash-table gradient, the 16-byte accesses of FusedAdamW) need aligned bases
+        ALIGN = 64
+        offsets, off = [], 0
+        for p in self.params:
+            offsets.append(off)
+            off += (p.numel() + ALIGN - 1) // ALIGN * ALIGN
+        total = off
         ref = self.params[0]
         self.flat = torch.zeros(total, device=ref.device, dtype=torch.float32)
-        off = 0
         self._views, self._offset = {}, {}
-        for p in self.params:
+        for p, off in zip(self.params, offsets):
             n = p.numel()
             p.grad = self.flat[off:off + n].view_as(p)
             self._views[p] = self.flat[off:off + n]
             self._offset[p] = off
-            off += n
-        self.n_small = sum(p.numel() for p in small)
+        self.n_small = offsets[len(small)] if big else total
         self.nbytes = total * 4
         self._pending = []          # (work, start, stop) of ranges handed to async collectives this step
         self._hooks = []
@@ -71,15 +81,19 @@ class GradAllReducer:
         self._suspended = False
         self.overlap = bool(overlap and big and self.world > 1 and dist.is_initialized())
         if self.overlap:
+            # only hash tables (the flat parameter of a HashGridEncoding: reached through b2n.hash_encode /
+            # hash_tri_blend, whose backward implements the sink protocol) can take gradients in place
+            tables = {id(m.params) for m in module.modules() if type(m).__name__ == "HashGridEncoding"}
             for p in big:
-                if direct == "always" or (direct and p.dim() == 1 and p.is_cuda):
+                if direct == "always" or (direct and id(p) in tables and p.is_cuda):
                     sink = GradSink(self._views[p], self._on_sink_ready)
                     sink.offset = self._offset[p]
                     p._b2n_grad_sink = sink
                     self._sinks.append((p, sink))
-                    # no hook for a table with a sink: autograd fires post-accumulate hooks even for the None gradient
-                    # the direct path returns, which cannot be told from a real accumulation.  Contract: such a table
-                    # receives gradient only through b2n.hash_encode (true for every model of src/core.py)
+                    # a tensor hook sees every DEFINED gradient autograd delivers to the leaf (the direct path returns
+                    # None): that is a contribution outside the contract -- refuse it rather than race with the
+                    # reduction that may already be in flight
+                    self._hooks.append(p.register_hook(self._refuse_autograd_gradient))
                     continue
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad_ready))
 
@@ -104,6 +118,14 @@ class GradAllReducer:
             raise RuntimeError("GradAllReducer: a gradient range was announced twice in one step (two backward passes "
                                "without reducer.no_sync() around the first?)")
         self._start(sink.offset + lo, sink.offset + hi)
+
+    @staticmethod
+    def _refuse_autograd_gradient(grad):
+        if grad is None:            # what the direct path returns: nothing came through autograd
+            return None
+        raise RuntimeError("GradAllReducer(direct=True): a hash table with a direct gradient sink received a gradient "
+                           "through autograd (a TV / regularisation term on the raw table in the loss?).  Move that "
+                           "term into b2n.optim.FusedAdamW(tv_weight=...) or build the reducer with direct=False")
 
     def _on_grad_ready(self, p):
         """Hook path (a large parameter whose gradient came through autograd's accumulation, e.g. a hash table used by

@@ -161,9 +161,14 @@ class _HashTriBlend(torch.autograd.Function):
 
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, x, t, t0, t1, t2, geom: HashGeometry, bound: float):
+    def forward(ctx, x, t, t0, t1, t2, geom: HashGeometry, bound: float, sinks):
         require_cuda(x, t, t0, t1, t2)
         ctx.rows = current_rows()
+        # data-parallel direct path (b2n.dp.GradSink, see _HashEncode): per-table in-place accumulation
+        ctx.sinks = [sk if (sk is not None and ctx.needs_input_grad[2 + i]) else None for i, sk in enumerate(sinks)]
+        for sk in ctx.sinks:
+            if sk is not None:
+                sk.uses += 1
         x, t, t0, t1, t2 = _c(x), _c(t).reshape(-1), _c(t0), _c(t1), _c(t2)
         if geom.n_features != 2:
             raise ValueError("hash_tri_blend needs 2 features per level")
@@ -187,18 +192,26 @@ class _HashTriBlend(torch.autograd.Function):
         if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
             raise RuntimeError("hash_tri_blend has no gradient w.r.t. positions or times")
         g = _c(g)
-        grads = [torch.zeros(shape, device=x.device) if ctx.needs_input_grad[2 + i] else None
-                 for i, shape in enumerate(ctx.shapes)]
+        sinks = ctx.sinks
+        grads = [(sinks[i].view if sinks[i] is not None else torch.zeros(shape, device=x.device))
+                 if ctx.needs_input_grad[2 + i] else None for i, shape in enumerate(ctx.shapes)]
         if any(gr is not None for gr in grads):
             call("b2n_hash_tri_bwd", ptr(x), ptr(t), x.shape[0], float(ctx.bound), geom.c_levels, geom.n_levels, ptr(g),
                  geom.out_dim, ptr(grads[0]), ptr(grads[1]), ptr(grads[2]), stream(),
                  work=(x.shape[0] * (16 + geom.n_levels * 2 * 4 * (1 + 2 * 2 * 8)), 0.0))
-        return None, None, grads[0], grads[1], grads[2], None, None
+        for i, sk in enumerate(sinks):
+            if sk is not None:
+                sk.uses -= 1
+                if sk.uses <= 0:
+                    sk.on_ready(sk, 0, sk.view.numel())
+                grads[i] = None                       # accumulated in place: nothing for autograd to add
+        return None, None, grads[0], grads[1], grads[2], None, None, None
 
 
 def hash_tri_blend(x, t, tables: Sequence[torch.Tensor], geom: HashGeometry, bound: float):
     """Tent-weighted blend of three hash grids sharing ``geom`` at per-point times t in [0, 1]: [P, L*2]."""
-    return _HashTriBlend.apply(x, t, tables[0], tables[1], tables[2], geom, bound)
+    return _HashTriBlend.apply(x, t, tables[0], tables[1], tables[2], geom, bound,
+                               [getattr(tb, "_b2n_grad_sink", None) for tb in tables])
 
 
 # ----------------------------------------------------------------------------

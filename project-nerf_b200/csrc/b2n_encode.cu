@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(256)
 k_hash_fwd_pair(const float* __restrict__ x, int64_t P, float bound, float two_bound, const float2* __restrict__ table,
                 const Levels lv, int nl, float* __restrict__ out, int ld, int col0, const int* __restrict__ rows) {
   P = clamp_rows(P, rows);
+  if ((int64_t)blockIdx.x * (blockDim.x >> 1) >= P) return;      // whole block behind the (device-side) row count
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t p = tid >> 1;
   const int s = threadIdx.x & 1;
@@ -366,6 +367,7 @@ k_hash_bwd_table_pair(const float* __restrict__ x, int64_t P, float bound, float
   P = clamp_rows(P, rows);
   // levels [lbeg, nl) of the table (lbeg a multiple of 4): a caller that overlaps the gradient all-reduce of the fine
   // levels with the scatter of the coarse ones launches this kernel once per level window
+  if ((int64_t)blockIdx.x * (blockDim.x >> 1) >= P) return;      // whole block behind the (device-side) row count
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t p = tid >> 1;
   const int lane = threadIdx.x & 31, s = lane & 1, pi = lane >> 1;     // pi: point index inside the warp (0..15)
@@ -651,6 +653,7 @@ extern "C" int b2n_hash_fwd(const float* x, int64_t P, float bound, const float*
   B2N_REQUIRE(fill_levels(levels_host, L, &lv) == 0, "bad level table");
   if (P == 0) return B2N_OK;
   B2N_REQUIRE(x && table && out, "null pointer");
+  B2N_REQUIRE((reinterpret_cast<uintptr_t>(table) & 15) == 0, "table must be 16-byte aligned (vector gathers)");
   B2N_REQUIRE(ld_out >= col0 + L * F && col0 >= 0, "output row too narrow");
   const unsigned grid = grid_for(P * L, 256);
   const float tb = 2.0f * bound;
@@ -679,6 +682,8 @@ extern "C" int b2n_hash_bwd(const float* x, int64_t P, float bound, const float*
   B2N_REQUIRE(x && g_out, "null pointer");
   B2N_REQUIRE(ld_g >= col0 + L * F && col0 >= 0, "gradient row too narrow");
   B2N_REQUIRE(!g_x || table, "input gradient needs the table");
+  B2N_REQUIRE((reinterpret_cast<uintptr_t>(g_table) & 15) == 0 && (reinterpret_cast<uintptr_t>(table) & 15) == 0,
+              "table / g_table must be 16-byte aligned (vector reductions)");
   const float tb = 2.0f * bound;
   cudaStream_t st = (cudaStream_t)stream;
   if (g_table && F == 2 && ((g_hash_variant & 2) || windowed)) {

@@ -162,6 +162,10 @@ def _sink_worker(rank, world, port, out):
     with pytest.raises(RuntimeError, match="no_sync"):
         model(x[a:b]).pow(2).mean().backward()
     red.allreduce()
+    # the contract of the direct path: no autograd-side gradient on a table with a sink
+    red.zero_grad()
+    with pytest.raises(RuntimeError, match="direct=True"):
+        (model(x[a:b]).pow(2).mean() + model.table.abs().mean()).backward()
     dist.destroy_process_group()
 
 

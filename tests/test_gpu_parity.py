@@ -982,3 +982,91 @@ def test_nerf_mlp_wgrad_tcgen05_vs_torch(mods, Pn, kx):
     # accumulation semantics: a second call doubles the result
     call("b2n_nerf_mlp_wgrad", *args)
     assert rel_err(dW[0], 2 * (dz[8].float().t() @ H[0].float())) < 2e-5
+
+
+# ------------------------------------------------------------------ render_image / render_image_safe
+def _image_case(mods, H=23, W=31):
+    """a full 8x256 vanilla field and the rays of one small synthetic view"""
+    from b2n import synthetic
+    sd = full_nerf_state_dict(31)
+    model = _model_from(mods, dict(mode="part2_nerf", L_embed=10, L_embed_dir=4), sd).eval()
+    pose = synthetic.hemisphere_poses(3, seed=4)[1]
+    ro, rd = synthetic.image_rays(pose, H=H, W=W)
+    return model, sd, ro.view(H, W, 3), rd.view(H, W, 3)
+
+
+def test_render_image_chunked_equals_unchunked_equals_oracle(mods):
+    """render_image (reference src/renderer.py:387-418): [H,W,3] in, chunk loop over render_rays(perturb=False), [H,W,3]
+    out.  A ragged last chunk, chunk = 1 ray short of / beyond the image and one single chunk all give the same image,
+    and that image is the CPU oracle's (fp32 path, 1e-4)."""
+    from oracle import nerf_oracle as O
+    model, sd, ro, rd = _image_case(mods)
+    H, W = ro.shape[:2]
+    render_image = mods["renderer"].render_image
+    with torch.no_grad():
+        whole = render_image(model=model, rays_o=cu(ro), rays_d=cu(rd), near=2.0, far=6.0, n_samples=48, chunk=10 ** 6,
+                             white_bkgd=True)
+        assert whole.shape == (H, W, 3) and whole.dtype == torch.float32
+        for chunk in (100, H * W - 1, H * W, 7):
+            img = render_image(model=model, rays_o=cu(ro), rays_d=cu(rd), near=2.0, far=6.0, n_samples=48, chunk=chunk,
+                               white_bkgd=True)
+            assert torch.equal(img, whole), chunk                  # per-ray arithmetic does not depend on the batch
+        ref = O.render_rays(O.OracleField(dict(mode="part2_nerf", L_embed=10, L_embed_dir=4), sd), ro.reshape(-1, 3),
+                            rd.reshape(-1, 3), 2.0, 6.0, 48, None, white_bkgd=True)[0].view(H, W, 3)
+    assert record("render_image:rgb_vs_oracle", rel_err(whole.cpu(), ref)) < TOL
+    black = render_image(model=model, rays_o=cu(ro), rays_d=cu(rd), near=2.0, far=6.0, n_samples=48, chunk=256,
+                         white_bkgd=False)
+    assert float((whole - black).abs().max()) > 1e-3               # the background flag reaches the compositing
+
+
+def test_render_image_800x800_single_chunk(mods, bf16_mode):
+    """one NeRF-Synthetic-sized frame (640 000 rays x 64 samples = 41 M points) in a single chunk on the tcgen05 decoder;
+    a strided sub-image rendered on its own agrees to the 16-bit class"""
+    from b2n import synthetic
+    sd = full_nerf_state_dict(31)
+    model = _model_from(mods, dict(mode="part2_nerf", L_embed=10, L_embed_dir=4), sd).eval()
+    pose = synthetic.hemisphere_poses(3, seed=4)[2]
+    ro, rd = (t.view(800, 800, 3).to(DEV) for t in synthetic.image_rays(pose))
+    with torch.no_grad():
+        img = mods["renderer"].render_image(model=model, rays_o=ro, rays_d=rd, near=2.0, far=6.0, n_samples=64,
+                                            chunk=800 * 800, white_bkgd=True)
+        sub = mods["renderer"].render_image(model=model, rays_o=ro[::40, ::40].contiguous(), rays_d=rd[::40, ::40].contiguous(),
+                                            near=2.0, far=6.0, n_samples=64, chunk=123, white_bkgd=True)
+    mods["b2n"].check_errors()
+    assert img.shape == (800, 800, 3) and torch.isfinite(img).all()
+    assert float(img.min()) >= 0.0 and float(img.max()) <= 1.0 + 1e-5
+    assert rel_err(img[::40, ::40], sub) < 1e-5
+
+
+def test_render_image_safe_halves_the_chunk_on_oom(mods):
+    """render_image_safe (reference src/utils.py:39-76): a CUDA OOM inside the renderer halves ``chunk`` (not below
+    1024) and retries; any other error and an OOM at the floor propagate."""
+    from src.utils import render_image_safe
+    model, sd, ro, rd = _image_case(mods, H=40, W=64)
+    seen = []
+
+    def flaky(model, rays_o, rays_d, near, far, n_samples, chunk, white_bkgd):
+        seen.append(chunk)
+        if chunk > 2048:
+            raise torch.cuda.OutOfMemoryError("synthetic OOM")
+        return mods["renderer"].render_image(model=model, rays_o=rays_o, rays_d=rays_d, near=near, far=far,
+                                             n_samples=n_samples, chunk=chunk, white_bkgd=white_bkgd)
+
+    with torch.no_grad():
+        img = render_image_safe(flaky, model, cu(ro), cu(rd), 2.0, 6.0, 32, 16384, True)
+        ref = mods["renderer"].render_image(model=model, rays_o=cu(ro), rays_d=cu(rd), near=2.0, far=6.0, n_samples=32,
+                                            chunk=4096, white_bkgd=True)
+    assert seen == [16384, 8192, 4096, 2048] and torch.equal(img, ref)
+
+    def always_oom(**kw):
+        seen.append(kw["chunk"])
+        raise torch.cuda.OutOfMemoryError("synthetic OOM")
+    seen.clear()
+    with pytest.raises(torch.cuda.OutOfMemoryError):
+        render_image_safe(always_oom, model, cu(ro), cu(rd), 2.0, 6.0, 32, 3000, True)
+    assert seen == [3000, 1500, 1024]
+
+    def other(**kw):
+        raise ValueError("not an OOM")
+    with pytest.raises(ValueError):
+        render_image_safe(other, model, cu(ro), cu(rd), 2.0, 6.0, 32, 3000, True)

@@ -220,13 +220,16 @@ int b2n_sigma_head_bwd(const float* h, int ldh, int64_t P, const float* g_sigma,
  *             ACCUMULATES into g_sigma_params / g_color_params (fp32).
  * The backward recomputes the forward; nothing but the inputs is saved.
  * ---------------------------------------------------------------------- */
+/* in_pad_value: what the PADDED input columns of the two FullyFusedMLPs hold (pos_dim .. pad16(pos_dim) of sigma_net,
+ * 16 + dir_dim .. pad16(16 + dir_dim) of color_net): 0 (this package, the oracle) or 1 (checkpoints of an upstream
+ * tiny-cuda-nn whose Network pads its inputs with ones, which makes those weight columns a bias: b2n.checkpoint). */
 int b2n_instant_mlp_fwd(const float* x_enc, int ldx, int pos_dim, const float* dirs, const float* dir_bands,
                         int L_dir, const float* sigma_params, const float* color_params, int64_t P, float* rgb,
-                        float* sigma, b2n_stream_t stream);
+                        float* sigma, float in_pad_value, b2n_stream_t stream);
 int b2n_instant_mlp_bwd(const float* x_enc, int ldx, int pos_dim, const float* dirs, const float* dir_bands,
                         int L_dir, const float* sigma_params, const float* color_params, int64_t P,
                         const float* g_rgb, const float* g_sigma, float* g_x_enc, int ldg, float* g_sigma_params,
-                        float* g_color_params, void* work4, b2n_stream_t stream);
+                        float* g_color_params, void* work4, float in_pad_value, b2n_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Fused small-width ReLU MLPs of the dynamic configs, bf16 tensor-core

@@ -244,15 +244,17 @@ def _matmul_t(h: Tensor, W: Tensor, emulate_bf16, exact_fwd: bool = False, famil
 
 def fused_mlp(x: Tensor, params: Tensor, n_in: int, n_out: int, n_neurons: int,
               n_hidden: int, out_act: str = "None", emulate_bf16=False, first_exact: bool = False,
-              family: str = "fmlp") -> Tensor:
+              family: str = "fmlp", pad_value: float = 0.0) -> Tensor:
     """ReLU MLP without bias terms.  Input columns beyond ``n_in`` are padded
     with ZEROS (SURVEY.md A4 fixes this choice), so the padded weight columns
     never contribute; the padded output rows are computed and sliced away.
-    ``first_exact`` (kernel emulation only): the first layer's forward product is not rounded."""
+    ``first_exact`` (kernel emulation only): the first layer's forward product is not rounded.
+    ``pad_value``: what the padded input columns hold instead -- 1.0 models an upstream tiny-cuda-nn whose Network
+    pads its inputs with ones (unverifiable offline; the padded weight columns then act as a bias)."""
     shapes = fused_mlp_shapes(n_in, n_out, n_neurons, n_hidden)
     h = x
     if shapes[0][1] != n_in:
-        h = F.pad(h, (0, shapes[0][1] - n_in))
+        h = F.pad(h, (0, shapes[0][1] - n_in), value=float(pad_value))
     off = 0
     for li, (r, c) in enumerate(shapes):
         W = params[off:off + r * c].view(r, c).to(h.dtype)
@@ -294,16 +296,17 @@ def nerf_decoder(sd, prefix: str, x: Tensor, d: Tensor, num_layers=8, skip_layer
     return rgb, sigma
 
 
-def instant_decoder(sd, prefix: str, x_enc: Tensor, d_enc: Tensor, hidden=64, emulate_bf16=False):
+def instant_decoder(sd, prefix: str, x_enc: Tensor, d_enc: Tensor, hidden=64, emulate_bf16=False, pad_value: float = 0.0):
     """sigma_net (in->64->16), sigma = softplus(h0-5), color_net on
     cat[h(16), d_enc] (->64->64->3, sigmoid)   (src/decoders.py:136-162).
     Kernel emulation: sigma_net's first layer (the one fed by the hash features) is a split-bf16 product."""
     pos_dim, dir_dim = x_enc.shape[-1], d_enc.shape[-1]
     h = fused_mlp(x_enc, sd[f"{prefix}.sigma_net.params"], pos_dim, 16, hidden, 1, emulate_bf16=emulate_bf16,
-                  first_exact=True, family="instant")
+                  first_exact=True, family="instant", pad_value=pad_value)
     sigma = F.softplus(h[..., 0:1] - 5.0)
     rgb = fused_mlp(torch.cat([h, d_enc], dim=-1), sd[f"{prefix}.color_net.params"],
-                    16 + dir_dim, 3, hidden, 2, out_act="Sigmoid", emulate_bf16=emulate_bf16, family="instant")
+                    16 + dir_dim, 3, hidden, 2, out_act="Sigmoid", emulate_bf16=emulate_bf16, family="instant",
+                    pad_value=pad_value)
     return rgb, sigma
 
 
@@ -335,10 +338,12 @@ def time_modulation(sd, prefix: str, t_feat: Tensor, num_layers=2, emulate_bf16=
     return torch.sigmoid(h)
 
 
-def hash_deform_decoder(sd, prefix: str, hash_feat: Tensor, time_mod: Tensor, hidden=64, emulate_bf16=False):
+def hash_deform_decoder(sd, prefix: str, hash_feat: Tensor, time_mod: Tensor, hidden=64, emulate_bf16=False,
+                        pad_value: float = 0.0):
     """fused MLP (cat -> 64 -> 64 -> 3) * displacement_scale (src/decoders.py:300-318)."""
     h = torch.cat([hash_feat, time_mod], dim=-1)
-    dx = fused_mlp(h, sd[f"{prefix}.deform_net.params"], h.shape[-1], 3, hidden, 2, emulate_bf16=emulate_bf16)
+    dx = fused_mlp(h, sd[f"{prefix}.deform_net.params"], h.shape[-1], 3, hidden, 2, emulate_bf16=emulate_bf16,
+                   pad_value=pad_value)
     return dx * sd[f"{prefix}.displacement_scale"].to(dx.dtype)
 
 
@@ -354,8 +359,9 @@ class OracleField:
     calls in the same order (so a shared CPU seed gives identical noise).
     """
 
-    def __init__(self, cfg: dict, sd: Dict[str, Tensor], emulate_bf16=False):
+    def __init__(self, cfg: dict, sd: Dict[str, Tensor], emulate_bf16=False, pad_value: float = 0.0):
         self.cfg, self.sd = cfg, sd
+        self.pad_value = pad_value             # content of the padded FullyFusedMLP input columns (see fused_mlp)
         self.mode = cfg["mode"]
         self.training = False
         # False | True | "kernel": arithmetic model of every decoder GEMM (see _matmul_t); the encoders, the blend and
@@ -423,7 +429,7 @@ class OracleField:
                 raise ValueError("part2_instant requires view directions.")
             h = self._hash("representation", x, self.levels, self.n_feat)
             return instant_decoder(self.sd, "decoder", h, self._pe("dir_representation", d), self.hidden,
-                                   emulate_bf16=self.emulate_bf16)
+                                   emulate_bf16=self.emulate_bf16, pad_value=self.pad_value)
         if m == "part3":
             if t is None:
                 raise ValueError("Part 3 requires time input 't'.")
@@ -442,7 +448,7 @@ class OracleField:
             if self._instant_canonical():
                 fc = self._hash("canonical_repr", xc, self.levels, self.n_feat)
                 rgb, sigma = instant_decoder(self.sd, "decoder", torch.cat([fc, feat_t], dim=-1), fd, self.hidden,
-                                             emulate_bf16=self.emulate_bf16)
+                                             emulate_bf16=self.emulate_bf16, pad_value=self.pad_value)
             else:
                 fc = self._pe("canonical_repr", xc)
                 rgb, sigma = self._nerf_dec("decoder", torch.cat([fc, feat_t], dim=-1), fd)
@@ -463,11 +469,12 @@ class OracleField:
             ws = w0 + w1 + w2 + 1e-8
             blend = (w0 / ws) * f0 + (w1 / ws) * f1 + (w2 / ws) * f2
             dx = hash_deform_decoder(self.sd, "deform_decoder", blend, tmod, self.cfg.get("deform_hidden_dim", 64),
-                                     emulate_bf16=self.emulate_bf16)
+                                     emulate_bf16=self.emulate_bf16, pad_value=self.pad_value)
             xc = x + dx
             fc = self._hash("canonical_repr", xc, self.levels, self.n_feat)
             rgb, sigma = instant_decoder(self.sd, "decoder", torch.cat([fc, feat_t], dim=-1),
-                                         self._pe("dir_representation", d), self.hidden, emulate_bf16=self.emulate_bf16)
+                                         self._pe("dir_representation", d), self.hidden, emulate_bf16=self.emulate_bf16,
+                                         pad_value=self.pad_value)
             return rgb, sigma, dx
         raise ValueError(f"mode {m!r} is outside the ray-marching hot path")
 

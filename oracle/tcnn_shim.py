@@ -34,7 +34,12 @@ class Encoding(nn.Module):
         self.params = nn.Parameter((torch.rand(n, generator=gen) * 2 - 1) * 1e-4)
 
     def forward(self, x):
-        return O.hash_encode(x, self.params, self.levels, self.n_feat)
+        return O.hash_encode(x, self.params.float(), self.levels, self.n_feat)
+
+
+# what the padded input columns of a Network hold: 0.0 (the oracle's choice) or 1.0 (the other plausible
+# upstream behaviour; tests/golden/make_golden.py writes a checkpoint fixture under it for b2n.checkpoint)
+INPUT_PAD_VALUE = 0.0
 
 
 class Network(nn.Module):
@@ -50,8 +55,8 @@ class Network(nn.Module):
         self.params = nn.Parameter(O._fused_init(n_input_dims, n_output_dims, self.n_neurons, self.n_hidden, gen))
 
     def forward(self, x):
-        return O.fused_mlp(x, self.params, self.n_input_dims, self.n_output_dims, self.n_neurons,
-                           self.n_hidden, self.out_act)
+        return O.fused_mlp(x, self.params.float(), self.n_input_dims, self.n_output_dims, self.n_neurons,
+                           self.n_hidden, self.out_act, pad_value=INPUT_PAD_VALUE)
 
 
 def install():

@@ -7,4 +7,4 @@ from . import _lib  # noqa: F401  (fails loudly when the .so is missing)
 from .ops import (HashGeometry, check_errors, composite, fourier_encode, fused_mlp, hash_encode, instant_mlp, linear,  # noqa: F401
                   mlp_precision,
                   set_mlp_precision, sigma_head)
-from . import graphs, march, ops, optim  # noqa: F401
+from . import checkpoint, graphs, march, ops, optim  # noqa: F401

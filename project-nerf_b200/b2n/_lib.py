@@ -44,8 +44,8 @@ SIGNATURES = {
     "b2n_act_bwd": [P, I, P, I, L, I, I, P],
     "b2n_sigma_head_fwd": [P, I, L, P, P],
     "b2n_sigma_head_bwd": [P, I, L, P, P, I, P],
-    "b2n_instant_mlp_fwd": [P, I, I, P, P, I, P, P, L, P, P, P],
-    "b2n_instant_mlp_bwd": [P, I, I, P, P, I, P, P, L, P, P, P, I, P, P, P, P],
+    "b2n_instant_mlp_fwd": [P, I, I, P, P, I, P, P, L, P, P, F, P],
+    "b2n_instant_mlp_bwd": [P, I, I, P, P, I, P, P, L, P, P, P, I, P, P, P, F, P],
     "b2n_fmlp_in_pad": [I],
     "b2n_fmlp_out_pad": [I],
     "b2n_fmlp_fwd": [P, I, I, P, I, I, I, I, P, P, P, I, I, L, P, I, P, P, P],

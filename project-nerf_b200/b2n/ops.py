@@ -103,7 +103,7 @@ class _HashEncode(torch.autograd.Function):
              work=(Pn * (12 + geom.n_levels * geom.n_features * 4 * 9), 0.0))
         ctx.save_for_backward(x, table)
         ctx.geom, ctx.bound = geom, bound
-        ctx.sink = sink if (sink is not None and ctx.needs_input_grad[1]) else None
+        ctx.sink = sink if (sink is not None and ctx.needs_input_grad[1] and torch.is_grad_enabled()) else None
         if ctx.sink is not None:
             ctx.sink.uses += 1
         return out
@@ -165,7 +165,8 @@ class _HashTriBlend(torch.autograd.Function):
         require_cuda(x, t, t0, t1, t2)
         ctx.rows = current_rows()
         # data-parallel direct path (b2n.dp.GradSink, see _HashEncode): per-table in-place accumulation
-        ctx.sinks = [sk if (sk is not None and ctx.needs_input_grad[2 + i]) else None for i, sk in enumerate(sinks)]
+        ctx.sinks = [sk if (sk is not None and ctx.needs_input_grad[2 + i] and torch.is_grad_enabled()) else None
+                     for i, sk in enumerate(sinks)]
         for sk in ctx.sinks:
             if sk is not None:
                 sk.uses += 1
@@ -419,8 +420,9 @@ def mlp_precision() -> str:
 class _InstantMLP(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, x_enc, dirs, bands, sigma_params, color_params):
+    def forward(ctx, x_enc, dirs, bands, sigma_params, color_params, pad_value):
         require_cuda(x_enc, dirs, bands, sigma_params, color_params)
+        ctx.pad_value = float(pad_value)
         ctx.rows = current_rows()
         x_enc, dirs, bands, sp, cp = _c(x_enc), _c(dirs), _c(bands), _c(sigma_params), _c(color_params)
         Pn, pos_dim = x_enc.shape
@@ -428,7 +430,7 @@ class _InstantMLP(torch.autograd.Function):
         sigma = _narrow_out(Pn, 1, device=x_enc.device)
         flops = 2.0 * Pn * (64 * pos_dim + 16 * 64 + 64 * 43 + 64 * 64 + 3 * 64)
         call("b2n_instant_mlp_fwd", ptr(x_enc), pos_dim, pos_dim, ptr(dirs), ptr(bands), bands.numel(), ptr(sp),
-             ptr(cp), Pn, ptr(rgb), ptr(sigma), stream(), work=(Pn * (4.0 * pos_dim + 12 + 16), flops))
+             ptr(cp), Pn, ptr(rgb), ptr(sigma), ctx.pad_value, stream(), work=(Pn * (4.0 * pos_dim + 12 + 16), flops))
         ctx.save_for_backward(x_enc, dirs, bands, sp, cp)
         return rgb, sigma
 
@@ -443,14 +445,16 @@ class _InstantMLP(torch.autograd.Function):
         work = torch.empty(1, device=x_enc.device, dtype=torch.int32)        # |g|-max of the gradient pre-pass
         flops = 6.0 * Pn * (64 * pos_dim + 16 * 64 + 64 * 43 + 64 * 64 + 3 * 64)
         call("b2n_instant_mlp_bwd", ptr(x_enc), pos_dim, pos_dim, ptr(dirs), ptr(bands), bands.numel(), ptr(sp),
-             ptr(cp), Pn, ptr(_c(g_rgb)), ptr(_c(g_sigma)), ptr(g_x), pos_dim, ptr(g_sp), ptr(g_cp), ptr(work), stream(),
+             ptr(cp), Pn, ptr(_c(g_rgb)), ptr(_c(g_sigma)), ptr(g_x), pos_dim, ptr(g_sp), ptr(g_cp), ptr(work),
+             ctx.pad_value, stream(),
              work=(Pn * (8.0 * pos_dim + 12 + 16), flops))
-        return g_x, None, None, g_sp, g_cp
+        return g_x, None, None, g_sp, g_cp, None
 
 
-def instant_mlp(x_enc, dirs, bands, sigma_params, color_params):
-    """Fused InstantNeRFDecoder on raw unit view directions: (rgb [P,3], sigma [P,1])."""
-    return _InstantMLP.apply(x_enc, dirs, bands, sigma_params, color_params)
+def instant_mlp(x_enc, dirs, bands, sigma_params, color_params, pad_value: float = 0.0):
+    """Fused InstantNeRFDecoder on raw unit view directions: (rgb [P,3], sigma [P,1]).  ``pad_value``: content of the
+    padded input columns of the two networks (0, or 1 for upstream-tcnn checkpoints: b2n.checkpoint)."""
+    return _InstantMLP.apply(x_enc, dirs, bands, sigma_params, color_params, pad_value)
 
 
 # ----------------------------------------------------------------------------
@@ -556,7 +560,8 @@ class _NerfMLP(torch.autograd.Function):
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, decoder, x_enc, d_enc, *params):
-        need_grad = any(ctx.needs_input_grad)
+        # (under torch.no_grad() -- every evaluation loop of run.py -- nothing is saved: the planes are 5 KB per point)
+        need_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad)
         rgb, sigma, saved, err = nerf_mlp_forward(decoder, x_enc, d_enc, save=need_grad)
         planes, masks = saved if saved is not None else (None, None)
         ctx.decoder = decoder
@@ -692,7 +697,7 @@ class _FusedMLP(torch.autograd.Function):
         d1 = x1.shape[1] if x1 is not None else 0
         hidden, n_hidden, out_dim = Ws[0].shape[0], n_layers - 1, Ws[-1].shape[0]
         dev = x0.device
-        need = any(ctx.needs_input_grad)
+        need = torch.is_grad_enabled() and any(ctx.needs_input_grad)      # no planes under torch.no_grad()
         in_pad = _lib.lib.b2n_fmlp_in_pad(d0 + d1)
         y = _narrow_out(Pn, out_dim, device=dev) if out_dim <= 4 else torch.empty(Pn, out_dim, device=dev)
         xin = torch.empty(Pn, in_pad, device=dev, dtype=torch.float16) if need else None

@@ -40,10 +40,14 @@ __device__ __forceinline__ void load_dir(const float* __restrict__ dirs, int64_t
   d[0] = d[1] = d[2] = 0.f;
   if (p < P) d[0] = __ldg(dirs + 3 * p), d[1] = __ldg(dirs + 3 * p + 1), d[2] = __ldg(dirs + 3 * p + 2);
 }
-__device__ __forceinline__ void dir_features(const float (&d)[3], const float* __restrict__ bands, int L, op16* dst) {
+__device__ __forceinline__ void dir_features(const float (&d)[3], const float* __restrict__ bands, int L, op16* dst,
+                                             float pad) {
+  // columns [3 + 6 L, pad16(16 + 3 + 6 L) - 16) are the INPUT PADDING of color_net (43 -> 48 at L = 4): they hold `pad`
+  // (0, or 1 for checkpoints of an upstream build whose padded inputs are ones: b2n.checkpoint), the rest zeros
+  const int dd = 3 + 6 * L, dpad = ((16 + dd + 15) & ~15) - 16;
   float f[32];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) f[i] = 0.f;
+  for (int i = 0; i < 32; ++i) f[i] = (i >= dd && i < dpad) ? pad : 0.f;
   f[0] = d[0], f[1] = d[1], f[2] = d[2];
   // band k+1 = 2 * band k (the reference's 2^k bands): double-angle recurrence instead of a fresh
   // sincosf (error grows ~2x per band from 1e-7: far below the bf16 rounding applied next)
@@ -125,8 +129,9 @@ __device__ __forceinline__ void prefetch_rows(const float* __restrict__ x, int l
 // split version of load_x for software pipelining: issue the loads now, pack (and stall) later
 template <int KT>
 __device__ __forceinline__ void load_x_raw(const float* __restrict__ x, int ldx, int pos_dim, int64_t p0, int64_t P,
-                                           float2 (&raw)[KT][4], int lane) {
+                                           float2 (&raw)[KT][4], int lane, float pad = 0.f) {
   const int g = lane >> 2, t = lane & 3;
+  const int in_pad = (pos_dim + 15) & ~15;      // columns [pos_dim, in_pad) are sigma_net's input padding: value `pad`
   const bool vec = ((ldx & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
 #pragma unroll
   for (int k = 0; k < KT; ++k)
@@ -143,7 +148,9 @@ __device__ __forceinline__ void load_x_raw(const float* __restrict__ x, int ldx,
             v = __ldcs(reinterpret_cast<const float2*>(src));
           } else {
             if (c < pos_dim) v.x = __ldcs(src);
+            else if (c < in_pad) v.x = pad;
             if (c + 1 < pos_dim) v.y = __ldcs(src + 1);
+            else if (c + 1 < in_pad) v.y = pad;
           }
         }
         raw[k][2 * h + r] = v;
@@ -219,7 +226,8 @@ template <int POS_K>
 __global__ void __launch_bounds__(MLP_THREADS, 2)
 k_instant_fwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __restrict__ dirs,
               const float* __restrict__ bands, int L_dir, const float* __restrict__ sp, const float* __restrict__ cp,
-              int64_t P, float* __restrict__ rgb, float* __restrict__ sigma, const int* __restrict__ rows) {
+              int64_t P, float* __restrict__ rgb, float* __restrict__ sigma, const int* __restrict__ rows,
+              float in_pad_value) {
   P = clamp_rows(P, rows);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   op16* sm = reinterpret_cast<op16*>(smem_raw);
@@ -242,8 +250,8 @@ k_instant_fwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
   float dnext[3] = {0.f, 0.f, 0.f};
   const int64_t tile0 = (int64_t)blockIdx.x * (MLP_THREADS / 32) + (threadIdx.x >> 5);
   if (PF) {
-    load_x_raw<KTP>(x, ldx, pos_dim, tile0 * 32, P, xraw[0], lane);
-    load_x_raw<KTP>(x, ldx, pos_dim, tile0 * 32 + 16, P, xraw[1], lane);
+    load_x_raw<KTP>(x, ldx, pos_dim, tile0 * 32, P, xraw[0], lane, in_pad_value);
+    load_x_raw<KTP>(x, ldx, pos_dim, tile0 * 32 + 16, P, xraw[1], lane, in_pad_value);
     load_dir(dirs, tile0 * 32 + lane, P, dnext);
   }
   for (int64_t tile = tile0; tile < n_tiles; tile += wstride) {
@@ -259,8 +267,8 @@ k_instant_fwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
           for (int i = 0; i < 4; ++i) pack_hl(xraw[m][k % KTP][i].x, xraw[m][k % KTP][i].y, ax[m][k][i], axl[m][k][i]);
       dcur[0] = dnext[0], dcur[1] = dnext[1], dcur[2] = dnext[2];
       const int64_t pn = (tile + wstride) * 32;
-      load_x_raw<KTP>(x, ldx, pos_dim, pn, P, xraw[0], lane);
-      load_x_raw<KTP>(x, ldx, pos_dim, pn + 16, P, xraw[1], lane);
+      load_x_raw<KTP>(x, ldx, pos_dim, pn, P, xraw[0], lane, in_pad_value);
+      load_x_raw<KTP>(x, ldx, pos_dim, pn + 16, P, xraw[1], lane, in_pad_value);
       load_dir(dirs, pn + lane, P, dnext);
     } else {
       prefetch_rows(x, ldx, dirs, (tile + wstride) * 32, 32, P, lane);
@@ -268,7 +276,7 @@ k_instant_fwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
 #pragma unroll
       for (int m = 0; m < 2; ++m) {
         float2 raw[KT1][4];
-        load_x_raw<KT1>(x, ldx, pos_dim, p0 + 16 * m, P, raw, lane);
+        load_x_raw<KT1>(x, ldx, pos_dim, p0 + 16 * m, P, raw, lane, in_pad_value);
         pack_x_hl<KT1>(raw, ax[m], axl[m]);
       }
     }
@@ -299,7 +307,7 @@ k_instant_fwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
         ac[m][0][0] = tmp[0][0], ac[m][0][1] = tmp[0][1], ac[m][0][2] = tmp[0][2], ac[m][0][3] = tmp[0][3];
       }
     }
-    dir_features(dcur, bands, L_dir, dstage + lane * DS);     // needed only now: the direction load had two layers to land
+    dir_features(dcur, bands, L_dir, dstage + lane * DS, in_pad_value);     // needed only now: the direction load had two layers to land
     __syncwarp();
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
@@ -431,7 +439,7 @@ k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
               const float* __restrict__ bands, int L_dir, const float* __restrict__ sp, const float* __restrict__ cp,
               int64_t P, const float* __restrict__ g_rgb, const float* __restrict__ g_sigma, float* __restrict__ g_x,
               int ldg, float* __restrict__ g_sp, float* __restrict__ g_cp, const unsigned int* __restrict__ absmax,
-              const int* __restrict__ rows) {
+              const int* __restrict__ rows, float in_pad_value) {
   P = clamp_rows(P, rows);
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const float gscale = grad_scale_from(__ldg(absmax));
@@ -455,7 +463,7 @@ k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
 
   const int64_t n_tiles = (P + 63) / 64;
   float2 xraw[KT1][4];       // this tile's x_enc rows as fp32: fetched one tile ahead, split into hi / lo at the top of the tile
-  load_x_raw<KT1>(x, ldx, pos_dim, (int64_t)blockIdx.x * 64 + row0, P, xraw, lane);
+  load_x_raw<KT1>(x, ldx, pos_dim, (int64_t)blockIdx.x * 64 + row0, P, xraw, lane, in_pad_value);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const int64_t p0 = tile * 64 + row0;
     // ---------------- forward recompute (staging every layer input)
@@ -499,7 +507,7 @@ k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
     }
     // next tile's inputs: the fragments are dead from here on, so the global loads are issued now and have the whole
     // rest of the tile to land (ncu: the first use of a prefetch issued only before the wgrad phase was the hottest stall)
-    load_x_raw<KT1>(x, ldx, pos_dim, (tile + gridDim.x) * 64 + row0, P, xraw, lane);
+    load_x_raw<KT1>(x, ldx, pos_dim, (tile + gridDim.x) * 64 + row0, P, xraw, lane, in_pad_value);
     float hs0 = 0.f, hs1 = 0.f;  // h[.,0] of rows g and g+8 (threads with t == 0)
     uint32_t ac[1][3][4];
     {
@@ -511,7 +519,7 @@ k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
       ac[0][0][0] = tmp[0][0], ac[0][0][1] = tmp[0][1], ac[0][0][2] = tmp[0][2], ac[0][0][3] = tmp[0][3];
       store_a<1>(tmp, sm + LY::in_c, LY::SC, row0, 0, lane);
     }
-    if (lane < 16) dir_features(dcur, bands, L_dir, sm + LY::in_c + (row0 + lane) * LY::SC + 16);
+    if (lane < 16) dir_features(dcur, bands, L_dir, sm + LY::in_c + (row0 + lane) * LY::SC + 16, in_pad_value);
     __syncwarp();
     ldsm_x4(ac[0][1], sm + LY::in_c + (row0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LY::SC + 16 + 8 * (lane >> 4));
     ldsm_x4(ac[0][2], sm + LY::in_c + (row0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * LY::SC + 32 + 8 * (lane >> 4));
@@ -665,7 +673,7 @@ static int check_mlp_args(const float* x, int ldx, int pos_dim, const float* dir
 
 extern "C" int b2n_instant_mlp_fwd(const float* x_enc, int ldx, int pos_dim, const float* dirs, const float* dir_bands,
                                    int L_dir, const float* sigma_params, const float* color_params, int64_t P,
-                                   float* rgb, float* sigma, b2n_stream_t stream) {
+                                   float* rgb, float* sigma, float in_pad_value, b2n_stream_t stream) {
   B2N_REQUIRE(P >= 0, "negative size");
   if (P == 0) return B2N_OK;
   int rc = check_mlp_args(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params, color_params);
@@ -679,13 +687,13 @@ extern "C" int b2n_instant_mlp_fwd(const float* x_enc, int ldx, int pos_dim, con
     cudaFuncSetAttribute(k_instant_fwd<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = persistent_grid((const void*)k_instant_fwd<32>, MLP_THREADS, smem, block_tiles);
     k_instant_fwd<32><<<grid, MLP_THREADS, smem, st>>>(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params,
-                                                       color_params, P, rgb, sigma, g_active_rows);
+                                                       color_params, P, rgb, sigma, g_active_rows, in_pad_value);
   } else {
     constexpr size_t smem = fwd_smem_bytes<64>();
     cudaFuncSetAttribute(k_instant_fwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = persistent_grid((const void*)k_instant_fwd<64>, MLP_THREADS, smem, block_tiles);
     k_instant_fwd<64><<<grid, MLP_THREADS, smem, st>>>(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params,
-                                                       color_params, P, rgb, sigma, g_active_rows);
+                                                       color_params, P, rgb, sigma, g_active_rows, in_pad_value);
   }
   return check_launch("b2n_instant_mlp_fwd");
 }
@@ -693,7 +701,8 @@ extern "C" int b2n_instant_mlp_fwd(const float* x_enc, int ldx, int pos_dim, con
 extern "C" int b2n_instant_mlp_bwd(const float* x_enc, int ldx, int pos_dim, const float* dirs, const float* dir_bands,
                                    int L_dir, const float* sigma_params, const float* color_params, int64_t P,
                                    const float* g_rgb, const float* g_sigma, float* g_x_enc, int ldg,
-                                   float* g_sigma_params, float* g_color_params, void* work4, b2n_stream_t stream) {
+                                   float* g_sigma_params, float* g_color_params, void* work4, float in_pad_value,
+                                   b2n_stream_t stream) {
   B2N_REQUIRE(P >= 0, "negative size");
   if (P == 0) return B2N_OK;
   int rc = check_mlp_args(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params, color_params);
@@ -715,14 +724,14 @@ extern "C" int b2n_instant_mlp_bwd(const float* x_enc, int ldx, int pos_dim, con
     const int grid = persistent_grid((const void*)k_instant_bwd<32>, MLP_THREADS, smem, tiles);
     k_instant_bwd<32><<<grid, MLP_THREADS, smem, st>>>(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params,
                                                        color_params, P, g_rgb, g_sigma, g_x_enc, ldg, g_sigma_params,
-                                                       g_color_params, absmax, g_active_rows);
+                                                       g_color_params, absmax, g_active_rows, in_pad_value);
   } else {
     constexpr size_t smem = bwd_smem_bytes<64>();
     cudaFuncSetAttribute(k_instant_bwd<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int grid = persistent_grid((const void*)k_instant_bwd<64>, MLP_THREADS, smem, tiles);
     k_instant_bwd<64><<<grid, MLP_THREADS, smem, st>>>(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params,
                                                        color_params, P, g_rgb, g_sigma, g_x_enc, ldg, g_sigma_params,
-                                                       g_color_params, absmax, g_active_rows);
+                                                       g_color_params, absmax, g_active_rows, in_pad_value);
   }
   return check_launch("b2n_instant_mlp_bwd");
 }

@@ -55,6 +55,16 @@ class FusedMLP(nn.Module):
             lim = math.sqrt(6.0 / (r + c_))
             chunks.append(((torch.rand(r, c_, generator=gen) * 2 - 1) * lim).reshape(-1))
         self.params = nn.Parameter(torch.cat(chunks))
+        # content of the padded input columns: 0 here and in the oracle; b2n.checkpoint sets 1.0 when it loads weights
+        # trained with an upstream tiny-cuda-nn whose Network pads its inputs with ones (those columns are then a bias)
+        self.input_pad_value = 0.0
+
+    def _pad_bias(self, W0, d_in):
+        """the padded input columns' contribution as a first-layer bias: pad * sum_j W0[:, j >= d_in] (differentiable,
+        so the gradient reaches the padded weight columns); None when there is nothing to add"""
+        if self.input_pad_value == 0.0 or W0.shape[1] <= d_in:
+            return None
+        return W0[:, d_in:].sum(dim=1) * self.input_pad_value
 
     def matrices(self):
         out, off = [], 0
@@ -72,15 +82,17 @@ class FusedMLP(nn.Module):
         """whole network as one tensor-core kernel each way (b2n_fmlp_*); input = [x0 | x1]"""
         mats = self.matrices()
         act = "sigmoid" if self.output_activation == "Sigmoid" else "none"
-        return b2n.ops.fused_mlp(x0, x1, mats[:-1] + [mats[-1][: self.n_output_dims]], [None] * len(mats), act)
+        d_in = x0.shape[-1] + (x1.shape[-1] if x1 is not None else 0)
+        biases = [self._pad_bias(mats[0], d_in)] + [None] * (len(mats) - 1)
+        return b2n.ops.fused_mlp(x0, x1, mats[:-1] + [mats[-1][: self.n_output_dims]], biases, act)
 
     def forward(self, x):
         if x.is_cuda and self.can_fuse(x.shape[-1]):
             return self.forward_fused(x)
         mats = self.matrices()
         h = x
-        for W in mats[:-1]:
-            h = b2n.linear(h, W, None, "relu")
+        for i, W in enumerate(mats[:-1]):
+            h = b2n.linear(h, W, self._pad_bias(W, x.shape[-1]) if i == 0 else None, "relu")
         act = "sigmoid" if self.output_activation == "Sigmoid" else "none"
         return b2n.linear(h, mats[-1][: self.n_output_dims], None, act)
 
@@ -157,7 +169,10 @@ class InstantNeRFDecoder(BaseDecoder):
     def forward_fused(self, x_enc, dirs, dir_encoder):
         """Whole decoder (+ direction Fourier features) as ONE tensor-core kernel each way
         (b2n_instant_mlp_fwd / _bwd); NeuralField.forward takes this path in bf16 mode."""
-        return b2n.instant_mlp(x_enc, dirs, dir_encoder.freq_bands, self.sigma_net.params, self.color_net.params)
+        if self.sigma_net.input_pad_value != self.color_net.input_pad_value:
+            raise ValueError("sigma_net and color_net must share one input_pad_value")
+        return b2n.instant_mlp(x_enc, dirs, dir_encoder.freq_bands, self.sigma_net.params, self.color_net.params,
+                               self.sigma_net.input_pad_value)
 
 
 class DeformationNetwork(BaseDecoder):

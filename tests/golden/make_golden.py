@@ -294,6 +294,49 @@ def gen_grid_update():
              grid1=g1, binary1=b1, grid2=grid.grid, binary2=grid.binary_grid, **sd_arrays(model))
 
 
+# ---------------------------------------------------------------- an upstream-style checkpoint
+def gen_checkpoint():
+    """What run.py:2084-2092 writes for a Part-4 model, in the two ways an upstream-tcnn checkpoint can differ from this
+    package's own: the tcnn ``params`` tensors stored in fp16, and FullyFusedMLP inputs padded with ONES (the padded
+    weight columns act as a bias).  The reference's own files produce the outputs, running on the shim with that
+    padding and with the fp16-rounded parameters."""
+    tcnn_shim.INPUT_PAD_VALUE = 1.0
+    try:
+        cfg = FIELD_CFGS["part4"]
+        model = build(cfg, 61).eval()
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if n.endswith(".params"):
+                    p.copy_(p.half().float())                      # the values an fp16 export can hold
+                if n.endswith("_net.params"):                      # make the padded columns matter
+                    p.add_(torch.randn_like(p) * 0.05)
+                    p.copy_(p.half().float())
+        torch.manual_seed(62)
+        P = 200
+        x = (torch.rand(P, 3) * 2 - 1) * 1.4
+        d = torch.randn(P, 3)
+        d = d / d.norm(dim=-1, keepdim=True)
+        t = torch.rand(P, 1)
+        rgb, sigma, dx = model(x, d, t=t)
+        gs = [torch.randn_like(o) for o in (rgb, sigma, dx)]
+        loss = (rgb * gs[0]).sum() + (sigma * gs[1]).sum() + (dx * gs[2]).sum()
+        names = ["decoder.sigma_net.params", "decoder.color_net.params", "deform_decoder.deform_net.params"]
+        params = dict(model.named_parameters())
+        grads = torch.autograd.grad(loss, [params[n] for n in names])
+        grid = R.DensityGrid(resolution=8, bound=cfg["scene_bound"], threshold=0.01)
+        grid.binary_grid = torch.rand(8, 8, 8) < 0.5
+        grid.grid = torch.rand(8, 8, 8)
+        sd = {k: (v.half() if k.endswith(".params") else v.clone()) for k, v in model.state_dict().items()}
+        torch.save({"model_state_dict": sd, "config": cfg, "step": 1234, "val_psnr": 29.56,
+                    "density_grid": grid.state_dict()}, os.path.join(HERE, "ckpt_part4_upstream.pth"))
+        save("ckpt_part4_upstream_io", cfg=cfg, x=x, d=d, t=t, rgb=rgb, sigma=sigma, dx=dx, g_rgb=gs[0], g_sigma=gs[1],
+             g_dx=gs[2], grid=grid.grid, binary_grid=grid.binary_grid,
+             **{"grad::" + n: g for n, g in zip(names, grads)})
+        print("ckpt_part4_upstream.pth", os.path.getsize(os.path.join(HERE, "ckpt_part4_upstream.pth")) // 1024, "KiB")
+    finally:
+        tcnn_shim.INPUT_PAD_VALUE = 0.0
+
+
 # ---------------------------------------------------------------- datasets (tiny synthetic scene on disk)
 def gen_dataset():
     from PIL import Image

@@ -1014,9 +1014,13 @@ def test_render_image_chunked_equals_unchunked_equals_oracle(mods):
         ref = O.render_rays(O.OracleField(dict(mode="part2_nerf", L_embed=10, L_embed_dir=4), sd), ro.reshape(-1, 3),
                             rd.reshape(-1, 3), 2.0, 6.0, 48, None, white_bkgd=True)[0].view(H, W, 3)
     assert record("render_image:rgb_vs_oracle", rel_err(whole.cpu(), ref)) < TOL
-    black = render_image(model=model, rays_o=cu(ro), rays_d=cu(rd), near=2.0, far=6.0, n_samples=48, chunk=256,
-                         white_bkgd=False)
-    assert float((whole - black).abs().max()) > 1e-3               # the background flag reaches the compositing
+    with torch.no_grad():                                          # an empty scene shows the background flag
+        model.decoder.sigma_layer.bias.fill_(-1e4)
+        white = render_image(model=model, rays_o=cu(ro), rays_d=cu(rd), near=2.0, far=6.0, n_samples=48, chunk=256,
+                             white_bkgd=True)
+        black = render_image(model=model, rays_o=cu(ro), rays_d=cu(rd), near=2.0, far=6.0, n_samples=48, chunk=256,
+                             white_bkgd=False)
+    assert float((white - 1.0).abs().max()) < 1e-6 and float(black.abs().max()) < 1e-6
 
 
 def test_render_image_800x800_single_chunk(mods, bf16_mode):

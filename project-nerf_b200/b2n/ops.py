@@ -103,7 +103,7 @@ class _HashEncode(torch.autograd.Function):
              work=(Pn * (12 + geom.n_levels * geom.n_features * 4 * 9), 0.0))
         ctx.save_for_backward(x, table)
         ctx.geom, ctx.bound = geom, bound
-        ctx.sink = sink if (sink is not None and ctx.needs_input_grad[1] and torch.is_grad_enabled()) else None
+        ctx.sink = sink if (sink is not None and ctx.needs_input_grad[1]) else None
         if ctx.sink is not None:
             ctx.sink.uses += 1
         return out
@@ -152,7 +152,8 @@ class _HashEncode(torch.autograd.Function):
 
 def hash_encode(x, table, geom: HashGeometry, bound: float):
     """x [P,3] world coords (bound > 0) or unit-cube coords (bound == 0) -> [P, L*F]."""
-    return _HashEncode.apply(x, table, geom, bound, getattr(table, "_b2n_grad_sink", None))
+    sink = getattr(table, "_b2n_grad_sink", None) if torch.is_grad_enabled() else None
+    return _HashEncode.apply(x, table, geom, bound, sink)
 
 
 class _HashTriBlend(torch.autograd.Function):
@@ -165,8 +166,7 @@ class _HashTriBlend(torch.autograd.Function):
         require_cuda(x, t, t0, t1, t2)
         ctx.rows = current_rows()
         # data-parallel direct path (b2n.dp.GradSink, see _HashEncode): per-table in-place accumulation
-        ctx.sinks = [sk if (sk is not None and ctx.needs_input_grad[2 + i] and torch.is_grad_enabled()) else None
-                     for i, sk in enumerate(sinks)]
+        ctx.sinks = [sk if (sk is not None and ctx.needs_input_grad[2 + i]) else None for i, sk in enumerate(sinks)]
         for sk in ctx.sinks:
             if sk is not None:
                 sk.uses += 1
@@ -211,8 +211,9 @@ class _HashTriBlend(torch.autograd.Function):
 
 def hash_tri_blend(x, t, tables: Sequence[torch.Tensor], geom: HashGeometry, bound: float):
     """Tent-weighted blend of three hash grids sharing ``geom`` at per-point times t in [0, 1]: [P, L*2]."""
+    on = torch.is_grad_enabled()
     return _HashTriBlend.apply(x, t, tables[0], tables[1], tables[2], geom, bound,
-                               [getattr(tb, "_b2n_grad_sink", None) for tb in tables])
+                               [getattr(tb, "_b2n_grad_sink", None) if on else None for tb in tables])
 
 
 # ----------------------------------------------------------------------------
@@ -451,6 +452,20 @@ class _InstantMLP(torch.autograd.Function):
         return g_x, None, None, g_sp, g_cp, None
 
 
+@torch.no_grad()
+def instant_sigma(x_enc, sigma_params, pad_value: float = 0.0):
+    """sigma [P,1] of the fused Instant decoder alone: b2n_instant_mlp_fwd with the colour network switched off (no view
+    directions, no colour layers).  Same sigma_net arithmetic as ``instant_mlp`` -- bit-identical sigma -- at ~40 % of its
+    time; no gradient (occupancy sweeps: DensityGrid.update)."""
+    require_cuda(x_enc, sigma_params)
+    x_enc, sp = _c(x_enc), _c(sigma_params)
+    Pn, pos_dim = x_enc.shape
+    sigma = _narrow_out(Pn, 1, device=x_enc.device)
+    call("b2n_instant_mlp_fwd", ptr(x_enc), pos_dim, pos_dim, None, None, 0, ptr(sp), None, Pn, None, ptr(sigma),
+         float(pad_value), stream(), work=(Pn * (4.0 * pos_dim + 4), 2.0 * Pn * (64 * pos_dim + 16 * 64)))
+    return sigma
+
+
 def instant_mlp(x_enc, dirs, bands, sigma_params, color_params, pad_value: float = 0.0):
     """Fused InstantNeRFDecoder on raw unit view directions: (rgb [P,3], sigma [P,1]).  ``pad_value``: content of the
     padded input columns of the two networks (0, or 1 for upstream-tcnn checkpoints: b2n.checkpoint)."""
@@ -559,9 +574,11 @@ class _NerfMLP(torch.autograd.Function):
 
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, decoder, x_enc, d_enc, *params):
-        # (under torch.no_grad() -- every evaluation loop of run.py -- nothing is saved: the planes are 5 KB per point)
-        need_grad = torch.is_grad_enabled() and any(ctx.needs_input_grad)
+    def forward(ctx, decoder, grad_on, x_enc, d_enc, *params):
+        # grad_on: torch.is_grad_enabled() of the CALLER (inside Function.forward grad mode is always off, and
+        # needs_input_grad stays True for parameters under torch.no_grad()).  Every evaluation loop of run.py runs under
+        # no_grad: nothing is saved there -- the planes are 5 KB per point, 195 GB for one 800 x 800 frame
+        need_grad = grad_on and any(ctx.needs_input_grad)
         rgb, sigma, saved, err = nerf_mlp_forward(decoder, x_enc, d_enc, save=need_grad)
         planes, masks = saved if saved is not None else (None, None)
         ctx.decoder = decoder
@@ -573,7 +590,7 @@ class _NerfMLP(torch.autograd.Function):
     def backward(ctx, g_rgb, g_sigma):
         x_enc, d_enc, rgb, sigma, planes, masks, err = ctx.saved_tensors
         dec = ctx.decoder
-        if ctx.needs_input_grad[2]:
+        if ctx.needs_input_grad[3]:
             raise RuntimeError("tcgen05 NeRFDecoder path does not produce view-direction gradients (use fp32 mode)")
         Pn = x_enc.shape[0]
         dev = x_enc.device
@@ -647,12 +664,12 @@ class _NerfMLP(torch.autograd.Function):
         for k in ("sigma", "feat", "view", "rgb"):
             out += list(grads[k])
         g_x = None
-        if ctx.needs_input_grad[1]:       # d x_enc = dZ0 W0 + dZ4 W4[:, 256:]
+        if ctx.needs_input_grad[2]:       # d x_enc = dZ0 W0 + dZ4 W4[:, 256:]
             g_x = torch.empty_like(x_enc)
             call("b2n_nerf_mlp_dx", ptr(dz[9]), ptr(dz[5]), ptr(ws[0]), ws[0].stride(0), ws[4].data_ptr() + 256 * 4,
                  ws[4].stride(0), pos_dim, Pn, ptr(g_x), pos_dim, stream(),
                  work=(Pn * (1024.0 + 4.0 * pos_dim), 2.0 * Pn * 512 * pos_dim))
-        return (None, g_x, None) + tuple(out)
+        return (None, None, g_x, None) + tuple(out)
 
 
 def _nerf_params(decoder):
@@ -668,7 +685,7 @@ def nerf_mlp(decoder, x_enc, d_enc):
     """(rgb [P,3], sigma [P,1]) of NeRFDecoder on the tensor cores, differentiable w.r.t. its parameters."""
     if d_enc.requires_grad:
         raise RuntimeError("nerf_mlp: view-direction gradients are not produced by the tcgen05 path")
-    return _NerfMLP.apply(decoder, x_enc, d_enc, *_nerf_params(decoder))
+    return _NerfMLP.apply(decoder, torch.is_grad_enabled(), x_enc, d_enc, *_nerf_params(decoder))
 
 
 # ----------------------------------------------------------------------------
@@ -686,7 +703,7 @@ class _FusedMLP(torch.autograd.Function):
 
     @staticmethod
     @custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, x0, x1, out_act, n_layers, *wb):
+    def forward(ctx, x0, x1, out_act, n_layers, grad_on, *wb):
         Ws, bs = list(wb[:n_layers]), list(wb[n_layers:])
         require_cuda(x0, x1, *Ws)
         ctx.rows = current_rows()
@@ -697,7 +714,7 @@ class _FusedMLP(torch.autograd.Function):
         d1 = x1.shape[1] if x1 is not None else 0
         hidden, n_hidden, out_dim = Ws[0].shape[0], n_layers - 1, Ws[-1].shape[0]
         dev = x0.device
-        need = torch.is_grad_enabled() and any(ctx.needs_input_grad)      # no planes under torch.no_grad()
+        need = grad_on and any(ctx.needs_input_grad)      # grad_on: the caller's grad mode (no planes under torch.no_grad())
         in_pad = _lib.lib.b2n_fmlp_in_pad(d0 + d1)
         y = _narrow_out(Pn, out_dim, device=dev) if out_dim <= 4 else torch.empty(Pn, out_dim, device=dev)
         xin = torch.empty(Pn, in_pad, device=dev, dtype=torch.float16) if need else None
@@ -770,9 +787,9 @@ class _FusedMLP(torch.autograd.Function):
                  arr_p(*[(gb[l].data_ptr() if has_b[l] else None) for l in range(n_layers)]), Pn, ptr(scale), stream(),
                  work=(2.0 * Pn * sum(a_.shape[1] + b_.shape[1] for a_, b_ in zip(dzs, ins)),
                        2.0 * Pn * sum(r * c for r, c in shapes)))
-        gW = [g if ctx.needs_input_grad[4 + l] else None for l, g in enumerate(gW)]
-        gb = [gb[l] if (has_b[l] and ctx.needs_input_grad[4 + n_layers + l]) else None for l in range(n_layers)]
-        return (g_x0, g_x1, None, None) + tuple(gW) + tuple(gb)
+        gW = [g if ctx.needs_input_grad[5 + l] else None for l, g in enumerate(gW)]
+        gb = [gb[l] if (has_b[l] and ctx.needs_input_grad[5 + n_layers + l]) else None for l in range(n_layers)]
+        return (g_x0, g_x1, None, None, None) + tuple(gW) + tuple(gb)
 
 
 def fused_mlp(x0, x1, weights: Sequence[torch.Tensor], biases: Sequence[Optional[torch.Tensor]], out_act: str = "none"):
@@ -783,4 +800,4 @@ def fused_mlp(x0, x1, weights: Sequence[torch.Tensor], biases: Sequence[Optional
     d_in = x0.shape[1] + (x1.shape[1] if x1 is not None else 0)
     if not fused_mlp_supported(d_in, hidden, n - 1, weights[-1].shape[0]):
         raise ValueError("fused_mlp: unsupported shape (hidden 64/128, 1..3 hidden layers, <= 96 inputs, <= 64 outputs)")
-    return _FusedMLP.apply(x0, x1, _ACT[out_act], n, *weights, *biases)
+    return _FusedMLP.apply(x0, x1, _ACT[out_act], n, torch.is_grad_enabled(), *weights, *biases)

@@ -97,6 +97,9 @@ class FusedAdamW(torch.optim.Optimizer):
                 tv = float(group.get("tv_weight", 0.0) or 0.0)
                 dev = p.device
                 keep.append(g)
+                # the kernels write the parameter through its raw pointer: tell autograd (version counter), so that
+                # anything keyed on "has this parameter changed" (DensityGrid's sweep cache, saved-tensor checks) sees it
+                torch.autograd.graph.increment_version(p)
                 descs.append(_OptTensor(p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(),
                                         n, float(group["lr"]), float(group["weight_decay"]), float(b1), float(b2),
                                         float(group["eps"]), 1.0, 1.0,

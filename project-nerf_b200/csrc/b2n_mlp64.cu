@@ -38,7 +38,7 @@ constexpr int MLP_THREADS = 128;
 // long-scoreboard stalls on the small per-tile loads as the top stall reason of both decoder kernels)
 __device__ __forceinline__ void load_dir(const float* __restrict__ dirs, int64_t p, int64_t P, float (&d)[3]) {
   d[0] = d[1] = d[2] = 0.f;
-  if (p < P) d[0] = __ldg(dirs + 3 * p), d[1] = __ldg(dirs + 3 * p + 1), d[2] = __ldg(dirs + 3 * p + 2);
+  if (dirs && p < P) d[0] = __ldg(dirs + 3 * p), d[1] = __ldg(dirs + 3 * p + 1), d[2] = __ldg(dirs + 3 * p + 2);
 }
 __device__ __forceinline__ void dir_features(const float (&d)[3], const float* __restrict__ bands, int L, op16* dst,
                                              float pad) {
@@ -122,7 +122,7 @@ __device__ __forceinline__ void prefetch_rows(const float* __restrict__ x, int l
     const char* a = reinterpret_cast<const char*>(x + (p0 + lane) * ldx);
     asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
     if (ldx > 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128));
-    if ((lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(dirs + 3 * (p0 + lane))));
+    if (dirs && (lane & 7) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(dirs + 3 * (p0 + lane))));
   }
 }
 
@@ -216,6 +216,7 @@ __device__ __forceinline__ void load_all_weights(const float* __restrict__ sp, c
     }
   }
   load_weights(sp + HID * in_pad, GEO, HID, HID, sm + L.w2);
+  if (!cp) return;                       // density only: no colour network
   load_weights(cp, HID, CIN, CIN, sm + L.v1);
   load_weights(cp + HID * CIN, HID, HID, HID, sm + L.v2);
   load_weights(cp + HID * CIN + HID * HID, 16, HID, HID, sm + L.v3);
@@ -307,6 +308,7 @@ k_instant_fwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
         ac[m][0][0] = tmp[0][0], ac[m][0][1] = tmp[0][1], ac[m][0][2] = tmp[0][2], ac[m][0][3] = tmp[0][3];
       }
     }
+    if (!rgb) continue;      // density sweep (DensityGrid.update): sigma is out, the colour network is skipped
     dir_features(dcur, bands, L_dir, dstage + lane * DS, in_pad_value);     // needed only now: the direction load had two layers to land
     __syncwarp();
 #pragma unroll
@@ -676,9 +678,12 @@ extern "C" int b2n_instant_mlp_fwd(const float* x_enc, int ldx, int pos_dim, con
                                    float* rgb, float* sigma, float in_pad_value, b2n_stream_t stream) {
   B2N_REQUIRE(P >= 0, "negative size");
   if (P == 0) return B2N_OK;
-  int rc = check_mlp_args(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params, color_params);
+  // rgb == NULL: density only -- dirs / dir_bands / color_params are not read and may be NULL
+  int rc = rgb ? check_mlp_args(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params, color_params)
+               : check_mlp_args(x_enc, ldx, pos_dim, x_enc, nullptr, 0, sigma_params, sigma_params);
   if (rc) return rc;
-  B2N_REQUIRE(rgb && sigma, "null pointer");
+  if (!rgb) dirs = nullptr, dir_bands = nullptr, L_dir = 0, color_params = nullptr;
+  B2N_REQUIRE(sigma, "null pointer");
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t warp_tiles = (P + 31) / 32;
   const int64_t block_tiles = (warp_tiles + 3) / 4;

@@ -167,14 +167,20 @@ class NeuralField(nn.Module):
     def density(self, x, t=None):
         """sigma [P,1] only.  ``DensityGrid.update`` (reference src/renderer.py:108-116) evaluates the whole model on
         the R^3 lattice with zero view directions and keeps sigma; with a hash-grid / 64-wide decoder the colour
-        branch (direction features + 2 of the 3 fused layers' worth of work) is skipped here: measured
-        7 % off a Part 3-Instant / Part 4 sweep (the hash encode dominates it).  The static Instant field in bf16 mode
-        keeps its single fused decoder kernel (1.18 ms per 128^3 sweep against 1.29 ms through the separate sigma
-        network), and the 256-wide NeRFDecoder has no separable density branch: both run ``forward`` and drop rgb."""
+        branch (direction features + 2 of the 3 fused layers' worth of work) is skipped here.  In the
+        16-bit mode sigma comes from the SAME fused decoder kernel as in ``forward`` with its colour network switched
+        off (b2n.instant_sigma: bit-identical sigma, so occupancy decisions agree with what is rendered); in fp32 mode
+        from the same layer-by-layer kernels as ``forward``.  The 256-wide NeRFDecoder has no separable density branch:
+        it runs ``forward`` and drops rgb."""
         mode = self.mode
-        instant = isinstance(self.decoder, InstantNeRFDecoder)
-        if mode == "part2_instant" and instant and not self.decoder.can_fuse(self.dir_representation):
-            return self.decoder.density(self.representation(x))     # (the one-kernel fused decoder is faster: below)
+        dec = self.decoder
+        instant = isinstance(dec, InstantNeRFDecoder)
+        fusable = instant and x.is_cuda and dec.can_fuse(self.dir_representation)
+        if mode == "part2_instant" and instant:
+            feat = self.representation(x)
+            if fusable:
+                return b2n.instant_sigma(feat, dec.sigma_net.params, dec.sigma_net.input_pad_value)
+            return dec.density(feat)
         if mode in ("part3", "part4") and instant and not getattr(self, "direct_time_conditioning", False):
             if t is None:
                 raise ValueError(f"{mode} requires time input 't'.")
@@ -184,7 +190,11 @@ class NeuralField(nn.Module):
                 delta_x = self.deform_net(self.pos_encoder_for_deform(xd), feat_t)
             else:
                 delta_x = self.deform_decoder(self._tri_blend(xd, td), self.time_modulation(feat_t))
-            return self.decoder.density(self.canonical_repr(x + delta_x), feat_t)
+            feat_can = self.canonical_repr(x + delta_x)
+            if fusable:
+                return b2n.instant_sigma(torch.cat([feat_can, feat_t], dim=-1), dec.sigma_net.params,
+                                         dec.sigma_net.input_pad_value)
+            return dec.density(feat_can, feat_t)
         out = self.forward(x, torch.zeros_like(x), t) if mode in ("part3", "part4") else self.forward(x, torch.zeros_like(x))
         return out[1]
 

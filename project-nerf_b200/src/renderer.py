@@ -61,34 +61,56 @@ class DensityGrid(nn.Module):
         R = self.resolution
         pts = self._lattice(device)
         mode = getattr(model, "mode", "unknown")
-        batch = 2 ** 18
+        # The reference sweeps the lattice in 2^18-point batches (a memory limit of its hardware, :73-80) and, for Part 4,
+        # once per time anchor (:65-86).  Every kernel here is per-point, so the batch size does not change a single bit
+        # of sigma: the sweep runs in calls of up to 2^21 points, and Part 4's three anchors ride in ONE pass (points
+        # repeated per anchor, each with its own time) followed by the max over the anchors.
+        batch = 2 ** 21
         density = getattr(model, "density", None)
+        n = pts.shape[0]
 
-        def sweep(tval):
-            out = torch.empty(pts.shape[0], device=pts.device)
-            for i in range(0, pts.shape[0], batch):
-                p = pts[i:i + batch]
-                tt = None if tval is None else tval.expand(p.shape[0], -1)
+        def sweep(times):
+            """sigma [len(times), n]: one (batched) evaluation per time value (None: static model)"""
+            k = len(times)
+            out = torch.empty(k, n, device=pts.device)
+            flat = out.view(-1)
+            if times[0] is not None:
+                tcol = torch.cat([tv.to(pts.device, torch.float32).reshape(1, 1).expand(n, 1) for tv in times])
+            for i in range(0, k * n, batch):
+                j = min(i + batch, k * n)
+                if k == 1 or (i // n == (j - 1) // n):                # inside one anchor: a view of the lattice
+                    p = pts[i % n:(j - 1) % n + 1]
+                else:                                                  # spans anchors: gather the wrapped range
+                    p = pts[torch.arange(i, j, device=pts.device) % n]
+                tt = None if times[0] is None else tcol[i:j]
                 if density is not None:
                     s = density(p) if tt is None else density(p, t=tt)
                 elif tt is None:
                     _, s = model(p, torch.zeros_like(p))
                 else:
                     _, s, _ = model(p, torch.zeros_like(p), t=tt)
-                out[i:i + batch] = s.reshape(-1)
+                flat[i:j] = s.reshape(-1)
             return out
 
         if mode == "part4":
-            cur = None
-            for a in (0.0, 0.5, 1.0):
-                s = sweep(torch.tensor([[a]], device=device))
-                cur = s if cur is None else torch.maximum(cur, s)
+            # run.py:1972-1986 calls update() three times in a row with different ``time`` arguments, which Part 4
+            # ignores (reference :65-86): the three sweeps see the same model and return the same sigma.  The sweep is
+            # re-used while no parameter of the model has changed (autograd's version counters, which every in-place
+            # optimizer update bumps -- b2n.optim.FusedAdamW included); decay / threshold are applied per call below
+            key = (tuple((id(p), p._version) for p in model.parameters()), bool(getattr(model, "training", False)),
+                   str(pts.device), R, float(self.bound))
+            cached = getattr(self, "_sweep_cache", None)
+            if cached is not None and cached[0] == key:
+                cur = cached[1]
+            else:
+                cur = sweep([torch.tensor(a) for a in (0.0, 0.5, 1.0)]).amax(dim=0)
+                self._sweep_cache = (key, cur)
         elif mode == "part3":
             if time is None:
                 raise ValueError("Part 3 density grid update requires a time parameter")
-            cur = sweep(time.to(device))
+            cur = sweep([time.reshape(-1)[0]])[0]
         else:
-            cur = sweep(None)
+            cur = sweep([None])[0]
         cur = cur.contiguous()
         # every buffer the kernel touches lives on the device of the sweep (the registered buffers may still sit on
         # the CPU or on another GPU when the caller never moved the grid: the reference simply rebinds them, :122-128)

@@ -466,8 +466,7 @@ def test_density_grid_update_golden(mods, tag):
 @pytest.mark.parametrize("tag", FIELDS)
 def test_density_branch_equals_forward_sigma(mods, tag):
     """NeuralField.density (the sigma-only sweep of DensityGrid.update) returns exactly the sigma that
-    forward(x, 0, t) returns (fp32 mode: same kernels, bit-identical); in bf16 mode the two use different fused
-    tensor-core kernels and agree to the bf16 class."""
+    forward(x, 0, t) returns, in both precision modes (same kernels, colour branch skipped)."""
     g = load(f"field_{tag}")
     model = _model_from(mods, g["cfg"], g["sd"]).eval()
     torch.manual_seed(3)
@@ -485,7 +484,9 @@ def test_density_branch_equals_forward_sigma(mods, tag):
             dens_b = model.density(x, t=t) if dyn else model.density(x)
         finally:
             mods["b2n"].set_mlp_precision("fp32")
-    assert rel_err(dens_b.cpu(), full_b.cpu()) < 1e-2 and rel_err(dens_b.cpu(), full.cpu()) < 2e-2
+    # 16-bit mode: hash-grid decoders take sigma from the SAME fused kernel with its colour network switched off
+    # (b2n.instant_sigma) -- bit-identical; the 256-wide decoder runs forward and drops rgb -- identical by construction
+    assert torch.equal(dens_b, full_b) and rel_err(dens_b.cpu(), full.cpu()) < 2e-2
 
 
 def test_density_grid_update_uses_density_branch(mods):

@@ -189,8 +189,22 @@ def occ_update():
         for label, mdl in (("density branch", model), ("full forward", NoDensity(model))):
             grid = DensityGrid(resolution=R, bound=1.5, threshold=0.01).cuda()
             t = None if tval is None else torch.tensor([[tval]], device="cuda")
-            med, best = timeit(lambda: grid.update(mdl, device="cuda", time=t), n=5, warm=2)
-            print(f"occ update {name}: {label}: median {med:.3f} ms best {best:.3f} ms")
+            p0 = next(model.parameters())
+
+            def once():
+                with torch.no_grad():
+                    p0.add_(0.0)                 # an optimizer step happened: version counter bumped, sweep cache invalid
+                grid.update(mdl, device="cuda", time=t)
+
+            def trio():                          # run.py:1972-1986: three update() calls in a row between two optimizer steps
+                with torch.no_grad():
+                    p0.add_(0.0)
+                for _ in range(3):
+                    grid.update(mdl, device="cuda", time=t, decay=0.95)
+            med, best = timeit(once, n=5, warm=2)
+            med3, best3 = timeit(trio, n=5, warm=2)
+            print(f"occ update {name}: {label}: one call median {med:.3f} ms best {best:.3f} ms; "
+                  f"three calls in a row (run.py pattern) median {med3:.3f} ms")
 
 
 def c1_step(P_rays=4096, N=64):

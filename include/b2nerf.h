@@ -332,6 +332,11 @@ int b2n_nerf_mlp_dx(const void* dz0, const void* dz4, const float* W0, int ldw0,
 /* out[p, 0:kpad] (bf16) = x[p, 0:width] (fp32) zero-padded; kpad a multiple of 8.  Builds x_bf16 / d_bf16 of
  * b2n_nerf_mlp_wgrad in one pass. */
 int b2n_pad_bf16(const float* x, int64_t P, int width, int kpad, void* out, b2n_stream_t stream);
+/* The two small heads of the same decoder (sigma_layer 1 x 256 on H_7, rgb_layer 3 x 128 on hv), one streaming pass:
+ * dz_small [P,4] fp32 of b2n_nerf_mlp_bwd, h7 / hv = planes 7 and 9 of b2n_nerf_mlp_fwd (bf16 [P][256]).  ACCUMULATES
+ * gw_sigma [256], gw_rgb [3][128], gb [4] (rgb biases, then the sigma bias). */
+int b2n_nerf_mlp_head_wgrad(const float* dz_small, const void* h7_plane, const void* hv_plane, int64_t P, float* gw_sigma,
+                            float* gw_rgb, float* gb, b2n_stream_t stream);
 int b2n_nerf_mlp_wgrad(const void* dz_planes, const void* fwd_planes, const void* x_bf16, int kx, const void* d_bf16,
                        int64_t P, float* dW, float* dW0, float* dW4x, float* dWv_h, float* dWv_d, float* db,
                        int* err_flag, b2n_stream_t stream);

@@ -54,6 +54,7 @@ SIGNATURES = {
     "b2n_fmlp_wgrad": [I, P, P, P, P, P, P, P, P, P, P, P, L, P, P],
     "b2n_nerf_mlp_wgrad": [P, P, P, I, P, L, P, P, P, P, P, P, P, P],
     "b2n_nerf_mlp_dx": [P, P, P, I, P, I, I, L, P, I, P],
+    "b2n_nerf_mlp_head_wgrad": [P, P, P, L, P, P, P, P],
     "b2n_nerf_mlp_packed_bytes": [],
     "b2n_nerf_mlp_pack": [P, P, P, I, I, P, P],
     "b2n_nerf_mlp_fwd": [P, I, P, I, P, P, P, P, P, L, P, P, P, P, P, P],

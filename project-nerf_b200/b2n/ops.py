@@ -651,13 +651,13 @@ class _NerfMLP(torch.autograd.Function):
             grads["feat"] = (_mm_f32(dz[1], H[7]), gb_all[1])
             gv = _mm_f32(dz[0], torch.cat([H[8], db], dim=1))[:128]       # [256(128 used), 256 + 64]
             grads["view"] = (gv[:, :256 + dir_dim], gb_all[0][:128])
-        # the two small heads share one GEMM per input plane: rows = (d rgb_pre[3], d sigma_pre) padded to 8
-        dzs16 = torch.nn.functional.pad(dz_small, (0, 4)).to(torch.bfloat16)      # [P, 8]
-        gs = _mm_f32(dzs16, H[7])                                                    # [8, 256]
-        gr = _mm_f32(dzs16, H[9])                                                    # [8, 256] (hv in cols 0..127)
-        small_sum = dz_small.sum(dim=0)
-        grads["sigma"] = (gs[3:4], small_sum[3:4])
-        grads["rgb"] = (gr[:3, :128], small_sum[:3])
+        # the two small heads (1 x 256 on H_7, 3 x 128 on hv) and their biases: one streaming kernel over the two planes
+        heads = torch.zeros(256 + 3 * 128 + 4, device=dev)
+        call("b2n_nerf_mlp_head_wgrad", ptr(dz_small), ptr(H[7]), ptr(H[9]), Pn, ptr(heads), heads.data_ptr() + 256 * 4,
+             heads.data_ptr() + (256 + 384) * 4, stream(), work=(Pn * (16.0 + 512 + 256), 2.0 * Pn * (256 + 384)))
+        small_sum = heads[640:644]
+        grads["sigma"] = (heads[:256].view(1, 256), small_sum[3:4])
+        grads["rgb"] = (heads[256:640].view(3, 128), small_sum[:3])
         out = []
         for l in range(8):
             out += list(grads[f"pts{l}"])

@@ -85,6 +85,72 @@ static int launch_nerf_dx(const bf16* dz0, const bf16* dz4, const float* W0, int
   return check_launch("b2n_nerf_mlp_dx");
 }
 
+// ------------------------------------------------------------------------------ head weight gradients of the 256-wide decoder
+// sigma_layer (1 x 256) and rgb_layer (3 x 128) (NeRFDecoder, src/decoders.py:60-66): dW = dz_small^T [H_7 | hv] over all
+// points, db = column sums of dz_small -- two 4-row "GEMMs" that are pure streaming (768 bytes of bf16 planes per point
+// against 12 multiply-adds per column): one pass over the two planes, 16-byte loads, one atomicAdd per output per CTA.
+// (These were two cuBLAS split-K GEMMs plus a pad, a cast and a reduction in round 1: 6 % of the C1 step.)
+__global__ void __launch_bounds__(128) k_nerf_head_wgrad(const float4* __restrict__ dzs, const uint4* __restrict__ h7,
+                                                         const uint4* __restrict__ hv, int64_t P, float* __restrict__ gw_sigma,
+                                                         float* __restrict__ gw_rgb, float* __restrict__ gb) {
+  // thread t < 32: 8 columns of H_7 (sigma head);  a plane row is 256 bf16 = 32 uint4; hv uses its first 128 columns = 16 uint4
+  const int t = threadIdx.x;
+  const int grp = t >> 5, l = t & 31;            // 4 point-groups per CTA, lane = 8-column chunk
+  float as[8] = {}, ar[3][8] = {};
+  float bsum[4] = {};
+  const int64_t stride = (int64_t)gridDim.x * 4;
+  for (int64_t p = (int64_t)blockIdx.x * 4 + grp; p < P; p += stride) {
+    const float4 d = __ldg(dzs + p);             // (d rgb_pre[3], d sigma_pre)
+    const uint4 a = __ldcs(h7 + p * 32 + l);
+    const __nv_bfloat162* a2 = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(a2[j]);
+      as[2 * j] += d.w * f.x, as[2 * j + 1] += d.w * f.y;
+    }
+    if (l < 16) {
+      const uint4 b = __ldcs(hv + p * 32 + l);
+      const __nv_bfloat162* b2 = reinterpret_cast<const __nv_bfloat162*>(&b);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(b2[j]);
+        ar[0][2 * j] += d.x * f.x, ar[0][2 * j + 1] += d.x * f.y;
+        ar[1][2 * j] += d.y * f.x, ar[1][2 * j + 1] += d.y * f.y;
+        ar[2][2 * j] += d.z * f.x, ar[2][2 * j + 1] += d.z * f.y;
+      }
+    }
+    if (l == 0) bsum[0] += d.x, bsum[1] += d.y, bsum[2] += d.z, bsum[3] += d.w;
+  }
+  // combine the 4 point-groups of the CTA in shared memory, then one atomicAdd per output
+  __shared__ float red[4][32][33];
+  float* mine = &red[grp][l][0];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mine[j] = as[j];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) mine[8 + 8 * r + j] = ar[r][j];
+  mine[32] = 0.f;
+  __shared__ float bred[4][4];
+  if (l == 0)
+    for (int j = 0; j < 4; ++j) bred[grp][j] = bsum[j];
+  __syncthreads();
+  if (grp == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(gw_sigma + 8 * l + j, red[0][l][j] + red[1][l][j] + red[2][l][j] + red[3][l][j]);
+    if (l < 16) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int k = 8 + 8 * r + j;
+          atomicAdd(gw_rgb + r * 128 + 8 * l + j, red[0][l][k] + red[1][l][k] + red[2][l][k] + red[3][l][k]);
+        }
+    }
+    if (l < 4) atomicAdd(gb + l, bred[0][l] + bred[1][l] + bred[2][l] + bred[3][l]);
+  }
+}
+
 }  // namespace ndx
 }  // namespace b2n
 
@@ -100,4 +166,21 @@ extern "C" int b2n_nerf_mlp_dx(const void* dz0, const void* dz4, const float* W0
   if (pos_dim <= 64)
     return launch_nerf_dx<8>((const bf16*)dz0, (const bf16*)dz4, W0, ldw0, W4x, ldw4, pos_dim, P, g_x, ldg, (cudaStream_t)stream);
   return launch_nerf_dx<12>((const bf16*)dz0, (const bf16*)dz4, W0, ldw0, W4x, ldw4, pos_dim, P, g_x, ldg, (cudaStream_t)stream);
+}
+
+// dz_small [P,4] fp32 (d rgb_pre[3], d sigma_pre) of b2n_nerf_mlp_bwd; h7 / hv: bf16 [P][256] planes 7 and 9 of b2n_nerf_mlp_fwd.
+// ACCUMULATES: gw_sigma [256] = sum_p dz[p,3] H_7[p,:], gw_rgb [3][128] = sum_p dz[p,r] hv[p,:128], gb [4] = sum_p dz[p,:]
+// (rgb biases 0..2, sigma bias 3).
+extern "C" int b2n_nerf_mlp_head_wgrad(const float* dz_small, const void* h7_plane, const void* hv_plane, int64_t P,
+                                       float* gw_sigma, float* gw_rgb, float* gb, b2n_stream_t stream) {
+  B2N_REQUIRE(P >= 0, "negative size");
+  if (P == 0) return B2N_OK;
+  B2N_REQUIRE(dz_small && h7_plane && hv_plane && gw_sigma && gw_rgb && gb, "null pointer");
+  B2N_REQUIRE(((reinterpret_cast<uintptr_t>(dz_small) | reinterpret_cast<uintptr_t>(h7_plane) |
+                reinterpret_cast<uintptr_t>(hv_plane)) & 15) == 0, "16-byte aligned buffers required");
+  int64_t blocks = (P + 63) / 64;
+  if (blocks > (int64_t)kSMs * 8) blocks = (int64_t)kSMs * 8;
+  k_nerf_head_wgrad<<<(unsigned)blocks, 128, 0, (cudaStream_t)stream>>>((const float4*)dz_small, (const uint4*)h7_plane,
+                                                                      (const uint4*)hv_plane, P, gw_sigma, gw_rgb, gb);
+  return check_launch("b2n_nerf_mlp_head_wgrad");
 }

@@ -314,6 +314,15 @@ k_hash_fwd_pair(const float* __restrict__ x, int64_t P, float bound, float two_b
   }
   float* orow = out + p * ld + col0;
   const bool vec = ((reinterpret_cast<uintptr_t>(out + col0) & 15) == 0) && ((ld & 3) == 0);
+  // When the feature rows are contiguous (the plain [P, 2L] output, 2L <= 32) a warp's 16 rows are one contiguous block:
+  // the levels are collected in shared memory and leave as fully coalesced 16-byte stores (4 lines per instruction instead
+  // of 16: one L1 wavefront per point instead of four)
+  __shared__ float4 stage[8][16 * 10];            // row stride 10 float4: (2 pi + s) mod 8 -- conflict-free 16-byte stores
+  // (only while the table leaves room in the 126 MB L2: with the 94 MB table of T = 2^20 the full-line stores evict table
+  // lines and the kernel gets 26 % slower -- measured, 24 M points)
+  const bool contig = vec && col0 == 0 && ld == 2 * nl && ld <= 32 && (nl & 1) == 0 &&
+                      (uint64_t)(lv.l[nl - 1].offset + lv.l[nl - 1].size) * 8u <= (64ull << 20);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, pi = lane >> 1;
   // 4 levels = 8 floats = one 32-byte sector of the point's feature row per chunk; lane s stores its 16-byte half
   for (int l0 = 0; l0 < nl; l0 += 4) {
     float keep0 = 0.f, keep1 = 0.f, keep2 = 0.f, keep3 = 0.f;
@@ -344,8 +353,10 @@ k_hash_fwd_pair(const float* __restrict__ x, int64_t P, float bound, float two_b
         else keep0 = a0, keep1 = a1;
       }
     }
-    if (live) {
-      const int lf = l0 + 2 * s;                       // first level this lane stores
+    const int lf = l0 + 2 * s;                         // first level this lane stores
+    if (contig) {
+      if (lf + 1 < nl) stage[warp][pi * 10 + (lf >> 1)] = make_float4(keep0, keep1, keep2, keep3);
+    } else if (live) {
       float* o = orow + 2 * lf;
       if (vec && lf + 1 < nl) {
         __stcs(reinterpret_cast<float4*>(o), make_float4(keep0, keep1, keep2, keep3));
@@ -353,6 +364,17 @@ k_hash_fwd_pair(const float* __restrict__ x, int64_t P, float bound, float two_b
         if (lf < nl) __stcs(o, keep0), __stcs(o + 1, keep1);
         if (lf + 1 < nl) __stcs(o + 2, keep2), __stcs(o + 3, keep3);
       }
+    }
+  }
+  if (contig) {
+    __syncwarp();
+    const int64_t p_warp = ((int64_t)blockIdx.x * blockDim.x + 32 * warp) >> 1;     // first point of this warp
+    const int per_row = ld >> 2;                                                        // float4 per feature row
+    const int n4 = 16 * per_row;
+    float4* dst = reinterpret_cast<float4*>(out + p_warp * ld);
+    for (int i = lane; i < n4; i += 32) {
+      const int row = i / per_row, col = i - row * per_row;
+      if (p_warp + row < P) __stcs(dst + i, stage[warp][row * 10 + col]);
     }
   }
 }
@@ -608,7 +630,7 @@ k_hash_tri_bwd(const float* __restrict__ x, const float* __restrict__ tval, int6
 // A/B switch of the F == 2 kernels (b2nerf_debug.h: b2n_debug_hash_variant): bit 0 = pair-lane forward, bit 1 = pair-lane
 // table gradient; g_merge_res = coarsest-level run merging threshold of the pair-lane table gradient.
 static int g_hash_variant = 3;
-static uint32_t g_merge_res = 64;
+static uint32_t g_merge_res = 128;      // measured on the C2 sample set: 64 -> 7.59 ms, 128 -> 7.49, 200 -> 7.44 (T = 2^20: 128 best)
 
 static int fill_levels(const b2n_hash_level* h, int L, Levels* out) {
   if (!h || L <= 0 || L > B2N_MAX_LEVELS) return -1;

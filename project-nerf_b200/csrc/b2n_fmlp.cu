@@ -231,9 +231,18 @@ __global__ void __launch_bounds__(256) k_fmlp_absmax(const float* __restrict__ g
   P = clamp_rows(P, rows);
   unsigned int m = 0u;
   const int64_t n = P * cols;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t p = i / cols;
-    m = max(m, __float_as_uint(__ldg(g + p * ld + (i - p * cols))) & 0x7fffffffu);
+  if (ld == cols && (n & 3) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0) {       // contiguous rows: flat 16-byte loads
+    const float4* g4 = reinterpret_cast<const float4*>(g);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (n >> 2); i += (int64_t)gridDim.x * blockDim.x) {
+      const float4 v = __ldg(g4 + i);
+      m = max(max(m, __float_as_uint(v.x) & 0x7fffffffu), __float_as_uint(v.y) & 0x7fffffffu);
+      m = max(max(m, __float_as_uint(v.z) & 0x7fffffffu), __float_as_uint(v.w) & 0x7fffffffu);
+    }
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t p = i / cols;
+      m = max(m, __float_as_uint(__ldg(g + p * ld + (i - p * cols))) & 0x7fffffffu);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));

@@ -34,7 +34,15 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "sm__inst_executed_pipe_tensor.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
            "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
            "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
-           "smsp__inst_executed.sum", "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
+           "smsp__inst_executed.sum",
+           # L1TEX line visits ("wavefronts") and L2 sector traffic of global loads / reductions: the units the hash-grid
+           # kernels are bound by (per (point, level): 4 gathers or reductions of an x-neighbour pair)
+           "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum",
+           "l1tex__data_pipe_lsu_wavefronts_mem_global_op_ld.sum" if False else "l1tex__data_pipe_lsu_wavefronts.sum",
+           "l1tex__t_requests_pipe_lsu_mem_global_op_red.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_red.sum",
+           "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum", "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum",
+           "lts__t_sectors_op_read.sum", "lts__t_sectors_op_red.sum", "lts__t_sectors_op_write.sum",
+           "smsp__warp_issue_stalled_long_scoreboard_per_warp_active.pct",
            "smsp__warp_issue_stalled_short_scoreboard_per_warp_active.pct",
            "smsp__warp_issue_stalled_barrier_per_warp_active.pct",
            "smsp__warp_issue_stalled_lg_throttle_per_warp_active.pct",

@@ -3,13 +3,14 @@
 # parts (default: all) = any of: plain launches c2 c1 c4 c3
 #   plain    plain bench line (never under a profiler)
 #   launches ncu launch list of the same command
+#   opt      `--set full` capture of the fused optimizer kernels (C5 tensors)
 #   c2/c1/c4/c3  `--set full` captures of the hot kernels of C2 (hash / MLP64 / composite / march), C1 (tcgen05),
 #                C4 (fused MLPs) and C3 (wide-input tcgen05 decoder)
 # (no --import-source, and at most ~60 MB of reports per call: gpurun returns at most 64 MiB of gpurun_out/)
 # Outputs land in gpurun_out/<tag>_*; profiles/summarize.py turns them into the committed summaries.
 set -u
 TAG=${1:-r1d}
-PARTS=${2:-"plain launches c2 c1 c4 c3"}
+PARTS=${2:-"plain launches c2 opt c1 c4 c3"}
 OUT=gpurun_out
 mkdir -p $OUT
 has() { [[ " $PARTS " == *" $1 "* ]]; }
@@ -21,8 +22,14 @@ if has launches; then
       python bench.py --steps 2 --warmup 3 --no-extras --no-cpu-baseline > $OUT/${TAG}_ncu1.log 2>&1
 fi
 if has c2; then
-  ncu --set full --clock-control none -k 'regex:k_hash|k_instant|k_composite|k_march' -s 36 -c 9 \
+  # 8 matching kernels per step (march mask / compact, hash fwd, decoder fwd, composite fwd / bwd, decoder bwd, hash bwd):
+  # skip three steps, capture the fourth
+  ncu --set full --clock-control none -k 'regex:k_hash|k_instant|k_composite|k_march' -s 24 -c 8 \
       -f -o $OUT/${TAG}_prof python bench.py --steps 1 --warmup 3 --no-extras --no-cpu-baseline > $OUT/${TAG}_ncu2.log 2>&1
+fi
+if has opt; then
+  ncu --set full --clock-control none -k 'regex:k_opt_' -s 8 -c 2 \
+      -f -o $OUT/${TAG}_prof_opt python bench.py --only c5_dualhash > $OUT/${TAG}_ncu6.log 2>&1
 fi
 if has c1; then
   ncu --set full --clock-control none -k 'regex:^k_mlp256$|k_wgrad256' -s 15 -c 3 \

@@ -451,22 +451,30 @@ def bench_dynamic(dev, name, steps=10, warm=4, occupancy="dense", world=1, rank=
         # the collective on its own: the flat gradient buffer all-reduced back to back (what a step pays when nothing overlaps)
         ms_ar = run(lambda i: reducer.allreduce(), 10, 3)
         out.update(allreduce_bytes_per_step=reducer.nbytes, allreduce_ms_alone=ms_ar)
-    # ---- (3) one GPU: the whole step as ONE CUDA graph (static-capacity march + FusedAdamW; constant LR inside the graph)
-    if world == 1:
+    # ---- (3) the whole step as ONE CUDA graph (static-capacity march + FusedAdamW; constant LR inside the graph).  Under
+    # data parallelism the gradient all-reduces (NCCL) are captured with it: at 1024 rays per GPU (C5 strong scaling at 8
+    # GPUs) the eager step is launch-bound, the replay is not
+    if world == 1 or os.environ.get("B2N_DP_GRAPH", "1") == "1":
         try:
             march.set_static_capacity(True)
             gopt = b2n.optim.FusedAdamW(
                 [{"params": [p for p in model.parameters() if id(p) in table_ids], "tv_weight": spec["tv"]},
                  {"params": [p for p in model.parameters() if id(p) not in table_ids]}], lr=spec["lr"], weight_decay=1e-5)
             gscaler = torch.amp.GradScaler("cuda", enabled=True)
-            for p in model.parameters():
-                p.grad = torch.zeros_like(p)
+            if reducer is None:
+                for p in model.parameters():
+                    p.grad = torch.zeros_like(p)
 
             def gstep(ro, rd, tgt, times):
                 loss = loss_of((ro, rd, tgt, times), False)
-                for p in model.parameters():
-                    p.grad.zero_()
+                if reducer is None:
+                    for p in model.parameters():
+                        p.grad.zero_()
+                else:
+                    reducer.zero_grad()
                 gscaler.scale(loss).backward()
+                if reducer is not None:
+                    reducer.allreduce()
                 gscaler.step(gopt, max_norm=1.0)
                 gscaler.update()
                 return loss
@@ -475,14 +483,16 @@ def bench_dynamic(dev, name, steps=10, warm=4, occupancy="dense", world=1, rank=
             graphed = b2n.graphs.GraphedStep(gstep, pool[0])
             ms_graph = run(lambda i: graphed(*pool[i % 3]), steps, warm)
             b2n.check_errors()
-            out.update(train_rays_per_s_static_capacity=B / ms_static * 1e3, train_rays_per_s_cuda_graph=B / ms_graph * 1e3,
+            out.update(train_rays_per_s_static_capacity=world * B / ms_static * 1e3,
+                       train_rays_per_s_cuda_graph=world * B / ms_graph * 1e3,
                        train_ms_per_step_cuda_graph=ms_graph, loss_after_graph_steps=float(graphed(*pool[0]).detach()))
         except Exception as exc:
             out["cuda_graph_error"] = f"{type(exc).__name__}: {exc}"[:300]
         finally:
             march.set_static_capacity(False)
-            for p in model.parameters():
-                p.grad = None
+            if reducer is None:
+                for p in model.parameters():
+                    p.grad = None
     model.eval()
     with torch.no_grad():
         ms_render = run(lambda i: render_rays(model, pool[i % 3][0], pool[i % 3][1], NEAR, FAR, N, False,
@@ -735,6 +745,8 @@ def main():
                       "c5_dualhash_dp_weak_ms_per_step": weak.get("train_ms_per_step"),
                       "c5_dualhash_dp_strong_rays_per_s": strong.get("train_rays_per_s"),
                       "c5_dualhash_dp_strong_ms_per_step": strong.get("train_ms_per_step"),
+                      "c5_dualhash_dp_strong_cuda_graph_rays_per_s": strong.get("train_rays_per_s_cuda_graph"),
+                      "c5_dualhash_dp_weak_cuda_graph_rays_per_s": weak.get("train_rays_per_s_cuda_graph"),
                       "c5_dualhash_dp_allreduce_ms_alone": weak.get("allreduce_ms_alone"),
                       "c5_dualhash_dp_allreduce_bytes": weak.get("allreduce_bytes_per_step")}
     if not args.no_extras and rank == 0:

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2N_ABI_VERSION 12
+#define B2N_ABI_VERSION 13
 
 #define B2N_OK 0
 #define B2N_EINVAL (-1)  /* bad argument (null pointer, size, unsupported shape) */
@@ -226,6 +226,13 @@ int b2n_sigma_head_bwd(const float* h, int ldh, int64_t P, const float* g_sigma,
 int b2n_instant_mlp_fwd(const float* x_enc, int ldx, int pos_dim, const float* dirs, const float* dir_bands,
                         int L_dir, const float* sigma_params, const float* color_params, int64_t P, float* rgb,
                         float* sigma, float in_pad_value, b2n_stream_t stream);
+/* The same forward (same arguments, same fp16 split arithmetic) with the layer products on tcgen05: a CTA owns 128
+ * points = the 128 TMEM lanes, activations round-trip TMEM -> registers -> shared memory between layers.  err_flag: a
+ * device int the kernel sets non-zero if it had to abort a stalled mbarrier wait (outputs are then invalid); it is never
+ * cleared by the kernel. */
+int b2n_instant_mlp_fwd_tc(const float* x_enc, int ldx, int pos_dim, const float* dirs, const float* dir_bands,
+                           int L_dir, const float* sigma_params, const float* color_params, int64_t P, float* rgb,
+                           float* sigma, float in_pad_value, int* err_flag, b2n_stream_t stream);
 int b2n_instant_mlp_bwd(const float* x_enc, int ldx, int pos_dim, const float* dirs, const float* dir_bands,
                         int L_dir, const float* sigma_params, const float* color_params, int64_t P,
                         const float* g_rgb, const float* g_sigma, float* g_x_enc, int ldg, float* g_sigma_params,

@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb2nerf.so")
 
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 P, L, I, F = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_float
 
@@ -45,6 +45,7 @@ SIGNATURES = {
     "b2n_sigma_head_fwd": [P, I, L, P, P],
     "b2n_sigma_head_bwd": [P, I, L, P, P, I, P],
     "b2n_instant_mlp_fwd": [P, I, I, P, P, I, P, P, L, P, P, F, P],
+    "b2n_instant_mlp_fwd_tc": [P, I, I, P, P, I, P, P, L, P, P, F, P, P],
     "b2n_instant_mlp_bwd": [P, I, I, P, P, I, P, P, L, P, P, P, I, P, P, P, F, P],
     "b2n_fmlp_in_pad": [I],
     "b2n_fmlp_out_pad": [I],

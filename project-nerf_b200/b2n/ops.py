@@ -17,6 +17,11 @@ from torch.amp import custom_bwd, custom_fwd
 from . import _lib
 from ._lib import HashLevelC, current_rows, ptr, require_cuda, stream, with_ctx_rows
 
+# forward of the fused Instant decoder: the tcgen05 kernel (b2n_mlp64tc.cu) or, when False, the mma.sync one
+# (b2n_mlp64.cu); same arithmetic (environment B2N_INSTANT_TC=0 selects the latter for A/B timing)
+import os as _os
+INSTANT_FWD_TC = _os.environ.get("B2N_INSTANT_TC", "1") != "0"
+
 
 def call(name, *args, work=(0.0, 0.0)):
     _lib.call(name, *args, work=work)        # late-bound so that _lib.PROFILER can be swapped at run time
@@ -430,8 +435,13 @@ class _InstantMLP(torch.autograd.Function):
         rgb = _narrow_out(Pn, 3, device=x_enc.device)
         sigma = _narrow_out(Pn, 1, device=x_enc.device)
         flops = 2.0 * Pn * (64 * pos_dim + 16 * 64 + 64 * 43 + 64 * 64 + 3 * 64)
-        call("b2n_instant_mlp_fwd", ptr(x_enc), pos_dim, pos_dim, ptr(dirs), ptr(bands), bands.numel(), ptr(sp),
-             ptr(cp), Pn, ptr(rgb), ptr(sigma), ctx.pad_value, stream(), work=(Pn * (4.0 * pos_dim + 12 + 16), flops))
+        if INSTANT_FWD_TC:
+            call("b2n_instant_mlp_fwd_tc", ptr(x_enc), pos_dim, pos_dim, ptr(dirs), ptr(bands), bands.numel(), ptr(sp),
+                 ptr(cp), Pn, ptr(rgb), ptr(sigma), ctx.pad_value, ptr(_sticky_err(x_enc.device)), stream(),
+                 work=(Pn * (4.0 * pos_dim + 12 + 16), flops))
+        else:
+            call("b2n_instant_mlp_fwd", ptr(x_enc), pos_dim, pos_dim, ptr(dirs), ptr(bands), bands.numel(), ptr(sp),
+                 ptr(cp), Pn, ptr(rgb), ptr(sigma), ctx.pad_value, stream(), work=(Pn * (4.0 * pos_dim + 12 + 16), flops))
         ctx.save_for_backward(x_enc, dirs, bands, sp, cp)
         return rgb, sigma
 
@@ -461,8 +471,13 @@ def instant_sigma(x_enc, sigma_params, pad_value: float = 0.0):
     x_enc, sp = _c(x_enc), _c(sigma_params)
     Pn, pos_dim = x_enc.shape
     sigma = _narrow_out(Pn, 1, device=x_enc.device)
-    call("b2n_instant_mlp_fwd", ptr(x_enc), pos_dim, pos_dim, None, None, 0, ptr(sp), None, Pn, None, ptr(sigma),
-         float(pad_value), stream(), work=(Pn * (4.0 * pos_dim + 4), 2.0 * Pn * (64 * pos_dim + 16 * 64)))
+    work = (Pn * (4.0 * pos_dim + 4), 2.0 * Pn * (64 * pos_dim + 16 * 64))
+    if INSTANT_FWD_TC:
+        call("b2n_instant_mlp_fwd_tc", ptr(x_enc), pos_dim, pos_dim, None, None, 0, ptr(sp), None, Pn, None, ptr(sigma),
+             float(pad_value), ptr(_sticky_err(x_enc.device)), stream(), work=work)
+    else:
+        call("b2n_instant_mlp_fwd", ptr(x_enc), pos_dim, pos_dim, None, None, 0, ptr(sp), None, Pn, None, ptr(sigma),
+             float(pad_value), stream(), work=work)
     return sigma
 
 
@@ -480,6 +495,7 @@ def instant_mlp(x_enc, dirs, bands, sigma_params, color_params, pad_value: float
 # the flag costs a host sync, so it is checked with a delay -- every 64th launch looks at the flags of earlier launches
 # (long finished) -- and a non-zero flag raises here rather than letting garbage activations train on.
 _ERR_FLAGS: dict = {}          # device index -> flags of launches not yet inspected
+_STICKY_ERR: dict = {}         # device index -> one flag shared by every tcgen05 Instant-decoder launch on that device
 
 
 def _raise_if_set(flags):
@@ -499,6 +515,17 @@ def _track_err(err: torch.Tensor):
         _raise_if_set(old)
 
 
+def _sticky_err(device) -> torch.Tensor:
+    """the abort flag of the fused Instant decoder (b2n_instant_mlp_fwd_tc): one int per device, never reset by the
+    kernels, read only by ``check_errors`` -- no per-call allocation, memset or host sync, and a stable address for CUDA
+    graphs"""
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    t = _STICKY_ERR.get(idx)
+    if t is None:
+        t = _STICKY_ERR[idx] = torch.zeros(1, device=torch.device("cuda", idx), dtype=torch.int32)
+    return t
+
+
 def check_errors():
     """Inspect the abort flags of EVERY tcgen05 launch not looked at yet (one host sync per device).  The delayed check
     above never sees the last < 64 launches of a run; call this where a sync happens anyway -- after ``loss.item()``,
@@ -508,6 +535,12 @@ def check_errors():
         flags, _ERR_FLAGS[dev] = _ERR_FLAGS[dev], []
         if flags:
             _raise_if_set(flags)
+    for t in _STICKY_ERR.values():
+        if int(t.item()) != 0:
+            code = int(t.item())
+            t.zero_()
+            raise RuntimeError(f"a tcgen05 Instant-decoder kernel aborted a stalled pipeline (code {code}); its outputs "
+                               f"are invalid")
 
 
 def nerf_mlp_supported(decoder, pos_dim: int, dir_dim: int) -> bool:

@@ -587,6 +587,36 @@ def test_instant_mlp_fp16_vs_oracle(mods, pos_dim, Pn, gscale):
     assert float(V3[3:].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("pos_dim,Pn,pad", [(32, 128 * 11 + 3, 0.0), (53, 777, 0.0), (64, 130, 0.0), (32, 5, 0.0),
+                                            (20, 1000, 1.0), (32, 300000, 0.0)])
+def test_instant_fwd_tcgen05_matches_mma_sync(mods, pos_dim, Pn, pad):
+    """The two forward kernels of the fused Instant decoder (tcgen05: b2n_mlp64tc.cu, mma.sync: b2n_mlp64.cu) implement
+    the same arithmetic (fp16 operands, fp32 accumulation, split first layer): they may differ by accumulation order
+    only.  Also the density-only mode and the ones-padded inputs of upstream checkpoints."""
+    from oracle import nerf_oracle as O
+    ops = mods["b2n"].ops
+    gen = torch.Generator().manual_seed(11)
+    sp = cu(O._fused_init(pos_dim, 16, 64, 1, gen))
+    cp = cu(O._fused_init(43, 3, 64, 2, gen))
+    x = torch.randn(Pn, pos_dim, device=DEV) * 0.5
+    d = torch.nn.functional.normalize(torch.randn(Pn, 3, device=DEV), dim=-1)
+    bands = cu(O.fourier_bands(4))
+    out = {}
+    prev = ops.INSTANT_FWD_TC
+    try:
+        for tc in (False, True):
+            ops.INSTANT_FWD_TC = tc
+            rgb, sigma = mods["b2n"].instant_mlp(x, d, bands, sp, cp, pad_value=pad)
+            out[tc] = (rgb.clone(), sigma.clone(), mods["b2n"].instant_sigma(x, sp, pad_value=pad).clone())
+    finally:
+        ops.INSTANT_FWD_TC = prev
+    mods["b2n"].check_errors()
+    tag = f"instant_fwd_tc[{pos_dim},{Pn}]"
+    assert record(f"{tag}:rgb", rel_err(out[True][0], out[False][0])) < 2e-5
+    assert record(f"{tag}:sigma", rel_err(out[True][1], out[False][1])) < 2e-5
+    assert torch.equal(out[True][2], out[True][1])            # density-only mode: the same sigma_net arithmetic
+
+
 def test_instant_mlp_nonfinite_gradient_propagates(mods):
     """GradScaler's overflow detection needs an inf / NaN incoming gradient to stay visible: the saturating fp16
     conversions of the kernel must not turn it into a large finite step."""

@@ -413,6 +413,29 @@ def composite(B=2 ** 18, N=128):
                   f"{v['bytes'] / v['ms'] / 1e6:.0f} GB/s algorithmic ({100 * v['bytes'] / v['ms'] / 1e6 / 6496.8:.1f} % of measured HBM peak)")
 
 
+def mlp64(P=1 << 22):
+    """fused Instant decoder: forward (mma.sync vs tcgen05) and backward, C2-sized (4.2 M points) and Part-3 width"""
+    from oracle import nerf_oracle as O
+    for pos_dim in (32, 53):
+        gen = torch.Generator().manual_seed(0)
+        sp = O._fused_init(pos_dim, 16, 64, 1, gen).cuda().requires_grad_(True)
+        cp = O._fused_init(43, 3, 64, 2, gen).cuda().requires_grad_(True)
+        x = (torch.randn(P, pos_dim, device="cuda") * 0.5).requires_grad_(True)
+        d = torch.nn.functional.normalize(torch.randn(P, 3, device="cuda"), dim=-1)
+        bands = O.fourier_bands(4).cuda()
+        for tc in (False, True):
+            ops.INSTANT_FWD_TC = tc
+            with torch.no_grad():
+                med, best = timeit(lambda: b2n.instant_mlp(x, d, bands, sp, cp))
+                meds, bests = timeit(lambda: b2n.instant_sigma(x, sp))
+            print(f"instant fwd pos_dim={pos_dim} P={P} tc={tc}: {med:.3f} ms (best {best:.3f}); sigma-only {meds:.3f} ms")
+        b2n.check_errors()
+        rgb, sigma = b2n.instant_mlp(x, d, bands, sp, cp)
+        g1, g2 = torch.randn_like(rgb), torch.randn_like(sigma)
+        med, best = timeit(lambda: torch.autograd.grad([rgb, sigma], [x, sp, cp], [g1, g2], retain_graph=True))
+        print(f"instant bwd pos_dim={pos_dim} P={P}: {med:.3f} ms (best {best:.3f})")
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "mlp256"
     P = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 262144
@@ -430,6 +453,8 @@ if __name__ == "__main__":
         red_bench()
     elif what == "l2":
         l2_gather()
+    elif what == "mlp64":
+        mlp64()
     elif what == "composite":
         composite()
         composite(8192, 64)

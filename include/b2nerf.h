@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define B2N_ABI_VERSION 13
+#define B2N_ABI_VERSION 14
 
 #define B2N_OK 0
 #define B2N_EINVAL (-1)  /* bad argument (null pointer, size, unsupported shape) */
@@ -237,6 +237,13 @@ int b2n_instant_mlp_bwd(const float* x_enc, int ldx, int pos_dim, const float* d
                         int L_dir, const float* sigma_params, const float* color_params, int64_t P,
                         const float* g_rgb, const float* g_sigma, float* g_x_enc, int ldg, float* g_sigma_params,
                         float* g_color_params, void* work4, float in_pad_value, b2n_stream_t stream);
+/* The same backward (same arguments and arithmetic) with the five weight gradients dW = dZ^T In on tcgen05: the staged
+ * 64-point tiles are MN-major SWIZZLE_128B operands, the fp32 accumulators live in TMEM for the whole persistent loop.
+ * err_flag as in b2n_instant_mlp_fwd_tc. */
+int b2n_instant_mlp_bwd_tc(const float* x_enc, int ldx, int pos_dim, const float* dirs, const float* dir_bands,
+                           int L_dir, const float* sigma_params, const float* color_params, int64_t P,
+                           const float* g_rgb, const float* g_sigma, float* g_x_enc, int ldg, float* g_sigma_params,
+                           float* g_color_params, void* work4, float in_pad_value, int* err_flag, b2n_stream_t stream);
 
 /* ------------------------------------------------------------------------
  * Fused small-width ReLU MLPs of the dynamic configs, bf16 tensor-core

@@ -21,6 +21,8 @@ from ._lib import HashLevelC, current_rows, ptr, require_cuda, stream, with_ctx_
 # (b2n_mlp64.cu); same arithmetic (environment B2N_INSTANT_TC=0 selects the latter for A/B timing)
 import os as _os
 INSTANT_FWD_TC = _os.environ.get("B2N_INSTANT_TC", "1") != "0"
+# backward: weight gradients on tcgen05 (k_instant_bwd_tc) or, when False, everything on mma.sync (k_instant_bwd)
+INSTANT_BWD_TC = _os.environ.get("B2N_INSTANT_BWD_TC", "1") != "0"
 
 
 def call(name, *args, work=(0.0, 0.0)):
@@ -455,10 +457,16 @@ class _InstantMLP(torch.autograd.Function):
         g_sp, g_cp = torch.zeros_like(sp), torch.zeros_like(cp)
         work = torch.empty(1, device=x_enc.device, dtype=torch.int32)        # |g|-max of the gradient pre-pass
         flops = 6.0 * Pn * (64 * pos_dim + 16 * 64 + 64 * 43 + 64 * 64 + 3 * 64)
-        call("b2n_instant_mlp_bwd", ptr(x_enc), pos_dim, pos_dim, ptr(dirs), ptr(bands), bands.numel(), ptr(sp),
-             ptr(cp), Pn, ptr(_c(g_rgb)), ptr(_c(g_sigma)), ptr(g_x), pos_dim, ptr(g_sp), ptr(g_cp), ptr(work),
-             ctx.pad_value, stream(),
-             work=(Pn * (8.0 * pos_dim + 12 + 16), flops))
+        if INSTANT_BWD_TC:
+            call("b2n_instant_mlp_bwd_tc", ptr(x_enc), pos_dim, pos_dim, ptr(dirs), ptr(bands), bands.numel(), ptr(sp),
+                 ptr(cp), Pn, ptr(_c(g_rgb)), ptr(_c(g_sigma)), ptr(g_x), pos_dim, ptr(g_sp), ptr(g_cp), ptr(work),
+                 ctx.pad_value, ptr(_sticky_err(x_enc.device)), stream(),
+                 work=(Pn * (8.0 * pos_dim + 12 + 16), flops))
+        else:
+            call("b2n_instant_mlp_bwd", ptr(x_enc), pos_dim, pos_dim, ptr(dirs), ptr(bands), bands.numel(), ptr(sp),
+                 ptr(cp), Pn, ptr(_c(g_rgb)), ptr(_c(g_sigma)), ptr(g_x), pos_dim, ptr(g_sp), ptr(g_cp), ptr(work),
+                 ctx.pad_value, stream(),
+                 work=(Pn * (8.0 * pos_dim + 12 + 16), flops))
         return g_x, None, None, g_sp, g_cp, None
 
 

@@ -1,0 +1,65 @@
+// tcgen05 / TMEM / mbarrier PTX wrappers shared by the 64-wide decoder kernels (b2n_mlp64tc.cu: forward on tcgen05;
+// b2n_mlp64.cu: weight gradients of the backward on tcgen05).  Same recipes as b2n_mlp256.cu / b2n_wgrad256.cu.
+#pragma once
+#include <cstdint>
+#include "b2n_common.cuh"
+
+namespace b2n {
+namespace tc {
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a stalled pipeline raises the error flag instead of hanging the GPU
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err) {
+  for (uint32_t it = 0; it < (1u << 24); ++it)
+    if (mbar_try(bar, parity)) return true;
+  atomicCAS(err, 0, 7);
+  return false;
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+               ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row atoms 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+// kind::f16 instruction descriptor: D = fp32, A = B = fp16 (format 0), both K-major, M = 128
+__device__ __forceinline__ uint32_t umma_idesc(int n) {
+  return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// byte offset of 16-byte chunk c (0..7) of row r inside a swizzled block of 128-byte rows
+__device__ __forceinline__ uint32_t swz(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+// MN-major SWIZZLE_128B operand (the contraction index is the ROW of the tile: [rows = K][64 columns = M or N], 128-byte
+// rows): 64-column blocks `blk` bytes apart, 8-row groups 1024 B apart; a K step of 16 rows advances the address by 2048 B
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t saddr, uint32_t blk) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((blk >> 4) & 0x3FFF) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// kind::f16 instruction descriptor, fp16 operands BOTH MN-major (bits 15 / 16), D = fp32, M = 128
+__device__ __forceinline__ uint32_t umma_idesc_mn(int n) {
+  return (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+}  // namespace tc
+}  // namespace b2n

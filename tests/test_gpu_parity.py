@@ -617,6 +617,37 @@ def test_instant_fwd_tcgen05_matches_mma_sync(mods, pos_dim, Pn, pad):
     assert torch.equal(out[True][2], out[True][1])            # density-only mode: the same sigma_net arithmetic
 
 
+@pytest.mark.parametrize("pos_dim,Pn", [(32, 64 * 37 + 5), (53, 777), (64, 130), (32, 5), (32, 200000)])
+def test_instant_bwd_tcgen05_wgrad_matches_mma_sync(mods, pos_dim, Pn):
+    """The two backward kernels of the fused Instant decoder differ only in where the weight gradients are accumulated
+    (tcgen05 + TMEM vs mma.sync + registers): same operands, fp32 accumulation in a different order."""
+    from oracle import nerf_oracle as O
+    ops = mods["b2n"].ops
+    gen = torch.Generator().manual_seed(13)
+    sp = cu(O._fused_init(pos_dim, 16, 64, 1, gen)).requires_grad_(True)
+    cp = cu(O._fused_init(43, 3, 64, 2, gen)).requires_grad_(True)
+    x = (torch.randn(Pn, pos_dim, device=DEV) * 0.5).requires_grad_(True)
+    d = torch.nn.functional.normalize(torch.randn(Pn, 3, device=DEV), dim=-1)
+    bands = cu(O.fourier_bands(4))
+    rgb, sigma = mods["b2n"].instant_mlp(x, d, bands, sp, cp)
+    g1, g2 = torch.randn_like(rgb), torch.randn_like(sigma)
+    out = {}
+    prev = ops.INSTANT_BWD_TC
+    try:
+        for tc in (False, True):
+            ops.INSTANT_BWD_TC = tc
+            out[tc] = torch.autograd.grad([rgb, sigma], [x, sp, cp], [g1, g2], retain_graph=True)
+    finally:
+        ops.INSTANT_BWD_TC = prev
+    mods["b2n"].check_errors()
+    tag = f"instant_bwd_tc[{pos_dim},{Pn}]"
+    assert torch.equal(out[True][0], out[False][0])                 # g_x: the same mma.sync chain
+    for a_, b_, name in zip(out[True][1:], out[False][1:], ("g_sigma_params", "g_color_params")):
+        assert record(f"{tag}:{name}", rel_err(a_, b_)) < 2e-5, name
+    V3 = out[True][2][64 * 48 + 64 * 64:].view(16, 64)
+    assert float(V3[3:].abs().max()) == 0.0
+
+
 def test_instant_mlp_nonfinite_gradient_propagates(mods):
     """GradScaler's overflow detection needs an inf / NaN incoming gradient to stay visible: the saturating fp16
     conversions of the kernel must not turn it into a large finite step."""

@@ -432,8 +432,11 @@ def mlp64(P=1 << 22):
         b2n.check_errors()
         rgb, sigma = b2n.instant_mlp(x, d, bands, sp, cp)
         g1, g2 = torch.randn_like(rgb), torch.randn_like(sigma)
-        med, best = timeit(lambda: torch.autograd.grad([rgb, sigma], [x, sp, cp], [g1, g2], retain_graph=True))
-        print(f"instant bwd pos_dim={pos_dim} P={P}: {med:.3f} ms (best {best:.3f})")
+        for tc in (False, True):
+            ops.INSTANT_BWD_TC = tc
+            med, best = timeit(lambda: torch.autograd.grad([rgb, sigma], [x, sp, cp], [g1, g2], retain_graph=True))
+            print(f"instant bwd pos_dim={pos_dim} P={P} tc={tc}: {med:.3f} ms (best {best:.3f})")
+        b2n.check_errors()
 
 
 if __name__ == "__main__":

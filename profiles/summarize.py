@@ -18,8 +18,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
 HERE = os.path.join(ROOT, "profiles")
 
-ENTRY_OF = {"k_hash_fwd": "b2n_hash_fwd", "k_hash_bwd_table": "b2n_hash_bwd", "k_instant_fwd": "b2n_instant_mlp_fwd",
-            "k_instant_bwd": "b2n_instant_mlp_bwd", "k_composite_fwd": "b2n_composite_fwd",
+ENTRY_OF = {"k_hash_fwd": "b2n_hash_fwd", "k_hash_bwd_table": "b2n_hash_bwd",
+            "itc::k_instant_fwd_tc": "b2n_instant_mlp_fwd_tc", "k_instant_fwd_tc": "b2n_instant_mlp_fwd_tc",
+            "k_instant_bwd_tc": "b2n_instant_mlp_bwd_tc", "k_instant_fwd<": "b2n_instant_mlp_fwd",
+            "k_instant_bwd<": "b2n_instant_mlp_bwd", "k_composite_fwd": "b2n_composite_fwd",
             "k_composite_bwd": "b2n_composite_bwd", "k_march_mask": "b2n_march_mask",
             "k_march_compact": "b2n_march_compact", "k_mlp256<0": "b2n_nerf_mlp_fwd", "k_mlp256<1": "b2n_nerf_mlp_bwd",
             "k_fmlp_fwd": "b2n_fmlp_fwd", "k_fmlp_bwd": "b2n_fmlp_bwd", "k_fmlp_wgrad": "b2n_fmlp_wgrad",
@@ -52,7 +54,7 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
 
 def short(name):
     name = name.split("(")[0]
-    for pre in ("void ", "b2n::", "fm::", "m256::", "wg256::", "opt::"):
+    for pre in ("void ", "b2n::", "fm::", "m256::", "wg256::", "opt::", "itc::"):
         name = name.replace(pre, "")
     return name.strip()
 

@@ -530,6 +530,9 @@ def _sticky_err(device) -> torch.Tensor:
     idx = device.index if device.index is not None else torch.cuda.current_device()
     t = _STICKY_ERR.get(idx)
     if t is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("the Instant decoder's abort flag must exist before CUDA-graph capture: run one eager "
+                               "step first (b2n.graphs.GraphedStep does)")
         t = _STICKY_ERR[idx] = torch.zeros(1, device=torch.device("cuda", idx), dtype=torch.int32)
     return t
 

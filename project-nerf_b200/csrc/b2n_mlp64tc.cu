@@ -8,11 +8,15 @@
 // lanes: thread t owns point t.  Per layer ONE elected thread issues the K/16 tcgen05.mma (A = the activation tile in shared
 // memory, K-major SWIZZLE_128B; B = the layer's weight tile, staged once per CTA; D = 128 x N fp32 in TMEM), commits to an
 // mbarrier, and every thread then drains ITS accumulator row with tcgen05.ld, applies the activation, and writes the row
-// back as the next layer's A operand -- in place: the MMA is done with the tile when the barrier fires.  ~110 registers,
-// 68 KB of shared memory -> 3 CTAs (12 warps) per SM.
+// back as the next layer's A operand -- in place: the MMA is done with the tile when the barrier fires.
+//
+// One layer step is a latency chain (issue -> MMA -> commit -> mbarrier -> tcgen05.ld -> pack -> st.shared ->
+// fence.proxy.async -> bar.sync, ~1800 cycles measured with one CTA per SM), so throughput comes from co-resident CTAs:
+// 52 KB of shared memory at pos_dim <= 32 (x_hi and x_lo share ONE 64-column tile) -> 4 CTAs per SM, 68 KB above -> 3.
+// Measured, 4.2 M points (tools/kbench.py mlp64): 0.42 ms against 0.62 ms for the mma.sync kernel (pos_dim 32), 0.66
+// against 0.86 ms (pos_dim 53); 1 / 2 / 3 / 4 CTAs per SM: 1.05 / 0.66 / 0.50 / 0.42 ms.
+// cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1 for this kernel; the grid is sized from shared memory instead.
 #include <cuda_fp16.h>
-#include <cstdio>
-#include <cstdlib>
 #include "b2n_common.cuh"
 #include "b2n_tc.cuh"
 
@@ -389,13 +393,6 @@ extern "C" int b2n_instant_mlp_fwd_tc(const float* x_enc, int ldx, int pos_dim, 
     int per_sm = (int)(232448u / (smem_bytes + 1024u));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8;                  // 8 x 64 TMEM columns = the 512 of an SM
-    if (const char* e = getenv("B2N_TC_CTAS")) {
-      cudaFuncAttributes fa;
-      cudaFuncGetAttributes(&fa, kern);
-      fprintf(stderr, "k_instant_fwd_tc: occupancy %d CTAs/SM (regs %d, static smem %zu, local %zu, max dyn %d, err %s)\n", per_sm,
-              fa.numRegs, fa.sharedSizeBytes, fa.localSizeBytes, fa.maxDynamicSharedSizeBytes, cudaGetErrorString(cudaPeekAtLastError()));
-      if (atoi(e) > 0) per_sm = atoi(e);
-    }
     int64_t grid = (int64_t)kSMs * per_sm;
     if (grid > tiles) grid = tiles;
     kern<<<(unsigned)grid, itc::THREADS, smem_bytes, st>>>(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params,

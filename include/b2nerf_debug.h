@@ -22,6 +22,11 @@ int b2n_debug_mlp256_flags(int flags);
  * Both produce the same results; the switch exists for A/B timing and parity tests. */
 int b2n_debug_mlp256_set_pair(int on);
 
+/* schedule of b2n_instant_mlp_bwd_tc at pos_dim <= 32: 1 (default) = two 4-warp CTAs per SM, 3 = one CTA per SM with
+ * three 4-warp groups and a single MMA issuer.  Same results up to the order of the fp32 accumulation.  Returns the
+ * previous value. */
+int b2n_debug_instant_bwd_groups(int groups);
+
 /* A/B switch of the F = 2 hash-grid kernels: variant bit 0 = pair-lane forward (default on), bit 1 = pair-lane table
  * gradient (default on); 0 = the (point, level)-per-lane kernels.  merge_res >= 0 sets the coarsest-level run-merging
  * threshold of the pair-lane table gradient (levels with res <= merge_res are reduced across runs of equal cells). */

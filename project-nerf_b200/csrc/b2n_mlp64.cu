@@ -647,22 +647,48 @@ k_instant_bwd(const float* __restrict__ x, int ldx, int pos_dim, const float* __
 
 // ------------------------------------------------------------------------------ backward, weight gradients on tcgen05
 // Same recompute + data-gradient chain as k_instant_bwd (mma.sync, a warp owns 16 points of a 64-point tile), but the
-// five weight gradients dW = dZ^T In -- a third of the kernel's tensor work, and the part that needs BOTH operands from
-// shared memory through ldmatrix.trans plus 88 accumulator registers per thread -- go to the 5th-generation tensor cores:
+// five weight gradients dW = dZ^T In -- a third of the kernel's tensor work, the part that needs BOTH operands from
+// shared memory through ldmatrix.trans, and 88 accumulator registers per thread -- go to the 5th-generation tensor cores:
 // the staged tiles are written in the SWIZZLE_128B layout (64 points x 128 B, 16-byte chunk c of row r at c ^ (r & 7)),
 // which read with the point as the contraction index is exactly tcgen05's MN-major operand form (b2n_wgrad256.cu), and
-// one thread issues, per tile, 12 MMAs (M = 128, K = 16 points each) into fp32 accumulators that live in TMEM for the
-// whole persistent loop.  The MMAs run asynchronously under the next tile's first layer.
-//   slot (8 KB each):   0 dz3 | 1 dz4 | 2 c | 3 c1 | 4 c2 | 5 h1 | 6 dz5 (cols 0..15), dz2 (cols 16..31) | 7 dz1 | 8 x
-//   D1 [128 x 128] = [dz3; dz4]^T [c | c1]   -> rows 0..63  x cols 0..47   = dV1,   rows 64..127 x cols 64..127 = dV2
-//   D2 [128 x 64]  = [c2; h1]^T  [dz5, dz2]  -> rows 0..63  x cols 0..2    = dV3^T, rows 64..127 x cols 16..31  = dW2^T
-//   D3 [128 x 64]  = [dz1; x]^T  [x]         -> rows 0..63  x cols 0..in_pad-1 = dW1
+// per tile 12 MMAs (M = 128, K = 16 points each) accumulate into fp32 accumulators that live in TMEM for the whole
+// persistent loop.  The MMAs run asynchronously under the next tile's first layer.
+//
+// pos_dim <= 32 (MERGED map, 8 slots of 8 KB; x, dz5 and dz2 share one 64-column tile X = [x | dz5 | dz2]):
+//   0 dz3 | 1 dz4 | 2 c | 3 c1 | 4 dz1 | 5 h1 | 6 c2 | 7 X
+//   D1 [128 x 128] = [dz3; dz4]^T [c | c1] -> rows 0..63 x cols 0..47 = dV1,       rows 64..127 x cols 64..127 = dV2
+//   D2 [128 x 64]  = [c2; X]^T    X        -> rows 0..63 x cols 32..34 = dV3^T
+//   D3 [128 x 64]  = [dz1; h1]^T  X        -> rows 0..63 x cols 0..in_pad-1 = dW1, rows 64..127 x cols 48..63 = dW2^T
+// wider inputs (9 slots):
+//   0 dz3 | 1 dz4 | 2 c | 3 c1 | 4 c2 | 5 h1 | 6 dz5 (cols 0..15), dz2 (cols 16..31) | 7 dz1 | 8 x
+//   D1 as above;  D2 = [c2; h1]^T [dz5, dz2] -> rows 0..63 x cols 0..2 = dV3^T, rows 64..127 x cols 16..31 = dW2^T;
+//   D3 = [dz1; x]^T [x] -> rows 0..63 x cols 0..in_pad-1 = dW1
 // (the off-diagonal blocks are by-products nobody reads; an M = 64 MMA costs the same tensor time as M = 128).
+//
+// GROUPS == 1: a CTA is one 4-warp group (two CTAs per SM: 8 warps); its thread 0 issues the MMAs after a __syncthreads.
+// GROUPS == 3 (pos_dim <= 32): ONE CTA per SM holds three 4-warp groups, each with its own tile slots and 168 registers
+// per thread -- 12 warps per SM for the latency-bound mma.sync chain -- that share the weights and ONE set of TMEM
+// accumulators; one thread of a fourth warpgroup (which hands its registers to the workers: setmaxnreg) is the only MMA
+// issuer (tcgen05.mma is ordered per issuing thread: one issuer keeps the read-modify-write of the shared accumulators
+// in order).  A group hands a staged tile over through an mbarrier
+// (128 arrivals) and gets it back through the issuer's tcgen05.commit.
 namespace bwtc {
 constexpr int SLOT = 8192;
-constexpr int N_SLOTS = 9;
-enum { S_DZ3 = 0, S_DZ4, S_C, S_C1, S_C2, S_H1, S_DZ25, S_DZ1, S_X };
 constexpr int D1 = 0, D2 = 128, D3 = 192, TMEM_COLS = 256;
+template <int POS_K>
+struct Slots {
+  static constexpr bool MERGED = POS_K == 32;
+  static constexpr int N = MERGED ? 8 : 9;
+  static constexpr int DZ3 = 0, DZ4 = 1, C = 2, C1 = 3;
+  static constexpr int DZ1 = MERGED ? 4 : 7, H1 = 5, C2 = MERGED ? 6 : 4, X = MERGED ? 7 : 8;
+  static constexpr int DZ25 = MERGED ? 7 : 6;            // tile holding dz5 / dz2 ...
+  static constexpr int COL_DZ5 = MERGED ? 32 : 0;        // ... and their first columns
+  static constexpr int COL_DZ2 = MERGED ? 48 : 16;
+  static constexpr int A2 = C2;                          // A operand of D2: [c2; next slot]
+  static constexpr int B2 = DZ25;
+  static constexpr int A3 = DZ1;                         // A operand of D3: [dz1; next slot]
+  static constexpr int B3 = X;
+};
 // element offset of (row, col) inside a 64 x 64 swizzled tile
 __device__ __forceinline__ int sw(int r, int c) { return r * 64 + ((((c >> 3) ^ r) & 7) << 3) + (c & 7); }
 template <int KT>
@@ -690,14 +716,27 @@ __device__ __forceinline__ void relu_mask_sw(float (&c)[NT][4], const op16* tile
     if (!(hi.y > 0.f)) c[j][3] = 0.f;
   }
 }
-template <int POS_K>
+template <int POS_K, int GROUPS>
 constexpr size_t smem_bytes() {
-  return (size_t)N_SLOTS * SLOT + (size_t)weight_layout<POS_K>().end * sizeof(op16) + 64;
+  return (size_t)GROUPS * Slots<POS_K>::N * SLOT + (size_t)weight_layout<POS_K>().end * sizeof(op16) + 128;
 }
+template <int GROUPS>
+constexpr int threads() { return GROUPS == 1 ? MLP_THREADS : (GROUPS + 1) * MLP_THREADS; }
 }  // namespace bwtc
 
-template <int POS_K>
-__global__ void __launch_bounds__(MLP_THREADS, 2)
+// ReLU gate of a packed gradient fragment by the packed ACTIVATION fragment of the same layer (forward A fragments and
+// c_to_a outputs share one (row, column) layout): 2 instructions per 2 elements, no shared-memory re-read
+template <int KT>
+__device__ __forceinline__ void relu_gate(uint32_t (&dz)[KT][4], const uint32_t (&act)[KT][4]) {
+  const __half2 zero = __floats2half2_rn(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < KT; ++k)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dz[k][i] &= __hgt2_mask(*reinterpret_cast<const __half2*>(&act[k][i]), zero);
+}
+
+template <int POS_K, int GROUPS>
+__global__ void __launch_bounds__(bwtc::threads<GROUPS>(), GROUPS == 1 ? 2 : 1)
 k_instant_bwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float* __restrict__ dirs,
                  const float* __restrict__ bands, int L_dir, const float* __restrict__ sp, const float* __restrict__ cp,
                  int64_t P, const float* __restrict__ g_rgb, const float* __restrict__ g_sigma, float* __restrict__ g_x,
@@ -705,36 +744,41 @@ k_instant_bwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
                  const int* __restrict__ rows, float in_pad_value, int* __restrict__ err) {
   using namespace bwtc;
   using namespace tc;
+  using SL = Slots<POS_K>;
+  // ReLU gate of the gradient chain: from the forward's A fragments kept in registers (48 registers, 1.57 -> 1.53 ms at
+  // pos_dim 32 with two CTAs per SM) or, where registers are short, from the staged activation tiles
+  constexpr bool GATE_REGS = POS_K == 32 && GROUPS == 1;
   P = clamp_rows(P, rows);
   // the operand tiles need a 1024-byte aligned base: dynamic shared memory starts on one when the kernel has no static
   // shared memory (checked: a misaligned base raises the error flag instead of computing garbage)
   extern __shared__ __align__(1024) unsigned char smem[];
-  if ((tc::s32(smem) & 1023u) != 0u) {
+  if ((s32(smem) & 1023u) != 0u) {
     if (threadIdx.x == 0) atomicCAS(err, 0, 8);
     return;
   }
   const float gscale = grad_scale_from(__ldg(absmax));
   const float inv_s = 1.f / gscale;
-  op16* tiles = reinterpret_cast<op16*>(smem);
-  auto T = [&](int slot) { return tiles + slot * (SLOT / 2); };
-  op16* sm = reinterpret_cast<op16*>(smem + N_SLOTS * SLOT);          // weights, padded rows (mma.sync B operands)
+  op16* sm = reinterpret_cast<op16*>(smem + GROUPS * SL::N * SLOT);          // weights, padded rows (mma.sync B operands)
   constexpr MlpSmem L = weight_layout<POS_K>();
   constexpr int SX = POS_K + PAD, SH = HID + PAD, SC = CIN + PAD;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.end);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
-  const uint32_t bar = s32(bars);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm + L.end);                  // done[GROUPS], full[GROUPS]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GROUPS);
   constexpr int KT1 = POS_K / 16;
   const int in_pad = (pos_dim + 15) & ~15;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int group = threadIdx.x / MLP_THREADS;                               // GROUPS: the issuer warp
+  const int lane = threadIdx.x & 31, warp = (threadIdx.x >> 5) & 3, g = lane >> 2, t = lane & 3;
   const int row0 = 16 * warp;  // this warp's slab inside the 64-point tile
   load_all_weights<POS_K>(sp, cp, in_pad, sm);
-  for (int i = threadIdx.x; i < N_SLOTS * SLOT / 16; i += blockDim.x)      // unused tile columns are operands too: finite
+  for (int i = threadIdx.x; i < GROUPS * SL::N * SLOT / 16; i += blockDim.x)      // unused tile columns are operands too: finite
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
   if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+    for (int i = 0; i < GROUPS; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bars + i)), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bars + GROUPS + i)), "r"(MLP_THREADS));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if (threadIdx.x < 32) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -742,213 +786,252 @@ k_instant_bwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tile_base = s32(smem);
-
   const int64_t n_tiles = (P + 63) / 64;
-  float2 xraw[KT1][4];       // this tile's x_enc rows as fp32: fetched one tile ahead, split into hi / lo at the top of the tile
-  load_x_raw<KT1>(x, ldx, pos_dim, (int64_t)blockIdx.x * 64 + row0, P, xraw, lane, in_pad_value);
-  uint32_t phase = 0;
-  bool pending = false, ok = true;
-  for (int64_t tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
-    const int64_t p0 = tile * 64 + row0;
-    // ---------------- forward recompute (staging every layer input)
-    uint32_t ax[1][KT1][4], axl[1][KT1][4];
-    pack_x_hl<KT1>(xraw, ax[0], axl[0]);
-    float dcur[3];
-    load_dir(dirs, p0 + (lane & 15), P, dcur);
-    float grgb[4] = {0.f, 0.f, 0.f, 0.f}, gsig[2] = {0.f, 0.f};
-    {
-      const int64_t pa = p0 + g, pb = pa + 8;
-      const int col = 2 * t;
-      if (col < 3) {
-        if (pa < P) {
-          grgb[0] = __ldcs(g_rgb + 3 * pa + col);
-          if (col + 1 < 3) grgb[1] = __ldcs(g_rgb + 3 * pa + col + 1);
-        }
-        if (pb < P) {
-          grgb[2] = __ldcs(g_rgb + 3 * pb + col);
-          if (col + 1 < 3) grgb[3] = __ldcs(g_rgb + 3 * pb + col + 1);
-        }
-      }
-      if (t == 0) {
-        if (pa < P) gsig[0] = __ldcs(g_sigma + pa);
-        if (pb < P) gsig[1] = __ldcs(g_sigma + pb);
-      }
+  const int64_t tile_first = (int64_t)blockIdx.x * GROUPS, tile_step = (int64_t)gridDim.x * GROUPS;
+
+  // the 12 weight-gradient MMAs of one staged tile group + the commit that hands the slots back
+  auto issue_wgrad = [&](int grp, uint32_t acc_first) {
+    const uint32_t base = s32(smem) + grp * SL::N * SLOT;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) grgb[i] *= gscale;      // the whole gradient chain runs on S * dL/dy
-      gsig[0] *= gscale, gsig[1] *= gscale;
+    for (int kk = 0; kk < 4; ++kk) {
+      const uint32_t o = base + kk * 2048;
+      const uint32_t acc = (acc_first | (uint32_t)kk) ? 1u : 0u;
+      tc_mma(tmem + D1, umma_desc_mn(o + SL::DZ3 * SLOT, SLOT), umma_desc_mn(o + SL::C * SLOT, SLOT), umma_idesc_mn(128), acc);
+      tc_mma(tmem + D2, umma_desc_mn(o + SL::A2 * SLOT, SLOT), umma_desc_mn(o + SL::B2 * SLOT, SLOT), umma_idesc_mn(64), acc);
+      tc_mma(tmem + D3, umma_desc_mn(o + SL::A3 * SLOT, SLOT), umma_desc_mn(o + SL::B3 * SLOT, SLOT), umma_idesc_mn(64), acc);
     }
-    uint32_t ah[1][4][4];
-    {
-      float c[1][8][4] = {};
-      gemm_fwd<1, 8, KT1>(c, axl, sm + L.w1, SX, lane);              // split product (see k_instant_fwd)
-      gemm_fwd<1, 8, KT1>(c, ax, sm + L.w1lo, SX, lane);
-      gemm_fwd<1, 8, KT1>(c, ax, sm + L.w1, SX, lane);
-      c_to_a<8, true>(c[0], ah[0]);
-    }
-    // the previous tile's weight-gradient MMAs have had the first layer to finish reading the staged tiles
-    if (pending) {
-      ok = mbar_wait(bar, phase, err);
-      phase ^= 1;
-      tc_fence_after();
-    }
-    store_a_sw<KT1>(ax[0], T(S_X), row0, 0, lane);
-    store_a_sw<4>(ah[0], T(S_H1), row0, 0, lane);
-    // next tile's inputs: the fragments are dead from here on
-    load_x_raw<KT1>(x, ldx, pos_dim, (tile + gridDim.x) * 64 + row0, P, xraw, lane, in_pad_value);
-    float hs0 = 0.f, hs1 = 0.f;  // h[.,0] of rows g and g+8 (threads with t == 0)
-    uint32_t ac[1][3][4];
-    {
-      float c[1][2][4] = {};
-      gemm_fwd<1, 2, 4>(c, ah, sm + L.w2, SH, lane);
-      hs0 = c[0][0][0], hs1 = c[0][0][2];
-      uint32_t tmp[1][4];
-      c_to_a<2, false>(c[0], tmp);
-      ac[0][0][0] = tmp[0][0], ac[0][0][1] = tmp[0][1], ac[0][0][2] = tmp[0][2], ac[0][0][3] = tmp[0][3];
-      store_a_sw<1>(tmp, T(S_C), row0, 0, lane);
-    }
-    if (lane < 16) dir_features(dcur, bands, L_dir, T(S_C) + (row0 + lane) * 64, in_pad_value, 2, (row0 + lane) & 7);
-    __syncwarp();
-    {
-      const int r = row0 + (lane & 7) + 8 * ((lane >> 3) & 1);
-      ldsm_x4(ac[0][1], T(S_C) + sw(r, 16 + 8 * (lane >> 4)));
-      ldsm_x4(ac[0][2], T(S_C) + sw(r, 32 + 8 * (lane >> 4)));
-    }
-    uint32_t a1[1][4][4], a2[1][4][4];
-    {
-      float c[1][8][4] = {};
-      gemm_fwd<1, 8, 3>(c, ac, sm + L.v1, SC, lane);
-      c_to_a<8, true>(c[0], a1[0]);
-      store_a_sw<4>(a1[0], T(S_C1), row0, 0, lane);
-    }
-    {
-      float c[1][8][4] = {};
-      gemm_fwd<1, 8, 4>(c, a1, sm + L.v2, SH, lane);
-      c_to_a<8, true>(c[0], a2[0]);
-      store_a_sw<4>(a2[0], T(S_C2), row0, 0, lane);
-    }
-    // ---------------- output layer + its gradient
-    uint32_t dz5[1][4];
-    {
-      float c[1][1][4] = {};
-      gemm_fwd<1, 1, 4>(c, a2, sm + L.v3, SH, lane);
-      float d[4] = {0.f, 0.f, 0.f, 0.f};
-      const int64_t pa = p0 + g, pb = pa + 8;
-      const int col = 2 * t;
-      if (col < 3) {
-        if (pa < P) {
-          const float y = sigmoidf(c[0][0][0]);
-          d[0] = grgb[0] * y * (1.f - y);
-          if (col + 1 < 3) {
-            const float y1 = sigmoidf(c[0][0][1]);
-            d[1] = grgb[1] * y1 * (1.f - y1);
-          }
-        }
-        if (pb < P) {
-          const float y = sigmoidf(c[0][0][2]);
-          d[2] = grgb[2] * y * (1.f - y);
-          if (col + 1 < 3) {
-            const float y1 = sigmoidf(c[0][0][3]);
-            d[3] = grgb[3] * y1 * (1.f - y1);
-          }
+    tc_commit(s32(bars + grp));
+  };
+
+  bool ok = true;
+  if (GROUPS > 1 && group == GROUPS) {
+    // ================================ MMA issuer (one thread of the fourth warpgroup) ================================
+    // registers are allocated per warpgroup: the kernel starts at 128 per thread (512 threads), the issuer's warpgroup
+    // gives back all but 32 and the three worker groups grow to 160
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+    if (threadIdx.x == GROUPS * MLP_THREADS) {
+      uint32_t issued = 0u;
+      for (int64_t base_tile = tile_first, it = 0; base_tile < n_tiles && ok; base_tile += tile_step, ++it) {
+        for (int grp = 0; grp < GROUPS && ok; ++grp) {
+          if (base_tile + grp >= n_tiles) break;
+          ok = mbar_wait(s32(bars + GROUPS + grp), (uint32_t)(it & 1), err);
+          tc_fence_after();
+          issue_wgrad(grp, issued);
+          issued = 1u;
         }
       }
-      dz5[0][0] = pack2(d[0], d[1]), dz5[0][1] = pack2(d[2], d[3]), dz5[0][2] = 0u, dz5[0][3] = 0u;
-      store_a_sw<1>(dz5, T(S_DZ25), row0, 0, lane);
     }
-    // ---------------- data-gradient chain
-    uint32_t dz[1][4][4];
-    {
-      float c[8][4] = {};
-      gemm_dgrad<8, 1>(c, dz5, sm + L.v3, SH, lane);          // d c2
-      relu_mask_sw<8>(c, T(S_C2), row0, lane);
-      c_to_a<8, false>(c, dz[0]);
-      store_a_sw<4>(dz[0], T(S_DZ4), row0, 0, lane);
-    }
-    {
-      float c[8][4] = {};
-      gemm_dgrad<8, 4>(c, dz[0], sm + L.v2, SH, lane);        // d c1
-      relu_mask_sw<8>(c, T(S_C1), row0, lane);
-      c_to_a<8, false>(c, dz[0]);
-      store_a_sw<4>(dz[0], T(S_DZ3), row0, 0, lane);
-    }
-    uint32_t dz2[1][4];
-    {
-      float c[2][4] = {};
-      gemm_dgrad<2, 4>(c, dz[0], sm + L.v1, SC, lane);        // d h (first 16 inputs of color_net)
-      if (t == 0) {                                           // density head: softplus'(h0 - 5)
+  } else {
+    // ================================ worker groups ================================
+    if (GROUPS > 1) asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+    op16* tiles = reinterpret_cast<op16*>(smem) + group * SL::N * (SLOT / 2);
+    auto T = [&](int slot) { return tiles + slot * (SLOT / 2); };
+    const uint32_t bar_done = s32(bars + group), bar_full = s32(bars + GROUPS + group);
+    float2 xraw[KT1][4];       // this tile's x_enc rows as fp32: fetched one tile ahead, split into hi / lo at the top of the tile
+    load_x_raw<KT1>(x, ldx, pos_dim, (tile_first + group) * 64 + row0, P, xraw, lane, in_pad_value);
+    uint32_t phase = 0;
+    bool pending = false;
+    for (int64_t tile = tile_first + group; tile < n_tiles && ok; tile += tile_step) {
+      const int64_t p0 = tile * 64 + row0;
+      // ---------------- forward recompute (staging every layer input)
+      uint32_t ax[1][KT1][4], axl[1][KT1][4];
+      pack_x_hl<KT1>(xraw, ax[0], axl[0]);
+      float dcur[3];
+      load_dir(dirs, p0 + (lane & 15), P, dcur);
+      float grgb[4] = {0.f, 0.f, 0.f, 0.f}, gsig[2] = {0.f, 0.f};
+      {
         const int64_t pa = p0 + g, pb = pa + 8;
-        if (pa < P) {
-          const float v = hs0 - 5.f;
-          c[0][0] += gsig[0] * (v > 20.f ? 1.f : sigmoidf(v));
+        const int col = 2 * t;
+        if (col < 3) {
+          if (pa < P) {
+            grgb[0] = __ldcs(g_rgb + 3 * pa + col);
+            if (col + 1 < 3) grgb[1] = __ldcs(g_rgb + 3 * pa + col + 1);
+          }
+          if (pb < P) {
+            grgb[2] = __ldcs(g_rgb + 3 * pb + col);
+            if (col + 1 < 3) grgb[3] = __ldcs(g_rgb + 3 * pb + col + 1);
+          }
         }
-        if (pb < P) {
-          const float v = hs1 - 5.f;
-          c[0][2] += gsig[1] * (v > 20.f ? 1.f : sigmoidf(v));
+        if (t == 0) {
+          if (pa < P) gsig[0] = __ldcs(g_sigma + pa);
+          if (pb < P) gsig[1] = __ldcs(g_sigma + pb);
         }
-      }
-      c_to_a<2, false>(c, dz2);
-      store_a_sw<1>(dz2, T(S_DZ25), row0, 16, lane);
-    }
-    {
-      float c[8][4] = {};
-      gemm_dgrad<8, 1>(c, dz2, sm + L.w2, SH, lane);          // d hidden1
-      relu_mask_sw<8>(c, T(S_H1), row0, lane);
-      c_to_a<8, false>(c, dz[0]);
-      store_a_sw<4>(dz[0], T(S_DZ1), row0, 0, lane);
-    }
-    proxy_fence();               // the staged tiles are read by the tensor cores (async proxy)
-    tc_fence_before();
-    __syncthreads();
-    // ---------------- weight gradients over the 64 staged points: 12 asynchronous MMAs
-    if (threadIdx.x == 0) {
-      tc_fence_after();
-      const uint32_t first = pending ? 1u : 0u;
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const uint32_t o = tile_base + kk * 2048;
-        const uint32_t acc = (first | (uint32_t)kk) ? 1u : 0u;
-        tc_mma(tmem + D1, umma_desc_mn(o + S_DZ3 * SLOT, SLOT), umma_desc_mn(o + S_C * SLOT, SLOT), umma_idesc_mn(128), acc);
-        tc_mma(tmem + D2, umma_desc_mn(o + S_C2 * SLOT, SLOT), umma_desc_mn(o + S_DZ25 * SLOT, SLOT), umma_idesc_mn(64), acc);
-        tc_mma(tmem + D3, umma_desc_mn(o + S_DZ1 * SLOT, SLOT), umma_desc_mn(o + S_X * SLOT, SLOT), umma_idesc_mn(64), acc);
+        for (int i = 0; i < 4; ++i) grgb[i] *= gscale;      // the whole gradient chain runs on S * dL/dy
+        gsig[0] *= gscale, gsig[1] *= gscale;
       }
-      tc_commit(bar);
-    }
-    pending = true;
-    if (g_x) {                   // d x_enc: registers + weights only, overlaps the MMAs
-      float c[POS_K / 8][4] = {};
-      gemm_dgrad<POS_K / 8, 4>(c, dz[0], sm + L.w1, SX, lane);
-      const int64_t pa = p0 + g, pb = pa + 8;
+      uint32_t ah[1][4][4];
+      {
+        float c[1][8][4] = {};
+        gemm_fwd<1, 8, KT1>(c, axl, sm + L.w1, SX, lane);              // split product (see k_instant_fwd)
+        gemm_fwd<1, 8, KT1>(c, ax, sm + L.w1lo, SX, lane);
+        gemm_fwd<1, 8, KT1>(c, ax, sm + L.w1, SX, lane);
+        c_to_a<8, true>(c[0], ah[0]);
+      }
+      // the previous tile's weight-gradient MMAs have had the first layer to finish reading the staged tiles
+      if (pending) {
+        ok = mbar_wait(bar_done, phase, err);
+        phase ^= 1;
+        tc_fence_after();
+      }
+      store_a_sw<KT1>(ax[0], T(SL::X), row0, 0, lane);
+      store_a_sw<4>(ah[0], T(SL::H1), row0, 0, lane);
+      // next tile's inputs: the fragments are dead from here on
+      load_x_raw<KT1>(x, ldx, pos_dim, (tile + tile_step) * 64 + row0, P, xraw, lane, in_pad_value);
+      float hs0 = 0.f, hs1 = 0.f;  // h[.,0] of rows g and g+8 (threads with t == 0)
+      uint32_t ac[1][3][4];
+      {
+        float c[1][2][4] = {};
+        gemm_fwd<1, 2, 4>(c, ah, sm + L.w2, SH, lane);
+        hs0 = c[0][0][0], hs1 = c[0][0][2];
+        uint32_t tmp[1][4];
+        c_to_a<2, false>(c[0], tmp);
+        ac[0][0][0] = tmp[0][0], ac[0][0][1] = tmp[0][1], ac[0][0][2] = tmp[0][2], ac[0][0][3] = tmp[0][3];
+        store_a_sw<1>(tmp, T(SL::C), row0, 0, lane);
+      }
+      if (lane < 16) dir_features(dcur, bands, L_dir, T(SL::C) + (row0 + lane) * 64, in_pad_value, 2, (row0 + lane) & 7);
+      __syncwarp();
+      {
+        const int r = row0 + (lane & 7) + 8 * ((lane >> 3) & 1);
+        ldsm_x4(ac[0][1], T(SL::C) + sw(r, 16 + 8 * (lane >> 4)));
+        ldsm_x4(ac[0][2], T(SL::C) + sw(r, 32 + 8 * (lane >> 4)));
+      }
+      uint32_t a1[1][4][4], a2[1][4][4];
+      {
+        float c[1][8][4] = {};
+        gemm_fwd<1, 8, 3>(c, ac, sm + L.v1, SC, lane);
+        c_to_a<8, true>(c[0], a1[0]);
+        store_a_sw<4>(a1[0], T(SL::C1), row0, 0, lane);
+      }
+      {
+        float c[1][8][4] = {};
+        gemm_fwd<1, 8, 4>(c, a1, sm + L.v2, SH, lane);
+        c_to_a<8, true>(c[0], a2[0]);
+        store_a_sw<4>(a2[0], T(SL::C2), row0, 0, lane);
+      }
+      // ---------------- output layer + its gradient
+      uint32_t dz5[1][4];
+      {
+        float c[1][1][4] = {};
+        gemm_fwd<1, 1, 4>(c, a2, sm + L.v3, SH, lane);
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+        const int64_t pa = p0 + g, pb = pa + 8;
+        const int col = 2 * t;
+        if (col < 3) {
+          if (pa < P) {
+            const float y = sigmoidf(c[0][0][0]);
+            d[0] = grgb[0] * y * (1.f - y);
+            if (col + 1 < 3) {
+              const float y1 = sigmoidf(c[0][0][1]);
+              d[1] = grgb[1] * y1 * (1.f - y1);
+            }
+          }
+          if (pb < P) {
+            const float y = sigmoidf(c[0][0][2]);
+            d[2] = grgb[2] * y * (1.f - y);
+            if (col + 1 < 3) {
+              const float y1 = sigmoidf(c[0][0][3]);
+              d[3] = grgb[3] * y1 * (1.f - y1);
+            }
+          }
+        }
+        dz5[0][0] = pack2(d[0], d[1]), dz5[0][1] = pack2(d[2], d[3]), dz5[0][2] = 0u, dz5[0][3] = 0u;
+        store_a_sw<1>(dz5, T(SL::DZ25), row0, SL::COL_DZ5, lane);
+      }
+      // ---------------- data-gradient chain
+      uint32_t dz[1][4][4];
+      {
+        float c[8][4] = {};
+        gemm_dgrad<8, 1>(c, dz5, sm + L.v3, SH, lane);          // d c2
+        if (!GATE_REGS) relu_mask_sw<8>(c, T(SL::C2), row0, lane);
+        c_to_a<8, false>(c, dz[0]);
+        if (GATE_REGS) relu_gate<4>(dz[0], a2[0]);
+        store_a_sw<4>(dz[0], T(SL::DZ4), row0, 0, lane);
+      }
+      {
+        float c[8][4] = {};
+        gemm_dgrad<8, 4>(c, dz[0], sm + L.v2, SH, lane);        // d c1
+        if (!GATE_REGS) relu_mask_sw<8>(c, T(SL::C1), row0, lane);
+        c_to_a<8, false>(c, dz[0]);
+        if (GATE_REGS) relu_gate<4>(dz[0], a1[0]);
+        store_a_sw<4>(dz[0], T(SL::DZ3), row0, 0, lane);
+      }
+      uint32_t dz2[1][4];
+      {
+        float c[2][4] = {};
+        gemm_dgrad<2, 4>(c, dz[0], sm + L.v1, SC, lane);        // d h (first 16 inputs of color_net)
+        if (t == 0) {                                           // density head: softplus'(h0 - 5)
+          const int64_t pa = p0 + g, pb = pa + 8;
+          if (pa < P) {
+            const float v = hs0 - 5.f;
+            c[0][0] += gsig[0] * (v > 20.f ? 1.f : sigmoidf(v));
+          }
+          if (pb < P) {
+            const float v = hs1 - 5.f;
+            c[0][2] += gsig[1] * (v > 20.f ? 1.f : sigmoidf(v));
+          }
+        }
+        c_to_a<2, false>(c, dz2);
+        store_a_sw<1>(dz2, T(SL::DZ25), row0, SL::COL_DZ2, lane);
+      }
+      {
+        float c[8][4] = {};
+        gemm_dgrad<8, 1>(c, dz2, sm + L.w2, SH, lane);          // d hidden1
+        if (!GATE_REGS) relu_mask_sw<8>(c, T(SL::H1), row0, lane);
+        c_to_a<8, false>(c, dz[0]);
+        if (GATE_REGS) relu_gate<4>(dz[0], ah[0]);
+        store_a_sw<4>(dz[0], T(SL::DZ1), row0, 0, lane);
+      }
+      // ---------------- weight gradients over the 64 staged points: 12 asynchronous MMAs
+      proxy_fence();               // the staged tiles are read by the tensor cores (async proxy)
+      if (GROUPS == 1) {
+        tc_fence_before();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          tc_fence_after();
+          issue_wgrad(0, pending ? 1u : 0u);
+        }
+      } else {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_full) : "memory");      // release: the issuer acquires
+      }
+      pending = true;
+      if (g_x) {                   // d x_enc: registers + weights only, overlaps the MMAs
+        float c[POS_K / 8][4] = {};
+        gemm_dgrad<POS_K / 8, 4>(c, dz[0], sm + L.w1, SX, lane);
+        const int64_t pa = p0 + g, pb = pa + 8;
 #pragma unroll
-      for (int j = 0; j < POS_K / 8; ++j) {
-        const int col = 8 * j + 2 * t;
-        if (pa < P) {
-          if (col < pos_dim) g_x[pa * ldg + col] = c[j][0] * inv_s;
-          if (col + 1 < pos_dim) g_x[pa * ldg + col + 1] = c[j][1] * inv_s;
-        }
-        if (pb < P) {
-          if (col < pos_dim) g_x[pb * ldg + col] = c[j][2] * inv_s;
-          if (col + 1 < pos_dim) g_x[pb * ldg + col + 1] = c[j][3] * inv_s;
+        for (int j = 0; j < POS_K / 8; ++j) {
+          const int col = 8 * j + 2 * t;
+          if (pa < P) {
+            if (col < pos_dim) g_x[pa * ldg + col] = c[j][0] * inv_s;
+            if (col + 1 < pos_dim) g_x[pa * ldg + col + 1] = c[j][1] * inv_s;
+          }
+          if (pb < P) {
+            if (col < pos_dim) g_x[pb * ldg + col] = c[j][2] * inv_s;
+            if (col + 1 < pos_dim) g_x[pb * ldg + col + 1] = c[j][3] * inv_s;
+          }
         }
       }
     }
+    if (pending && ok) ok = mbar_wait(bar_done, phase, err);      // this group's last MMAs are complete
   }
   // ---------------- flush: TMEM accumulators -> one red per weight per CTA
-  if (pending && ok) ok = mbar_wait(bar, phase, err);
+  tc_fence_before();
+  __syncthreads();                 // every group's MMAs are complete (each group waited for its own)
   tc_fence_after();
-  if (pending && ok) {
+  if (group == 0 && ok && tile_first < n_tiles) {
     const uint32_t lane_base = tmem + ((uint32_t)(32 * warp) << 16);
     const int f = 32 * (warp & 1) + lane;                   // feature index of this TMEM lane within its 64-row block
     const bool upper = warp >= 2;
-    auto drain = [&](int col0, int ncols, float* dst, int stride_col, int col_lo, int col_hi) {
-      // accumulator columns [col0, col0 + ncols): element j goes to dst[j * stride_col] for col_lo <= j < col_hi
+    auto drain = [&](int col0, int ncols, float* dst, int stride_col, int n_valid) {
+      // accumulator columns [col0, col0 + ncols): element j < n_valid goes to dst[j * stride_col]
       for (int c0 = 0; c0 < ncols; c0 += 16) {
         uint32_t v[16];
         tc_ld16(lane_base + col0 + c0, v);
         tc_ld_wait();
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (c0 + j >= col_lo && c0 + j < col_hi) atomicAdd(dst + (size_t)(c0 + j) * stride_col, __uint_as_float(v[j]) * inv_s);
+          if (c0 + j < n_valid) atomicAdd(dst + (size_t)(c0 + j) * stride_col, __uint_as_float(v[j]) * inv_s);
       }
     };
     float* gV1 = g_cp;
@@ -957,17 +1040,17 @@ k_instant_bwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
     float* gW1 = g_sp;
     float* gW2 = g_sp + HID * in_pad;
     if (!upper) {
-      drain(D1, 48, gV1 + f * CIN, 1, 0, CIN);                       // dV1[f][k]
-      drain(D2, 16, gV3 + f, HID, 0, 3);                             // dV3[o][f], o < 3 (rows 3..15 are padding)
-      drain(D3, POS_K, gW1 + f * in_pad, 1, 0, in_pad);              // dW1[f][k]
+      drain(D1, 48, gV1 + f * CIN, 1, CIN);                          // dV1[f][k]
+      drain(D2 + SL::COL_DZ5, 16, gV3 + f, HID, 3);                  // dV3[o][f], o < 3 (rows 3..15 are padding)
+      drain(D3, POS_K, gW1 + f * in_pad, 1, in_pad);                 // dW1[f][k]
     } else {
-      drain(D1 + 64, 64, gV2 + f * HID, 1, 0, HID);                  // dV2[f][k]
-      drain(D2 + 16, 16, gW2 + f, HID, 0, GEO);                      // dW2[o][f]
+      drain(D1 + 64, 64, gV2 + f * HID, 1, HID);                     // dV2[f][k]
+      drain((SL::MERGED ? D3 : D2) + SL::COL_DZ2, 16, gW2 + f, HID, GEO);      // dW2[o][f]
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
 }
 
 template <int POS_K>
@@ -1069,6 +1152,17 @@ extern "C" int b2n_instant_mlp_bwd(const float* x_enc, int ldx, int pos_dim, con
   return check_launch("b2n_instant_mlp_bwd");
 }
 
+// groups per CTA of k_instant_bwd_tc at pos_dim <= 32: 1 (two 4-warp CTAs per SM, default) or 3 (one CTA per SM with 12
+// worker warps + the issuer).  Measured at 4.2 M points: 1.55 ms both -- the 12-warp schedule issues 26 % more
+// instructions (160 registers: ReLU gates re-read from shared memory, spills) for its 25 % higher issue rate, so the
+// simpler one is the default; ncu: `wait` (fixed-latency dependencies) is the top stall of both
+static int g_bwd_groups = 1;
+extern "C" int b2n_debug_instant_bwd_groups(int groups) {
+  const int prev = g_bwd_groups;
+  if (groups == 1 || groups == 3) g_bwd_groups = groups;
+  return prev;
+}
+
 // The same backward with the weight gradients on tcgen05 (k_instant_bwd_tc); err_flag as in b2n_instant_mlp_fwd_tc.
 extern "C" int b2n_instant_mlp_bwd_tc(const float* x_enc, int ldx, int pos_dim, const float* dirs, const float* dir_bands,
                                       int L_dir, const float* sigma_params, const float* color_params, int64_t P,
@@ -1090,18 +1184,23 @@ extern "C" int b2n_instant_mlp_bwd_tc(const float* x_enc, int ldx, int pos_dim, 
     const unsigned grid = (unsigned)((n + 1023) / 1024 < (int64_t)kSMs * 8 ? (n + 1023) / 1024 : (int64_t)kSMs * 8);
     k_grad_absmax<<<grid, 256, 0, st>>>(g_rgb, g_sigma, P, absmax, g_active_rows);
   }
-  auto launch = [&](auto kern, size_t smem) {
+  auto launch = [&](auto kern, size_t smem, int groups) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-    // two CTAs per SM by construction (shared memory <= 113 KB, 256 of the 512 TMEM columns each); the occupancy API
-    // reports 1 for tcgen05 kernels (see b2n_instant_mlp_fwd_tc)
-    int64_t grid = (int64_t)kSMs * 2;
-    if (grid > tiles) grid = tiles;
-    kern<<<(unsigned)grid, MLP_THREADS, smem, st>>>(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params, color_params, P,
-                                                    g_rgb, g_sigma, g_x_enc, ldg, g_sigma_params, g_color_params, absmax,
-                                                    g_active_rows, in_pad_value, err_flag);
+    // CTAs per SM by construction: two 4-warp CTAs (shared memory <= 113 KB, 256 of the 512 TMEM columns each) or one
+    // CTA of three groups; the occupancy API reports 1 for tcgen05 kernels (see b2n_instant_mlp_fwd_tc)
+    const int64_t units = groups == 1 ? tiles : (tiles + groups - 1) / groups;
+    int64_t grid = groups == 1 ? (int64_t)kSMs * 2 : (int64_t)kSMs;
+    if (grid > units) grid = units;
+    kern<<<(unsigned)grid, groups == 1 ? MLP_THREADS : (groups + 1) * MLP_THREADS, smem, st>>>(
+        x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params, color_params, P, g_rgb, g_sigma, g_x_enc, ldg,
+        g_sigma_params, g_color_params, absmax, g_active_rows, in_pad_value, err_flag);
   };
-  if (pos_dim <= 32) launch(k_instant_bwd_tc<32>, bwtc::smem_bytes<32>());
-  else launch(k_instant_bwd_tc<64>, bwtc::smem_bytes<64>());
+  if (pos_dim <= 32) {
+    if (g_bwd_groups == 3) launch(k_instant_bwd_tc<32, 3>, bwtc::smem_bytes<32, 3>(), 3);
+    else launch(k_instant_bwd_tc<32, 1>, bwtc::smem_bytes<32, 1>(), 1);
+  } else {
+    launch(k_instant_bwd_tc<64, 1>, bwtc::smem_bytes<64, 1>(), 1);
+  }
   return check_launch("b2n_instant_mlp_bwd_tc");
 }

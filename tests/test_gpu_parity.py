@@ -617,7 +617,8 @@ def test_instant_fwd_tcgen05_matches_mma_sync(mods, pos_dim, Pn, pad):
     assert torch.equal(out[True][2], out[True][1])            # density-only mode: the same sigma_net arithmetic
 
 
-@pytest.mark.parametrize("pos_dim,Pn", [(32, 64 * 37 + 5), (53, 777), (64, 130), (32, 5), (32, 200000)])
+@pytest.mark.parametrize("pos_dim,Pn", [(32, 64 * 37 + 5), (53, 777), (64, 130), (32, 5), (32, 200000), (20, 64 * 148 * 3 + 1),
+                                        (32, 1500000)])
 def test_instant_bwd_tcgen05_wgrad_matches_mma_sync(mods, pos_dim, Pn):
     """The two backward kernels of the fused Instant decoder differ only in where the weight gradients are accumulated
     (tcgen05 + TMEM vs mma.sync + registers): same operands, fp32 accumulation in a different order."""
@@ -631,21 +632,26 @@ def test_instant_bwd_tcgen05_wgrad_matches_mma_sync(mods, pos_dim, Pn):
     bands = cu(O.fourier_bands(4))
     rgb, sigma = mods["b2n"].instant_mlp(x, d, bands, sp, cp)
     g1, g2 = torch.randn_like(rgb), torch.randn_like(sigma)
+    lib = mods["b2n"]._lib.lib
     out = {}
     prev = ops.INSTANT_BWD_TC
+    prev_groups = lib.b2n_debug_instant_bwd_groups(1)
     try:
-        for tc in (False, True):
+        for key, tc, groups in (("mma", False, 1), ("tc1", True, 1), ("tc3", True, 3)):      # groups: see b2nerf_debug.h
             ops.INSTANT_BWD_TC = tc
-            out[tc] = torch.autograd.grad([rgb, sigma], [x, sp, cp], [g1, g2], retain_graph=True)
+            lib.b2n_debug_instant_bwd_groups(groups)
+            out[key] = torch.autograd.grad([rgb, sigma], [x, sp, cp], [g1, g2], retain_graph=True)
     finally:
         ops.INSTANT_BWD_TC = prev
+        lib.b2n_debug_instant_bwd_groups(prev_groups)
     mods["b2n"].check_errors()
-    tag = f"instant_bwd_tc[{pos_dim},{Pn}]"
-    assert torch.equal(out[True][0], out[False][0])                 # g_x: the same mma.sync chain
-    for a_, b_, name in zip(out[True][1:], out[False][1:], ("g_sigma_params", "g_color_params")):
-        assert record(f"{tag}:{name}", rel_err(a_, b_)) < 2e-5, name
-    V3 = out[True][2][64 * 48 + 64 * 64:].view(16, 64)
-    assert float(V3[3:].abs().max()) == 0.0
+    for key in ("tc1", "tc3"):
+        tag = f"instant_bwd_{key}[{pos_dim},{Pn}]"
+        assert torch.equal(out[key][0], out["mma"][0])                 # g_x: the same mma.sync chain
+        for a_, b_, name in zip(out[key][1:], out["mma"][1:], ("g_sigma_params", "g_color_params")):
+            assert record(f"{tag}:{name}", rel_err(a_, b_)) < 2e-5, name
+        V3 = out[key][2][64 * 48 + 64 * 64:].view(16, 64)
+        assert float(V3[3:].abs().max()) == 0.0
 
 
 def test_instant_mlp_nonfinite_gradient_propagates(mods):

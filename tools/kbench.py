@@ -10,7 +10,7 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "project-nerf_b200")]
 import torch  # noqa: E402
 
 import b2n  # noqa: E402
-from b2n import ops  # noqa: E402
+from b2n import _lib, ops  # noqa: E402
 from src.core import NeuralField  # noqa: E402
 
 
@@ -432,10 +432,11 @@ def mlp64(P=1 << 22):
         b2n.check_errors()
         rgb, sigma = b2n.instant_mlp(x, d, bands, sp, cp)
         g1, g2 = torch.randn_like(rgb), torch.randn_like(sigma)
-        for tc in (False, True):
+        for tc, groups in ((False, 1), (True, 1), (True, 3)):
             ops.INSTANT_BWD_TC = tc
+            _lib.lib.b2n_debug_instant_bwd_groups(groups)
             med, best = timeit(lambda: torch.autograd.grad([rgb, sigma], [x, sp, cp], [g1, g2], retain_graph=True))
-            print(f"instant bwd pos_dim={pos_dim} P={P} tc={tc}: {med:.3f} ms (best {best:.3f})")
+            print(f"instant bwd pos_dim={pos_dim} P={P} tc={tc} groups={groups}: {med:.3f} ms (best {best:.3f})")
         b2n.check_errors()
 
 

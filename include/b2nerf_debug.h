@@ -22,8 +22,8 @@ int b2n_debug_mlp256_flags(int flags);
  * Both produce the same results; the switch exists for A/B timing and parity tests. */
 int b2n_debug_mlp256_set_pair(int on);
 
-/* schedule of b2n_instant_mlp_bwd_tc at pos_dim <= 32: 1 (default) = two 4-warp CTAs per SM, 3 = one CTA per SM with
- * three 4-warp groups and a single MMA issuer.  Same results up to the order of the fp32 accumulation.  Returns the
+/* schedule of b2n_instant_mlp_bwd_tc at pos_dim <= 32: 3 (default) = one CTA per SM with three 4-warp groups and a
+ * single MMA issuer, 1 = two 4-warp CTAs per SM.  Same results up to the order of the fp32 accumulation.  Returns the
  * previous value. */
 int b2n_debug_instant_bwd_groups(int groups);
 

@@ -691,29 +691,30 @@ struct Slots {
 };
 // element offset of (row, col) inside a 64 x 64 swizzled tile
 __device__ __forceinline__ int sw(int r, int c) { return r * 64 + ((((c >> 3) ^ r) & 7) << 3) + (c & 7); }
+// A fragments of a 16-row slab -> swizzled tile: one stmatrix per 16 x 16 block (the four 8 x 8 matrices of an A fragment
+// are rows g / g+8 x columns 0..7 / 8..15; lane i supplies the address of row i % 8 of matrix i / 8)
 template <int KT>
 __device__ __forceinline__ void store_a_sw(const uint32_t (&a)[KT][4], op16* tile, int row0, int col0, int lane) {
-  const int g = lane >> 2, t = lane & 3;
+  const int r = row0 + (lane & 7) + 8 * ((lane >> 3) & 1);
+  const int cb = col0 + 8 * (lane >> 4);
+#pragma unroll
+  for (int k = 0; k < KT; ++k)
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(tile + sw(r, cb + 16 * k))),
+                 "r"(a[k][0]), "r"(a[k][1]), "r"(a[k][2]), "r"(a[k][3]) : "memory");
+}
+// ReLU gate of packed gradient fragments by the staged activation tile (read back as A fragments with ldmatrix)
+template <int KT>
+__device__ __forceinline__ void relu_gate_sw(uint32_t (&dz)[KT][4], const op16* tile, int row0, int lane) {
+  const int r = row0 + (lane & 7) + 8 * ((lane >> 3) & 1);
+  const int cb = 8 * (lane >> 4);
+  const __half2 zero = __floats2half2_rn(0.f, 0.f);
+  __syncwarp();                  // the tile rows were written by other lanes of this warp (stmatrix)
 #pragma unroll
   for (int k = 0; k < KT; ++k) {
-    const int c = col0 + 16 * k + 2 * t;
-    *reinterpret_cast<uint32_t*>(tile + sw(row0 + g, c)) = a[k][0];
-    *reinterpret_cast<uint32_t*>(tile + sw(row0 + g + 8, c)) = a[k][1];
-    *reinterpret_cast<uint32_t*>(tile + sw(row0 + g, c + 8)) = a[k][2];
-    *reinterpret_cast<uint32_t*>(tile + sw(row0 + g + 8, c + 8)) = a[k][3];
-  }
-}
-template <int NT>
-__device__ __forceinline__ void relu_mask_sw(float (&c)[NT][4], const op16* tile, int row0, int lane) {
-  const int g = lane >> 2, t = lane & 3;
+    uint32_t act[4];
+    ldsm_x4(act, tile + sw(r, cb + 16 * k));
 #pragma unroll
-  for (int j = 0; j < NT; ++j) {
-    const float2 lo = unpack2(*reinterpret_cast<const uint32_t*>(tile + sw(row0 + g, 8 * j + 2 * t)));
-    const float2 hi = unpack2(*reinterpret_cast<const uint32_t*>(tile + sw(row0 + g + 8, 8 * j + 2 * t)));
-    if (!(lo.x > 0.f)) c[j][0] = 0.f;
-    if (!(lo.y > 0.f)) c[j][1] = 0.f;
-    if (!(hi.x > 0.f)) c[j][2] = 0.f;
-    if (!(hi.y > 0.f)) c[j][3] = 0.f;
+    for (int i = 0; i < 4; ++i) dz[k][i] &= __hgt2_mask(*reinterpret_cast<const __half2*>(&act[i]), zero);
   }
 }
 template <int POS_K, int GROUPS>
@@ -786,6 +787,7 @@ k_instant_bwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  const bool gx_vec = g_x && ((ldg & 1) == 0) && ((pos_dim & 1) == 0) && ((reinterpret_cast<uintptr_t>(g_x) & 7) == 0);
   const int64_t n_tiles = (P + 63) / 64;
   const int64_t tile_first = (int64_t)blockIdx.x * GROUPS, tile_step = (int64_t)gridDim.x * GROUPS;
 
@@ -943,16 +945,16 @@ k_instant_bwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
       {
         float c[8][4] = {};
         gemm_dgrad<8, 1>(c, dz5, sm + L.v3, SH, lane);          // d c2
-        if (!GATE_REGS) relu_mask_sw<8>(c, T(SL::C2), row0, lane);
         c_to_a<8, false>(c, dz[0]);
+        if (!GATE_REGS) relu_gate_sw<4>(dz[0], T(SL::C2), row0, lane);
         if (GATE_REGS) relu_gate<4>(dz[0], a2[0]);
         store_a_sw<4>(dz[0], T(SL::DZ4), row0, 0, lane);
       }
       {
         float c[8][4] = {};
         gemm_dgrad<8, 4>(c, dz[0], sm + L.v2, SH, lane);        // d c1
-        if (!GATE_REGS) relu_mask_sw<8>(c, T(SL::C1), row0, lane);
         c_to_a<8, false>(c, dz[0]);
+        if (!GATE_REGS) relu_gate_sw<4>(dz[0], T(SL::C1), row0, lane);
         if (GATE_REGS) relu_gate<4>(dz[0], a1[0]);
         store_a_sw<4>(dz[0], T(SL::DZ3), row0, 0, lane);
       }
@@ -977,8 +979,8 @@ k_instant_bwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
       {
         float c[8][4] = {};
         gemm_dgrad<8, 1>(c, dz2, sm + L.w2, SH, lane);          // d hidden1
-        if (!GATE_REGS) relu_mask_sw<8>(c, T(SL::H1), row0, lane);
         c_to_a<8, false>(c, dz[0]);
+        if (!GATE_REGS) relu_gate_sw<4>(dz[0], T(SL::H1), row0, lane);
         if (GATE_REGS) relu_gate<4>(dz[0], ah[0]);
         store_a_sw<4>(dz[0], T(SL::DZ1), row0, 0, lane);
       }
@@ -999,16 +1001,28 @@ k_instant_bwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
         float c[POS_K / 8][4] = {};
         gemm_dgrad<POS_K / 8, 4>(c, dz[0], sm + L.w1, SX, lane);
         const int64_t pa = p0 + g, pb = pa + 8;
+        float* ra = g_x + pa * ldg + 2 * t;
+        float* rb = g_x + pb * ldg + 2 * t;
+        if (gx_vec) {              // column pairs are contiguous and 8-byte aligned: one full 32-byte sector per row and store
 #pragma unroll
-        for (int j = 0; j < POS_K / 8; ++j) {
-          const int col = 8 * j + 2 * t;
-          if (pa < P) {
-            if (col < pos_dim) g_x[pa * ldg + col] = c[j][0] * inv_s;
-            if (col + 1 < pos_dim) g_x[pa * ldg + col + 1] = c[j][1] * inv_s;
+          for (int j = 0; j < POS_K / 8; ++j) {
+            if (8 * j + 2 * t < pos_dim) {
+              if (pa < P) __stcs(reinterpret_cast<float2*>(ra + 8 * j), make_float2(c[j][0] * inv_s, c[j][1] * inv_s));
+              if (pb < P) __stcs(reinterpret_cast<float2*>(rb + 8 * j), make_float2(c[j][2] * inv_s, c[j][3] * inv_s));
+            }
           }
-          if (pb < P) {
-            if (col < pos_dim) g_x[pb * ldg + col] = c[j][2] * inv_s;
-            if (col + 1 < pos_dim) g_x[pb * ldg + col + 1] = c[j][3] * inv_s;
+        } else {
+#pragma unroll
+          for (int j = 0; j < POS_K / 8; ++j) {
+            const int col = 8 * j + 2 * t;
+            if (pa < P) {
+              if (col < pos_dim) ra[8 * j] = c[j][0] * inv_s;
+              if (col + 1 < pos_dim) ra[8 * j + 1] = c[j][1] * inv_s;
+            }
+            if (pb < P) {
+              if (col < pos_dim) rb[8 * j] = c[j][2] * inv_s;
+              if (col + 1 < pos_dim) rb[8 * j + 1] = c[j][3] * inv_s;
+            }
           }
         }
       }
@@ -1152,11 +1166,11 @@ extern "C" int b2n_instant_mlp_bwd(const float* x_enc, int ldx, int pos_dim, con
   return check_launch("b2n_instant_mlp_bwd");
 }
 
-// groups per CTA of k_instant_bwd_tc at pos_dim <= 32: 1 (two 4-warp CTAs per SM, default) or 3 (one CTA per SM with 12
-// worker warps + the issuer).  Measured at 4.2 M points: 1.55 ms both -- the 12-warp schedule issues 26 % more
-// instructions (160 registers: ReLU gates re-read from shared memory, spills) for its 25 % higher issue rate, so the
-// simpler one is the default; ncu: `wait` (fixed-latency dependencies) is the top stall of both
-static int g_bwd_groups = 1;
+// groups per CTA of k_instant_bwd_tc at pos_dim <= 32: 3 (default: one CTA per SM with 12 worker warps + the issuer) or
+// 1 (two 4-warp CTAs per SM).  Measured at 4.2 M points (tools/kbench.py mlp64): 1.37 ms against 1.44 ms, the mma.sync
+// kernel 1.70 ms.  The 12-warp schedule only paid off once the d x_enc stores were vectorised (the LSU was the shared
+// limit: 1.55 ms both before); ncu: `wait` (fixed-latency dependencies) is the top stall of both schedules
+static int g_bwd_groups = 3;
 extern "C" int b2n_debug_instant_bwd_groups(int groups) {
   const int prev = g_bwd_groups;
   if (groups == 1 || groups == 3) g_bwd_groups = groups;

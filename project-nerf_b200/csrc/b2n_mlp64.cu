@@ -1173,7 +1173,7 @@ extern "C" int b2n_instant_mlp_bwd(const float* x_enc, int ldx, int pos_dim, con
 static int g_bwd_groups = 3;
 extern "C" int b2n_debug_instant_bwd_groups(int groups) {
   const int prev = g_bwd_groups;
-  if (groups == 1 || groups == 3) g_bwd_groups = groups;
+  if (groups == 1 || groups == 3 || groups == 4) g_bwd_groups = groups;      // 4: groups = 1 with ONE CTA per SM (overlap experiments)
   return prev;
 }
 
@@ -1204,7 +1204,7 @@ extern "C" int b2n_instant_mlp_bwd_tc(const float* x_enc, int ldx, int pos_dim, 
     // CTAs per SM by construction: two 4-warp CTAs (shared memory <= 113 KB, 256 of the 512 TMEM columns each) or one
     // CTA of three groups; the occupancy API reports 1 for tcgen05 kernels (see b2n_instant_mlp_fwd_tc)
     const int64_t units = groups == 1 ? tiles : (tiles + groups - 1) / groups;
-    int64_t grid = groups == 1 ? (int64_t)kSMs * 2 : (int64_t)kSMs;
+    int64_t grid = groups == 1 && g_bwd_groups != 4 ? (int64_t)kSMs * 2 : (int64_t)kSMs;
     if (grid > units) grid = units;
     kern<<<(unsigned)grid, groups == 1 ? MLP_THREADS : (groups + 1) * MLP_THREADS, smem, st>>>(
         x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params, color_params, P, g_rgb, g_sigma, g_x_enc, ldg,

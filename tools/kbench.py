@@ -440,6 +440,60 @@ def mlp64(P=1 << 22):
         b2n.check_errors()
 
 
+def overlap(P=12_000_000):
+    """can the L2-atomic-bound table scatter and the SM-bound decoder backward share the SMs?  Independent inputs, two streams."""
+    from oracle import nerf_oracle as O
+    from src.embeddings import HashGridEncoding
+    gen = torch.Generator().manual_seed(0)
+    sp = O._fused_init(32, 16, 64, 1, gen).cuda().requires_grad_(True)
+    cp = O._fused_init(43, 3, 64, 2, gen).cuda().requires_grad_(True)
+    x = (torch.randn(P, 32, device="cuda") * 0.5).requires_grad_(True)
+    d = torch.nn.functional.normalize(torch.randn(P, 3, device="cuda"), dim=-1)
+    bands = O.fourier_bands(4).cuda()
+    # autograd runs a backward node on the stream of its forward: issue each forward on the stream its backward should use
+    s1, s2 = torch.cuda.Stream(priority=-1), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s1):
+        rgb, sigma = b2n.instant_mlp(x, d, bands, sp, cp)
+        g1, g2 = torch.randn_like(rgb), torch.randn_like(sigma)
+    enc = HashGridEncoding(3, dict(otype="HashGrid", n_levels=16, n_features_per_level=2, log2_hashmap_size=19,
+                                   base_resolution=16, per_level_scale=1.5)).cuda()
+    # ray-ordered samples like the training step: 128 samples along random rays
+    B = P // 128
+    o = (torch.rand(B, 1, 3, device="cuda") - 0.5) * 2
+    dd = torch.nn.functional.normalize(torch.randn(B, 1, 3, device="cuda"), dim=-1)
+    tt = torch.linspace(0, 2.0, 128, device="cuda").view(1, 128, 1)
+    pts = ((o + dd * tt).reshape(-1, 3).clamp(-1.5, 1.5) / 3.0 + 0.5).contiguous()          # unit cube
+    torch.cuda.synchronize()
+    with torch.cuda.stream(s2):
+        feat = enc(pts)
+        gf = torch.randn_like(feat)
+    torch.cuda.synchronize()
+
+    def mlp():
+        torch.autograd.grad([rgb, sigma], [x, sp, cp], [g1, g2], retain_graph=True)
+
+    def hashb():
+        torch.autograd.grad(feat, enc.params, gf, retain_graph=True)
+
+    def both():
+        cur = torch.cuda.current_stream()
+        s1.wait_stream(cur), s2.wait_stream(cur)
+        with torch.cuda.stream(s1):
+            mlp()
+        with torch.cuda.stream(s2):
+            hashb()
+        cur.wait_stream(s1), cur.wait_stream(s2)
+
+    for groups in (3, 1, 4):
+        _lib.lib.b2n_debug_instant_bwd_groups(groups)
+        tm, _ = timeit(mlp)
+        th, _ = timeit(hashb)
+        tb, _ = timeit(both)
+        print(f"groups={groups}: decoder bwd {tm:.3f} ms, table scatter {th:.3f} ms, both on two streams {tb:.3f} ms (sum {tm + th:.3f})")
+    _lib.lib.b2n_debug_instant_bwd_groups(3)
+
+
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "mlp256"
     P = int(sys.argv[2]) if len(sys.argv) > 2 and sys.argv[2].isdigit() else 262144
@@ -457,6 +511,8 @@ if __name__ == "__main__":
         red_bench()
     elif what == "l2":
         l2_gather()
+    elif what == "overlap":
+        overlap()
     elif what == "mlp64":
         mlp64()
     elif what == "composite":

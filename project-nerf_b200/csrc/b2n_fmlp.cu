@@ -46,9 +46,6 @@ struct Args {
   float* g_x1; int ldg1;
   unsigned int* work;   // [0] |g_y|-max bits (pre-pass), [1] the gradient scale S as a float (written by the kernel)
   const int* rows;      // optional device-side row count (b2n_set_active_rows)
-  int64_t Pcap;         // rows the planes were allocated for (the host-side P): the stride between layer planes
-  int64_t Ppad;         // rows [P, Ppad) of the saved planes are ZERO-filled: the tcgen05 weight-gradient kernel streams
-                        // whole 64-row tiles, and with a device-side row count the rows behind it were never written
 };
 
 template <int H, int KT_IN, int NT_OUT>
@@ -100,7 +97,7 @@ __device__ __forceinline__ float* stage_weights(const Args& a, op16* sm, bool sk
 
 // A fragments of 16 rows of the (virtually concatenated) input [x0 | x1 | 0]
 template <int KT>
-__device__ __forceinline__ void load_in(const Args& a, int64_t p0, uint32_t (&f)[KT][4], int lane) {
+__device__ __forceinline__ void load_in(const Args& a, int64_t P, int64_t p0, uint32_t (&f)[KT][4], int lane) {
   const int g = lane >> 2, t = lane & 3;
   const int din = a.d0 + a.d1;
 #pragma unroll
@@ -112,7 +109,7 @@ __device__ __forceinline__ void load_in(const Args& a, int64_t p0, uint32_t (&f)
         const int64_t p = p0 + g + 8 * r;
         const int c = 16 * k + 8 * h + 2 * t;
         float v[2] = {0.f, 0.f};
-        if (p < a.P) {
+        if (p < P) {
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             const int cc = c + j;
@@ -126,7 +123,7 @@ __device__ __forceinline__ void load_in(const Args& a, int64_t p0, uint32_t (&f)
 
 // split version for software pipelining: issue the loads of a tile now, pack (and wait for them) one tile later
 template <int KT>
-__device__ __forceinline__ void load_in_raw(const Args& a, int64_t p0, float (&raw)[KT][4][2], int lane) {
+__device__ __forceinline__ void load_in_raw(const Args& a, int64_t P, int64_t p0, float (&raw)[KT][4][2], int lane) {
   const int g = lane >> 2, t = lane & 3;
   const int din = a.d0 + a.d1;
 #pragma unroll
@@ -138,7 +135,7 @@ __device__ __forceinline__ void load_in_raw(const Args& a, int64_t p0, float (&r
         const int64_t p = p0 + g + 8 * r;
         const int c = 16 * k + 8 * h + 2 * t;
         raw[k][2 * h + r][0] = raw[k][2 * h + r][1] = 0.f;
-        if (p < a.P) {
+        if (p < P) {
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
             const int cc = c + j;
@@ -258,11 +255,13 @@ __device__ __forceinline__ float fmlp_scale_from(unsigned int bits) {
 
 // ------------------------------------------------------------------------------ forward
 template <int H, int KT_IN, int NT_OUT, int MT>
-__global__ void __launch_bounds__(THREADS) k_fmlp_fwd(const Args a_in) {
-  Args a = a_in;
-  a.P = clamp_rows(a_in.P, a_in.rows);
-  a.Pcap = a_in.P;
-  a.Ppad = min(a_in.P, (a.P + 63) & ~(int64_t)63);
+__global__ void __launch_bounds__(THREADS) k_fmlp_fwd(const Args a) {
+  // NOT a local copy of `a`: the layer arrays are indexed dynamically, and a modified copy of a kernel parameter lives in
+  // local memory (272-byte stack frame, every a.* an LDL); the row counts are plain locals instead
+  const int64_t P = clamp_rows(a.P, a.rows);              // valid rows (device-side count, b2n_set_active_rows)
+  const int64_t Pcap = a.P;                               // rows the planes were allocated for: stride between layer planes
+  const int64_t Ppad = min(a.P, (P + 63) & ~(int64_t)63);    // rows [P, Ppad) of the saved planes are zero-filled (the tcgen05
+                                                          // weight-gradient kernel streams whole 64-row tiles)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   op16* sm = reinterpret_cast<op16*>(smem_raw);
   using LY = Layout<H, KT_IN, NT_OUT>;
@@ -270,14 +269,14 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_fwd(const Args a_in) {
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   constexpr int ROWS = 16 * MT;
-  const int64_t n_tiles = (a.Ppad + ROWS - 1) / ROWS;
+  const int64_t n_tiles = (Ppad + ROWS - 1) / ROWS;
   const int64_t wstride = (int64_t)gridDim.x * (THREADS / 32);
   // single-slab variants (H = 128) have registers to spare: the next tile's input rows are fetched one tile ahead
   constexpr bool PF = (MT == 1);
   constexpr int KTP = PF ? KT_IN : 1;
   float raw[KTP][4][2];
   const int64_t tile0 = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
-  if (PF) load_in_raw<KTP>(a, tile0 * ROWS, raw, lane);
+  if (PF) load_in_raw<KTP>(a, P, tile0 * ROWS, raw, lane);
   for (int64_t tile = tile0; tile < n_tiles; tile += wstride) {
     const int64_t p0 = tile * ROWS;
     uint32_t ah[MT][H / 16][4];
@@ -288,13 +287,13 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_fwd(const Args a_in) {
         for (int k = 0; k < KT_IN; ++k)
 #pragma unroll
           for (int i = 0; i < 4; ++i) ax[0][k][i] = pack2(raw[k % KTP][i][0], raw[k % KTP][i][1]);
-        load_in_raw<KTP>(a, (tile + wstride) * ROWS, raw, lane);
-        if (a.xin) store_plane<KT_IN>(ax[0], a.xin, LY::IN_PAD, p0, a.P, lane, a.Ppad);
+        load_in_raw<KTP>(a, P, (tile + wstride) * ROWS, raw, lane);
+        if (a.xin) store_plane<KT_IN>(ax[0], a.xin, LY::IN_PAD, p0, P, lane, Ppad);
       } else {
 #pragma unroll
         for (int m = 0; m < MT; ++m) {
-          load_in<KT_IN>(a, p0 + 16 * m, ax[m], lane);
-          if (a.xin) store_plane<KT_IN>(ax[m], a.xin, LY::IN_PAD, p0 + 16 * m, a.P, lane, a.Ppad);
+          load_in<KT_IN>(a, P, p0 + 16 * m, ax[m], lane);
+          if (a.xin) store_plane<KT_IN>(ax[m], a.xin, LY::IN_PAD, p0 + 16 * m, P, lane, Ppad);
         }
       }
       float c[MT][H / 8][4];
@@ -304,7 +303,7 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_fwd(const Args a_in) {
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
         c_to_a<H / 8, true>(c[m], ah[m]);
-        if (a.hplanes) store_plane<H / 16>(ah[m], a.hplanes, H, p0 + 16 * m, a.P, lane, a.Ppad);
+        if (a.hplanes) store_plane<H / 16>(ah[m], a.hplanes, H, p0 + 16 * m, P, lane, Ppad);
       }
     }
 #pragma unroll 1
@@ -316,7 +315,7 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_fwd(const Args a_in) {
 #pragma unroll
       for (int m = 0; m < MT; ++m) {
         c_to_a<H / 8, true>(c[m], ah[m]);
-        if (a.hplanes) store_plane<H / 16>(ah[m], a.hplanes + (size_t)l * a.Pcap * H, H, p0 + 16 * m, a.P, lane, a.Ppad);
+        if (a.hplanes) store_plane<H / 16>(ah[m], a.hplanes + (size_t)l * Pcap * H, H, p0 + 16 * m, P, lane, Ppad);
       }
     }
     {
@@ -333,7 +332,7 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_fwd(const Args a_in) {
           for (int i = 0; i < 4; ++i) {
             const int col = 8 * j + 2 * t + (i & 1);
             const int64_t p = (i & 2) ? pb : pa;
-            if (col < a.out_dim && p < a.P) {
+            if (col < a.out_dim && p < P) {
               float v = c[m][j][i];
               if (a.out_act == B2N_ACT_SIGMOID) v = sigm(v);
               else if (a.out_act == B2N_ACT_RELU) v = fmaxf(v, 0.f);
@@ -348,11 +347,12 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_fwd(const Args a_in) {
 
 // ------------------------------------------------------------------------------ backward (data gradients)
 template <int H, int KT_IN, int NT_OUT>
-__global__ void __launch_bounds__(THREADS) k_fmlp_bwd(const Args a_in) {
-  Args a = a_in;
-  a.P = clamp_rows(a_in.P, a_in.rows);
-  a.Pcap = a_in.P;
-  a.Ppad = min(a_in.P, (a.P + 63) & ~(int64_t)63);
+__global__ void __launch_bounds__(THREADS) k_fmlp_bwd(const Args a) {
+  // NOT a local copy of `a`: the layer arrays are indexed dynamically, and a modified copy of a kernel parameter lives in
+  // local memory (272-byte stack frame, every a.* an LDL); the row counts are plain locals instead
+  const int64_t P = clamp_rows(a.P, a.rows);              // valid rows (device-side count, b2n_set_active_rows)
+  const int64_t Pcap = a.P;                               // rows the planes were allocated for: stride between layer planes
+  const int64_t Ppad = min(a.P, (P + 63) & ~(int64_t)63);    // rows [P, Ppad) of the saved planes are zero-filled
   extern __shared__ __align__(16) unsigned char smem_raw[];
   op16* sm = reinterpret_cast<op16*>(smem_raw);
   using LY = Layout<H, KT_IN, NT_OUT>;
@@ -365,12 +365,12 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_bwd(const Args a_in) {
   __syncthreads();
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   constexpr int KTO = LY::OUT_ROWS / 16;
-  const int64_t n_tiles = (a.Ppad + 15) / 16;
+  const int64_t n_tiles = (Ppad + 15) / 16;
   const int64_t wstride = (int64_t)gridDim.x * (THREADS / 32);
   for (int64_t tile = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5); tile < n_tiles; tile += wstride) {
     const int64_t p0 = tile * 16;
     uint32_t ga[H / 8], gb[H / 8];      // ReLU gate words of the layer about to be gated
-    load_gate<H / 8>(a.hplanes + (size_t)(a.n_hidden - 1) * a.Pcap * H, H, p0, a.P, ga, gb, lane);
+    load_gate<H / 8>(a.hplanes + (size_t)(a.n_hidden - 1) * Pcap * H, H, p0, P, ga, gb, lane);
     // ---- dZ of the output layer
     uint32_t dzo[KTO][4];
 #pragma unroll
@@ -382,7 +382,7 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_bwd(const Args a_in) {
           const int64_t p = p0 + g + 8 * r;
           const int c = 16 * k + 8 * h + 2 * t;
           float v[2] = {0.f, 0.f};
-          if (p < a.P) {
+          if (p < P) {
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
               if (c + j < a.out_dim) {
@@ -397,25 +397,25 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_bwd(const Args a_in) {
           }
           dzo[k][2 * h + r] = pack2(v[0], v[1]);
         }
-    store_plane<KTO>(dzo, a.dz_out, LY::OUT_ROWS, p0, a.P, lane, a.Ppad);
+    store_plane<KTO>(dzo, a.dz_out, LY::OUT_ROWS, p0, P, lane, Ppad);
     // ---- last hidden layer
     uint32_t dz[H / 16][4];
     {
       float c[H / 8][4] = {};
       gemm_dgrad<H / 8, KTO>(c, dzo, sm + LY::wo, LY::SH, lane);
       apply_gate<H / 8>(c, ga, gb);
-      if (a.n_hidden > 1) load_gate<H / 8>(a.hplanes + (size_t)(a.n_hidden - 2) * a.Pcap * H, H, p0, a.P, ga, gb, lane);
+      if (a.n_hidden > 1) load_gate<H / 8>(a.hplanes + (size_t)(a.n_hidden - 2) * Pcap * H, H, p0, P, ga, gb, lane);
       c_to_a<H / 8, false>(c, dz);
-      store_plane<H / 16>(dz, a.dz_h + (size_t)(a.n_hidden - 1) * a.Pcap * H, H, p0, a.P, lane, a.Ppad);
+      store_plane<H / 16>(dz, a.dz_h + (size_t)(a.n_hidden - 1) * Pcap * H, H, p0, P, lane, Ppad);
     }
 #pragma unroll 1
     for (int l = a.n_hidden - 1; l >= 1; --l) {
       float c[H / 8][4] = {};
       gemm_dgrad<H / 8, H / 16>(c, dz, sm + LY::wh + (l - 1) * H * LY::SH, LY::SH, lane);
       apply_gate<H / 8>(c, ga, gb);
-      if (l > 1) load_gate<H / 8>(a.hplanes + (size_t)(l - 2) * a.Pcap * H, H, p0, a.P, ga, gb, lane);
+      if (l > 1) load_gate<H / 8>(a.hplanes + (size_t)(l - 2) * Pcap * H, H, p0, P, ga, gb, lane);
       c_to_a<H / 8, false>(c, dz);
-      store_plane<H / 16>(dz, a.dz_h + (size_t)(l - 1) * a.Pcap * H, H, p0, a.P, lane, a.Ppad);
+      store_plane<H / 16>(dz, a.dz_h + (size_t)(l - 1) * Pcap * H, H, p0, P, lane, Ppad);
     }
     if (a.g_x0 || a.g_x1) {
       float c[2 * KT_IN][4] = {};
@@ -427,7 +427,7 @@ __global__ void __launch_bounds__(THREADS) k_fmlp_bwd(const Args a_in) {
         for (int i = 0; i < 4; ++i) {
           const int col = 8 * j + 2 * t + (i & 1);
           const int64_t p = p0 + g + ((i & 2) ? 8 : 0);
-          if (p < a.P) {
+          if (p < P) {
             if (col < a.d0) {
               if (a.g_x0) a.g_x0[p * a.ldg0 + col] = c[j][i] * inv_s;
             } else if (col < din) {
@@ -486,9 +486,8 @@ __device__ __forceinline__ void wg_load_tile(const WgLayer& L, int64_t p0, int64
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(WG_THREADS) k_fmlp_wgrad(const WgArgs a_in) {
-  WgArgs a = a_in;
-  a.P = clamp_rows(a_in.P, a_in.rows);
+__global__ void __launch_bounds__(WG_THREADS) k_fmlp_wgrad(const WgArgs a) {
+  const int64_t P = clamp_rows(a.P, a.rows);        // (no local copy of `a`: see k_fmlp_fwd)
   extern __shared__ __align__(16) unsigned char smem_raw[];
   op16* sm = reinterpret_cast<op16*>(smem_raw);
   const WgLayer& L = a.L[blockIdx.y];
@@ -500,16 +499,16 @@ __global__ void __launch_bounds__(WG_THREADS) k_fmlp_wgrad(const WgArgs a_in) {
   float acc[8][4] = {};
   float bsum = 0.f;
   const float inv_s = a.scale ? 1.f / __ldg(a.scale) : 1.f;
-  const int64_t n_tiles = (a.P + WG_TILE - 1) / WG_TILE;
+  const int64_t n_tiles = (P + WG_TILE - 1) / WG_TILE;
   int buf = 0;
-  if ((int64_t)blockIdx.x < n_tiles) wg_load_tile(L, (int64_t)blockIdx.x * WG_TILE, a.P, sm, sm + WG_TILE * WG_S);
+  if ((int64_t)blockIdx.x < n_tiles) wg_load_tile(L, (int64_t)blockIdx.x * WG_TILE, P, sm, sm + WG_TILE * WG_S);
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     op16* dzs = sm + buf * 2 * WG_TILE * WG_S;
     op16* ins = dzs + WG_TILE * WG_S;
     const int64_t next = tile + gridDim.x;
     if (next < n_tiles) {
       op16* nz = sm + (buf ^ 1) * 2 * WG_TILE * WG_S;
-      wg_load_tile(L, next * WG_TILE, a.P, nz, nz + WG_TILE * WG_S);
+      wg_load_tile(L, next * WG_TILE, P, nz, nz + WG_TILE * WG_S);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
     } else {
       asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -614,7 +613,7 @@ static int fill_args(Args* a, bool need_inputs, const float* x0, int ld0, int d0
     a->W[l] = W[l], a->ldw[l] = ldw[l], a->b[l] = b ? b[l] : nullptr;
   }
   a->n_hidden = n_hidden, a->out_dim = out_dim, a->out_act = out_act, a->P = P;
-  a->rows = g_active_rows, a->Ppad = P;
+  a->rows = g_active_rows;
   return B2N_OK;
 }
 

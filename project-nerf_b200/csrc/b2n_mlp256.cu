@@ -127,6 +127,7 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 }
 // bounded wait: false = aborted (either this wait timed out or another role raised the flag)
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* err, int code) {
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 22); ++it) {
     if (mbar_try(bar, parity)) return true;
     if ((it & 255) == 255 && *abort_flag) return false;

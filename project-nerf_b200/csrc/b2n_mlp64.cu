@@ -70,8 +70,10 @@ __device__ __forceinline__ void dir_features(const float (&d)[3], const float* _
           // view directions are unit vectors and the first band is 1: |arg| <= pi, where the MUFU sin/cos (abs.
           // error ~1e-6) is far inside the bf16 rounding applied below; larger arguments take the accurate path
           const float arg = __fmul_rn(__fmul_rn(d[j], fr), 3.14159274101257324f);
-          if (fabsf(arg) <= 3.2f) __sincosf(arg, &s, &c);
-          else sincosf(arg, &s, &c);
+          // beyond +-pi (non-unit directions, custom bands): one fp32 reduction step to [-pi, pi] instead of libm's
+          // Payne-Hanek path (hundreds of instructions and local memory in a kernel whose code must stay cache-resident)
+          const float red = fabsf(arg) <= 3.2f ? arg : __fmaf_rn(-6.28318530717958648f, rintf(arg * 0.159154943091895336f), arg);
+          __sincosf(red, &s, &c);
         }
         ps[j] = s, pc[j] = c;
         f[3 + 6 * k + j] = s;

@@ -111,8 +111,10 @@ __device__ __forceinline__ void dir_features(const float (&d)[3], const float* _
           c = 1.f - 2.f * ps[j] * ps[j];
         } else {
           const float arg = __fmul_rn(__fmul_rn(d[j], fr), 3.14159274101257324f);
-          if (fabsf(arg) <= 3.2f) __sincosf(arg, &s, &c);
-          else sincosf(arg, &s, &c);
+          // beyond +-pi (non-unit directions, custom bands): one fp32 reduction step to [-pi, pi] instead of libm's
+          // Payne-Hanek path (hundreds of instructions and local memory in a kernel whose code must stay cache-resident)
+          const float red = fabsf(arg) <= 3.2f ? arg : __fmaf_rn(-6.28318530717958648f, rintf(arg * 0.159154943091895336f), arg);
+          __sincosf(red, &s, &c);
         }
         ps[j] = s, pc[j] = c;
         f[3 + 6 * k + j] = s;

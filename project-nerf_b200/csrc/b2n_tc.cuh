@@ -16,6 +16,7 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 }
 // bounded wait: a stalled pipeline raises the error flag instead of hanging the GPU
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err) {
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 24); ++it)
     if (mbar_try(bar, parity)) return true;
   atomicCAS(err, 0, 7);

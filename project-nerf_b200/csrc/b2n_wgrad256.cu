@@ -60,6 +60,7 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 }
 // bounded wait: a protocol bug must not hang the GPU
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, volatile int* abort_flag, int* err, int code) {
+#pragma unroll 1
   for (uint32_t it = 0; it < (1u << 24); ++it) {
     if (mbar_try(bar, parity)) return true;
     if ((it & 1023) == 1023 && *abort_flag) return false;

@@ -14,6 +14,13 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
                : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
+// non-blocking probe (try_wait may suspend the thread for a while; a poller that serves several barriers must not)
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+               : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
 // bounded wait: a stalled pipeline raises the error flag instead of hanging the GPU
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err) {
 #pragma unroll 1

@@ -202,11 +202,7 @@ k_instant_fwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
   // coalesced: consecutive threads read consecutive 16 bytes of a row
   constexpr int Q = POS_K / 4;
   float4 xr[Q];
-  float dn[3];
   auto load_rows = [&](int64_t t) {
-    const int64_t pt = t * TILE + tid;
-    dn[0] = dn[1] = dn[2] = 0.f;
-    if (dirs && pt < P) dn[0] = __ldg(dirs + 3 * pt), dn[1] = __ldg(dirs + 3 * pt + 1), dn[2] = __ldg(dirs + 3 * pt + 2);
 #pragma unroll
     for (int it = 0; it < Q; ++it) {
       const int idx = it * THREADS + tid;
@@ -235,7 +231,10 @@ k_instant_fwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
     const int64_t p = tile * TILE + tid;
     const bool live = p < P;
     // ---- the tile's input rows (fetched one tile ahead) -> x_hi / x_lo; only the POS_K columns the first layer reads
-    float d[3] = {dn[0], dn[1], dn[2]};
+    // this point's view direction: needed after two layer steps -- loaded now, not a tile ahead (a prefetched value that
+    // gets spilled makes the spill store wait for the load: 5 % of the stall samples, ncu)
+    float d[3] = {0.f, 0.f, 0.f};
+    if (dirs && live) d[0] = __ldg(dirs + 3 * p), d[1] = __ldg(dirs + 3 * p + 1), d[2] = __ldg(dirs + 3 * p + 2);
 #pragma unroll
     for (int it = 0; it < Q; ++it) {
       const int idx = it * THREADS + tid;

@@ -14,26 +14,31 @@ namespace b2n {
 // (range-reduced) sincosf is required, never __sinf.
 #define B2N_PI_F 3.14159274101257324f
 
-__global__ void k_pe_fwd(const float* __restrict__ x, int64_t P, int D, const float* __restrict__ bands, int L,
-                         float* __restrict__ out, int ld, int col0, const int* __restrict__ rows) {
+// one thread per (point, band slot): slot 0 copies the D inputs, slot k >= 1 writes the 2 D contiguous values
+// [sin(x f_k pi) (D), cos(x f_k pi) (D)] of band k -- the threads of a point cover its output row contiguously.  A block
+// owns 256 / (L + 1) whole points, so the index arithmetic is 32-bit and small (the first version spent more on a 64-bit
+// division per output element than on the sincosf)
+__global__ void __launch_bounds__(256) k_pe_fwd(const float* __restrict__ x, int64_t P, int D, const float* __restrict__ bands,
+                                                int L, float* __restrict__ out, int ld, int col0, const int* __restrict__ rows) {
   P = clamp_rows(P, rows);
-  // one thread per (point, input dim, band); band index L means the identity column
-  const int per_pt = D * (L + 1);
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P * per_pt) return;
-  const int64_t p = i / per_pt;
-  const int rem = (int)(i - p * per_pt);
-  const int k = rem / D, d = rem - k * D;
-  const float xv = x[p * D + d];
+  const int slots = L + 1, pts = 256 / slots;
+  const int lp = threadIdx.x / slots, k = threadIdx.x - lp * slots;
+  const int64_t p = (int64_t)blockIdx.x * pts + lp;
+  if (lp >= pts || p >= P) return;
+  const float* xp = x + p * D;
   float* row = out + p * ld + col0;
   if (k == 0) {
-    row[d] = xv;
+    for (int d = 0; d < D; ++d) row[d] = xp[d];
   } else {
-    const float arg = __fmul_rn(__fmul_rn(xv, __ldg(bands + k - 1)), B2N_PI_F);
-    float s, c;
-    sincosf(arg, &s, &c);
-    row[D + 2 * (k - 1) * D + d] = s;
-    row[D + (2 * (k - 1) + 1) * D + d] = c;
+    const float f = __ldg(bands + k - 1);
+    float* dst = row + D + 2 * (k - 1) * D;
+    for (int d = 0; d < D; ++d) {
+      const float arg = __fmul_rn(__fmul_rn(xp[d], f), B2N_PI_F);
+      float sn, cs;
+      sincosf(arg, &sn, &cs);
+      dst[d] = sn;
+      dst[D + d] = cs;
+    }
   }
 }
 
@@ -42,7 +47,7 @@ __global__ void k_pe_bwd(const float* __restrict__ x, int64_t P, int D, const fl
   P = clamp_rows(P, rows);
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P * D) return;
-  const int64_t p = i / D;
+  const int64_t p = (P * D < (1LL << 31)) ? (int64_t)((uint32_t)i / (uint32_t)D) : i / D;      // 64-bit division only when needed
   const int d = (int)(i - p * D);
   const float xv = x[i];
   const float* row = g + p * ld + col0;
@@ -652,7 +657,10 @@ extern "C" int b2n_pe_fwd(const float* x, int64_t P, int D, const float* bands, 
   if (P == 0) return B2N_OK;
   B2N_REQUIRE(x && out && (L == 0 || bands), "null pointer");
   B2N_REQUIRE(ld_out >= col0 + D + 2 * D * L && col0 >= 0, "output row too narrow");
-  k_pe_fwd<<<grid_for(P * D * (L + 1), 256), 256, 0, (cudaStream_t)stream>>>(x, P, D, bands, L, out, ld_out, col0, g_active_rows);
+  const int pts_per_block = 256 / (L + 1);
+  const int64_t blocks = (P + pts_per_block - 1) / pts_per_block;
+  B2N_REQUIRE(blocks <= 0x7fffffffLL, "too many points for one launch");
+  k_pe_fwd<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x, P, D, bands, L, out, ld_out, col0, g_active_rows);
   return check_launch("b2n_pe_fwd");
 }
 

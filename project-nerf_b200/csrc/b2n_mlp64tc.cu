@@ -142,9 +142,11 @@ __device__ __forceinline__ void drain_to_tile(uint32_t tmem_row, uint32_t tile, 
     uint32_t p[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float a = __uint_as_float(v[h][2 * j]), b = __uint_as_float(v[h][2 * j + 1]);
-      if (RELU) a = fmaxf(a, 0.f), b = fmaxf(b, 0.f);
-      p[j] = pack2(a, b);
+      p[j] = pack2(__uint_as_float(v[h][2 * j]), __uint_as_float(v[h][2 * j + 1]));
+      if (RELU) {              // on the packed pair: one HMNMX2 for two values (rounding is monotone, 0 exact)
+        const __half2 r = __hmax2(*reinterpret_cast<__half2*>(&p[j]), __floats2half2_rn(0.f, 0.f));
+        p[j] = *reinterpret_cast<const uint32_t*>(&r);
+      }
     }
     sts128(tile + swz(r, c0 + 2 * h), p[0], p[1], p[2], p[3]);
     sts128(tile + swz(r, c0 + 2 * h + 1), p[4], p[5], p[6], p[7]);

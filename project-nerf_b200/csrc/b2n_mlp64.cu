@@ -161,6 +161,20 @@ __device__ __forceinline__ void load_x_raw(const float* __restrict__ x, int ldx,
         raw[k][2 * h + r] = v;
       }
 }
+// interior tiles of a full-width, 8-byte aligned input: the same loads without the per-element predicates
+template <int KT>
+__device__ __forceinline__ void load_x_raw_full(const float* __restrict__ x, int ldx, int64_t p0, float2 (&raw)[KT][4], int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const float* r0 = x + (p0 + g) * ldx + 2 * t;
+  const float* r1 = r0 + 8 * (int64_t)ldx;
+#pragma unroll
+  for (int k = 0; k < KT; ++k)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      raw[k][2 * h] = __ldcs(reinterpret_cast<const float2*>(r0 + 16 * k + 8 * h));
+      raw[k][2 * h + 1] = __ldcs(reinterpret_cast<const float2*>(r1 + 16 * k + 8 * h));
+    }
+}
 template <int KT>
 __device__ __forceinline__ void pack_x(const float2 (&raw)[KT][4], uint32_t (&a)[KT][4]) {
 #pragma unroll
@@ -836,7 +850,12 @@ k_instant_bwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
     auto T = [&](int slot) { return tiles + slot * (SLOT / 2); };
     const uint32_t bar_done = s32(bars + group), bar_full = s32(bars + GROUPS + group);
     float2 xraw[KT1][4];       // this tile's x_enc rows as fp32: fetched one tile ahead, split into hi / lo at the top of the tile
-    load_x_raw<KT1>(x, ldx, pos_dim, (tile_first + group) * 64 + row0, P, xraw, lane, in_pad_value);
+    const bool x_full = pos_dim == POS_K && ((ldx & 1) == 0) && ((reinterpret_cast<uintptr_t>(x) & 7) == 0);
+    auto fetch_x = [&](int64_t t) {
+      if (x_full && (t + 1) * 64 <= P) load_x_raw_full<KT1>(x, ldx, t * 64 + row0, xraw, lane);
+      else load_x_raw<KT1>(x, ldx, pos_dim, t * 64 + row0, P, xraw, lane, in_pad_value);
+    };
+    fetch_x(tile_first + group);
     uint32_t phase = 0;
     bool pending = false;
     for (int64_t tile = tile_first + group; tile < n_tiles && ok; tile += tile_step) {
@@ -882,7 +901,7 @@ k_instant_bwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
       store_a_sw<KT1>(ax[0], T(SL::X), row0, 0, lane);
       store_a_sw<4>(ah[0], T(SL::H1), row0, 0, lane);
       // next tile's inputs: the fragments are dead from here on
-      load_x_raw<KT1>(x, ldx, pos_dim, (tile + tile_step) * 64 + row0, P, xraw, lane, in_pad_value);
+      fetch_x(tile + tile_step);
       float hs0 = 0.f, hs1 = 0.f;  // h[.,0] of rows g and g+8 (threads with t == 0)
       uint32_t ac[1][3][4];
       {
@@ -1006,7 +1025,13 @@ k_instant_bwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
         const int64_t pa = p0 + g, pb = pa + 8;
         float* ra = g_x + pa * ldg + 2 * t;
         float* rb = g_x + pb * ldg + 2 * t;
-        if (gx_vec) {              // column pairs are contiguous and 8-byte aligned: one full 32-byte sector per row and store
+        if (gx_vec && pos_dim == POS_K && (tile + 1) * 64 <= P) {      // interior tile, full width: no predicates
+#pragma unroll
+          for (int j = 0; j < POS_K / 8; ++j) {
+            __stcs(reinterpret_cast<float2*>(ra + 8 * j), make_float2(c[j][0] * inv_s, c[j][1] * inv_s));
+            __stcs(reinterpret_cast<float2*>(rb + 8 * j), make_float2(c[j][2] * inv_s, c[j][3] * inv_s));
+          }
+        } else if (gx_vec) {       // column pairs are contiguous and 8-byte aligned: one full 32-byte sector per row and store
 #pragma unroll
           for (int j = 0; j < POS_K / 8; ++j) {
             if (8 * j + 2 * t < pos_dim) {

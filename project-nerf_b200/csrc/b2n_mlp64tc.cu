@@ -204,7 +204,17 @@ k_instant_fwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
   // coalesced: consecutive threads read consecutive 16 bytes of a row
   constexpr int Q = POS_K / 4;
   float4 xr[Q];
+  const bool full_rows = vec && pos_dim == POS_K;       // every 16-byte piece of a row is a plain vector load
   auto load_rows = [&](int64_t t) {
+    if (full_rows && (t + 1) * TILE <= P) {              // interior tile: no per-element predicates
+      const float* base = x + t * TILE * (int64_t)ldx;
+#pragma unroll
+      for (int it = 0; it < Q; ++it) {
+        const int idx = it * THREADS + tid;
+        xr[it] = ldg_stream(base + (int64_t)(idx / Q) * ldx + 4 * (idx % Q));
+      }
+      return;
+    }
 #pragma unroll
     for (int it = 0; it < Q; ++it) {
       const int idx = it * THREADS + tid;

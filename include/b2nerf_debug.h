@@ -22,6 +22,11 @@ int b2n_debug_mlp256_flags(int flags);
  * Both produce the same results; the switch exists for A/B timing and parity tests. */
 int b2n_debug_mlp256_set_pair(int on);
 
+/* point tiles a CTA of b2n_instant_mlp_fwd_tc keeps in flight at pos_dim <= 32: 1 (default: 4 CTAs = 4 tiles per SM) or 2 (the
+ * epilogue of one tile runs under the MMAs of the other; 3 CTAs = 6 tiles per SM; measured equal).  Same results.  Returns the previous
+ * value. */
+int b2n_debug_instant_fwd_slots(int slots);
+
 /* schedule of b2n_instant_mlp_bwd_tc at pos_dim <= 32: 3 (default) = one CTA per SM with three 4-warp groups and a
  * single MMA issuer, 1 = two 4-warp CTAs per SM.  Same results up to the order of the fp32 accumulation.  Returns the
  * previous value. */

@@ -75,6 +75,7 @@ DEBUG_SIGNATURES = {
     "b2n_debug_mlp256_set_pair": [ctypes.c_int],
     "b2n_debug_hash_variant": [I, I],
     "b2n_debug_instant_bwd_groups": [I],
+    "b2n_debug_instant_fwd_slots": [I],
     "b2n_debug_gather_bench": [P, L, I, I, P, P],
     "b2n_debug_red_bench": [P, L, I, I, I, P],
     "b2n_debug_mnmajor_probe": [P, P, P, I, I, I, I, P],

@@ -30,11 +30,12 @@ constexpr uint32_t W64_BYTES = 8192;      // [64 x 64]
 constexpr uint32_t W16_BYTES = 2048;      // [16 x 64]
 // shared-memory map.  POS_K == 32: ONE activation tile -- x_hi in columns 0..31 and x_lo in columns 32..63 of the same
 // 64-wide rows (the first layer multiplies it by [W1_hi | W1_hi] and by [W1_lo | 0]); POS_K == 64: x_lo has its own tile.
-template <int POS_K>
+template <int POS_K, int NS>
 struct Map {
+  static constexpr uint32_t SLOT = POS_K == 64 ? 2 * A_BYTES : A_BYTES;      // activation tile(s) of one in-flight point tile
   static constexpr uint32_t A0 = 0;                          // x_hi (| x_lo) -> h1 -> c -> c1 -> c2 (in place)
   static constexpr uint32_t A1 = A0 + A_BYTES;               // x_lo (POS_K == 64 only)
-  static constexpr uint32_t W1H = POS_K == 64 ? A1 + A_BYTES : A1;
+  static constexpr uint32_t W1H = NS * SLOT;
   static constexpr uint32_t W1L = W1H + W64_BYTES;
   static constexpr uint32_t W2 = W1L + W64_BYTES;
   static constexpr uint32_t V1 = W2 + W16_BYTES;
@@ -158,8 +159,14 @@ __device__ __forceinline__ void drain_to_tile(uint32_t tmem_row, uint32_t tile, 
   }
 }
 
-template <int POS_K>      // 32 or 64: padded width of the sigma-net input held in the x tiles
-__global__ void __launch_bounds__(THREADS, POS_K == 32 ? 4 : 3)
+// POS_K: 32 or 64, the padded width of the sigma-net input held in the x tiles.  NS: point tiles a CTA keeps in flight -- with
+// two, the CTA works on tile B's epilogue while the tensor core runs tile A's next layer (and vice versa): the MMA, its commit
+// and the barrier wake-up leave the critical path.  NS = 2 costs one more activation tile (16 KB) and 32 prefetch registers
+// (68 KB -> 3 CTAs = 6 tiles per SM instead of 4).  Measured after the instruction-count work (4.2 M points): 0.351 ms against
+// 0.345 ms for NS = 1 with four CTAs per SM -- with four co-resident tiles the kernel is no longer waiting for its MMAs but
+// bound by TMEM drain + packing + stores, so NS = 1 stays the default and NS = 2 an A/B variant (b2n_debug_instant_fwd_slots).
+template <int POS_K, int NS>
+__global__ void __launch_bounds__(THREADS, POS_K == 32 ? (NS == 1 ? 4 : 3) : 3)
 k_instant_fwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float* __restrict__ dirs,
                  const float* __restrict__ bands, int L_dir, const float* __restrict__ sp, const float* __restrict__ cp,
                  int64_t P, float* __restrict__ rgb, float* __restrict__ sigma, const int* __restrict__ rows,
@@ -167,15 +174,14 @@ k_instant_fwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
   P = clamp_rows(P, rows);
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  using M = Map<POS_K>;
+  using M = Map<POS_K, NS>;
   constexpr bool MERGED = POS_K == 32;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + M::BAR);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 1);
-  const uint32_t bar = s32(bars);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + NS);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int in_pad = (pos_dim + 15) & ~15;
   constexpr int KS1 = POS_K / 16;
-  // ---- one-time set-up: weights as B operands, barrier, TMEM
+  // ---- one-time set-up: weights as B operands, barriers, TMEM
   stage_weight(sp, 64, in_pad, 64, smem + M::W1H, false, MERGED);
   stage_weight(sp, 64, in_pad, 64, smem + M::W1L, true);
   stage_weight(sp + 64 * in_pad, 16, 64, 16, smem + M::W2, false);
@@ -185,11 +191,11 @@ k_instant_fwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
     stage_weight(cp + 64 * 48 + 64 * 64, 16, 64, 16, smem + M::V3, false);
   }
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1));
+    for (int s = 0; s < NS; ++s) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bars + s)), "r"(1));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(64));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)), "r"(64 * NS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
   proxy_fence();
@@ -198,7 +204,7 @@ k_instant_fwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_row = tmem + ((uint32_t)(32 * warp) << 16);          // this thread's lane group
-  const uint32_t a0 = s32(smem + M::A0), a1 = s32(smem + M::A1);
+  const uint32_t a_base = s32(smem + M::A0), bar0 = s32(bars);
   const uint32_t w1h = s32(smem + M::W1H), w1l = s32(smem + M::W1L), w2 = s32(smem + M::W2);
   const uint32_t v1 = s32(smem + M::V1), v2 = s32(smem + M::V2), v3 = s32(smem + M::V3);
   const bool vec = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
@@ -206,17 +212,18 @@ k_instant_fwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
   bool ok = true;
 
   const int64_t n_tiles = (P + TILE - 1) / TILE;
+  const int64_t n_units = (n_tiles + NS - 1) / NS;
   // coalesced: consecutive threads read consecutive 16 bytes of a row
   constexpr int Q = POS_K / 4;
-  float4 xr[Q];
+  float4 xr[NS][Q];
   const bool full_rows = vec && pos_dim == POS_K;       // every 16-byte piece of a row is a plain vector load
-  auto load_rows = [&](int64_t t) {
+  auto load_rows = [&](int64_t t, float4 (&dst)[Q]) {
     if (full_rows && (t + 1) * TILE <= P) {              // interior tile: no per-element predicates
       const float* base = x + t * TILE * (int64_t)ldx;
 #pragma unroll
       for (int it = 0; it < Q; ++it) {
         const int idx = it * THREADS + tid;
-        xr[it] = ldg_stream(base + (int64_t)(idx / Q) * ldx + 4 * (idx % Q));
+        dst[it] = ldg_stream(base + (int64_t)(idx / Q) * ldx + 4 * (idx % Q));
       }
       return;
     }
@@ -240,71 +247,90 @@ k_instant_fwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
           f = make_float4(e[0], e[1], e[2], e[3]);
         }
       }
-      xr[it] = f;
+      dst[it] = f;
     }
   };
-  load_rows(blockIdx.x);
-  for (int64_t tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
-    const int64_t p = tile * TILE + tid;
-    const bool live = p < P;
-    // ---- the tile's input rows (fetched one tile ahead) -> x_hi / x_lo; only the POS_K columns the first layer reads
-    // this point's view direction: needed after two layer steps -- loaded now, not a tile ahead (a prefetched value that
-    // gets spilled makes the spill store wait for the load: 5 % of the stall samples, ncu)
-    float d[3] = {0.f, 0.f, 0.f};
-    if (dirs && live) d[0] = __ldg(dirs + 3 * p), d[1] = __ldg(dirs + 3 * p + 1), d[2] = __ldg(dirs + 3 * p + 2);
-#pragma unroll
-    for (int it = 0; it < Q; ++it) {
-      const int idx = it * THREADS + tid;
-      const int r = idx / Q, q = idx % Q;
-      const float4 f = xr[it];
-      const uint32_t h0 = pack2(f.x, f.y), h1 = pack2(f.z, f.w);
-      const float2 b0 = unpack2(h0), b1 = unpack2(h1);
-      const uint32_t l0 = pack2(f.x - b0.x, f.y - b0.y), l1 = pack2(f.z - b1.x, f.w - b1.y);
-      sts64(a0 + swz(r, q >> 1) + 8 * (q & 1), h0, h1);
-      if (MERGED) sts64(a0 + swz(r, 4 + (q >> 1)) + 8 * (q & 1), l0, l1);
-      else sts64(a1 + swz(r, q >> 1) + 8 * (q & 1), l0, l1);
-    }
-    load_rows(tile + gridDim.x);            // lands during the five layer phases below
-    proxy_fence();
-    tc_fence_before();
-    __syncthreads();
-    // ---- sigma_net layer 1: split product, small terms first
-    if (tid == 0) {
-      tc_fence_after();
+  // one elected thread issues a layer of slot s and commits to the slot's barrier
+  auto issue = [&](int layer, int s) {
+    const uint32_t a0 = a_base + s * M::SLOT, a1 = a0 + A_BYTES, acc = tmem + 64 * s;
+    tc_fence_after();
+    if (layer == 0) {            // sigma_net layer 1: split product, small terms first
       const uint32_t id = umma_idesc(64);
       // x_lo W_hi: the merged tile holds x_lo in its upper 32 columns, facing the second copy of W_hi
 #pragma unroll
       for (int k = 0; k < KS1; ++k)
-        tc_mma(tmem, umma_desc(MERGED ? a0 : a1) + 2 * (MERGED ? k + KS1 : k), umma_desc(w1h) + 2 * (MERGED ? k + KS1 : k), id, k > 0);
+        tc_mma(acc, umma_desc(MERGED ? a0 : a1) + 2 * (MERGED ? k + KS1 : k), umma_desc(w1h) + 2 * (MERGED ? k + KS1 : k), id, k > 0);
 #pragma unroll
-      for (int k = 0; k < KS1; ++k) tc_mma(tmem, umma_desc(a0) + 2 * k, umma_desc(w1l) + 2 * k, id, 1u);
+      for (int k = 0; k < KS1; ++k) tc_mma(acc, umma_desc(a0) + 2 * k, umma_desc(w1l) + 2 * k, id, 1u);
 #pragma unroll
-      for (int k = 0; k < KS1; ++k) tc_mma(tmem, umma_desc(a0) + 2 * k, umma_desc(w1h) + 2 * k, id, 1u);
-      tc_commit(bar);
+      for (int k = 0; k < KS1; ++k) tc_mma(acc, umma_desc(a0) + 2 * k, umma_desc(w1h) + 2 * k, id, 1u);
+    } else {
+      // 1: sigma_net layer 2 (64 -> 16)   2: color_net layer 1 (48 -> 64)   3: color_net layer 2   4: output layer (64 -> 3 of 16)
+      const uint32_t w = layer == 1 ? w2 : (layer == 2 ? v1 : (layer == 3 ? v2 : v3));
+      const uint32_t id = umma_idesc((layer == 1 || layer == 4) ? 16 : 64);
+      const int ks = layer == 2 ? 3 : 4;
+      for (int k = 0; k < ks; ++k) tc_mma(acc, umma_desc(a0) + 2 * k, umma_desc(w) + 2 * k, id, k > 0);
     }
-    ok = mbar_wait(bar, phase, err);
-    phase ^= 1;
-    tc_fence_after();
-    drain_to_tile<4, true>(tmem_row, a0, tid, 0);                 // h1 (64) over x_hi
+    tc_commit(bar0 + 8 * s);
+  };
+
+#pragma unroll
+  for (int s = 0; s < NS; ++s) load_rows((int64_t)blockIdx.x * NS + s, xr[s]);
+  for (int64_t unit = blockIdx.x; unit < n_units && ok; unit += gridDim.x) {
+    float d[NS][3];
+    // ---- input rows (fetched one unit ahead) -> x_hi / x_lo; only the POS_K columns the first layer reads
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const uint32_t a0 = a_base + s * M::SLOT, a1 = a0 + A_BYTES;
+      const int64_t p = (unit * NS + s) * TILE + tid;
+      // this point's view direction: needed after two layer steps -- loaded now, not a tile ahead (a prefetched value that
+      // gets spilled makes the spill store wait for the load: 5 % of the stall samples, ncu)
+      d[s][0] = d[s][1] = d[s][2] = 0.f;
+      if (dirs && p < P) d[s][0] = __ldg(dirs + 3 * p), d[s][1] = __ldg(dirs + 3 * p + 1), d[s][2] = __ldg(dirs + 3 * p + 2);
+#pragma unroll
+      for (int it = 0; it < Q; ++it) {
+        const int idx = it * THREADS + tid;
+        const int r = idx / Q, q = idx % Q;
+        const float4 f = xr[s][it];
+        const uint32_t h0 = pack2(f.x, f.y), h1 = pack2(f.z, f.w);
+        const float2 b0 = unpack2(h0), b1 = unpack2(h1);
+        const uint32_t l0 = pack2(f.x - b0.x, f.y - b0.y), l1 = pack2(f.z - b1.x, f.w - b1.y);
+        sts64(a0 + swz(r, q >> 1) + 8 * (q & 1), h0, h1);
+        if (MERGED) sts64(a0 + swz(r, 4 + (q >> 1)) + 8 * (q & 1), l0, l1);
+        else sts64(a1 + swz(r, q >> 1) + 8 * (q & 1), l0, l1);
+      }
+      load_rows((unit + gridDim.x) * NS + s, xr[s]);            // lands during the layer phases below
+    }
     proxy_fence();
     tc_fence_before();
     __syncthreads();
-    // ---- sigma_net layer 2 -> h (16), density head
     if (tid == 0) {
-      tc_fence_after();
-      const uint32_t id = umma_idesc(16);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) tc_mma(tmem, umma_desc(a0) + 2 * k, umma_desc(w2) + 2 * k, id, k > 0);
-      tc_commit(bar);
+      for (int s = 0; s < NS; ++s) issue(0, s);
     }
-    ok = ok && mbar_wait(bar, phase, err);
+    // ---- h1 = relu(layer 1) over x_hi; then layer 2
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      ok = ok && mbar_wait(bar0 + 8 * s, phase, err);
+      tc_fence_after();
+      drain_to_tile<4, true>(tmem_row + 64 * s, a_base + s * M::SLOT, tid, 0);
+      proxy_fence();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) issue(1, s);
+    }
     phase ^= 1;
-    tc_fence_after();
-    {
+    // ---- h (16): density head; colour-net input = [h | direction features]
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const uint32_t a0 = a_base + s * M::SLOT;
+      const int64_t p = (unit * NS + s) * TILE + tid;
+      ok = ok && mbar_wait(bar0 + 8 * s, phase, err);
+      tc_fence_after();
       uint32_t v[16];
-      tc_ld16(tmem_row, v);
+      tc_ld16(tmem_row + 64 * s, v);
       tc_ld_wait();
-      if (live) __stcs(sigma + p, softplus_m5(__uint_as_float(v[0])));
+      if (p < P) __stcs(sigma + p, softplus_m5(__uint_as_float(v[0])));
       if (rgb) {
         uint32_t q[8];
 #pragma unroll
@@ -312,81 +338,68 @@ k_instant_fwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
         sts128(a0 + swz(tid, 0), q[0], q[1], q[2], q[3]);
         sts128(a0 + swz(tid, 1), q[4], q[5], q[6], q[7]);
         uint4 df[4];
-        dir_features(d, bands, L_dir, in_pad_value, df);
+        dir_features(d[s], bands, L_dir, in_pad_value, df);
 #pragma unroll
         for (int i = 0; i < 4; ++i) sts128(a0 + swz(tid, 2 + i), df[i].x, df[i].y, df[i].z, df[i].w);      // layer 1 of color_net reads K = 48 only
+        proxy_fence();
       }
-    }
-    tc_fence_before();
-    if (!rgb) {                   // density sweep: the colour network is skipped
+      tc_fence_before();
       __syncthreads();
-      continue;
+      if (rgb && tid == 0) issue(2, s);
     }
-    proxy_fence();
-    __syncthreads();
-    // ---- color_net layer 1 (48 -> 64)
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t id = umma_idesc(64);
-#pragma unroll
-      for (int k = 0; k < 3; ++k) tc_mma(tmem, umma_desc(a0) + 2 * k, umma_desc(v1) + 2 * k, id, k > 0);
-      tc_commit(bar);
-    }
-    ok = ok && mbar_wait(bar, phase, err);
     phase ^= 1;
-    tc_fence_after();
-    drain_to_tile<4, true>(tmem_row, a0, tid, 0);
-    proxy_fence();
-    tc_fence_before();
-    __syncthreads();
-    // ---- color_net layer 2 (64 -> 64)
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t id = umma_idesc(64);
+    if (!rgb) continue;           // density sweep: the colour network is skipped
+    // ---- color_net hidden layers
 #pragma unroll
-      for (int k = 0; k < 4; ++k) tc_mma(tmem, umma_desc(a0) + 2 * k, umma_desc(v2) + 2 * k, id, k > 0);
-      tc_commit(bar);
-    }
-    ok = ok && mbar_wait(bar, phase, err);
-    phase ^= 1;
-    tc_fence_after();
-    drain_to_tile<4, true>(tmem_row, a0, tid, 0);
-    proxy_fence();
-    tc_fence_before();
-    __syncthreads();
-    // ---- color_net output layer (64 -> 3, padded to 16) + sigmoid
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t id = umma_idesc(16);
+    for (int layer = 3; layer <= 4; ++layer) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) tc_mma(tmem, umma_desc(a0) + 2 * k, umma_desc(v3) + 2 * k, id, k > 0);
-      tc_commit(bar);
+      for (int s = 0; s < NS; ++s) {
+        ok = ok && mbar_wait(bar0 + 8 * s, phase, err);
+        tc_fence_after();
+        drain_to_tile<4, true>(tmem_row + 64 * s, a_base + s * M::SLOT, tid, 0);
+        proxy_fence();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) issue(layer, s);
+      }
+      phase ^= 1;
     }
-    ok = ok && mbar_wait(bar, phase, err);
-    phase ^= 1;
-    tc_fence_after();
-    {
+    // ---- output layer + sigmoid
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int64_t p = (unit * NS + s) * TILE + tid;
+      ok = ok && mbar_wait(bar0 + 8 * s, phase, err);
+      tc_fence_after();
       uint32_t v[16];
-      tc_ld16(tmem_row, v);
+      tc_ld16(tmem_row + 64 * s, v);
       tc_ld_wait();
-      if (live) {
+      if (p < P) {
         rgb[3 * p] = sigmoidf(__uint_as_float(v[0]));
         rgb[3 * p + 1] = sigmoidf(__uint_as_float(v[1]));
         rgb[3 * p + 2] = sigmoidf(__uint_as_float(v[2]));
       }
     }
+    phase ^= 1;
     tc_fence_before();
-    __syncthreads();              // the accumulator and the A tile are free for the next tile
+    __syncthreads();              // the accumulators are free for the next unit
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(64 * NS));
 }
 
 }  // namespace itc
 }  // namespace b2n
 
 using namespace b2n;
+
+// point tiles in flight per CTA of k_instant_fwd_tc at pos_dim <= 32 (b2n_debug_instant_fwd_slots): see the kernel
+static int g_fwd_slots = 1;
+extern "C" int b2n_debug_instant_fwd_slots(int slots) {
+  const int prev = g_fwd_slots;
+  if (slots == 1 || slots == 2) g_fwd_slots = slots;
+  return prev;
+}
 
 // Same contract as b2n_instant_mlp_fwd (b2n_mlp64.cu dispatches here unless the mma.sync variant is selected through
 // b2n_debug_instant_variant); err_flag: device int, set non-zero if a stalled barrier aborted a tile.
@@ -402,22 +415,24 @@ extern "C" int b2n_instant_mlp_fwd_tc(const float* x_enc, int ldx, int pos_dim, 
   if (!rgb) dirs = nullptr, dir_bands = nullptr, L_dir = 0, color_params = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t tiles = (P + itc::TILE - 1) / itc::TILE;
-  auto launch = [&](auto kern, uint32_t smem_bytes) {
+  auto launch = [&](auto kern, uint32_t smem_bytes, int ns) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     // CTAs per SM by shared memory (227 KB, 1 KB reserved per CTA); cudaOccupancyMaxActiveBlocksPerMultiprocessor answers 1
     // for this kernel although the hardware co-schedules 3-4 (measured: 1.05 -> 0.49 ms with three per SM); registers
-    // (<= 168 x 128) and TMEM (64 of 512 columns) allow more than shared memory does
+    // (<= 168 x 128) and TMEM (64 * ns of 512 columns) allow more than shared memory does
     int per_sm = (int)(232448u / (smem_bytes + 1024u));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 8) per_sm = 8;                  // 8 x 64 TMEM columns = the 512 of an SM
+    if (per_sm > 8 / ns) per_sm = 8 / ns;        // 512 TMEM columns per SM
+    const int64_t units = (tiles + ns - 1) / ns;
     int64_t grid = (int64_t)kSMs * per_sm;
-    if (grid > tiles) grid = tiles;
+    if (grid > units) grid = units;
     kern<<<(unsigned)grid, itc::THREADS, smem_bytes, st>>>(x_enc, ldx, pos_dim, dirs, dir_bands, L_dir, sigma_params,
-                                                               color_params, P, rgb, sigma, g_active_rows, in_pad_value,
-                                                               err_flag);
+                                                          color_params, P, rgb, sigma, g_active_rows, in_pad_value,
+                                                          err_flag);
   };
-  if (pos_dim <= 32) launch(itc::k_instant_fwd_tc<32>, itc::Map<32>::BYTES);
-  else launch(itc::k_instant_fwd_tc<64>, itc::Map<64>::BYTES);
+  if (pos_dim <= 32 && g_fwd_slots == 2) launch(itc::k_instant_fwd_tc<32, 2>, itc::Map<32, 2>::BYTES, 2);
+  else if (pos_dim <= 32) launch(itc::k_instant_fwd_tc<32, 1>, itc::Map<32, 1>::BYTES, 1);
+  else launch(itc::k_instant_fwd_tc<64, 1>, itc::Map<64, 1>::BYTES, 1);
   return check_launch("b2n_instant_mlp_fwd_tc");
 }

@@ -601,20 +601,26 @@ def test_instant_fwd_tcgen05_matches_mma_sync(mods, pos_dim, Pn, pad):
     x = torch.randn(Pn, pos_dim, device=DEV) * 0.5
     d = torch.nn.functional.normalize(torch.randn(Pn, 3, device=DEV), dim=-1)
     bands = cu(O.fourier_bands(4))
+    lib = mods["b2n"]._lib.lib
     out = {}
     prev = ops.INSTANT_FWD_TC
+    prev_slots = lib.b2n_debug_instant_fwd_slots(1)
     try:
-        for tc in (False, True):
+        for key, tc, slots in (("mma", False, 1), ("tc1", True, 1), ("tc2", True, 2)):       # slots: see b2nerf_debug.h
             ops.INSTANT_FWD_TC = tc
+            lib.b2n_debug_instant_fwd_slots(slots)
             rgb, sigma = mods["b2n"].instant_mlp(x, d, bands, sp, cp, pad_value=pad)
-            out[tc] = (rgb.clone(), sigma.clone(), mods["b2n"].instant_sigma(x, sp, pad_value=pad).clone())
+            out[key] = (rgb.clone(), sigma.clone(), mods["b2n"].instant_sigma(x, sp, pad_value=pad).clone())
     finally:
         ops.INSTANT_FWD_TC = prev
+        lib.b2n_debug_instant_fwd_slots(prev_slots)
     mods["b2n"].check_errors()
-    tag = f"instant_fwd_tc[{pos_dim},{Pn}]"
-    assert record(f"{tag}:rgb", rel_err(out[True][0], out[False][0])) < 2e-5
-    assert record(f"{tag}:sigma", rel_err(out[True][1], out[False][1])) < 2e-5
-    assert torch.equal(out[True][2], out[True][1])            # density-only mode: the same sigma_net arithmetic
+    for key in ("tc1", "tc2"):
+        tag = f"instant_fwd_{key}[{pos_dim},{Pn}]"
+        assert record(f"{tag}:rgb", rel_err(out[key][0], out["mma"][0])) < 2e-5
+        assert record(f"{tag}:sigma", rel_err(out[key][1], out["mma"][1])) < 2e-5
+        assert torch.equal(out[key][2], out[key][1])            # density-only mode: the same sigma_net arithmetic
+    assert torch.equal(out["tc2"][0], out["tc1"][0]) and torch.equal(out["tc2"][1], out["tc1"][1])      # same MMAs, other schedule
 
 
 @pytest.mark.parametrize("pos_dim,Pn", [(32, 64 * 37 + 5), (53, 777), (64, 130), (32, 5), (32, 200000), (20, 64 * 148 * 3 + 1),

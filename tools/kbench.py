@@ -423,12 +423,13 @@ def mlp64(P=1 << 22):
         x = (torch.randn(P, pos_dim, device="cuda") * 0.5).requires_grad_(True)
         d = torch.nn.functional.normalize(torch.randn(P, 3, device="cuda"), dim=-1)
         bands = O.fourier_bands(4).cuda()
-        for tc in (False, True):
+        for tc, slots in ((False, 1), (True, 1), (True, 2)):
             ops.INSTANT_FWD_TC = tc
+            _lib.lib.b2n_debug_instant_fwd_slots(slots)
             with torch.no_grad():
                 med, best = timeit(lambda: b2n.instant_mlp(x, d, bands, sp, cp))
                 meds, bests = timeit(lambda: b2n.instant_sigma(x, sp))
-            print(f"instant fwd pos_dim={pos_dim} P={P} tc={tc}: {med:.3f} ms (best {best:.3f}); sigma-only {meds:.3f} ms")
+            print(f"instant fwd pos_dim={pos_dim} P={P} tc={tc} slots={slots}: {med:.3f} ms (best {best:.3f}); sigma-only {meds:.3f} ms")
         b2n.check_errors()
         rgb, sigma = b2n.instant_mlp(x, d, bands, sp, cp)
         g1, g2 = torch.randn_like(rgb), torch.randn_like(sigma)

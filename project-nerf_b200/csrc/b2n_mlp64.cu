@@ -835,9 +835,9 @@ k_instant_bwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
     if (threadIdx.x == GROUPS * MLP_THREADS) {
       // groups are served IN ORDER: a group that is early waits for its neighbours (ncu: ~11 try_wait rounds per tile in the
       // workers' wait for their slots), which keeps the three groups a third of a tile period apart -- their HMMA-heavy and
-      // LSU-heavy phases interleave.  Serving whichever group is ready first (mbarrier.test_wait polling with a 100 ns back-off,
-      // with and without an initial stagger of the groups) was measured: 1.45 ms against 1.12 ms per 4.2 M points -- the
-      // hardware-suspended try_wait reacts at once, the poller a sleep period late, and the workers wait for their slots
+      // LSU-heavy phases interleave.  Serving whichever group is ready first was measured three ways (test_wait polling with a
+      // 100 ns back-off, the same with an initial stagger of the groups, try_wait with a 200 ns suspend hint rotating over the
+      // groups): 1.44-1.45 ms against 1.12 ms per 4.2 M points -- it is the enforced round-robin that pays
       uint32_t issued = 0u;
       for (int64_t base_tile = tile_first, it = 0; base_tile < n_tiles && ok; base_tile += tile_step, ++it) {
         for (int grp = 0; grp < GROUPS && ok; ++grp) {

@@ -893,9 +893,8 @@ k_instant_bwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
       uint32_t ah[1][4][4];
       {
         float c[1][8][4] = {};
-        gemm_fwd<1, 8, KT1>(c, axl, sm + L.w1, SX, lane);              // split product (see k_instant_fwd)
-        gemm_fwd<1, 8, KT1>(c, ax, sm + L.w1lo, SX, lane);
-        gemm_fwd<1, 8, KT1>(c, ax, sm + L.w1, SX, lane);
+        gemm_fwd<1, 8, KT1>(c, ax, sm + L.w1lo, SX, lane);             // split product: x_hi W_lo, then (x_lo + x_hi) W_hi with
+        gemm_fwd_hl<8, KT1>(c[0], ax[0], axl[0], sm + L.w1, SX, lane);  // every W_hi fragment read from shared memory once
         c_to_a<8, true>(c[0], ah[0]);
       }
       // the previous tile's weight-gradient MMAs have had the first layer to finish reading the staged tiles

@@ -112,6 +112,30 @@ __device__ __forceinline__ void gemm_fwd(float (&c)[MT][NT][4], const uint32_t (
   }
 }
 
+// C[j] += (A_lo + A_hi) * W^T for one 16-row slab: the two products of the split first layer that share W_hi, with every
+// weight fragment read from shared memory ONCE (lo term first).  KT even.
+template <int NT, int KT>
+__device__ __forceinline__ void gemm_fwd_hl(float (&c)[NT][4], const uint32_t (&a_hi)[KT][4], const uint32_t (&a_lo)[KT][4],
+                                            const op16* W, int S, int lane) {
+  static_assert(KT % 2 == 0, "k-tile pairs");
+  const op16* base = W + (lane & 7) * S + 8 * (lane >> 3);
+#pragma unroll
+  for (int q = 0; q < KT / 2; ++q) {
+    uint32_t b[NT][4];
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      ldsm_x4(b[j], base + 8 * j * S + 32 * q);
+      mma16816(c[j], a_lo[2 * q], b[j][0], b[j][1]);
+    }
+#pragma unroll
+    for (int j = 0; j < NT; ++j) mma16816(c[j], a_lo[2 * q + 1], b[j][2], b[j][3]);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) mma16816(c[j], a_hi[2 * q], b[j][0], b[j][1]);
+#pragma unroll
+    for (int j = 0; j < NT; ++j) mma16816(c[j], a_hi[2 * q + 1], b[j][2], b[j][3]);
+  }
+}
+
 // dIn[16 x 8*NTo] += dZ[16 x 16*KTz] * W ; W in smem as [n][k] (n is the reduction index).
 // Reduction index outer so that consecutive mma.sync hit different accumulators.
 template <int NTo, int KTz>

@@ -515,6 +515,60 @@ k_hash_bwd_input(const float* __restrict__ x, int64_t P, float bound, float two_
   }
 }
 
+// The same with the pair-lane mapping of k_hash_fwd_pair (F == 2): lanes 2i / 2i+1 share point i and take the x = 0 / x = 1
+// corner column, so the two 8-byte gathers of an x-neighbour pair ride in one instruction on one line / sector (4 instead of
+// 8 line visits per (point, level)), and twice as many threads walk the levels.  Per lane: d/dx needs t_s = sum_k w_yz[k]
+// <g, T[x_s, k]> of BOTH columns (ddx = t_1 - t_0), d/dy and d/dz are sums over the lane's own column weighted by w_x[s];
+// all three are linear in the per-lane terms, so the pair is combined once, after the level loop.
+__global__ void __launch_bounds__(256)
+k_hash_bwd_input_pair(const float* __restrict__ x, int64_t P, float bound, float two_bound, const float2* __restrict__ table,
+                      const Levels lv, int nl, const float* __restrict__ g, int ld, int col0, float* __restrict__ gx,
+                      int accumulate, const int* __restrict__ rows) {
+  P = clamp_rows(P, rows);
+  if ((int64_t)blockIdx.x * (blockDim.x >> 1) >= P) return;      // whole block behind the (device-side) row count
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t p = tid >> 1;
+  const int s = threadIdx.x & 1;
+  const bool live = p < P;
+  bool in[3] = {false, false, false};
+  float x01[3] = {0.f, 0.f, 0.f};
+  if (live) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) x01[d] = to_unit(__ldg(x + 3 * p + d), bound, two_bound, &in[d]);
+  }
+  const float* gi = g + p * ld + col0;
+  const bool gvec = ((reinterpret_cast<uintptr_t>(g + col0) & 7) == 0) && ((ld & 1) == 0);
+  float gsx = 0.f, gsy = 0.f, gsz = 0.f;
+  for (int l = 0; l < nl; ++l) {                       // warp-uniform
+    const b2n_hash_level L = lv.l[l];
+    const Cell c = locate(x01, L.scale);
+    const uint32_t cx = c.g[0] + (uint32_t)s;
+    float2 gv = make_float2(0.f, 0.f);
+    if (live) gv = gvec ? __ldg(reinterpret_cast<const float2*>(gi + 2 * l)) : make_float2(__ldg(gi + 2 * l), __ldg(gi + 2 * l + 1));
+    float dot[4];                                      // <g, table[x_s, y, z]>, k = y + 2 z
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t e = corner_entry(L, cx, c.g[1] + (k & 1), c.g[2] + (k >> 1));
+      const float2 v = live ? __ldg(table + e) : make_float2(0.f, 0.f);
+      dot[k] = gv.x * v.x + gv.y * v.y;
+    }
+    const float wx = s ? c.w[0] : 1.f - c.w[0], wy = c.w[1], wz = c.w[2];
+    const float t = (1.f - wy) * (1.f - wz) * dot[0] + wy * (1.f - wz) * dot[1] + (1.f - wy) * wz * dot[2] + wy * wz * dot[3];
+    gsx += L.scale * (s ? t : -t);
+    gsy += L.scale * wx * ((1.f - wz) * (dot[1] - dot[0]) + wz * (dot[3] - dot[2]));
+    gsz += L.scale * wx * ((1.f - wy) * (dot[2] - dot[0]) + wy * (dot[3] - dot[1]));
+  }
+  gsx = pair_sum(gsx), gsy = pair_sum(gsy), gsz = pair_sum(gsz);
+  if (live && s == 0) {
+    const float gs[3] = {gsx, gsy, gsz};
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      const float v = in[d] ? (bound > 0.f ? gs[d] / two_bound : gs[d]) : 0.f;
+      gx[3 * p + d] = accumulate ? gx[3 * p + d] + v : v;
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------- tri-grid temporal blend (Part 4)
 // deform_feat = sum_i w_i(t) * HashGrid_i(x), i = start / mid / end anchors at t = 0, 0.5, 1 with tent weights of
 // half-width 0.5, normalised (src/core.py:308-335).  The three grids share one geometry, so cell, corner indices and
@@ -738,7 +792,10 @@ extern "C" int b2n_hash_bwd(const float* x, int64_t P, float bound, const float*
   }
   if (g_x) {
     const unsigned grid = grid_for(P, 256);
-    if (F == 2) k_hash_bwd_input<2><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, g_out, ld_g, col0, g_x, accumulate_x, g_active_rows);
+    if (F == 2 && (g_hash_variant & 1))
+      k_hash_bwd_input_pair<<<grid_for(2 * P, 256), 256, 0, st>>>(x, P, bound, tb, reinterpret_cast<const float2*>(table), lv, L, g_out,
+                                                                ld_g, col0, g_x, accumulate_x, g_active_rows);
+    else if (F == 2) k_hash_bwd_input<2><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, g_out, ld_g, col0, g_x, accumulate_x, g_active_rows);
     else if (F == 4) k_hash_bwd_input<4><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, g_out, ld_g, col0, g_x, accumulate_x, g_active_rows);
     else k_hash_bwd_input<1><<<grid, 256, 0, st>>>(x, P, bound, tb, table, lv, L, g_out, ld_g, col0, g_x, accumulate_x, g_active_rows);
   }

@@ -771,6 +771,8 @@ def make_state_dict(cfg: dict, seed: int = 0, table_scale: float = 1.0) -> Dict[
 # --------------------------------------------------------------------------
 # synthetic NeRF-Synthetic-shaped inputs       (src/dataset.py:73-122,
 #                                               look-at poses as run.py:1394-1417)
+# (b2n/synthetic.py holds the same generators for the product side, which may not import oracle/;
+#  tests/test_synthetic.py pins the two copies to each other)
 # --------------------------------------------------------------------------
 
 CAMERA_ANGLE_X = 0.6911112070083618

@@ -4,6 +4,10 @@ Host-side data generation only (numpy/torch CPU); nothing here computes the hot 
 Scene shape follows the reference's loaders: 800x800 views, camera_angle_x of the Blender
 sets, pinhole rays built as in src/dataset.py:84-96,147-171, look-at poses on the upper
 hemisphere as in run.py:1394-1417.
+
+The same generators exist once more in oracle/nerf_oracle.py (synthetic_poses / synthetic_rays / ball_occupancy) ON PURPOSE:
+the product may not import oracle/, and the oracle -- which also feeds the CPU reference arm of bench.py -- may not depend on
+the product.  tests/test_synthetic.py pins the two copies to each other bit for bit.
 """
 import numpy as np
 import torch

@@ -438,10 +438,22 @@ __global__ void __launch_bounds__(256) k_grad_absmax(const float* __restrict__ a
   P = clamp_rows(P, rows);
   const int64_t na = 3 * P, nb = P;              // a = g_rgb [P,3], b = g_sigma [P]
   unsigned int m = 0u;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < na + nb; i += (int64_t)gridDim.x * blockDim.x) {
-    const float v = i < na ? __ldg(a + i) : __ldg(b + (i - na));
-    m = max(m, __float_as_uint(v) & 0x7fffffffu);
-  }
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
+  auto scan = [&](const float* __restrict__ v, int64_t n) {
+    // 16-byte loads over the aligned body (the first version read 4 bytes per thread per step: 2.3 TB/s), scalars at the ends
+    const int64_t head = min(n, (int64_t)((16 - (reinterpret_cast<uintptr_t>(v) & 15)) & 15) >> 2);
+    const int64_t n4 = (n - head) >> 2;
+    const float4* v4 = reinterpret_cast<const float4*>(v + head);
+    for (int64_t i = t0; i < n4; i += nt) {
+      const float4 q = __ldcs(v4 + i);
+      m = max(max(m, __float_as_uint(q.x) & 0x7fffffffu), __float_as_uint(q.y) & 0x7fffffffu);
+      m = max(max(m, __float_as_uint(q.z) & 0x7fffffffu), __float_as_uint(q.w) & 0x7fffffffu);
+    }
+    for (int64_t i = t0; i < head; i += nt) m = max(m, __float_as_uint(__ldg(v + i)) & 0x7fffffffu);
+    for (int64_t i = head + 4 * n4 + t0; i < n; i += nt) m = max(m, __float_as_uint(__ldg(v + i)) & 0x7fffffffu);
+  };
+  scan(a, na);
+  scan(b, nb);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);

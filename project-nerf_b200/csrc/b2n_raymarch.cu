@@ -101,6 +101,68 @@ k_march_mask(const float* __restrict__ rays_o, const float* __restrict__ rays_d,
   }
 }
 
+// The same for N <= 32 WC with the chunk loop unrolled: the WC jitter loads of a ray are issued before the first use, the WC
+// voxel-bit gathers are independent, and the stratum bounds stay in registers across rays (the rolled loop had one 128-byte
+// load in flight per warp: 0.144 ms for a 0.06 ms stream at 2^18 rays x 128 samples)
+template <int WC>
+__global__ void __launch_bounds__(256)
+k_march_mask_u(const float* __restrict__ rays_o, const float* __restrict__ rays_d, const float* __restrict__ z_base,
+               const float* __restrict__ z_lo, const float* __restrict__ z_hi, const float* __restrict__ u,
+               const uint32_t* __restrict__ bits, int R, float offset, float scale, int64_t B, int N,
+               float* __restrict__ z_out, uint32_t* __restrict__ mask_words, int32_t* __restrict__ ray_count) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int W = (N + 31) >> 5;
+  float lo[WC], hi[WC];                      // stratum bounds (or the fixed depths) of this lane's samples: the same for every ray
+#pragma unroll
+  for (int k = 0; k < WC; ++k) {
+    const int s = (k << 5) + lane;
+    lo[k] = hi[k] = 0.f;
+    if (s < N) {
+      if (u) lo[k] = __ldg(z_lo + s), hi[k] = __ldg(z_hi + s);
+      else lo[k] = __ldg(z_base + s);
+    }
+  }
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < B; r += warps) {
+    float uu[WC];
+#pragma unroll
+    for (int k = 0; k < WC; ++k) {
+      const int s = (k << 5) + lane;
+      uu[k] = (u && s < N) ? __ldcs(u + r * N + s) : 0.f;
+    }
+    const float ox = __ldg(rays_o + 3 * r), oy = __ldg(rays_o + 3 * r + 1), oz = __ldg(rays_o + 3 * r + 2);
+    const float dx = __ldg(rays_d + 3 * r), dy = __ldg(rays_d + 3 * r + 1), dz = __ldg(rays_d + 3 * r + 2);
+    bool act[WC];
+#pragma unroll
+    for (int k = 0; k < WC; ++k) {
+      const int s = (k << 5) + lane;
+      act[k] = false;
+      if (s < N) {
+        const float z = u ? __fadd_rn(lo[k], __fmul_rn(__fsub_rn(hi[k], lo[k]), uu[k])) : lo[k];
+        __stcs(z_out + r * N + s, z);
+        if (bits) {
+          const float px = __fadd_rn(ox, __fmul_rn(dx, z));
+          const float py = __fadd_rn(oy, __fmul_rn(dy, z));
+          const float pz = __fadd_rn(oz, __fmul_rn(dz, z));
+          act[k] = voxel_active(px, py, pz, bits, R, offset, scale);
+        } else {
+          act[k] = true;
+        }
+      }
+    }
+    int count = 0;
+#pragma unroll
+    for (int k = 0; k < WC; ++k) {
+      const uint32_t w = __ballot_sync(0xffffffffu, act[k]);
+      if (k < W) {
+        if (lane == 0) mask_words[r * W + k] = w;
+        count += __popc(w);
+      }
+    }
+    if (lane == 0) ray_count[r] = count;
+  }
+}
+
 // ---- exclusive scan of ray_count (three small kernels) --------------------------------
 constexpr int kScanThreads = 256;
 constexpr int kScanPerThread = 8;
@@ -288,8 +350,15 @@ extern "C" int b2n_march_mask(const float* rays_o, const float* rays_d, const fl
   B2N_REQUIRE(!u || (z_lo && z_hi), "jitter needs the stratum bounds");
   B2N_REQUIRE(!bits || (R > 0 && R <= 1024), "bad grid resolution");
   B2N_REQUIRE(B * (int64_t)N < (int64_t)1 << 31, "B*N must fit int32");
-  k_march_mask<<<ray_grid(B), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, z_base, z_lo, z_hi, u, bits, R, offset,
-                                                             scale, B, N, z, mask_words, ray_count);
+  if (N <= 64)
+    k_march_mask_u<2><<<ray_grid(B), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, z_base, z_lo, z_hi, u, bits, R, offset,
+                                                                    scale, B, N, z, mask_words, ray_count);
+  else if (N <= 128)
+    k_march_mask_u<4><<<ray_grid(B), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, z_base, z_lo, z_hi, u, bits, R, offset,
+                                                                    scale, B, N, z, mask_words, ray_count);
+  else
+    k_march_mask<<<ray_grid(B), 256, 0, (cudaStream_t)stream>>>(rays_o, rays_d, z_base, z_lo, z_hi, u, bits, R, offset,
+                                                               scale, B, N, z, mask_words, ray_count);
   return check_launch("b2n_march_mask");
 }
 

@@ -985,8 +985,7 @@ k_instant_bwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
         float c[8][4] = {};
         gemm_dgrad<8, 1>(c, dz5, sm + L.v3, SH, lane);          // d c2
         c_to_a<8, false>(c, dz[0]);
-        if (!GATE_REGS) relu_gate_sw<4>(dz[0], T(SL::C2), row0, lane);
-        if (GATE_REGS) relu_gate<4>(dz[0], a2[0]);
+        relu_gate<4>(dz[0], a2[0]);            // c2's fragments are still live here in every variant (the output layer just read them)
         store_a_sw<4>(dz[0], T(SL::DZ4), row0, 0, lane);
       }
       {

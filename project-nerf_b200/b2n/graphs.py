@@ -3,8 +3,12 @@
 The small-batch configurations (vanilla NeRF at 4096 rays x 64 samples: ~40 kernels of 5-500 us each) are bound by
 launch and Python overhead, not by the kernels.  When every shape of a step is static -- no occupancy grid, so the
 number of evaluated samples is B * N -- the whole step (march, encode, tcgen05 decoder, composite, loss, backward,
-optimizer) can be captured once and replayed with one launch.  Steps behind an occupancy grid size their compact
-buffers from a device count (one 4-byte read per step, b2n/march.py) and cannot be captured.
+optimizer) can be captured once and replayed with one launch.  Steps behind an occupancy grid become capturable with
+``b2n.march.set_static_capacity(True)``: capacity-sized compact buffers and a device-side row count that every kernel
+honours (``b2n_set_active_rows``) replace the 4-byte host read of the active-sample count.
+
+The abort flags of tcgen05 launches captured into a graph are re-zeroed and re-written by every replay;
+``b2n.check_errors()`` inspects them (state of the latest replay) together with the eager launches' flags.
 
 All kernels of this package are launched on ``torch.cuda.current_stream()`` and allocate through torch, so
 ``torch.cuda.graph`` captures them like any torch op; tensor maps (TMA) are encoded on the host at capture time from
@@ -38,9 +42,15 @@ class GraphedStep:
                 fn(*self.static_inputs)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        from . import ops
+        n0 = len(ops._GRAPH_FLAGS)
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.static_outputs = fn(*self.static_inputs)
+        # abort flags of the tcgen05 launches inside the graph: owned here (freed with the graph), read by b2n.check_errors()
+        self._err_flags = ops._GRAPH_FLAGS[n0:]
+        del ops._GRAPH_FLAGS[n0:]
+        ops._GRAPH_OWNERS.add(self)
 
     def __call__(self, *inputs: torch.Tensor):
         for dst, src in zip(self.static_inputs, inputs):

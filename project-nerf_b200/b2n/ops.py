@@ -504,6 +504,8 @@ def instant_mlp(x_enc, dirs, bands, sigma_params, color_params, pad_value: float
 # (long finished) -- and a non-zero flag raises here rather than letting garbage activations train on.
 _ERR_FLAGS: dict = {}          # device index -> flags of launches not yet inspected
 _STICKY_ERR: dict = {}         # device index -> one flag shared by every tcgen05 Instant-decoder launch on that device
+_GRAPH_FLAGS: list = []        # abort flags of launches captured into CUDA graphs (state of the latest replay) ...
+_GRAPH_OWNERS = __import__("weakref").WeakSet()      # ... or owned by a b2n.graphs.GraphedStep (`_err_flags`), which frees them with itself
 
 
 def _raise_if_set(flags):
@@ -514,7 +516,10 @@ def _raise_if_set(flags):
 
 def _track_err(err: torch.Tensor):
     if torch.cuda.is_current_stream_capturing():
-        return          # inside a CUDA graph (b2n.graphs): no host reads; GraphedStep checks its own flags after replays
+        # inside a CUDA graph (b2n.graphs): no host reads now.  The flag lives in the graph's memory pool, is re-zeroed and
+        # re-written by every replay, and is inspected by check_errors() like the sticky flags
+        _GRAPH_FLAGS.append(err)
+        return
     lst = _ERR_FLAGS.setdefault(err.device.index, [])
     lst.append(err)
     if len(lst) >= 64:
@@ -546,6 +551,14 @@ def check_errors():
         flags, _ERR_FLAGS[dev] = _ERR_FLAGS[dev], []
         if flags:
             _raise_if_set(flags)
+    graph_flags = list(_GRAPH_FLAGS)
+    for owner in list(_GRAPH_OWNERS):
+        graph_flags += owner._err_flags
+    by_dev: dict = {}
+    for t in graph_flags:
+        by_dev.setdefault(t.device.index, []).append(t)
+    for flags in by_dev.values():
+        _raise_if_set(flags)
     for t in _STICKY_ERR.values():
         if int(t.item()) != 0:
             code = int(t.item())

@@ -166,6 +166,13 @@ def test_cuda_graph_step_equals_eager_step():
                 fn = step
             losses = [float(fn(*batches[i % 3]).detach()) for i in range(6)]
             torch.cuda.synchronize()
+            if graphed:      # the abort flags of the captured tcgen05 launches belong to the graph and are seen by check_errors()
+                assert len(fn._err_flags) >= 1 and all(int(t.item()) == 0 for t in fn._err_flags)
+                b2n.check_errors()
+                fn._err_flags[0].fill_(3)
+                with pytest.raises(RuntimeError, match="aborted"):
+                    b2n.check_errors()
+                fn._err_flags[0].zero_()
             finals.append((losses, {k: v.detach().clone() for k, v in model.named_parameters()}))
         (l0, p0), (l1, p1) = finals
         assert all(abs(a - b) < 2e-3 * max(abs(a), 1e-6) for a, b in zip(l0, l1)), (l0, l1)

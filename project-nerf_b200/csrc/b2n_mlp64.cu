@@ -992,8 +992,7 @@ k_instant_bwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
         float c[8][4] = {};
         gemm_dgrad<8, 4>(c, dz[0], sm + L.v2, SH, lane);        // d c1
         c_to_a<8, false>(c, dz[0]);
-        if (!GATE_REGS) relu_gate_sw<4>(dz[0], T(SL::C1), row0, lane);
-        if (GATE_REGS) relu_gate<4>(dz[0], a1[0]);
+        relu_gate<4>(dz[0], a1[0]);            // c1's fragments kept live across four stages: 16 registers against 4 ldmatrix + a warp sync
         store_a_sw<4>(dz[0], T(SL::DZ3), row0, 0, lane);
       }
       uint32_t dz2[1][4];

@@ -735,21 +735,6 @@ __device__ __forceinline__ void store_a_sw(const uint32_t (&a)[KT][4], op16* til
     asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(tile + sw(r, cb + 16 * k))),
                  "r"(a[k][0]), "r"(a[k][1]), "r"(a[k][2]), "r"(a[k][3]) : "memory");
 }
-// ReLU gate of packed gradient fragments by the staged activation tile (read back as A fragments with ldmatrix)
-template <int KT>
-__device__ __forceinline__ void relu_gate_sw(uint32_t (&dz)[KT][4], const op16* tile, int row0, int lane) {
-  const int r = row0 + (lane & 7) + 8 * ((lane >> 3) & 1);
-  const int cb = 8 * (lane >> 4);
-  const __half2 zero = __floats2half2_rn(0.f, 0.f);
-  __syncwarp();                  // the tile rows were written by other lanes of this warp (stmatrix)
-#pragma unroll
-  for (int k = 0; k < KT; ++k) {
-    uint32_t act[4];
-    ldsm_x4(act, tile + sw(r, cb + 16 * k));
-#pragma unroll
-    for (int i = 0; i < 4; ++i) dz[k][i] &= __hgt2_mask(*reinterpret_cast<const __half2*>(&act[i]), zero);
-  }
-}
 template <int POS_K, int GROUPS>
 constexpr size_t smem_bytes() {
   return (size_t)GROUPS * Slots<POS_K>::N * SLOT + (size_t)weight_layout<POS_K>().end * sizeof(op16) + 128;
@@ -779,9 +764,8 @@ k_instant_bwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
   using namespace bwtc;
   using namespace tc;
   using SL = Slots<POS_K>;
-  // ReLU gate of the gradient chain: from the forward's A fragments kept in registers (48 registers, 1.57 -> 1.53 ms at
-  // pos_dim 32 with two CTAs per SM) or, where registers are short, from the staged activation tiles
-  constexpr bool GATE_REGS = POS_K == 32 && GROUPS == 1;
+  // the ReLU gates of the gradient chain use the forward's A fragments, kept live in registers (HSET2 + LOP3 per pair;
+  // re-reading the staged tiles with ldmatrix was measured: 1.11 against 1.085 ms per 4.2 M points)
   P = clamp_rows(P, rows);
   // the operand tiles need a 1024-byte aligned base: dynamic shared memory starts on one when the kernel has no static
   // shared memory (checked: a misaligned base raises the error flag instead of computing garbage)
@@ -1017,8 +1001,7 @@ k_instant_bwd_tc(const float* __restrict__ x, int ldx, int pos_dim, const float*
         float c[8][4] = {};
         gemm_dgrad<8, 1>(c, dz2, sm + L.w2, SH, lane);          // d hidden1
         c_to_a<8, false>(c, dz[0]);
-        if (!GATE_REGS) relu_gate_sw<4>(dz[0], T(SL::H1), row0, lane);
-        if (GATE_REGS) relu_gate<4>(dz[0], ah[0]);
+        relu_gate<4>(dz[0], ah[0]);
         store_a_sw<4>(dz[0], T(SL::DZ1), row0, 0, lane);
       }
       // ---------------- weight gradients over the 64 staged points: 12 asynchronous MMAs
